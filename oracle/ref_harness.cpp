@@ -1,0 +1,276 @@
+// TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
+//
+// In-memory harness around the UNMODIFIED reference implementation
+// (/root/reference/Source, compiled where it lies by oracle/Makefile into
+// oracle/_ref/libaisref*.so).  It instantiates the reference's own
+// AIS::ModelDefault / ModelStandard / ModelBase (Source/DSP/Model.h:180-228),
+// feeds them RAW blocks of a caller-chosen chunk length through a
+// Device::Device subclass (Source/Device/Device.h:58) exactly as a device thread
+// would (Source/Device/FileRAW.cpp:121-137), and records
+//   * every AIS::Message the model publishes (Source/DSP/Model.h:87,96), and
+//   * optional float taps on the internal Connection<>s of the chain
+// so that the CPU restatement in oracle/ais_oracle.c and the CUDA path can be
+// compared against the real thing.  Built with -fno-access-control so private
+// block members (CGF_a, FC_a, CD_EMA_a[], ...) can be tapped without touching
+// the reference sources.  Nothing here is copied from the reference: it only
+// *uses* its public block interface (Source/Library/Stream.h:36-167).
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs may load the resulting library.
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "Model.h"
+#include "Device.h"
+
+void StopRequest() {} // Source/Library/Common.h:72 -- the application normally defines it
+
+namespace {
+
+struct MemDevice : public Device::Device {
+	void push(void *p, int bytes, Format f) {
+		RAW r{f, p, bytes};
+		Send(&r, 1, tag);
+	}
+};
+
+struct RecC : public StreamIn<CFLOAT32> {
+	std::vector<float> v, ppm;
+	void Receive(const CFLOAT32 *d, int len, TAG &tag) {
+		const float *f = (const float *)d;
+		v.insert(v.end(), f, f + 2 * (size_t)len);
+		ppm.push_back(tag.ppm);
+	}
+};
+
+struct RecF : public StreamIn<FLOAT32> {
+	std::vector<float> v;
+	void Receive(const FLOAT32 *d, int len, TAG &) { v.insert(v.end(), d, d + len); }
+};
+
+struct MsgSink : public StreamIn<AIS::Message> {
+	std::string text;
+	long count = 0;
+	void Receive(const AIS::Message *m, int len, TAG &tag) {
+		for (int i = 0; i < len; i++) {
+			char buf[128];
+			const AIS::Message &x = m[i];
+			int nbytes = (x.getLength() + 7) / 8;
+			snprintf(buf, sizeof(buf), "%c|%d|%lld|%lld|%.9g|%.9g|", x.getChannel(), x.getLength(),
+					 (long long)x.start_idx, (long long)x.end_idx, (double)tag.level, (double)tag.ppm);
+			text += buf;
+			for (int b = 0; b < nbytes; b++) {
+				snprintf(buf, sizeof(buf), "%02X", x.data[b]);
+				text += buf;
+			}
+			text += "|";
+			bool first = true;
+			for (const auto &s : x.sentences()) {
+				if (!first) text += " ";
+				text += s;
+				first = false;
+			}
+			text += "\n";
+			count++;
+		}
+	}
+};
+
+enum { MODEL_STANDARD = 0, MODEL_BASE = 1, MODEL_DEFAULT = 2 };
+enum { FLAG_PS_EMA = 1, FLAG_AFC_WIDE = 2, FLAG_DROOP = 4, FLAG_TAPS = 8 };
+static const int NTAPS_C = 9;  // 0: ROT in, 1/2: ROT up/down, 3/4: C_a/C_b, 5/6: CGF or (unused), 7/8: FC
+static const int NTAPS_F = 14; // 0..4 / 5..9: per-phase decoder inputs ch A / B; 10/11: FM out; 12/13: FR out
+
+struct Handle {
+	MemDevice dev;
+	AIS::ModelDefault *md = nullptr;
+	AIS::ModelStandard *ms = nullptr;
+	AIS::ModelBase *mb = nullptr;
+	AIS::ModelFrontend *fe = nullptr;
+	MsgSink sink;
+	RecC tc[NTAPS_C];
+	RecF tf[NTAPS_F];
+	Format fmt = Format::CF32;
+	int seq = 0; // per-handle stand-in for the process-global Message::ID (Source/Marine/Message.cpp:28)
+	~Handle() {
+		delete md;
+		delete ms;
+		delete mb;
+	}
+};
+
+template <typename T>
+bool feeds(Connection<T> &c, StreamIn<T> *s) {
+	for (auto p : c.connections)
+		if (p == s) return true;
+	return false;
+}
+
+} // namespace
+
+extern "C" {
+
+void *aisref_create(int model, int sample_rate, int format, unsigned flags, int own_mmsi) {
+	Handle *h = new Handle();
+	try {
+		switch (format) {
+		case 0: h->fmt = Format::CF32; break;
+		case 1: h->fmt = Format::CU8; break;
+		case 2: h->fmt = Format::CS8; break;
+		case 3: h->fmt = Format::CS16; break;
+		default: delete h; return nullptr;
+		}
+		const char *droop = (flags & FLAG_DROOP) ? "on" : "off";
+		if (model == MODEL_DEFAULT) {
+			h->md = new AIS::ModelDefault();
+			h->fe = h->md;
+			h->md->SetKey(AIS::KEY_SETTING_PS_EMA, (flags & FLAG_PS_EMA) ? "on" : "off");
+			h->md->SetKey(AIS::KEY_SETTING_AFC_WIDE, (flags & FLAG_AFC_WIDE) ? "on" : "off");
+		}
+		else if (model == MODEL_STANDARD) {
+			h->ms = new AIS::ModelStandard();
+			h->fe = h->ms;
+		}
+		else if (model == MODEL_BASE) {
+			h->mb = new AIS::ModelBase();
+			h->fe = h->mb;
+		}
+		else {
+			delete h;
+			return nullptr;
+		}
+		h->fe->SetKey(AIS::KEY_SETTING_DROOP, droop);
+		h->fe->setOwnMMSI(own_mmsi);
+		h->dev.setFormat(h->fmt);
+		h->dev.setSampleRate(sample_rate);
+		h->fe->buildModel('A', 'B', sample_rate, false, &h->dev);
+		h->fe->Output() >> h->sink;
+
+		if (flags & FLAG_TAPS) {
+			AIS::ModelFrontend *fe = h->fe;
+			// whichever Connection feeds ROT (depends on the rate, Source/DSP/Model.cpp:157-338)
+			Connection<CFLOAT32> *cands[] = {&fe->FDC.out, &fe->DS2_1.out, &fe->DSK.out, &fe->US.out, &fe->convert.out};
+			for (auto c : cands)
+				if (feeds<CFLOAT32>(*c, &fe->ROT)) {
+					c->Connect(&h->tc[0]);
+					break;
+				}
+			fe->ROT.up.Connect(&h->tc[1]);
+			fe->ROT.down.Connect(&h->tc[2]);
+			fe->C_a->Connect(&h->tc[3]);
+			fe->C_b->Connect(&h->tc[4]);
+			if (h->md) {
+				h->md->CGF_a.out.Connect(&h->tc[5]);
+				h->md->CGF_b.out.Connect(&h->tc[6]);
+				h->md->FC_a.out.Connect(&h->tc[7]);
+				h->md->FC_b.out.Connect(&h->tc[8]);
+				for (int i = 0; i < 5; i++) {
+					if (flags & FLAG_PS_EMA) {
+						h->md->CD_EMA_a[i].out.Connect(&h->tf[i]);
+						h->md->CD_EMA_b[i].out.Connect(&h->tf[5 + i]);
+					}
+					else {
+						h->md->CD_a[i].out.Connect(&h->tf[i]);
+						h->md->CD_b[i].out.Connect(&h->tf[5 + i]);
+					}
+				}
+			}
+			if (h->ms) {
+				h->ms->FM_a.out.Connect(&h->tf[10]);
+				h->ms->FM_b.out.Connect(&h->tf[11]);
+				h->ms->FR_a.out.Connect(&h->tf[12]);
+				h->ms->FR_b.out.Connect(&h->tf[13]);
+				for (int i = 0; i < 5; i++) {
+					h->ms->S_a.out[i].Connect(&h->tf[i]);
+					h->ms->S_b.out[i].Connect(&h->tf[5 + i]);
+				}
+			}
+			if (h->mb) {
+				h->mb->FM_a.out.Connect(&h->tf[10]);
+				h->mb->FM_b.out.Connect(&h->tf[11]);
+				h->mb->FR_a.out.Connect(&h->tf[12]);
+				h->mb->FR_b.out.Connect(&h->tf[13]);
+				h->mb->sampler_a.out.Connect(&h->tf[0]);
+				h->mb->sampler_b.out.Connect(&h->tf[5]);
+			}
+		}
+	}
+	catch (const std::exception &e) {
+		fprintf(stderr, "aisref_create: %s\n", e.what());
+		delete h;
+		return nullptr;
+	}
+	return h;
+}
+
+// one RAW block == one Device callback (chunk length is part of the parity contract)
+int aisref_push(void *hv, const void *data, long nbytes) {
+	Handle *h = (Handle *)hv;
+	AIS::Message::ID.store(h->seq);
+	h->dev.push((void *)data, (int)nbytes, h->fmt);
+	h->seq = AIS::Message::ID.load();
+	return 0;
+}
+
+// complex taps (interleaved re,im floats): returns float count; copies up to max and clears when dst != NULL
+long aisref_tap_c(void *hv, int tap, float *dst, long max) {
+	Handle *h = (Handle *)hv;
+	if (tap < 0 || tap >= NTAPS_C) return -1;
+	std::vector<float> &v = h->tc[tap].v;
+	long n = (long)v.size();
+	if (dst) {
+		long k = n < max ? n : max;
+		memcpy(dst, v.data(), k * sizeof(float));
+		v.clear();
+	}
+	return n;
+}
+
+// tag.ppm seen at each Receive of a complex tap (one value per CGF block for taps 5..8)
+long aisref_tap_ppm(void *hv, int tap, float *dst, long max) {
+	Handle *h = (Handle *)hv;
+	if (tap < 0 || tap >= NTAPS_C) return -1;
+	std::vector<float> &v = h->tc[tap].ppm;
+	long n = (long)v.size();
+	if (dst) {
+		long k = n < max ? n : max;
+		memcpy(dst, v.data(), k * sizeof(float));
+		v.clear();
+	}
+	return n;
+}
+
+long aisref_tap_f(void *hv, int tap, float *dst, long max) {
+	Handle *h = (Handle *)hv;
+	if (tap < 0 || tap >= NTAPS_F) return -1;
+	std::vector<float> &v = h->tf[tap].v;
+	long n = (long)v.size();
+	if (dst) {
+		long k = n < max ? n : max;
+		memcpy(dst, v.data(), k * sizeof(float));
+		v.clear();
+	}
+	return n;
+}
+
+long aisref_msg_count(void *hv) { return ((Handle *)hv)->sink.count; }
+
+// newline-separated records "ch|nbits|start_idx|end_idx|level|ppm|HEXPAYLOAD|nmea1 nmea2"
+long aisref_messages(void *hv, char *dst, long max) {
+	Handle *h = (Handle *)hv;
+	long n = (long)h->sink.text.size();
+	if (dst) {
+		long k = n < max ? n : max;
+		memcpy(dst, h->sink.text.data(), k);
+		h->sink.text.clear();
+	}
+	return n;
+}
+
+void aisref_destroy(void *hv) { delete (Handle *)hv; }
+
+} // extern "C"
