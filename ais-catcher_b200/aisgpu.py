@@ -1,0 +1,174 @@
+"""ctypes binding of the C ABI in include/aisgpu.h (test / bench harness side).
+
+The product is libaisgpu.so (csrc/*.cu, built by __graft_entry__.build()); this file only marshals
+arguments.  It fails loudly when the library is missing -- there is no fallback implementation.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libaisgpu.so")
+
+MODEL_STANDARD, MODEL_BASE, MODEL_DEFAULT = 0, 1, 2
+FMT_CF32, FMT_CU8, FMT_CS8, FMT_CS16 = 0, 1, 2, 3
+TAP_C, TAP_CGF, TAP_FIR, TAP_ROT, TAP_DEC, TAP_FM = 0, 1, 2, 3, 4, 5
+
+EXPORTS = ["aisgpu_abi_version", "aisgpu_default_config", "aisgpu_create", "aisgpu_submit", "aisgpu_submit_device",
+           "aisgpu_sync", "aisgpu_poll", "aisgpu_tap", "aisgpu_counters", "aisgpu_cuda_stream",
+           "aisgpu_last_frontend_ms", "aisgpu_last_launches", "aisgpu_last_error", "aisgpu_destroy"]
+
+
+class Config(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("model", C.c_int32), ("sample_rate", C.c_int32), ("format", C.c_int32),
+                ("n_streams", C.c_int32), ("max_chunk_samples", C.c_int32), ("ps_ema", C.c_int32), ("afc_wide", C.c_int32),
+                ("droop", C.c_int32), ("channel_a", C.c_char), ("channel_b", C.c_char), ("station", C.c_int32),
+                ("own_mmsi", C.c_int32), ("tag_mode", C.c_uint32), ("device", C.c_int32), ("enable_taps", C.c_int32),
+                ("max_frames", C.c_int32)]
+
+
+class MsgStruct(C.Structure):
+    _fields_ = [("stream", C.c_int32), ("channel", C.c_char), ("nbits", C.c_int32), ("start_idx", C.c_int64),
+                ("end_idx", C.c_int64), ("level", C.c_float), ("ppm", C.c_float), ("chunk", C.c_int64),
+                ("data", C.c_uint8 * 140), ("n_sentences", C.c_int32), ("nmea", (C.c_char * 100) * 4)]
+
+
+class Msg:
+    __slots__ = ("stream", "channel", "nbits", "start_idx", "end_idx", "level", "ppm", "chunk", "payload", "nmea")
+
+    def __init__(self, m):
+        self.stream = m.stream
+        self.channel = m.channel.decode()
+        self.nbits = m.nbits
+        self.start_idx = m.start_idx
+        self.end_idx = m.end_idx
+        self.level = m.level
+        self.ppm = m.ppm
+        self.chunk = m.chunk
+        self.payload = bytes(m.data[:(m.nbits + 7) // 8])
+        self.nmea = [m.nmea[i].value.decode() for i in range(min(m.n_sentences, 4))]
+
+    def key(self):
+        return (self.channel, self.nbits, self.payload, tuple(self.nmea))
+
+    def __repr__(self):
+        return "Msg(s%d,%s,%d,%s)" % (self.stream, self.channel, self.nbits, " ".join(self.nmea))
+
+
+_lib = None
+
+
+def load():
+    """dlopen libaisgpu.so and declare prototypes.  Raises if the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.aisgpu_abi_version.restype = C.c_int
+    lib.aisgpu_default_config.argtypes = [C.POINTER(Config)]
+    lib.aisgpu_default_config.restype = None
+    lib.aisgpu_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    lib.aisgpu_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.aisgpu_submit_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+    lib.aisgpu_sync.argtypes = [C.c_void_p]
+    lib.aisgpu_poll.argtypes = [C.c_void_p, C.POINTER(MsgStruct), C.c_int, C.POINTER(C.c_int)]
+    lib.aisgpu_tap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.aisgpu_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.aisgpu_cuda_stream.argtypes = [C.c_void_p]
+    lib.aisgpu_cuda_stream.restype = C.c_void_p
+    lib.aisgpu_last_frontend_ms.argtypes = [C.c_void_p]
+    lib.aisgpu_last_frontend_ms.restype = C.c_float
+    lib.aisgpu_last_launches.argtypes = [C.c_void_p]
+    lib.aisgpu_last_error.argtypes = [C.c_void_p]
+    lib.aisgpu_last_error.restype = C.c_char_p
+    lib.aisgpu_destroy.argtypes = [C.c_void_p]
+    lib.aisgpu_destroy.restype = None
+    _lib = lib
+    return lib
+
+
+class AisGpuError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One batch engine == one AIS::Model instance per stream of the batch (reference Source/DSP/Model.h:76-126)."""
+
+    def __init__(self, model=MODEL_DEFAULT, sample_rate=1536000, fmt=FMT_CF32, n_streams=1, max_chunk=131072,
+                 ps_ema=True, afc_wide=True, droop=True, own_mmsi=-1, device=0, taps=False, max_frames=0, tag_mode=3):
+        self.lib = load()
+        cfg = Config()
+        self.lib.aisgpu_default_config(C.byref(cfg))
+        cfg.model, cfg.sample_rate, cfg.format = model, sample_rate, fmt
+        cfg.n_streams, cfg.max_chunk_samples = n_streams, max_chunk
+        cfg.ps_ema, cfg.afc_wide, cfg.droop = int(ps_ema), int(afc_wide), int(droop)
+        cfg.own_mmsi, cfg.device, cfg.enable_taps, cfg.max_frames, cfg.tag_mode = own_mmsi, device, int(taps), max_frames, tag_mode
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        rc = self.lib.aisgpu_create(C.byref(cfg), C.byref(self.h))
+        if rc:
+            raise AisGpuError("aisgpu_create rc=%d: %s" % (rc, self.lib.aisgpu_last_error(None).decode()))
+        self.n_streams = n_streams
+        self.fmt = fmt
+
+    def _chk(self, rc):
+        if rc:
+            raise AisGpuError("rc=%d: %s" % (rc, self.lib.aisgpu_last_error(self.h).decode()))
+
+    def submit(self, host_array, n_samples):
+        """host_array: contiguous numpy array holding n_streams x n_samples samples (stream-major)."""
+        a = np.ascontiguousarray(host_array)
+        self._chk(self.lib.aisgpu_submit(self.h, a.ctypes.data_as(C.c_void_p), n_samples))
+
+    def submit_ptr(self, host_ptr, n_samples):
+        self._chk(self.lib.aisgpu_submit(self.h, C.c_void_p(host_ptr), n_samples))
+
+    def submit_device(self, dev_ptr, stride_samples, n_samples):
+        self._chk(self.lib.aisgpu_submit_device(self.h, C.c_void_p(dev_ptr), stride_samples, n_samples))
+
+    def sync(self):
+        self._chk(self.lib.aisgpu_sync(self.h))
+
+    def poll(self, batch=256):
+        out = []
+        buf = (MsgStruct * batch)()
+        n = C.c_int(0)
+        while True:
+            self._chk(self.lib.aisgpu_poll(self.h, buf, batch, C.byref(n)))
+            if n.value == 0:
+                break
+            out.extend(Msg(buf[i]) for i in range(n.value))
+        return out
+
+    def tap(self, tap, stream=0, channel=0, dtype=np.complex64, max_elems=1 << 22):
+        out = np.empty(max_elems, dtype=dtype)
+        n = C.c_size_t(0)
+        self._chk(self.lib.aisgpu_tap(self.h, tap, stream, channel, out.ctypes.data_as(C.c_void_p), out.nbytes, C.byref(n)))
+        return out[:n.value].copy()
+
+    def counters(self):
+        c = (C.c_uint64 * 8)()
+        self._chk(self.lib.aisgpu_counters(self.h, c))
+        return list(c)
+
+    def cuda_stream(self):
+        return self.lib.aisgpu_cuda_stream(self.h)
+
+    def last_frontend_ms(self):
+        return float(self.lib.aisgpu_last_frontend_ms(self.h))
+
+    def last_launches(self):
+        return int(self.lib.aisgpu_last_launches(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.aisgpu_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

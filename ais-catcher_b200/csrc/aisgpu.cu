@@ -1,0 +1,831 @@
+// aisgpu.cu -- host side of the C ABI declared in include/aisgpu.h.
+//
+// Mirrors, for a batch of streams, what AIS::ModelFrontend::buildModel + ModelDefault/Standard/Base::buildModel
+// wire up for one stream (reference Source/DSP/Model.cpp:27-356, 419-438, 484-577): the rate -> chain table, the
+// filter parameters, and the per-submit launch sequence of the kernels in aisgpu_kernels.cuh.  The only
+// arithmetic done on the host is the libm-dependent constant tables (Rotate step, FFT twiddles, CGF phasor
+// steps, Model.cpp:31, FFT.h:81-83, DSP.cpp:457-458) and the per-frame tail of AIS::Decoder::processData
+// (dB level, validate, buildNMEA: AIS.cpp:66-96, Message.cpp:398-413, 569-686).  No CPU fallback exists.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/aisgpu.h"
+#include "aisgpu_kernels.cuh"
+
+using namespace aisgpu;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+const float PI_F = 3.14159265358979323846f; // Library/Common.h:318
+
+float2 polar1(float theta) { // std::polar(1.0f, theta) through sincosf, as the reference build resolves it
+	float s, c;
+	sincosf(theta, &s, &c);
+	return make_float2(1.0f * c, 1.0f * s);
+}
+
+const float H_TAPS_RECEIVER[37] = { // DSP/Filters.h:24-33
+	0.00119025f, -0.00148464f, -0.00282428f, -0.00200561f, -0.00068852f, 0.00343044f, 0.00902093f, 0.01367867f,
+	0.01147965f, 0.0027259f, -0.01766614f, -0.04244429f, -0.0577468f, -0.05245161f, -0.01072754f, 0.0732564f,
+	0.17643278f, 0.25582214f, 0.28200453f, 0.25582214f, 0.17643278f, 0.0732564f, -0.01072754f, -0.05245161f,
+	-0.0577468f, -0.04244429f, -0.01766614f, 0.0027259f, 0.01147965f, 0.01367867f, 0.00902093f, 0.00343044f,
+	-0.00068852f, -0.00200561f, -0.00282428f, -0.00148464f, 0.00119025f };
+const float H_TAPS_COHERENT[17] = { // DSP/Filters.h:35-41
+	2.06995719e-06f, 3.18610148e-05f, 3.40605309e-04f, 2.52892989e-03f, 1.30411453e-02f, 4.67076746e-02f,
+	1.16186141e-01f, 2.00730781e-01f, 2.40861391e-01f, 2.00730781e-01f, 1.16186141e-01f, 4.67076746e-02f,
+	1.30411453e-02f, 2.52892989e-03f, 3.40605309e-04f, 3.18610148e-05f, 2.06995719e-06f };
+const float H_PS_COS[8] = { 9.9518472640441780e-01f, 9.5694033335306883e-01f, 8.8192125790916542e-01f, 7.7301044123076901e-01f,
+							6.3439326515712957e-01f, 4.7139671032286945e-01f, 2.9028464326824349e-01f, 9.8017099547459546e-02f }; // Demod.h:29-31
+const float H_PS_SIN[8] = { 9.8017143048367339e-02f, 2.9028468509743588e-01f, 4.7139674887287397e-01f, 6.3439329894649099e-01f,
+							7.7301046896098113e-01f, 8.8192127851457169e-01f, 9.5694034604181499e-01f, 9.9518473068888236e-01f };
+
+constexpr int HC = 512; // room in front of new 48 kHz samples: unconsumed CGF samples (<512) or FM/FIR history (37)
+constexpr int HE = 8;   // room in front of new symbol-stage samples: an incomplete group of 5 (<=4)
+
+int bytes_per_sample(int fmt) { return fmt == AISGPU_FMT_CF32 ? 8 : (fmt == AISGPU_FMT_CS16 ? 4 : 2); }
+
+} // namespace
+
+struct aisgpu_handle {
+	aisgpu_config cfg;
+	int k = 0, P = 0, P96 = 0, tile = 0, bps = 8;
+	int use_fdc = 0;
+	float fdc_alpha = 0, fdc_beta = 1;
+	int rows = 0;
+	int max_n48 = 0;
+	cudaStream_t stream = nullptr, copy_stream = nullptr;
+	cudaEvent_t ev_fe0 = nullptr, ev_fe1 = nullptr, ev_copy[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr };
+	bool fe_timed = false;
+	// input staging for host submits
+	unsigned char *d_in[2] = { nullptr, nullptr };
+	int in_cur = 0;
+	bool in_used[2] = { false, false };
+	unsigned char *d_tail[2] = { nullptr, nullptr };
+	int tail_cur = 0;
+	// Rotate
+	float2 *d_rot[2] = { nullptr, nullptr };
+	int rot_n96[2] = { 0, 0 };
+	int rot_cur = 0;
+	bool rot_valid = false;
+	float2 *d_rot_state = nullptr;
+	float2 mult;
+	// 48 kHz channel buffer
+	float2 *d_C = nullptr;
+	long long c_stride = 0;
+	int c_hist = 0; // samples kept in front of HC
+	// CGF
+	long long cgf_abs = 0;
+	int *d_stepidx = nullptr;
+	float2 *d_steptab = nullptr, *d_omega = nullptr, *d_cgf_rot = nullptr, *d_rots = nullptr;
+	float *d_ppmtab = nullptr;
+	long long r_stride = 0;
+	float2 *d_fir_hist[2] = { nullptr, nullptr };
+	int fir_cur = 0;
+	float2 *d_tap_cgf = nullptr;
+	// symbol stage
+	float2 *d_Ec = nullptr;
+	float *d_Ef = nullptr;
+	long long e_stride = 0;
+	int e_left = 0;
+	long long e_abs = 0;
+	PsState *d_ps = nullptr;
+	float *d_ps_mem = nullptr;
+	DecState *d_dec = nullptr;
+	uint32_t *d_dec_data = nullptr;
+	PllState *d_pll = nullptr;
+	float *d_tap_dec = nullptr, *d_tap_fm = nullptr;
+	int *d_tap_cnt = nullptr;
+	// frames
+	FrameRec *d_ring = nullptr;
+	int *d_ring_count = nullptr;
+	int ring_cap = 0;
+	std::vector<FrameRec> h_ring;
+	std::vector<aisgpu_msg> out_queue;
+	size_t out_pos = 0;
+	std::vector<int> seq; // per-stream multi-sentence sequence id (Message.cpp:28-39 is process-global in the reference)
+	// last-submit geometry (for taps)
+	int last_n = 0, last_n48 = 0, last_nE = 0, last_nsym = 0, last_e_begin = 0, last_launches = 0;
+	uint64_t counters[8] = { 0 };
+	long long chunk = 0;
+	float last_fe_ms = -1.0f;
+	std::string err;
+	FeParams fe;
+};
+
+namespace {
+
+#define CU(call)                                                                                   \
+	do {                                                                                           \
+		cudaError_t e_ = (call);                                                                   \
+		if (e_ != cudaSuccess) {                                                                   \
+			char b_[256];                                                                          \
+			snprintf(b_, sizeof(b_), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+			h->err = b_;                                                                           \
+			return AISGPU_ECUDA;                                                                   \
+		}                                                                                          \
+	} while (0)
+
+template <typename T>
+int dalloc(aisgpu_handle *h, T **p, size_t n) {
+	CU(cudaMalloc((void **)p, n * sizeof(T)));
+	CU(cudaMemsetAsync(*p, 0, n * sizeof(T), h->stream));
+	return 0;
+}
+
+// Model.cpp:129-338: which bucket, how many CIC stages, droop taps.  Returns <0 when unsupported.
+int plan_frontend(aisgpu_handle *h) {
+	const int sr = h->cfg.sample_rate;
+	if (sr < 96000 || sr > 12288000) {
+		h->err = "Model: sample rate must be between 96K and 12288K (inclusive).";
+		return AISGPU_EINVAL;
+	}
+	int k = -1;
+	for (int i = 0; i <= 7; i++)
+		if ((96000 << i) == sr) k = i;
+	if (k < 0) {
+		h->err = "sample rate is not one of the 96k*2^k buckets; the interpolated (Upsample) and /3 (DownsampleKFilter) "
+				 "front ends are not built yet";
+		return AISGPU_EINVAL;
+	}
+	h->k = k;
+	h->use_fdc = (h->cfg.droop && k > 0) ? 1 : 0;
+	float a = 0.0f;
+	switch (sr) {
+	case 12288000: case 6144000: a = -2.0f; break;
+	case 3072000: a = -1.5f; break;
+	case 1536000: case 768000: a = -1.2f; break;
+	case 384000: a = -1.1f; break;
+	case 192000: a = -0.8f; break;
+	default: break;
+	}
+	h->fdc_alpha = a;
+	h->fdc_beta = 1 - 2 * a; // DSP.h:293-297
+	// history needed in input samples: h_0 = 17 (FDC 2 + DS2 5 + FCIC5 2*5), h_l = 2 h_{l-1} + 5
+	int hk = 17;
+	for (int i = 0; i < k; i++) hk = 2 * hk + 5;
+	const int q = 1 << (k + 2);
+	h->P = (hk + q - 1) / q * q;
+	h->P96 = h->P >> k;
+	return 0;
+}
+
+void layout_frontend(aisgpu_handle *h, int tile) {
+	FeParams &p = h->fe;
+	const int k = h->k;
+	int off = 0;
+	auto take = [&](int n) {
+		int o = off;
+		off += (FE_HIST + n + FE_SLACK + 1) & ~1;
+		return o;
+	};
+	for (int l = 0; l <= k; l++) p.off_lv[l] = take(tile >> l);
+	p.off_up = take(tile >> k);
+	p.off_dn = take(tile >> k);
+	p.off_wa = take(tile >> (k + 1));
+	p.off_wb = take(tile >> (k + 1));
+	p.smem_f2 = off;
+	p.tile = tile;
+	h->tile = tile;
+}
+
+int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int N) {
+	FeParams &p = h->fe;
+	const int q = 1 << (h->k + 2);
+	int tile = 2560;
+	if (tile % q) tile = (tile / q + 1) * q;
+	if (tile > N) tile = N;
+	if (tile != p.tile) layout_frontend(h, tile);
+	const int B = h->cfg.n_streams;
+	int n_seg = (6000 + B - 1) / B;
+	int tiles_total = (N + tile - 1) / tile;
+	if (n_seg > tiles_total) n_seg = tiles_total;
+	if (n_seg < 1) n_seg = 1;
+	int tiles_per_seg = (tiles_total + n_seg - 1) / n_seg;
+	p.seg_len = tiles_per_seg * tile;
+	n_seg = (N + p.seg_len - 1) / p.seg_len;
+	p.in = dev_in;
+	p.tail = h->d_tail[h->tail_cur];
+	p.in_stride = stride;
+	p.format = h->cfg.format;
+	p.k = h->k;
+	p.N = N;
+	p.P = h->P;
+	p.use_fdc = h->use_fdc;
+	p.fdc_alpha = h->fdc_alpha;
+	p.fdc_beta = h->fdc_beta;
+	p.rot = h->d_rot[h->rot_cur];
+	p.C = h->d_C;
+	p.c_stride = h->c_stride;
+	p.c_off = HC;
+	const size_t smem = (size_t)p.smem_f2 * sizeof(float2);
+	dim3 grid(n_seg, B);
+	switch (h->cfg.format) {
+	case AISGPU_FMT_CF32:
+		CU(cudaFuncSetAttribute(k_frontend<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		k_frontend<0><<<grid, FE_THREADS, smem, h->stream>>>(p);
+		break;
+	case AISGPU_FMT_CU8:
+		CU(cudaFuncSetAttribute(k_frontend<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		k_frontend<1><<<grid, FE_THREADS, smem, h->stream>>>(p);
+		break;
+	case AISGPU_FMT_CS8:
+		CU(cudaFuncSetAttribute(k_frontend<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		k_frontend<2><<<grid, FE_THREADS, smem, h->stream>>>(p);
+		break;
+	default:
+		CU(cudaFuncSetAttribute(k_frontend<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		k_frontend<3><<<grid, FE_THREADS, smem, h->stream>>>(p);
+		break;
+	}
+	CU(cudaGetLastError());
+	return 0;
+}
+
+template <typename T>
+int carry(aisgpu_handle *h, T *buf, long long stride, int src_begin, int dst_begin, int cnt) {
+	if (cnt <= 0 || src_begin == dst_begin) return 0;
+	k_carry<T><<<h->rows, 128, cnt * sizeof(T), h->stream>>>(buf, stride, src_begin, dst_begin, cnt);
+	CU(cudaGetLastError());
+	h->last_launches++;
+	return 0;
+}
+
+int run_symbols(aisgpu_handle *h, int n_new) {
+	// n_new samples were appended at [HE, HE + n_new) of every row of Ec/Ef; e_left older ones sit just before HE
+	const int total = h->e_left + n_new;
+	const int nsym = total / 5;
+	const int e_begin = HE - h->e_left;
+	h->last_nsym = nsym;
+	h->last_e_begin = e_begin;
+	if (nsym > 0) {
+		K3Params p;
+		memset(&p, 0, sizeof(p));
+		p.model = h->cfg.model;
+		p.ps_ema = h->cfg.ps_ema;
+		p.rows = h->rows;
+		p.nsym = nsym;
+		p.e_stride = h->e_stride;
+		p.e_begin = e_begin;
+		p.abs_begin = h->e_abs;
+		p.Ec = h->d_Ec;
+		p.Ef = h->d_Ef;
+		p.ps = h->d_ps;
+		p.ps_mem = h->d_ps_mem;
+		p.dec = h->d_dec;
+		p.dec_data = h->d_dec_data;
+		p.ring = h->d_ring;
+		p.ring_count = h->d_ring_count;
+		p.ring_cap = h->ring_cap;
+		p.chunk = (int)h->chunk;
+		p.mode_level = (h->cfg.tag_mode & 1) ? 1 : 0;
+		if (h->cfg.model == AISGPU_MODEL_DEFAULT) {
+			p.stepidx = h->d_stepidx;
+			p.ppmtab = h->d_ppmtab;
+			p.blk_abs0 = h->cgf_abs;
+			p.nblk = n_new / CGF_N;
+		}
+		p.tap_dec = h->cfg.enable_taps ? h->d_tap_dec : nullptr;
+		const int warps = (h->rows + K3_GROUPS_PER_WARP - 1) / K3_GROUPS_PER_WARP;
+		const int ctas = (warps + K3_THREADS / 32 - 1) / (K3_THREADS / 32);
+		k_symbols<<<ctas, K3_THREADS, 0, h->stream>>>(p);
+		CU(cudaGetLastError());
+		h->last_launches++;
+	}
+	const int new_left = total - nsym * 5;
+	if (h->cfg.model == AISGPU_MODEL_DEFAULT) {
+		if (carry(h, h->d_Ec, h->e_stride, e_begin + nsym * 5, HE - new_left, new_left)) return AISGPU_ECUDA;
+	}
+	else {
+		if (carry(h, h->d_Ef, h->e_stride, e_begin + nsym * 5, HE - new_left, new_left)) return AISGPU_ECUDA;
+	}
+	h->e_left = new_left;
+	h->e_abs += (long long)nsym * 5;
+	return 0;
+}
+
+int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N) {
+	const int q = 1 << (h->k + 2);
+	if (N <= 0 || N > h->cfg.max_chunk_samples || (N % q) != 0) {
+		char b[160];
+		snprintf(b, sizeof(b), "n_samples=%d must be a positive multiple of %d and <= max_chunk_samples=%d", N, q, h->cfg.max_chunk_samples);
+		h->err = b;
+		return AISGPU_EINVAL;
+	}
+	h->last_launches = 0;
+	const int k = h->k, B = h->cfg.n_streams;
+	const int n96 = N >> k, n48 = n96 >> 1;
+	// ---- K0: Rotate phasor table ----
+	{
+		const int nxt = h->rot_cur ^ 1;
+		const float2 *prev_tail = h->rot_valid ? h->d_rot[h->rot_cur] + h->rot_n96[h->rot_cur] : nullptr;
+		k_rot_table<<<1, 32, 0, h->stream>>>(h->d_rot[nxt], prev_tail, h->d_rot_state, h->mult, h->P96, n96);
+		CU(cudaGetLastError());
+		h->rot_cur = nxt;
+		h->rot_n96[nxt] = n96;
+		h->rot_valid = true;
+		h->last_launches++;
+	}
+	// ---- K1: fused front end ----
+	CU(cudaEventRecord(h->ev_fe0, h->stream));
+	if (int rc = launch_frontend(h, dev_in, stride, N)) return rc;
+	CU(cudaEventRecord(h->ev_fe1, h->stream));
+	h->fe_timed = true;
+	h->last_launches++;
+	// ---- front-end history for the next submit ----
+	{
+		const int nxt = h->tail_cur ^ 1;
+		dim3 grid((unsigned)std::min<long long>(64, ((long long)h->P * h->bps + 255) / 256), B);
+		k_tail_update<<<grid, 256, 0, h->stream>>>(h->d_tail[nxt], h->d_tail[h->tail_cur], (const unsigned char *)dev_in, stride, N, h->P, h->bps);
+		CU(cudaGetLastError());
+		h->tail_cur = nxt;
+		h->last_launches++;
+	}
+	h->last_n = N;
+	h->last_n48 = n48;
+	h->last_nE = 0;
+	h->last_nsym = 0;
+	// ---- back end ----
+	if (h->cfg.model == AISGPU_MODEL_DEFAULT) {
+		const int cnt = h->c_hist; // unconsumed samples in front of HC
+		const int total = cnt + n48;
+		const int nblk = total / CGF_N;
+		const int c_begin = HC - cnt;
+		if (nblk > 0) {
+			const int total_blocks = h->rows * nblk;
+			const int ctas = (total_blocks + CGF_BLK_PER_CTA - 1) / CGF_BLK_PER_CTA;
+			const size_t smem = 4096 + 2 * (size_t)CGF_BLK_PER_CTA * CGF_ROWP * 4;
+			k_cgf_estimate<<<ctas, CGF_THREADS, smem, h->stream>>>(h->d_C, h->c_stride, c_begin, nblk, total_blocks, h->d_omega,
+																	 h->cfg.afc_wide, h->d_stepidx);
+			CU(cudaGetLastError());
+			k_cgf_rot<<<(h->rows + 31) / 32, 32, 0, h->stream>>>(h->d_stepidx, h->d_steptab, h->d_cgf_rot, h->d_rots, h->r_stride, nblk, h->rows);
+			CU(cudaGetLastError());
+			const int nE = nblk * CGF_N;
+			dim3 grid((nE + FIRC_TILE - 1) / FIRC_TILE, h->rows);
+			k_cgf_derot_fir<<<grid, FIRC_TILE, 0, h->stream>>>(h->d_C, h->c_stride, c_begin, h->d_rots, h->r_stride, nE, h->d_fir_hist[h->fir_cur],
+																 h->d_fir_hist[h->fir_cur ^ 1], h->d_Ec, h->e_stride, HE,
+																 h->cfg.enable_taps ? h->d_tap_cgf : nullptr, h->r_stride);
+			CU(cudaGetLastError());
+			h->fir_cur ^= 1;
+			h->last_launches += 3;
+			h->last_nE = nE;
+			if (int rc = run_symbols(h, nE)) return rc;
+			h->cgf_abs += nE;
+		}
+		const int newcnt = total - nblk * CGF_N;
+		if (int rc = carry(h, h->d_C, h->c_stride, c_begin + nblk * CGF_N, HC - newcnt, newcnt)) return rc;
+		h->c_hist = newcnt;
+	}
+	else {
+		dim3 grid((n48 + FIRF_TILE - 1) / FIRF_TILE, h->rows);
+		k_fm_fir<<<grid, FIRF_TILE, 0, h->stream>>>(h->d_C, h->c_stride, HC, n48, h->d_Ef, h->e_stride, HE,
+													 h->cfg.enable_taps ? h->d_tap_fm : nullptr, h->r_stride);
+		CU(cudaGetLastError());
+		h->last_launches++;
+		h->last_nE = n48;
+		if (int rc = carry(h, h->d_C, h->c_stride, HC + n48 - FIRF_T, HC - FIRF_T, FIRF_T)) return rc;
+		if (h->cfg.model == AISGPU_MODEL_STANDARD) {
+			if (int rc = run_symbols(h, n48)) return rc;
+		}
+		else {
+			k_base<<<(h->rows + K3_THREADS - 1) / K3_THREADS, K3_THREADS, 0, h->stream>>>(
+				h->d_Ef, h->e_stride, HE, n48, h->rows, h->d_pll, h->d_dec, h->d_dec_data, h->d_ring, h->d_ring_count, h->ring_cap, (int)h->chunk,
+				h->cfg.enable_taps ? h->d_tap_dec : nullptr, h->cfg.enable_taps ? h->d_tap_cnt : nullptr);
+			CU(cudaGetLastError());
+			h->last_launches++;
+		}
+	}
+	h->counters[2] += (uint64_t)N;
+	h->counters[3] += 1;
+	h->chunk++;
+	return 0;
+}
+
+// Message::getLetter (Message.cpp:643-662)
+char msg_letter(const uint8_t *data, int length, int pos) {
+	int start = pos * 6, end = start + 6;
+	if (end > 1064 || start < 0) return 0;
+	int x = start >> 3, y = start & 7;
+	unsigned w = ((unsigned)data[x] << 8) | data[x + 1];
+	int l = (w >> (16 - 6 - y)) & 0x3F;
+	int overrun = end - length;
+	if (overrun > 0) l &= 0x3F << overrun;
+	return (char)(l < 40 ? l + 48 : l + 56);
+}
+
+bool msg_validate(const uint8_t *d, int length) { // Message.cpp:398-413
+	static const int ml[28] = { 149, 149, 149, 168, 418, 88, 72, 56, 168, 70, 168, 72, 40, 40, 88, 92, 80, 168, 312, 70, 271, 145, 154, 160, 72, 60, 96, 168 };
+	if (length == 0) return true;
+	if (length > 1064) return false;
+	unsigned t = d[0] >> 2;
+	if (t < 1 || t > 28) return false;
+	return length >= ml[t - 1];
+}
+
+void build_nmea(aisgpu_handle *h, aisgpu_msg &m) { // Message.cpp:569-631
+	static const char hex[] = "0123456789ABCDEF";
+	const uint8_t *data = m.data;
+	const int length = m.nbits;
+	const unsigned mmsi = ((unsigned)data[1] << 22) | (data[2] << 14) | (data[3] << 6) | (data[4] >> 2);
+	int nletters = (length + 5) / 6;
+	int nsent = nletters == 0 ? 1 : (nletters + 55) / 56;
+	char own = (h->cfg.own_mmsi == (int)mmsi) ? 'O' : 'M';
+	char seq = 0;
+	if (nsent > 1) {
+		int &s = h->seq[m.stream];
+		seq = (char)(s + '0');
+		s = (s + 1) % 10;
+	}
+	m.n_sentences = nsent;
+	for (int s = 0, l = 0; s < nsent && s < 4; s++) {
+		char *p = m.nmea[s];
+		memcpy(p, "!AIVDM,X,X,", 11);
+		p[5] = own;
+		p[7] = (char)(nsent + '0');
+		p[9] = (char)(s + 1 + '0');
+		int i = 11;
+		if (seq) p[i++] = seq;
+		p[i++] = ',';
+		if (m.channel != '?') p[i++] = m.channel;
+		p[i++] = ',';
+		int letters = std::min(nletters - l, 56);
+		for (int k = 0; k < letters; k++) p[i++] = msg_letter(data, length, l + k);
+		l += letters;
+		p[i++] = ',';
+		p[i++] = (char)(((s == nsent - 1) ? nletters * 6 - length : 0) + '0');
+		int c = 0;
+		for (int k = 1; k < i; k++) c ^= (unsigned char)p[k];
+		p[i++] = '*';
+		p[i++] = hex[(c >> 4) & 0xF];
+		p[i++] = hex[c & 0xF];
+		p[i] = 0;
+	}
+}
+
+int drain_ring(aisgpu_handle *h) {
+	CU(cudaStreamSynchronize(h->stream));
+	int count = 0;
+	CU(cudaMemcpy(&count, h->d_ring_count, sizeof(int), cudaMemcpyDeviceToHost));
+	if (count <= 0) return 0;
+	int n = std::min(count, h->ring_cap);
+	if (count > h->ring_cap) h->counters[4] += (uint64_t)(count - h->ring_cap);
+	h->h_ring.resize(n);
+	CU(cudaMemcpy(h->h_ring.data(), h->d_ring, (size_t)n * sizeof(FrameRec), cudaMemcpyDeviceToHost));
+	CU(cudaMemset(h->d_ring_count, 0, sizeof(int)));
+	// reference emission order: per submit, stream-major, channel A (ROT.up) before B (DSP.cpp:312-313), then time
+	std::stable_sort(h->h_ring.begin(), h->h_ring.end(), [](const FrameRec &a, const FrameRec &b) {
+		if (a.chunk != b.chunk) return a.chunk < b.chunk;
+		return a.row < b.row;
+	});
+	for (const FrameRec &r : h->h_ring) {
+		h->counters[0]++;
+		aisgpu_msg m;
+		memset(&m, 0, sizeof(m));
+		m.stream = r.row >> 1;
+		m.channel = (r.row & 1) ? h->cfg.channel_b : h->cfg.channel_a;
+		m.nbits = (r.nbits >= 0 && r.nbits <= 1064) ? r.nbits : 0; // Message::setLength (Message.h:288-292)
+		m.start_idx = r.start_idx;
+		m.end_idx = r.end_idx;
+		m.ppm = r.ppm;
+		m.chunk = r.chunk;
+		float lvl = r.level;
+		if ((h->cfg.tag_mode & 1) && lvl != 0.0) lvl = (float)(10.0f * log10(lvl)); // AIS.cpp:74-75
+		m.level = lvl;
+		memcpy(m.data, r.data, 140);
+		if (!msg_validate(m.data, m.nbits)) continue; // AIS.cpp:87-93: dropped, siblings were still reset
+		build_nmea(h, m);
+		h->counters[1]++;
+		h->counters[(r.row & 1) ? 6 : 5]++;
+		h->out_queue.push_back(m);
+	}
+	return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int aisgpu_abi_version(void) { return AISGPU_ABI_VERSION; }
+
+void aisgpu_default_config(aisgpu_config *cfg) {
+	memset(cfg, 0, sizeof(*cfg));
+	cfg->struct_size = sizeof(*cfg);
+	cfg->model = AISGPU_MODEL_DEFAULT;
+	cfg->sample_rate = 1536000;
+	cfg->format = AISGPU_FMT_CF32;
+	cfg->n_streams = 1;
+	cfg->max_chunk_samples = 131072;
+	cfg->ps_ema = 1;
+	cfg->afc_wide = 1;
+	cfg->droop = 1;
+	cfg->channel_a = 'A';
+	cfg->channel_b = 'B';
+	cfg->station = 0;
+	cfg->own_mmsi = -1;
+	cfg->tag_mode = 3;
+	cfg->device = 0;
+	cfg->enable_taps = 0;
+	cfg->max_frames = 0;
+}
+
+const char *aisgpu_last_error(aisgpu_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+static int create_impl(aisgpu_handle *h) {
+	const aisgpu_config &c = h->cfg;
+	if (c.model != AISGPU_MODEL_DEFAULT && c.model != AISGPU_MODEL_STANDARD && c.model != AISGPU_MODEL_BASE) {
+		h->err = "unknown model kind";
+		return AISGPU_EINVAL;
+	}
+	if (c.format < 0 || c.format > 3 || c.n_streams < 1 || c.max_chunk_samples < 1) {
+		h->err = "bad format / n_streams / max_chunk_samples";
+		return AISGPU_EINVAL;
+	}
+	if (int rc = plan_frontend(h)) return rc;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+		h->err = "no CUDA device (the B200 path has no CPU fallback)";
+		return AISGPU_ENODEV;
+	}
+	if (c.device < 0 || c.device >= ndev) {
+		h->err = "CUDA device ordinal out of range";
+		return AISGPU_ENODEV;
+	}
+	CU(cudaSetDevice(c.device));
+	CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+	CU(cudaEventCreate(&h->ev_fe0));
+	CU(cudaEventCreate(&h->ev_fe1));
+	for (int i = 0; i < 2; i++) {
+		CU(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+	}
+	const int B = c.n_streams, k = h->k;
+	const int q = 1 << (k + 2);
+	const int maxN = (c.max_chunk_samples + q - 1) / q * q;
+	h->cfg.max_chunk_samples = maxN;
+	h->rows = 2 * B;
+	h->bps = bytes_per_sample(c.format);
+	h->max_n48 = maxN >> (k + 1);
+	h->seq.assign(B, 0);
+	for (int i = 0; i < 2; i++) {
+		if (int rc = dalloc(h, &h->d_tail[i], (size_t)B * h->P * h->bps)) return rc;
+		if (int rc = dalloc(h, &h->d_rot[i], (size_t)h->P96 + (maxN >> k) + 8)) return rc;
+		if (int rc = dalloc(h, &h->d_fir_hist[i], (size_t)h->rows * 16)) return rc;
+	}
+	if (int rc = dalloc(h, &h->d_rot_state, 1)) return rc;
+	{
+		float2 one = make_float2(1.0f, 0.0f);
+		CU(cudaMemcpyAsync(h->d_rot_state, &one, sizeof(one), cudaMemcpyHostToDevice, h->stream));
+		h->mult = polar1((float)(PI_F * 25000.0 / 48000.0)); // Model.cpp:31
+	}
+	h->c_stride = (HC + h->max_n48 + 8 + 1) & ~1LL;
+	if (int rc = dalloc(h, &h->d_C, (size_t)h->rows * h->c_stride)) return rc;
+	const int nEmax = HC + h->max_n48;
+	h->e_stride = (HE + nEmax + 8 + 1) & ~1LL;
+	h->r_stride = nEmax;
+	if (int rc = dalloc(h, &h->d_dec, (size_t)h->rows * 5)) return rc;
+	if (int rc = dalloc(h, &h->d_dec_data, (size_t)h->rows * 5 * DEC_WORDS)) return rc;
+	if (c.model == AISGPU_MODEL_DEFAULT) {
+		h->c_hist = 0;
+		if (int rc = dalloc(h, &h->d_stepidx, (size_t)h->rows * (nEmax / CGF_N + 1))) return rc;
+		if (int rc = dalloc(h, &h->d_rots, (size_t)h->rows * h->r_stride)) return rc;
+		if (int rc = dalloc(h, &h->d_cgf_rot, (size_t)h->rows)) return rc;
+		if (int rc = dalloc(h, &h->d_Ec, (size_t)h->rows * h->e_stride)) return rc;
+		if (int rc = dalloc(h, &h->d_ps, (size_t)h->rows * 5)) return rc;
+		if (!c.ps_ema)
+			if (int rc = dalloc(h, &h->d_ps_mem, (size_t)h->rows * 5 * 16 * 12)) return rc;
+		if (int rc = dalloc(h, &h->d_steptab, CGF_NIDX)) return rc;
+		if (int rc = dalloc(h, &h->d_ppmtab, CGF_NIDX)) return rc;
+		if (int rc = dalloc(h, &h->d_omega, CGF_N)) return rc;
+		std::vector<float2> one(h->rows, make_float2(1.0f, 0.0f));
+		CU(cudaMemcpyAsync(h->d_cgf_rot, one.data(), one.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+		std::vector<float2> om(CGF_N), st(CGF_NIDX);
+		std::vector<float> pp(CGF_NIDX);
+		for (int s = 0; s < CGF_N; s++) om[s] = polar1((float)(-2.0 * PI_F) * (float)s / (float)CGF_N); // FFT.h:81-83
+		for (int idx = 0; idx < CGF_NIDX; idx++) { // DSP.cpp:453,457-458,466
+			float fz = -1;
+			if (idx != CGF_IDX_NONE) {
+				int i = idx - CGF_IDX_OFFSET;
+				fz = (CGF_N / 2 - (i + 102 / 2.0f));
+			}
+			float f = fz / 2.0f / CGF_N;
+			st[idx] = polar1((float)(f * 2 * PI_F));
+			pp[idx] = f * 48000.0f / 162.0f;
+		}
+		CU(cudaMemcpyAsync(h->d_omega, om.data(), om.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+		CU(cudaMemcpyAsync(h->d_steptab, st.data(), st.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+		CU(cudaMemcpyAsync(h->d_ppmtab, pp.data(), pp.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+		CU(cudaStreamSynchronize(h->stream)); // host vectors go out of scope
+		CU(cudaFuncSetAttribute(k_cgf_estimate, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 + 2 * CGF_BLK_PER_CTA * CGF_ROWP * 4));
+		if (c.enable_taps)
+			if (int rc = dalloc(h, &h->d_tap_cgf, (size_t)h->rows * h->r_stride)) return rc;
+	}
+	else {
+		h->c_hist = FIRF_T;
+		if (int rc = dalloc(h, &h->d_Ef, (size_t)h->rows * h->e_stride)) return rc;
+		if (c.model == AISGPU_MODEL_BASE) {
+			if (int rc = dalloc(h, &h->d_pll, (size_t)h->rows)) return rc;
+			std::vector<PllState> pl(h->rows);
+			for (auto &x : pl) { x.prev = 0; x.pll = 0.0f; x.fast = 1; }
+			CU(cudaMemcpyAsync(h->d_pll, pl.data(), pl.size() * sizeof(PllState), cudaMemcpyHostToDevice, h->stream));
+			CU(cudaStreamSynchronize(h->stream));
+		}
+		if (c.enable_taps) {
+			if (int rc = dalloc(h, &h->d_tap_fm, (size_t)h->rows * h->r_stride)) return rc;
+			if (int rc = dalloc(h, &h->d_tap_cnt, (size_t)h->rows)) return rc;
+		}
+	}
+	if (c.enable_taps)
+		if (int rc = dalloc(h, &h->d_tap_dec, (size_t)h->rows * 5 * (nEmax / 5 + 2))) return rc;
+	CU(cudaMemcpyToSymbol(c_taps_coherent, H_TAPS_COHERENT, sizeof(H_TAPS_COHERENT)));
+	CU(cudaMemcpyToSymbol(c_taps_receiver, H_TAPS_RECEIVER, sizeof(H_TAPS_RECEIVER)));
+	CU(cudaMemcpyToSymbol(c_ps_cos, H_PS_COS, sizeof(H_PS_COS)));
+	CU(cudaMemcpyToSymbol(c_ps_sin, H_PS_SIN, sizeof(H_PS_SIN)));
+	h->ring_cap = c.max_frames > 0 ? c.max_frames : std::max(4096, B * 64);
+	if (int rc = dalloc(h, &h->d_ring, (size_t)h->ring_cap)) return rc;
+	if (int rc = dalloc(h, &h->d_ring_count, 1)) return rc;
+	memset(&h->fe, 0, sizeof(h->fe));
+	CU(cudaStreamSynchronize(h->stream));
+	return 0;
+}
+
+int aisgpu_create(const aisgpu_config *cfg, aisgpu_handle **out) {
+	if (!cfg || !out || cfg->struct_size != sizeof(aisgpu_config)) {
+		g_create_error = "aisgpu_create: null argument or struct_size mismatch";
+		return AISGPU_EINVAL;
+	}
+	aisgpu_handle *h = new aisgpu_handle();
+	h->cfg = *cfg;
+	int rc = create_impl(h);
+	if (rc) {
+		g_create_error = h->err;
+		aisgpu_destroy(h);
+		*out = nullptr;
+		return rc;
+	}
+	*out = h;
+	return 0;
+}
+
+int aisgpu_submit_device(aisgpu_handle *h, const void *dev_samples, int64_t stride_samples, int n_samples) {
+	if (!h || !dev_samples) return AISGPU_EINVAL;
+	CU(cudaSetDevice(h->cfg.device));
+	if (stride_samples < n_samples || (stride_samples & 1)) {
+		h->err = "stride_samples must be even and >= n_samples";
+		return AISGPU_EINVAL;
+	}
+	return submit_common(h, dev_samples, stride_samples, n_samples);
+}
+
+int aisgpu_submit(aisgpu_handle *h, const void *host_samples, int n_samples) {
+	if (!h || !host_samples) return AISGPU_EINVAL;
+	CU(cudaSetDevice(h->cfg.device));
+	const int q = 1 << (h->k + 2);
+	if (n_samples <= 0 || n_samples > h->cfg.max_chunk_samples || (n_samples % q) != 0) {
+		char b[160];
+		snprintf(b, sizeof(b), "n_samples=%d must be a positive multiple of %d and <= max_chunk_samples=%d", n_samples, q, h->cfg.max_chunk_samples);
+		h->err = b;
+		return AISGPU_EINVAL;
+	}
+	const size_t bytes = (size_t)h->cfg.n_streams * n_samples * h->bps;
+	const int cur = h->in_cur;
+	if (!h->d_in[cur]) CU(cudaMalloc((void **)&h->d_in[cur], (size_t)h->cfg.n_streams * h->cfg.max_chunk_samples * h->bps));
+	// the staging buffer may still be read by the kernels of the submit before last
+	if (h->in_used[cur]) CU(cudaStreamWaitEvent(h->copy_stream, h->ev_done[cur], 0));
+	CU(cudaMemcpyAsync(h->d_in[cur], host_samples, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+	CU(cudaEventRecord(h->ev_copy[cur], h->copy_stream));
+	CU(cudaStreamWaitEvent(h->stream, h->ev_copy[cur], 0));
+	int rc = submit_common(h, h->d_in[cur], n_samples, n_samples);
+	if (rc) return rc;
+	CU(cudaEventRecord(h->ev_done[cur], h->stream));
+	h->in_used[cur] = true;
+	h->in_cur ^= 1;
+	// the caller's buffer is only borrowed for the call (Stream.h:41 semantics): wait for the copy, not for the kernels
+	CU(cudaEventSynchronize(h->ev_copy[cur]));
+	return 0;
+}
+
+int aisgpu_sync(aisgpu_handle *h) {
+	if (!h) return AISGPU_EINVAL;
+	CU(cudaStreamSynchronize(h->stream));
+	return 0;
+}
+
+int aisgpu_poll(aisgpu_handle *h, aisgpu_msg *out, int max, int *n) {
+	if (!h || !n || (max > 0 && !out)) return AISGPU_EINVAL;
+	CU(cudaSetDevice(h->cfg.device));
+	if (h->out_pos >= h->out_queue.size()) {
+		h->out_queue.clear();
+		h->out_pos = 0;
+		if (int rc = drain_ring(h)) return rc;
+	}
+	int k = 0;
+	while (k < max && h->out_pos < h->out_queue.size()) out[k++] = h->out_queue[h->out_pos++];
+	*n = k;
+	return 0;
+}
+
+int aisgpu_tap(aisgpu_handle *h, int tap, int stream, int channel, void *dst, size_t dst_bytes, size_t *n_out) {
+	if (!h || !n_out || stream < 0 || stream >= h->cfg.n_streams || channel < 0 || channel > 9) return AISGPU_EINVAL;
+	CU(cudaSetDevice(h->cfg.device));
+	CU(cudaStreamSynchronize(h->stream));
+	const int row = stream * 2 + (channel & 1);
+	const void *src = nullptr;
+	size_t n = 0, esz = 8;
+	switch (tap) {
+	case AISGPU_TAP_C:
+		src = h->d_C + (long long)row * h->c_stride + HC; // note: valid until the next submit only for [0, n48)
+		n = h->last_n48;
+		break;
+	case AISGPU_TAP_CGF:
+		if (!h->d_tap_cgf) { h->err = "taps not enabled or not a ModelDefault engine"; return AISGPU_EINVAL; }
+		src = h->d_tap_cgf + (long long)row * h->r_stride;
+		n = h->last_nE;
+		break;
+	case AISGPU_TAP_FIR:
+		if (h->cfg.model == AISGPU_MODEL_DEFAULT) src = h->d_Ec + (long long)row * h->e_stride + HE;
+		else { src = h->d_Ef + (long long)row * h->e_stride + HE; esz = 4; }
+		n = h->last_nE;
+		break;
+	case AISGPU_TAP_ROT:
+		src = h->d_rot[h->rot_cur] + h->P96;
+		n = h->rot_n96[h->rot_cur];
+		break;
+	case 4: { // decoder input of sampling phase (channel / 2): channel = ch + 2 * phase
+		if (!h->d_tap_dec) { h->err = "taps not enabled"; return AISGPU_EINVAL; }
+		const int phase = channel >> 1;
+		esz = 4;
+		if (h->cfg.model == AISGPU_MODEL_BASE) {
+			int cnt = 0;
+			CU(cudaMemcpy(&cnt, h->d_tap_cnt + row, sizeof(int), cudaMemcpyDeviceToHost));
+			src = h->d_tap_dec + (long long)row * h->last_nE;
+			n = cnt;
+		}
+		else {
+			src = h->d_tap_dec + (long long)(row * 5 + phase) * h->last_nsym;
+			n = h->last_nsym;
+		}
+		break;
+	}
+	case 5:
+		if (!h->d_tap_fm) { h->err = "taps not enabled or not an FM engine"; return AISGPU_EINVAL; }
+		src = h->d_tap_fm + (long long)row * h->r_stride;
+		n = h->last_nE;
+		esz = 4;
+		break;
+	default:
+		h->err = "unknown tap";
+		return AISGPU_EINVAL;
+	}
+	if (dst_bytes < n * esz) n = dst_bytes / esz;
+	if (n && dst) CU(cudaMemcpy(dst, src, n * esz, cudaMemcpyDeviceToHost));
+	*n_out = n;
+	return 0;
+}
+
+int aisgpu_counters(aisgpu_handle *h, uint64_t counters[8]) {
+	if (!h || !counters) return AISGPU_EINVAL;
+	memcpy(counters, h->counters, sizeof(h->counters));
+	return 0;
+}
+
+void *aisgpu_cuda_stream(aisgpu_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+float aisgpu_last_frontend_ms(aisgpu_handle *h) {
+	if (!h || !h->fe_timed) return -1.0f;
+	if (cudaEventSynchronize(h->ev_fe1) != cudaSuccess) return -1.0f;
+	float ms = -1.0f;
+	if (cudaEventElapsedTime(&ms, h->ev_fe0, h->ev_fe1) != cudaSuccess) return -1.0f;
+	return ms;
+}
+
+int aisgpu_last_launches(aisgpu_handle *h) { return h ? h->last_launches : 0; }
+
+void aisgpu_destroy(aisgpu_handle *h) {
+	if (!h) return;
+	if (h->stream) cudaStreamSynchronize(h->stream);
+	void *ptrs[] = { h->d_in[0], h->d_in[1], h->d_tail[0], h->d_tail[1], h->d_rot[0], h->d_rot[1], h->d_rot_state, h->d_C, h->d_stepidx,
+					 h->d_steptab, h->d_omega, h->d_cgf_rot, h->d_rots, h->d_ppmtab, h->d_fir_hist[0], h->d_fir_hist[1], h->d_tap_cgf, h->d_Ec,
+					 h->d_Ef, h->d_ps, h->d_ps_mem, h->d_dec, h->d_dec_data, h->d_pll, h->d_tap_dec, h->d_tap_fm, h->d_tap_cnt, h->d_ring,
+					 h->d_ring_count };
+	for (void *p : ptrs)
+		if (p) cudaFree(p);
+	if (h->ev_fe0) cudaEventDestroy(h->ev_fe0);
+	if (h->ev_fe1) cudaEventDestroy(h->ev_fe1);
+	for (int i = 0; i < 2; i++) {
+		if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
+		if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+	}
+	if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+	if (h->stream) cudaStreamDestroy(h->stream);
+	delete h;
+}
+
+} // extern "C"

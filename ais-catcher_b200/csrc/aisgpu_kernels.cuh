@@ -1,0 +1,959 @@
+// aisgpu_kernels.cuh -- sm_100a kernels of the AIS demodulation hot path.
+//
+// Every kernel reproduces the IEEE binary32 operation order of the reference block it replaces
+// (file:line cited per kernel, relative to /root/reference/Source) so that results are bit-identical:
+// all arithmetic goes through __fadd_rn/__fsub_rn/__fmul_rn/__fdiv_rn (never contracted to FMA), std::abs of a
+// complex is evaluated as glibc's hypotf does ((float)sqrt((double)x*x+(double)y*y)), libm-dependent
+// constants (twiddles, phasor steps) come from host tables, and atan2f is the fdlibm algorithm glibc 2.39 ships.
+//
+// Layout in HBM (one engine == one batch of B independent IQ streams, "row" = stream*2 + channel):
+//   in     [B][N]              input samples of one submit (CF32 float2, or CU8/CS8/CS16)
+//   tail   [B][P]              last P input samples of the previous submit (front-end warm-up history)
+//   rot    [P96 + N>>k]        Rotate phasor table of the submit (shared by all streams), with P96 history
+//   Cbuf   [2B][HC + n48max]   48 kHz channel samples; new samples land at offset HC, unconsumed/history before
+//   rots   [2B][nE]            CGF derotation phasors of the submit
+//   Ebuf   [2B][HE + nEmax]    samples entering the symbol-timing stage (FIR17 out, or FIR37 out for FM models)
+//   state  PS/decoder/CGF/FIR  small per-row / per-(row,phase) structs
+//   frames ring of FrameRec    decoded frames of the submit
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace aisgpu {
+
+// ---------------------------------------------------------------------------------------------
+// exact arithmetic helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(__fmul_rn(a.x, s), __fmul_rn(a.y, s)); }
+// std::complex<float> product (ac-bd, ad+bc), every product and sum rounded separately
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+	return make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+}
+// std::abs(std::complex<float>) == cabsf == glibc 2.39 hypotf for finite inputs (checked on 5e7 patterns)
+__device__ __forceinline__ float habs(float2 a) {
+	double x = (double)a.x, y = (double)a.y;
+	return __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y))));
+}
+__device__ __forceinline__ float2 cnormalize(float2 r) { // rot /= std::abs(rot)
+	float a = habs(r);
+	return make_float2(__fdiv_rn(r.x, a), __fdiv_rn(r.y, a));
+}
+
+// fdlibm atanf/atan2f (the algorithm behind glibc 2.39 __ieee754_atan2f; verified bit-identical on 5e7 inputs)
+__device__ __forceinline__ float fd_atanf(float x) {
+	const float atanhi[4] = { 4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f };
+	const float atanlo[4] = { 5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f };
+	const float aT[11] = { 3.3333334327e-01f, -2.0000000298e-01f, 1.4285714924e-01f, -1.1111110449e-01f, 9.0908870101e-02f,
+						   -7.6918758452e-02f, 6.6610731184e-02f, -5.8335702866e-02f, 4.9768779427e-02f, -3.6531571299e-02f, 1.6285819933e-02f };
+	int hx = __float_as_int(x), ix = hx & 0x7fffffff, id;
+	float hi = 0.f, lo = 0.f;
+	if (ix >= 0x4c000000) {
+		if (ix > 0x7f800000) return __fadd_rn(x, x);
+		float r = __fadd_rn(atanhi[3], atanlo[3]);
+		return hx > 0 ? r : -r;
+	}
+	if (ix < 0x3ee00000) {
+		if (ix < 0x31000000) return x;
+		id = -1;
+	}
+	else {
+		x = fabsf(x);
+		if (ix < 0x3f980000) {
+			if (ix < 0x3f300000) { id = 0; hi = atanhi[0]; lo = atanlo[0]; x = __fdiv_rn(__fsub_rn(__fmul_rn(2.0f, x), 1.0f), __fadd_rn(2.0f, x)); }
+			else { id = 1; hi = atanhi[1]; lo = atanlo[1]; x = __fdiv_rn(__fsub_rn(x, 1.0f), __fadd_rn(x, 1.0f)); }
+		}
+		else {
+			if (ix < 0x401c0000) { id = 2; hi = atanhi[2]; lo = atanlo[2]; x = __fdiv_rn(__fsub_rn(x, 1.5f), __fadd_rn(1.0f, __fmul_rn(1.5f, x))); }
+			else { id = 3; hi = atanhi[3]; lo = atanlo[3]; x = __fdiv_rn(-1.0f, x); }
+		}
+	}
+	float z = __fmul_rn(x, x), w = __fmul_rn(z, z);
+	float s1 = __fmul_rn(z, __fadd_rn(aT[0], __fmul_rn(w, __fadd_rn(aT[2], __fmul_rn(w, __fadd_rn(aT[4], __fmul_rn(w, __fadd_rn(aT[6], __fmul_rn(w, __fadd_rn(aT[8], __fmul_rn(w, aT[10])))))))))));
+	float s2 = __fmul_rn(w, __fadd_rn(aT[1], __fmul_rn(w, __fadd_rn(aT[3], __fmul_rn(w, __fadd_rn(aT[5], __fmul_rn(w, __fadd_rn(aT[7], __fmul_rn(w, aT[9])))))))));
+	float xs = __fmul_rn(x, __fadd_rn(s1, s2));
+	if (id < 0) return __fsub_rn(x, xs);
+	z = __fsub_rn(hi, __fsub_rn(__fsub_rn(xs, lo), x));
+	return hx < 0 ? -z : z;
+}
+__device__ __forceinline__ float fd_atan2f(float y, float x) {
+	const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
+	int hx = __float_as_int(x), ix = hx & 0x7fffffff, hy = __float_as_int(y), iy = hy & 0x7fffffff;
+	if (ix > 0x7f800000 || iy > 0x7f800000) return __fadd_rn(x, y);
+	if (hx == 0x3f800000) return fd_atanf(y);
+	int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+	if (iy == 0) {
+		switch (m) {
+		case 0: case 1: return y;
+		case 2: return __fadd_rn(pi, tiny);
+		default: return __fsub_rn(-pi, tiny);
+		}
+	}
+	if (ix == 0) return hy < 0 ? __fsub_rn(-pi_o_2, tiny) : __fadd_rn(pi_o_2, tiny);
+	if (ix == 0x7f800000) {
+		if (iy == 0x7f800000) {
+			switch (m) {
+			case 0: return __fadd_rn(pi_o_4, tiny);
+			case 1: return __fsub_rn(-pi_o_4, tiny);
+			case 2: return __fadd_rn(__fmul_rn(3.0f, pi_o_4), tiny);
+			default: return __fsub_rn(__fmul_rn(-3.0f, pi_o_4), tiny);
+			}
+		}
+		else {
+			switch (m) {
+			case 0: return 0.0f;
+			case 1: return -0.0f;
+			case 2: return __fadd_rn(pi, tiny);
+			default: return __fsub_rn(-pi, tiny);
+			}
+		}
+	}
+	if (iy == 0x7f800000) return hy < 0 ? __fsub_rn(-pi_o_2, tiny) : __fadd_rn(pi_o_2, tiny);
+	int k = (iy - ix) >> 23;
+	float z;
+	if (k > 60) z = __fadd_rn(pi_o_2, __fmul_rn(0.5f, pi_lo));
+	else if (hx < 0 && k < -60) z = 0.0f;
+	else z = fd_atanf(fabsf(__fdiv_rn(y, x)));
+	switch (m) {
+	case 0: return z;
+	case 1: return __int_as_float(__float_as_int(z) ^ 0x80000000);
+	case 2: return __fsub_rn(pi, __fsub_rn(z, pi_lo));
+	default: return __fsub_rn(__fsub_rn(z, pi_lo), pi);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0: Rotate phasor table (DSP/DSP.cpp:296-316: rot *= mult per 96 kHz sample, rot /= |rot| once per call)
+// The phasor depends only on the sequence of chunk lengths, never on the data, so one table per submit serves
+// every stream of the batch.  tab[P96 + i] is the phasor that multiplies 96 kHz sample i of this submit;
+// tab[0..P96) repeats the last P96 phasors of the previous submit (warm-up history of the front end).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_rot_table(float2 *__restrict__ tab, const float2 *__restrict__ prev_tail, float2 *__restrict__ rot_state,
+							float2 mult, int P96, int n96) {
+	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+	for (int i = 0; i < P96; i++) tab[i] = prev_tail ? prev_tail[i] : make_float2(1.0f, 0.0f);
+	float2 rot = *rot_state;
+	float2 *o = tab + P96;
+	for (int i = 0; i < n96; i++) {
+		o[i] = rot;
+		rot = cmul(rot, mult);
+	}
+	*rot_state = cnormalize(rot);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: fused front end.  input rate -> k x Downsample2CIC5 (DSP.cpp:93-117) -> FilterComplex3Tap (DSP.cpp:283-293)
+//     -> Rotate (DSP.cpp:296-316) -> per channel Downsample2CIC5 -> FilterCIC5 (DSP.cpp:132-157) -> Cbuf.
+// One CTA owns (segment, stream) and walks the segment tile by tile, every stage array living in shared memory
+// as [HIST history | tile]; the history is what the reference keeps in h0..h4 / h1,h2 / rot.  A segment starts P
+// samples early (from the previous submit's tail for segment 0) with zero history: after P >= h_k samples every
+// stage's history is exact because each CIC stage is a pure function of its last 6 inputs
+// (u_{s+1}[n] = fl(u_s[n] + u_s[n-1]), y[j] = u_5[2j]/32).
+// ---------------------------------------------------------------------------------------------
+constexpr int FE_THREADS = 256;
+constexpr int FE_HIST = 6;   // >= 5, even so that even sample indices stay 16-byte aligned
+constexpr int FE_SLACK = 12; // over-read room behind each array for partial runs
+constexpr int FE_MAXK = 7;
+
+struct FeParams {
+	const void *in;       // [B][in_stride] samples
+	const void *tail;     // [B][P]
+	long long in_stride;  // in samples
+	int format, k, N, P, seg_len, tile;
+	int use_fdc;
+	float fdc_alpha, fdc_beta;
+	const float2 *rot;    // [P96 + N>>k]
+	float2 *C;            // [2B][c_stride]
+	long long c_stride;
+	int c_off;
+	int off_lv[FE_MAXK + 1]; // smem offsets (float2 units) of level arrays
+	int off_up, off_dn, off_wa, off_wb;
+	int smem_f2;          // total float2
+};
+
+template <int FMT>
+__device__ __forceinline__ void fe_load_pair(const void *base, long long idx, float2 &a, float2 &b) {
+	// two consecutive samples starting at even index idx
+	if (FMT == 0) {
+		float4 v = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float2 *>(base) + idx));
+		a = make_float2(v.x, v.y);
+		b = make_float2(v.z, v.w);
+	}
+	else if (FMT == 1) { // CU8: (u-128)/128  (Utilities/Convert.cpp:255-264); /128 is an exact scaling
+		uchar4 v = __ldg(reinterpret_cast<const uchar4 *>(reinterpret_cast<const uchar2 *>(base) + idx));
+		a = make_float2(__fmul_rn((float)((int)v.x - 128), 0.0078125f), __fmul_rn((float)((int)v.y - 128), 0.0078125f));
+		b = make_float2(__fmul_rn((float)((int)v.z - 128), 0.0078125f), __fmul_rn((float)((int)v.w - 128), 0.0078125f));
+	}
+	else if (FMT == 2) { // CS8 (Convert.cpp:266-275)
+		char4 v = __ldg(reinterpret_cast<const char4 *>(reinterpret_cast<const char2 *>(base) + idx));
+		a = make_float2(__fmul_rn((float)v.x, 0.0078125f), __fmul_rn((float)v.y, 0.0078125f));
+		b = make_float2(__fmul_rn((float)v.z, 0.0078125f), __fmul_rn((float)v.w, 0.0078125f));
+	}
+	else { // CS16 (Convert.cpp:277-286)
+		short4 v = __ldg(reinterpret_cast<const short4 *>(reinterpret_cast<const short2 *>(base) + idx));
+		a = make_float2(__fmul_rn((float)v.x, 3.0517578125e-05f), __fmul_rn((float)v.y, 3.0517578125e-05f));
+		b = make_float2(__fmul_rn((float)v.z, 3.0517578125e-05f), __fmul_rn((float)v.w, 3.0517578125e-05f));
+	}
+}
+
+// R consecutive outputs of one Downsample2CIC5 from 2R+4 inputs held in registers: 9R+6 complex adds.
+// in points at sample 0 of the stage input (history at negative indices); j0 = first output index.
+template <int R>
+__device__ __forceinline__ void ds2_run(const float2 *__restrict__ in, float2 *__restrict__ out, int j0, int n_out) {
+	float2 v[2 * R + 6];
+	const float4 *p = reinterpret_cast<const float4 *>(in + 2 * j0 - 6);
+#pragma unroll
+	for (int q = 0; q < R + 3; q++) {
+		float4 t = p[q];
+		v[2 * q] = make_float2(t.x, t.y);
+		v[2 * q + 1] = make_float2(t.z, t.w);
+	}
+#pragma unroll
+	for (int s = 1; s <= 4; s++) {
+#pragma unroll
+		for (int n = 2 * R + 4; n >= s + 1; n--) v[n] = cadd(v[n], v[n - 1]);
+	}
+#pragma unroll
+	for (int q = 0; q < R; q++) {
+		int n = 6 + 2 * q;
+		float2 o = cscale(cadd(v[n], v[n - 1]), 0.03125f);
+		if (j0 + q < n_out) out[j0 + q] = o;
+	}
+}
+
+template <int R>
+__device__ __forceinline__ void ds2_stage(const float2 *__restrict__ in, float2 *__restrict__ out, int n_out) {
+	for (int j0 = threadIdx.x * R; j0 < n_out; j0 += FE_THREADS * R) ds2_run<R>(in, out, j0, n_out);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(FE_THREADS) k_frontend(const FeParams p) {
+	extern __shared__ __align__(16) float2 sm[];
+	const int tid = threadIdx.x;
+	const int stream = blockIdx.y;
+	const int k = p.k;
+	const long long seg_start = (long long)blockIdx.x * p.seg_len;
+	if (seg_start >= p.N) return;
+	const long long seg_end = min((long long)p.N, seg_start + p.seg_len);
+
+	for (int i = tid; i < p.smem_f2; i += FE_THREADS) sm[i] = make_float2(0.f, 0.f);
+	__syncthreads();
+
+	float2 *lv0 = sm + p.off_lv[0] + FE_HIST;
+	float2 *d = sm + p.off_lv[k] + FE_HIST;
+	float2 *up = sm + p.off_up + FE_HIST, *dn = sm + p.off_dn + FE_HIST;
+	float2 *wa = sm + p.off_wa + FE_HIST, *wb = sm + p.off_wb + FE_HIST;
+	const int P96 = p.P >> k;
+
+	long long pos = seg_start - p.P;
+	while (pos < seg_end) {
+		const bool warm = pos < seg_start;
+		const int len = (int)min((long long)p.tile, (warm ? seg_start : seg_end) - pos);
+		// ---- load tile into level 0 (converted to float2) ----
+		{
+			const void *src;
+			long long base;
+			if (pos < 0) { // only segment 0 warm-up: previous submit's tail
+				src = p.tail;
+				base = (long long)stream * p.P + (p.P + pos);
+			}
+			else {
+				src = p.in;
+				base = (long long)stream * p.in_stride + pos;
+			}
+			for (int i = tid * 2; i < len; i += FE_THREADS * 2) {
+				float2 a, b;
+				fe_load_pair<FMT>(src, base + i, a, b);
+				*reinterpret_cast<float4 *>(lv0 + i) = make_float4(a.x, a.y, b.x, b.y);
+			}
+		}
+		__syncthreads();
+		// ---- k cascaded Downsample2CIC5 at the input rate ----
+		for (int l = 0; l < k; l++) {
+			ds2_stage<5>(sm + p.off_lv[l] + FE_HIST, sm + p.off_lv[l + 1] + FE_HIST, len >> (l + 1));
+			__syncthreads();
+		}
+		// ---- FilterComplex3Tap + Rotate at 96 kHz ----
+		const int n96 = len >> k;
+		const long long i96 = (pos >> k) + P96; // table index of 96 kHz sample 0 of this tile
+		for (int i = tid; i < n96; i += FE_THREADS) {
+			float2 x = d[i];
+			if (p.use_fdc) { // alpha * (h1 + data[i]) + h2 * beta
+				float2 t = cadd(d[i - 2], x);
+				float2 h2 = d[i - 1];
+				x = make_float2(__fadd_rn(__fmul_rn(p.fdc_alpha, t.x), __fmul_rn(h2.x, p.fdc_beta)),
+								__fadd_rn(__fmul_rn(p.fdc_alpha, t.y), __fmul_rn(h2.y, p.fdc_beta)));
+			}
+			float2 r = __ldg(p.rot + i96 + i);
+			float RR = __fmul_rn(x.x, r.x), II = __fmul_rn(x.y, r.y), RI = __fmul_rn(x.x, r.y), IR = __fmul_rn(x.y, r.x);
+			up[i] = make_float2(__fsub_rn(RR, II), __fadd_rn(IR, RI));
+			dn[i] = make_float2(__fadd_rn(RR, II), __fsub_rn(IR, RI));
+		}
+		__syncthreads();
+		// ---- per channel Downsample2CIC5 96k -> 48k ----
+		const int n48 = n96 >> 1;
+		for (int j = tid; j < 2 * n48; j += FE_THREADS) {
+			if (j < n48) ds2_run<1>(up, wa, j, n48);
+			else ds2_run<1>(dn, wb, j - n48, n48);
+		}
+		__syncthreads();
+		// ---- per channel FilterCIC5 at 48k, straight to HBM ----
+		if (!warm) {
+			const long long m0 = pos >> (k + 1);
+			for (int j = tid; j < 2 * n48; j += FE_THREADS) {
+				const int ch = j >= n48;
+				const int m = ch ? j - n48 : j;
+				const float2 *w = ch ? wb : wa;
+				float2 v[6];
+#pragma unroll
+				for (int q = 0; q < 6; q++) v[q] = w[m - 5 + q];
+#pragma unroll
+				for (int s = 1; s <= 5; s++) {
+#pragma unroll
+					for (int n = 5; n >= s; n--) v[n] = cadd(v[n], v[n - 1]);
+				}
+				p.C[(long long)(stream * 2 + ch) * p.c_stride + p.c_off + m0 + m] = cscale(v[5], 0.03125f);
+			}
+		}
+		__syncthreads();
+		// ---- carry the last HIST entries of every stage array to its front ----
+		{
+			const int narr = k + 1 + 4;
+			const int w = tid >> 5, lane = tid & 31;
+			for (int a = w; a < narr; a += FE_THREADS / 32) {
+				float2 *arr;
+				int n;
+				if (a <= k) { arr = sm + p.off_lv[a]; n = len >> a; }
+				else if (a == k + 1) { arr = sm + p.off_up; n = n96; }
+				else if (a == k + 2) { arr = sm + p.off_dn; n = n96; }
+				else if (a == k + 3) { arr = sm + p.off_wa; n = n48; }
+				else { arr = sm + p.off_wb; n = n48; }
+				float2 t = make_float2(0.f, 0.f);
+				if (lane < FE_HIST) t = arr[n + lane];
+				__syncwarp();
+				if (lane < FE_HIST) arr[lane] = t;
+			}
+		}
+		__syncthreads();
+		pos += len;
+	}
+}
+
+// new_tail[i] = last P samples of (old_tail ++ chunk); works for any N (raw bytes, bps bytes per sample)
+__global__ void k_tail_update(unsigned char *__restrict__ new_tail, const unsigned char *__restrict__ old_tail,
+							  const unsigned char *__restrict__ in, long long in_stride, int N, int P, int bps) {
+	const int stream = blockIdx.y;
+	const long long nbytes = (long long)P * bps;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += (long long)gridDim.x * blockDim.x) {
+		const long long s = i / bps + (long long)N - P; // sample index relative to chunk start
+		const int b = (int)(i % bps);
+		unsigned char v;
+		if (s >= 0) v = in[((long long)stream * in_stride + s) * bps + b];
+		else v = old_tail[((long long)stream * P + (s + P)) * bps + b];
+		new_tail[(long long)stream * nbytes + i] = v;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// small utility: move `cnt` trailing elements of each row to the slot just before `dst_end`
+// (keeps unconsumed samples / filter history in front of the next submit's data)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_carry(T *__restrict__ buf, long long stride, int src_begin, int dst_begin, int cnt) {
+	extern __shared__ __align__(16) unsigned char carry_sm[];
+	T *tmp = reinterpret_cast<T *>(carry_sm);
+	T *row = buf + (long long)blockIdx.x * stride;
+	for (int i = threadIdx.x; i < cnt; i += blockDim.x) tmp[i] = row[src_begin + i];
+	__syncthreads();
+	for (int i = threadIdx.x; i < cnt; i += blockDim.x) row[dst_begin + i] = tmp[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2a: SquareFreqOffsetCorrection, estimation half (DSP.cpp:417-455, FFT.h:93-130).
+// One warp per 512-sample block: x^2 in bit-reversed order, the reference's radix-2 DIT butterflies stage by
+// stage, |F| in fftshift order; then (one lane per block) the sequential float cumsum, then the parallel
+// first-maximum searches.  Result: an index into the host-built phasor-step table.
+// ---------------------------------------------------------------------------------------------
+constexpr int CGF_N = 512;
+constexpr int CGF_BLK_PER_CTA = 16;
+constexpr int CGF_THREADS = 256;
+constexpr int CGF_ROWP = 513;           // padded row (floats) so 16 lanes scanning 16 rows hit 16 banks
+constexpr int CGF_IDX_OFFSET = 3;       // idx = i + 3, i in [-3, 410]
+constexpr int CGF_IDX_NONE = 414;       // no bin above zero: fz = -1
+constexpr int CGF_NIDX = 415;
+
+__global__ void __launch_bounds__(CGF_THREADS) k_cgf_estimate(const float2 *__restrict__ Cbuf, long long c_stride, int c_begin, int nblk,
+																 int total_blocks, const float2 *__restrict__ omega_g, int wide,
+																 int *__restrict__ stepidx) {
+	extern __shared__ __align__(16) unsigned char cgf_sm[];
+	float2 *omega = reinterpret_cast<float2 *>(cgf_sm);                      // 512 float2
+	float *mag = reinterpret_cast<float *>(cgf_sm + 4096);                   // [16][513]
+	unsigned char *scratch = cgf_sm + 4096 + CGF_BLK_PER_CTA * CGF_ROWP * 4; // fft buffers, later cumsum [16][513]
+	float2 *fftbuf = reinterpret_cast<float2 *>(scratch);
+	float *cum = reinterpret_cast<float *>(scratch);
+
+	const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+	for (int i = tid; i < CGF_N; i += CGF_THREADS) omega[i] = omega_g[i];
+	__syncthreads();
+
+	const int blk0 = blockIdx.x * CGF_BLK_PER_CTA;
+	float2 *x = fftbuf + w * CGF_N;
+	for (int rep = 0; rep < 2; rep++) {
+		const int lb = w + rep * 8;
+		const int id = blk0 + lb;
+		if (id < total_blocks) {
+			const int row = id / nblk, b = id - row * nblk;
+			const float2 *src = Cbuf + (long long)row * c_stride + c_begin + (long long)b * CGF_N;
+			for (int i = lane; i < CGF_N; i += 32) {
+				float2 v = src[i];
+				x[__brev((unsigned)i) >> 23] = cmul(v, v);
+			}
+			__syncwarp();
+			for (int s = 0; s < 9; s++) {
+				const int m2 = 1 << s;
+				for (int q = lane; q < 256; q += 32) {
+					const int j = q & (m2 - 1);
+					const int lo = ((q >> s) << (s + 1)) + j, hi = lo + m2;
+					const float2 o = omega[j << (8 - s)];
+					const float2 t = cmul(o, x[hi]);
+					const float2 a = x[lo];
+					x[hi] = csub(a, t);
+					x[lo] = cadd(a, t);
+				}
+				__syncwarp();
+			}
+			float *mg = mag + lb * CGF_ROWP;
+			for (int i = lane; i < CGF_N; i += 32) mg[i] = habs(x[(i + 256) & 511]);
+		}
+		__syncwarp();
+	}
+	__syncthreads(); // all FFT buffers dead, mags complete
+	if (wide && tid < CGF_BLK_PER_CTA && blk0 + tid < total_blocks) {
+		const float *mg = mag + tid * CGF_ROWP;
+		float *cs = cum + tid * CGF_ROWP;
+		float c = 0.0f;
+		cs[0] = 0.0f;
+		for (int i = 1; i < CGF_N; i++) {
+			c = __fadd_rn(c, mg[i]);
+			cs[i] = c;
+		}
+	}
+	__syncthreads();
+	for (int rep = 0; rep < 2; rep++) {
+		const int lb = w + rep * 8;
+		const int id = blk0 + lb;
+		if (id >= total_blocks) continue;
+		const float *mg = mag + lb * CGF_ROWP;
+		const float *cs = cum + lb * CGF_ROWP;
+		int wi = 0;
+		if (wide) { // DSP.cpp:424-446: M = 133, ofs = 15, delta = 102
+			float bv = -1.0f;
+			int bi = 1 << 30;
+			for (int i = lane; i < CGF_N - 133; i += 32) {
+				float v = __fadd_rn(__fsub_rn(cs[i + 133], cs[i]), __fmul_rn(0.6f, __fadd_rn(mg[i + 15], mg[i + 117])));
+				if (v > bv) { bv = v; bi = i; }
+			}
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) {
+				float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+				int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+				if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+			}
+			wi = (bi == (1 << 30)) ? 0 : bi;
+			wi = wi + 66 - 256;
+		}
+		// DSP.cpp:448-455: i in [wi+187, wi+223)
+		float bv = 0.0f;
+		int bi = 1 << 30;
+		for (int c = lane; c < 36; c += 32) {
+			const int i = wi + 187 + c;
+			float h = __fadd_rn(mg[i & 511], mg[(i + 102) & 511]);
+			if (h > bv) { bv = h; bi = i; }
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+			int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+			if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+		}
+		if (lane == 0) stepidx[id] = (bi == (1 << 30)) ? CGF_IDX_NONE : bi + CGF_IDX_OFFSET;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2b: the CGF derotation phasor chain (DSP.cpp:457-465): rot *= rot_step per sample, rot /= |rot| per block.
+// Strictly sequential per (stream, channel); one thread per row, all rows in flight at once.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_cgf_rot(const int *__restrict__ stepidx, const float2 *__restrict__ steptab, float2 *__restrict__ rot_state,
+						  float2 *__restrict__ rots, long long r_stride, int nblk, int rows) {
+	const int row = blockIdx.x * blockDim.x + threadIdx.x;
+	if (row >= rows) return;
+	float2 rot = rot_state[row];
+	float2 *o = rots + (long long)row * r_stride;
+	for (int b = 0; b < nblk; b++) {
+		const float2 st = steptab[stepidx[row * nblk + b]];
+		for (int i = 0; i < CGF_N; i++) {
+			rot = cmul(rot, st);
+			o[b * CGF_N + i] = rot;
+		}
+		rot = cnormalize(rot);
+	}
+	rot_state[row] = rot;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2c: output[i] *= rot (DSP.cpp:462) fused with FilterComplex 17 taps (DSP.cpp:215-246, Filters.h:35-41).
+// ---------------------------------------------------------------------------------------------
+constexpr int FIRC_T = 17;
+constexpr int FIRC_TILE = 256;
+__constant__ float c_taps_coherent[FIRC_T];
+__constant__ float c_taps_receiver[37];
+
+__global__ void __launch_bounds__(FIRC_TILE) k_cgf_derot_fir(const float2 *__restrict__ Cbuf, long long c_stride, int c_begin,
+																const float2 *__restrict__ rots, long long r_stride, int nE,
+																const float2 *__restrict__ hist_old, float2 *__restrict__ hist_new,
+																float2 *__restrict__ Ebuf, long long e_stride, int e_off,
+																float2 *__restrict__ tap_cgf, long long tap_stride) {
+	__shared__ float2 der[FIRC_TILE + FIRC_T - 1];
+	const int row = blockIdx.y, t0 = blockIdx.x * FIRC_TILE, tid = threadIdx.x;
+	for (int i = tid; i < FIRC_TILE + FIRC_T - 1; i += FIRC_TILE) {
+		const int n = t0 + i - (FIRC_T - 1);
+		float2 v = make_float2(0.f, 0.f);
+		if (n < 0) v = hist_old[row * (FIRC_T - 1) + (FIRC_T - 1) + n];
+		else if (n < nE) {
+			v = cmul(Cbuf[(long long)row * c_stride + c_begin + n], rots[(long long)row * r_stride + n]);
+			if (tap_cgf && i >= FIRC_T - 1) tap_cgf[(long long)row * tap_stride + n] = v;
+		}
+		der[i] = v;
+	}
+	__syncthreads();
+	const int n = t0 + tid;
+	if (n < nE) {
+		float2 x = make_float2(0.f, 0.f);
+#pragma unroll
+		for (int k = 0; k < FIRC_T; k++) {
+			const float2 dd = der[tid + k];
+			x.x = __fadd_rn(x.x, __fmul_rn(c_taps_coherent[k], dd.x));
+			x.y = __fadd_rn(x.y, __fmul_rn(c_taps_coherent[k], dd.y));
+		}
+		Ebuf[(long long)row * e_stride + e_off + n] = x;
+	}
+	if (t0 + FIRC_TILE >= nE) { // the CTA holding the end of the row saves the next history
+		for (int i = tid; i < FIRC_T - 1; i += FIRC_TILE) {
+			const int nn = nE - (FIRC_T - 1) + i; // nE >= 512
+			hist_new[row * (FIRC_T - 1) + i] = der[nn - t0 + (FIRC_T - 1)];
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2-FM: Demod::FM (Demod.cpp:27-37) fused with DSP::Filter 37 taps (DSP.cpp:249-280, Filters.h:24-33).
+// Cbuf keeps 37 samples of history in front of the new ones, so the FM values feeding the FIR history are
+// recomputed instead of stored.
+// ---------------------------------------------------------------------------------------------
+constexpr int FIRF_T = 37;
+constexpr int FIRF_TILE = 256;
+__global__ void __launch_bounds__(FIRF_TILE) k_fm_fir(const float2 *__restrict__ Cbuf, long long c_stride, int c_new, int n,
+														 float *__restrict__ Fbuf, long long f_stride, int f_off,
+														 float *__restrict__ tap_fm, long long tap_stride) {
+	__shared__ float fm[FIRF_TILE + FIRF_T - 1];
+	const int row = blockIdx.y, t0 = blockIdx.x * FIRF_TILE, tid = threadIdx.x;
+	const float2 *c = Cbuf + (long long)row * c_stride + c_new; // c[i] = new sample i, history at negative i
+	for (int i = tid; i < FIRF_TILE + FIRF_T - 1; i += FIRF_TILE) {
+		const int m = t0 + i - (FIRF_T - 1);
+		float v = 0.0f;
+		if (m < n) {
+			const float2 a = c[m], pv = c[m - 1];
+			// data[i] * conj(prev): re = a.re*p.re - a.im*(-p.im), im = a.re*(-p.im) + a.im*p.re
+			const float re = __fsub_rn(__fmul_rn(a.x, pv.x), __fmul_rn(a.y, -pv.y));
+			const float im = __fadd_rn(__fmul_rn(a.x, -pv.y), __fmul_rn(a.y, pv.x));
+			v = __fdiv_rn(fd_atan2f(im, re), 3.14159265358979323846f);
+			if (tap_fm && m >= 0 && i >= FIRF_T - 1) tap_fm[(long long)row * tap_stride + m] = v;
+		}
+		fm[i] = v;
+	}
+	__syncthreads();
+	const int m = t0 + tid;
+	if (m < n) {
+		float x = 0.0f;
+#pragma unroll
+		for (int k = 0; k < FIRF_T; k++) x = __fadd_rn(x, __fmul_rn(c_taps_receiver[k], fm[tid + k]));
+		Fbuf[(long long)row * f_stride + f_off + m] = x;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: symbol timing + demodulation + bit decoder.
+//   ModelDefault : ScatterPLL (DSP.h:95-117) -> 5 x PhaseSearchEMA / PhaseSearch (Demod.cpp:39-170) -> 5 x Decoder
+//   ModelStandard: Deinterleave (DSP.h:65-73) -> 5 x Decoder
+//   ModelBase    : SimplePLL (DSP.cpp:28-57) -> 1 x Decoder
+// One thread per (row, sampling phase); the five phases of a row sit in five adjacent lanes of one warp so the
+// decoder's Reset broadcast (AIS.cpp:47-49, Model.cpp:566-573) is a warp vote.  Frame bits live in shared memory.
+// ---------------------------------------------------------------------------------------------
+enum { ST_TRAINING = 0, ST_STARTFLAG = 1, ST_DATAFCS = 3 };
+constexpr int DEC_WORDS = 35;     // 140 bytes (Message.h:69 data[MAX_AIS_FRAME_BYTES + 4])
+constexpr int MAX_FRAME_BITS = 1087; // MAX_AIS_FRAME_LENGTH (Message.h:41)
+constexpr int K3_THREADS = 128;
+constexpr int K3_GROUPS_PER_WARP = 6;
+
+struct DecState { // one per (row, phase); persisted between submits (frame bits live in a separate array)
+	int state, lastBit, prev, position, one_seq;
+	float level;
+	long long start_idx;
+};
+struct PsState { // PhaseSearchEMA (Demod.h:68-86) / PhaseSearch (Demod.h:41-66)
+	float ma[16];
+	uint32_t plane[5]; // plane[d] bit h = decision of hypothesis h, d symbols ago (bits[h] >> d & 1)
+	int max_idx, rot, last;
+};
+struct FrameRec {
+	int row, phase, nbits;
+	float level;          // TAG::level before the dB conversion (AIS.h:147)
+	float ppm;
+	int chunk;            // ordinal of the submit
+	long long start_idx, end_idx;
+	uint32_t data[DEC_WORDS];
+	int pad2;
+};
+
+struct DecCtx {
+	uint32_t *frame; // shared memory, word w of this thread at frame[w * K3_THREADS]
+	int mode_level;
+};
+
+__device__ __forceinline__ uint32_t frame_word(const DecCtx &c, int w) { return c.frame[w * K3_THREADS]; }
+__device__ __forceinline__ int dec_type(const DecCtx &c) { return (frame_word(c, 0) & 0xff) >> 2; }
+__device__ __forceinline__ unsigned dec_mmsi(const DecCtx &c) {
+	const uint32_t w0 = frame_word(c, 0), w1 = frame_word(c, 1);
+	const unsigned d1 = (w0 >> 8) & 0xff, d2 = (w0 >> 16) & 0xff, d3 = (w0 >> 24) & 0xff, d4 = w1 & 0xff;
+	return (d1 << 22) | (d2 << 14) | (d3 << 6) | (d4 >> 2);
+}
+__device__ __forceinline__ bool dec_cannot_be_valid(const DecCtx &c, int len) { // AIS.cpp:111-142
+	if (len < 30) return false;
+	const int t = dec_type(c);
+	switch (len) {
+	case 30: return t > 28 || t == 0;
+	case 62: return dec_mmsi(c) > 999999999u;
+	case 96: return t == 10;
+	case 168: return t == 16;
+	case 184: return t == 15 || t == 20 || t == 23;
+	case 192: return t == 1 || t == 2 || t == 3 || t == 4 || t == 7 || t == 9 || t == 11 || t == 18 || t == 22 || t == 24 || t == 25 || t == 27 || t == 28;
+	case 336: return t == 19;
+	case 385: return t == 21;
+	case 448: return t == 5;
+	}
+	return false;
+}
+__device__ __forceinline__ bool dec_crc16(const DecCtx &c, int len) { // AIS.cpp:55-64
+	unsigned crc = 0xFFFF;
+	for (int i = 0; i < len; i++) {
+		const unsigned bit = (frame_word(c, i >> 5) >> (i & 31)) & 1u;
+		crc = ((bit ^ crc) & 1u) ? ((crc >> 1) ^ 0x8408u) : (crc >> 1);
+	}
+	return crc == 0xF0B8u;
+}
+
+// One Decoder::Run (AIS.h:91-181).  Returns true when a frame with a good CRC just completed (processData true);
+// in that case fr_len = payload bits + 16 and the caller emits and performs the FOUNDMESSAGE/Reset protocol.
+__device__ __forceinline__ bool dec_step(DecState &d, const DecCtx &c, float sample, float sample_lvl, long long sample_idx, int &fr_len,
+										 float &fr_level, int &lastBit_before) {
+	const int dd = sample > 0.0f;
+	const int Bit = !(dd ^ d.prev);
+	d.prev = dd;
+	lastBit_before = d.lastBit;
+	bool found = false;
+	switch (d.state) {
+	case ST_TRAINING:
+		if (Bit != d.lastBit) d.position++;
+		else {
+			if (d.position > 4) {
+				d.start_idx = sample_idx;
+				d.state = ST_STARTFLAG;
+				d.position = Bit ? 3 : 1;
+				d.one_seq = 0;
+			}
+			else { d.state = ST_TRAINING; d.position = 0; d.one_seq = 0; }
+		}
+		break;
+	case ST_STARTFLAG:
+		if (d.position == 7) {
+			if (Bit == 0) {
+				d.state = ST_DATAFCS; d.position = 0; d.one_seq = 0;
+				d.level = 0.0f;
+				for (int w = 0; w < DEC_WORDS; w++) c.frame[w * K3_THREADS] = 0u; // msg.clear()
+			}
+			else { d.state = ST_TRAINING; d.position = 0; d.one_seq = 0; }
+		}
+		else {
+			if (Bit == 1) d.position++;
+			else { d.state = ST_TRAINING; d.position = 0; d.one_seq = 0; }
+		}
+		break;
+	case ST_DATAFCS: {
+		const int pos = d.position++;
+		if (pos < MAX_FRAME_BITS) { // Message::setBit (Message.h:264-273)
+			uint32_t *wp = &c.frame[(pos >> 5) * K3_THREADS];
+			const uint32_t m = 1u << (pos & 31);
+			*wp = Bit ? (*wp | m) : (*wp & ~m);
+		}
+		if (c.mode_level) d.level = __fadd_rn(d.level, sample_lvl);
+		if (Bit == 1) {
+			if (d.one_seq == 5) {
+				fr_level = c.mode_level ? __fdiv_rn(d.level, (float)d.position) : 0.0f;
+				const int len = d.position - 7;
+				if (len >= 16 && dec_crc16(c, len)) {
+					found = true;
+					fr_len = len;
+				}
+				d.state = ST_TRAINING; d.position = 0; d.one_seq = 0;
+			}
+			else d.one_seq++;
+		}
+		else {
+			if (d.one_seq == 5) d.position--;
+			d.one_seq = 0;
+		}
+		if (d.position == MAX_FRAME_BITS || dec_cannot_be_valid(c, d.position)) { d.state = ST_TRAINING; d.position = 0; d.one_seq = 0; }
+		break;
+	}
+	default: break;
+	}
+	d.lastBit = Bit;
+	return found;
+}
+
+__device__ __forceinline__ void emit_frame(FrameRec *__restrict__ ring, int *__restrict__ ring_count, int ring_cap, int chunk, const DecCtx &c,
+										   int row, int phase, int len, float level, float ppm, long long start_idx, long long end_idx) {
+	const int slot = atomicAdd(ring_count, 1);
+	if (slot >= ring_cap) return;
+	FrameRec &r = ring[slot];
+	r.row = row;
+	r.phase = phase;
+	r.nbits = len - 16;
+	r.level = level;
+	r.ppm = ppm;
+	r.chunk = chunk;
+	r.start_idx = start_idx;
+	r.end_idx = end_idx;
+	for (int w = 0; w < DEC_WORDS; w++) r.data[w] = frame_word(c, w);
+}
+
+__constant__ float c_ps_cos[8];
+__constant__ float c_ps_sin[8];
+
+struct K3Params {
+	int model;            // 0 standard, 2 default
+	int ps_ema;
+	int rows;
+	int nsym;             // symbols (groups of 5 samples) to process this submit
+	long long e_stride;
+	int e_begin;          // index in the row of the first sample of the first group
+	long long abs_begin;  // absolute per-channel index of that sample (TAG::sample_idx, DSP.h:110)
+	const float2 *Ec;     // ModelDefault: FIR17 output
+	const float *Ef;      // FM models: FIR37 output
+	PsState *ps;
+	float *ps_mem;        // PhaseSearch history |t| [16*12][rows*5] (only when !ps_ema)
+	DecState *dec;
+	uint32_t *dec_data;   // [DEC_WORDS][rows*5]
+	FrameRec *ring;
+	int *ring_count;
+	int ring_cap;
+	int chunk;
+	int mode_level;
+	// tag.ppm lookup (ModelDefault): block index of a sample = (abs_idx - blk_abs0) >> 9
+	const int *stepidx;
+	const float *ppmtab;
+	long long blk_abs0;
+	int nblk;
+	float *tap_dec;       // optional: decoder input samples [rows*5][nsym]
+};
+
+__global__ void __launch_bounds__(K3_THREADS) k_symbols(const K3Params p) {
+	__shared__ uint32_t frames[DEC_WORDS * K3_THREADS];
+	__shared__ float ma_s[16 * K3_THREADS];
+	const int tid = threadIdx.x, lane = tid & 31;
+	const int warp_global = blockIdx.x * (K3_THREADS / 32) + (tid >> 5);
+	const int grp = lane / 5, phase = lane - grp * 5;
+	const int row = warp_global * K3_GROUPS_PER_WARP + grp;
+	const bool active = grp < K3_GROUPS_PER_WARP && row < p.rows;
+	const unsigned grp_mask = active ? (0x1fu << (grp * 5)) : 0u;
+
+	DecCtx ctx;
+	ctx.frame = frames + tid;
+	ctx.mode_level = p.mode_level;
+	DecState d;
+	PsState ps;
+	float *ma_mine = ma_s + tid;
+	const int sidx = row * 5 + phase;
+	const long long nthr_total = (long long)p.rows * 5;
+	if (active) {
+		d = p.dec[sidx];
+		for (int w = 0; w < DEC_WORDS; w++) frames[w * K3_THREADS + tid] = p.dec_data[(long long)w * nthr_total + sidx];
+		if (p.model == 2) {
+			ps = p.ps[sidx];
+			for (int h = 0; h < 16; h++) ma_mine[h * K3_THREADS] = ps.ma[h];
+		}
+	}
+	else {
+		d.state = ST_TRAINING; d.lastBit = 0; d.prev = 0; d.position = 0; d.one_seq = 0; d.level = 0.f; d.start_idx = 0;
+	}
+	const float weight = 0.85f, omw = __fsub_rn(1.0f, 0.85f);
+	const long long e_row = (long long)row * p.e_stride + p.e_begin;
+
+	for (int s = 0; s < p.nsym; s++) {
+		float b = 0.0f, sample_lvl = 0.0f;
+		const long long sample_idx = p.abs_begin + (long long)s * 5 + phase;
+		float ppm = 0.0f;
+		if (active) {
+			if (p.model == 2) {
+				const float2 x = p.Ec[e_row + (long long)s * 5 + phase];
+				// ScatterPLL level: ((((0+n0)+n1)+n2)+n3)+n4, then / 5 (DSP.h:100-106)
+				const float nrm = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
+				float acc = 0.0f;
+#pragma unroll
+				for (int j = 0; j < 5; j++) acc = __fadd_rn(acc, __shfl_sync(grp_mask, nrm, grp * 5 + j));
+				sample_lvl = __fdiv_rn(acc, 5.0f);
+				// pre-rotation by (1j)^rot (Demod.cpp:44-65)
+				float re, im;
+				switch (ps.rot) {
+				case 0: re = x.x; im = x.y; break;
+				case 1: im = x.x; re = -x.y; break;
+				case 2: re = -x.x; im = -x.y; break;
+				default: im = -x.x; re = x.y; break;
+				}
+				ps.rot = (ps.rot + 1) & 3;
+				uint32_t dec_mask = 0;
+				float absv[16];
+#pragma unroll
+				for (int j = 0; j < 8; j++) {
+					const float a = __fmul_rn(re, c_ps_cos[j]), bb = __fmul_rn(im, c_ps_sin[j]);
+					const float t1 = __fadd_rn(a, bb), t2 = __fsub_rn(a, bb);
+					dec_mask |= (t1 > 0.0f ? 1u : 0u) << j;
+					dec_mask |= (t2 > 0.0f ? 1u : 0u) << (15 - j);
+					absv[j] = fabsf(t1);
+					absv[15 - j] = fabsf(t2);
+				}
+				ps.plane[4] = ps.plane[3]; ps.plane[3] = ps.plane[2]; ps.plane[2] = ps.plane[1]; ps.plane[1] = ps.plane[0];
+				ps.plane[0] = dec_mask;
+				if (!p.ps_ema) { // PhaseSearch (Demod.cpp:129-160): 12-sample sums, search prev-2..prev+2
+					float *mem = p.ps_mem + sidx;
+#pragma unroll
+					for (int h = 0; h < 16; h++) mem[(long long)(h * 12 + ps.last) * nthr_total] = absv[h];
+					ps.last = (ps.last + 1) % 12;
+					float max_val = 0.0f;
+					const int prev_max = ps.max_idx;
+					for (int q = 16 + prev_max - 2; q <= 16 + prev_max + 2; q++) {
+						const int j = q & 15;
+						float avg = mem[(long long)(j * 12) * nthr_total];
+						for (int l = 1; l < 12; l++) avg = __fadd_rn(avg, mem[(long long)(j * 12 + l) * nthr_total]);
+						if (avg > max_val) { max_val = avg; ps.max_idx = j; }
+					}
+				}
+				else { // PhaseSearchEMA (Demod.cpp:67-91)
+#pragma unroll
+					for (int h = 0; h < 16; h++) {
+						ps.ma[h] = __fadd_rn(__fmul_rn(weight, ps.ma[h]), __fmul_rn(omw, absv[h]));
+						ma_mine[h * K3_THREADS] = ps.ma[h];
+					}
+					int idx = (ps.max_idx - 1) & 15;
+					float max_val = ma_mine[idx * K3_THREADS];
+					int best = idx;
+#pragma unroll
+					for (int q = 0; q < 2; q++) {
+						idx = (idx + 1) & 15;
+						const float v = ma_mine[idx * K3_THREADS];
+						if (v > max_val) { max_val = v; best = idx; }
+					}
+					ps.max_idx = best;
+				}
+				const int b1 = (ps.plane[3] >> ps.max_idx) & 1, b2 = (ps.plane[4] >> ps.max_idx) & 1;
+				b = (b1 ^ b2) ? 1.0f : -1.0f;
+				if (p.ppmtab) {
+					const long long last_of_group = p.abs_begin + (long long)s * 5 + 4;
+					int bi = (int)((last_of_group - p.blk_abs0) >> 9);
+					bi = bi < 0 ? 0 : (bi >= p.nblk ? p.nblk - 1 : bi);
+					ppm = p.ppmtab[p.stepidx[row * p.nblk + bi]];
+				}
+			}
+			else {
+				b = p.Ef[e_row + (long long)s * 5 + phase];
+			}
+			if (p.tap_dec) p.tap_dec[(long long)sidx * p.nsym + s] = b;
+		}
+		int fr_len = 0, lastBit_before = 0;
+		float fr_level = 0.0f;
+		const float level_before = d.level;
+		const long long start_before = d.start_idx;
+		bool found = active && dec_step(d, ctx, b, sample_lvl, sample_idx, fr_len, fr_level, lastBit_before);
+		const unsigned vote = __ballot_sync(0xffffffffu, found);
+		if (vote) { // rare: FOUNDMESSAGE -> Reset to the four sibling decoders (AIS.cpp:47-49,98-108)
+			const unsigned gv = vote & grp_mask;
+			if (gv) {
+				const int winner = __ffs(gv) - 1; // lowest phase runs first (DSP.h:108-112)
+				if (lane == winner) {
+					emit_frame(p.ring, p.ring_count, p.ring_cap, p.chunk, ctx, row, phase, fr_len, fr_level, ppm, d.start_idx, sample_idx);
+				}
+				else if (lane < winner) { // already stepped this symbol, then reset
+					d.state = ST_TRAINING; d.position = 0; d.one_seq = 0;
+				}
+				else { // reset first, then step this symbol from TRAINING/0: only the NRZI memory survives
+					const int Bit = d.lastBit; // dec_step stored the new Bit there
+					d.level = level_before;
+					d.start_idx = start_before;
+					d.state = ST_TRAINING;
+					d.one_seq = 0;
+					d.position = (Bit != lastBit_before) ? 1 : 0;
+				}
+			}
+		}
+	}
+	if (active) {
+		for (int w = 0; w < DEC_WORDS; w++) p.dec_data[(long long)w * nthr_total + sidx] = frames[w * K3_THREADS + tid];
+		p.dec[sidx] = d;
+		if (p.model == 2) p.ps[sidx] = ps;
+	}
+}
+
+// ModelBase: SimplePLL (DSP.cpp:28-57) + one Decoder per row; strictly sequential per row.
+struct PllState { int prev; float pll; int fast; };
+__global__ void __launch_bounds__(K3_THREADS) k_base(const float *__restrict__ Ef, long long e_stride, int e_begin, int n, int rows,
+													   PllState *__restrict__ pll, DecState *__restrict__ dec, uint32_t *__restrict__ dec_data, FrameRec *__restrict__ ring,
+													   int *__restrict__ ring_count, int ring_cap, int chunk, float *__restrict__ tap_dec, int *__restrict__ tap_cnt) {
+	__shared__ uint32_t frames[DEC_WORDS * K3_THREADS];
+	const int tid = threadIdx.x;
+	const int row = blockIdx.x * K3_THREADS + tid;
+	if (row >= rows) return;
+	DecCtx ctx;
+	ctx.frame = frames + tid;
+	ctx.mode_level = 1;
+	DecState d = dec[row * 5];
+	const long long nthr_total = (long long)rows * 5;
+	for (int w = 0; w < DEC_WORDS; w++) frames[w * K3_THREADS + tid] = dec_data[(long long)w * nthr_total + row * 5];
+	PllState pl = pll[row];
+	const float *e = Ef + (long long)row * e_stride + e_begin;
+	int ntap = 0;
+	for (int i = 0; i < n; i++) {
+		const float x = e[i];
+		const int bit = x > 0.0f;
+		if (bit != pl.prev) pl.pll = __fadd_rn(pl.pll, __fmul_rn(__fsub_rn(0.5f, pl.pll), pl.fast ? 0.6f : 0.05f));
+		pl.pll = __fadd_rn(pl.pll, 0.2f);
+		if (pl.pll >= 1.0f) {
+			if (tap_dec) tap_dec[(long long)row * n + ntap++] = x;
+			int fr_len = 0, lb = 0;
+			float fr_level = 0.f;
+			const bool found = dec_step(d, ctx, x, 0.0f, 0, fr_len, fr_level, lb);
+			if (found) emit_frame(ring, ring_count, ring_cap, chunk, ctx, row, 0, fr_len, fr_level, 0.0f, d.start_idx, 0);
+			// DecoderMessage -> SimplePLL::Signal (Model.cpp:434-435; DSP.cpp:46-57): the last NextState decides
+			pl.fast = (d.state == ST_TRAINING) ? 1 : (d.state == ST_STARTFLAG ? 0 : pl.fast);
+			pl.pll = __fsub_rn(pl.pll, (float)(int)pl.pll);
+		}
+		pl.prev = bit;
+	}
+	for (int w = 0; w < DEC_WORDS; w++) dec_data[(long long)w * nthr_total + row * 5] = frames[w * K3_THREADS + tid];
+	dec[row * 5] = d;
+	pll[row] = pl;
+	if (tap_cnt) tap_cnt[row] = ntap;
+}
+
+} // namespace aisgpu

@@ -1,0 +1,145 @@
+/* aisgpu.h -- C ABI of the B200-native AIS demodulation engine.
+ *
+ * Drop-in boundary for ONE hot path of jvde-github/AIS-catcher: raw IQ ->
+ * decimate -> +/-25 kHz channelise -> (CGF, FIR, coherent phase search | FM
+ * discriminator, FIR) -> 5-phase symbol timing -> NRZI/HDLC/CRC -> AIS frames
+ * (reference Source/DSP/Model.cpp:27-356 ModelFrontend, :419-438 ModelBase,
+ * :484-518 ModelStandard, :520-577 ModelDefault; Source/Marine/AIS.h:91-181),
+ * run over a batch of independent IQ streams on one GPU.
+ *
+ * The reference has no FFI for this path (it is a C++ class graph wired with
+ * operator>>, Source/Library/Stream.h:136-167); what a maintainer binds is one
+ * more AIS::Model subclass (Source/DSP/Model.h:76-126) whose buildModel()
+ * connects the device's Connection<RAW> to a sink that forwards every RAW block
+ * to aisgpu_submit() and publishes the frames returned by aisgpu_poll() through
+ * the inherited Util::PassThrough<Message> output.  That adapter is
+ * ais-catcher_b200/host/ModelGPU.h; INTEGRATION.md shows the three registration
+ * edits.  Every entry point below cites the reference interface it stands for.
+ *
+ * Conventions: all functions return 0 on success, a negative AISGPU_E* code on
+ * failure (never throw, never abort); aisgpu_last_error() gives the text.  The
+ * caller's thread model is the reference's: one thread per handle
+ * (Source/Device/FileRAW.cpp:205-206).  There is NO CPU fallback: without a
+ * CUDA device aisgpu_create() fails with AISGPU_ENODEV.
+ */
+#ifndef AISGPU_H
+#define AISGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AISGPU_ABI_VERSION 1
+
+/* model kinds: the reference's "-m" numbers (Source/Application/Receiver.cpp:155-195) */
+#define AISGPU_MODEL_STANDARD 0 /* FM -> FIR37 -> 5-phase deinterleave -> 5 decoders (Model.cpp:484-518) */
+#define AISGPU_MODEL_BASE 1     /* FM -> FIR37 -> SimplePLL -> 1 decoder            (Model.cpp:419-438) */
+#define AISGPU_MODEL_DEFAULT 2  /* CGF -> FIR17 -> 5 x PhaseSearch[EMA] -> 5 decoders (Model.cpp:520-577) */
+
+/* input sample formats: subset of enum class Format (Source/Library/Common.h:89-104) */
+#define AISGPU_FMT_CF32 0
+#define AISGPU_FMT_CU8 1
+#define AISGPU_FMT_CS8 2
+#define AISGPU_FMT_CS16 3
+
+#define AISGPU_OK 0
+#define AISGPU_EINVAL -1   /* bad argument / unsupported configuration (reference: std::runtime_error at buildModel, Model.cpp:109-110) */
+#define AISGPU_ENODEV -2   /* no usable CUDA device */
+#define AISGPU_ECUDA -3    /* CUDA runtime error; adapter converts to Error()<<...; StopRequest() (FileRAW.cpp:111-115) */
+#define AISGPU_ENOMEM -4
+#define AISGPU_EOVERFLOW -5 /* frame ring overflowed; frames were dropped */
+
+/* tap ids for aisgpu_tap(): intermediates for parity tests */
+#define AISGPU_TAP_C 0     /* 48 kHz channel samples after FilterCIC5 (Model.cpp:345-346 C_a/C_b), float2 */
+#define AISGPU_TAP_CGF 1   /* after SquareFreqOffsetCorrection (DSP.cpp:475-489), float2, whole 512-blocks of this submit */
+#define AISGPU_TAP_FIR 2   /* after FilterComplex (ModelDefault, float2) or Filter (FM models, float) */
+#define AISGPU_TAP_ROT 3   /* the Rotate phasor table of the last submit (DSP.cpp:296-316), float2 */
+
+typedef struct aisgpu_config {
+	uint32_t struct_size;       /* = sizeof(aisgpu_config) */
+	int32_t model;              /* AISGPU_MODEL_*                                   (Receiver.cpp:155-195) */
+	int32_t sample_rate;        /* 96000..12288000; non-bucket rates are upsampled   (Model.cpp:109-149) */
+	int32_t format;             /* AISGPU_FMT_*                                      (Common.h:290-295 RAW.format) */
+	int32_t n_streams;          /* batch of independent IQ streams, >= 1 */
+	int32_t max_chunk_samples;  /* upper bound of n_samples per stream per submit */
+	int32_t ps_ema;             /* -go PS_EMA   (Model.cpp:583-585), default 1 */
+	int32_t afc_wide;           /* -go AFC_WIDE (Model.cpp:586-588), default 1 */
+	int32_t droop;              /* -go DROOP    (Model.cpp:384-386), default 1 */
+	char channel_a, channel_b;  /* CH1/CH2 of buildModel (Model.cpp:547-548), default 'A','B' */
+	int32_t station;            /* Model::station  (Model.h:79) */
+	int32_t own_mmsi;           /* Model::own_mmsi (Model.h:80): sentences of this MMSI read !AIVDO */
+	uint32_t tag_mode;          /* TAG::mode (Common.h:242): bit0 = signal level, default 3 */
+	int32_t device;             /* CUDA device ordinal */
+	int32_t enable_taps;        /* keep intermediates readable through aisgpu_tap() */
+	int32_t max_frames;         /* capacity of the device frame ring per submit (0 = default) */
+} aisgpu_config;
+
+/* One decoded frame == one AIS::Message the reference would Send (Source/Marine/AIS.cpp:66-96). */
+typedef struct aisgpu_msg {
+	int32_t stream;             /* index in the batch */
+	char channel;               /* Message::channel (Message.h:300-305) */
+	int32_t nbits;              /* Message::getLength() */
+	int64_t start_idx, end_idx; /* Message::start_idx/end_idx: 48 kHz symbol-sample counters (AIS.h:112,151) */
+	float level;                /* TAG::level in dB (AIS.cpp:74-75) */
+	float ppm;                  /* TAG::ppm   (DSP.cpp:484) */
+	int64_t chunk;              /* ordinal of the submit that completed the frame */
+	uint8_t data[140];          /* Message::data (Message.h:69), payload bytes, MSB-first fields */
+	int32_t n_sentences;        /* Message::sentences().size() */
+	char nmea[4][100];          /* NUL-terminated !AIVDM sentences (Message.cpp:569-631) */
+} aisgpu_msg;
+
+typedef struct aisgpu_handle aisgpu_handle;
+
+/* Fills *cfg with the reference's defaults (Model.h:218-222, 138-143; Common.h:242). */
+void aisgpu_default_config(aisgpu_config *cfg);
+
+/* == AIS::Model::buildModel(CH1, CH2, sample_rate, timerOn, device) (Model.h:94, Model.cpp:27,520). */
+int aisgpu_create(const aisgpu_config *cfg, aisgpu_handle **out);
+
+/* == StreamIn<RAW>::Receive(const RAW*, 1, TAG&) for every stream of the batch (Stream.h:41; Model.cpp:33).
+ * host_samples: n_streams contiguous runs of n_samples samples (stream-major), borrowed for the call only
+ * (copied to a pinned staging buffer before returning).  n_samples must be a multiple of 2*fs/48000
+ * rounded up to a power of two (DSP.cpp:94,135 assert(len%2==0) at every CIC stage).  Asynchronous. */
+int aisgpu_submit(aisgpu_handle *h, const void *host_samples, int n_samples);
+
+/* Same, with the batch already resident in device memory ([n_streams][stride_samples], first n_samples used). */
+int aisgpu_submit_device(aisgpu_handle *h, const void *dev_samples, int64_t stride_samples, int n_samples);
+
+/* Waits for all submitted work (cudaStreamSynchronize). */
+int aisgpu_sync(aisgpu_handle *h);
+
+/* == Model::Output() / StreamOut<Message> (Model.h:96): returns frames completed by submits so far, in the
+ * reference's emission order (per submit: stream-major, channel A before B, then time; DSP.cpp:312-313).
+ * Implies aisgpu_sync().  *n receives the count written (<= max); call again until *n == 0. */
+int aisgpu_poll(aisgpu_handle *h, aisgpu_msg *out, int max, int *n);
+
+/* Intermediates of the LAST submit for one stream/channel; *n_out = elements written (float2 or float). */
+int aisgpu_tap(aisgpu_handle *h, int tap, int stream, int channel, void *dst, size_t dst_bytes, size_t *n_out);
+
+/* counters[0]=frames (CRC ok), [1]=messages published (validate ok), [2]=samples/stream, [3]=submits,
+ * [4]=frames dropped by ring overflow, [5]=ch A messages, [6]=ch B messages, [7]=reserved */
+int aisgpu_counters(aisgpu_handle *h, uint64_t counters[8]);
+
+/* The CUDA stream the kernels are launched on (cudaStream_t as void*), for event timing by the caller. */
+void *aisgpu_cuda_stream(aisgpu_handle *h);
+
+/* Device time of the front-end kernel of the last submit in ms (CUDA events on the launch stream), <0 if n/a. */
+float aisgpu_last_frontend_ms(aisgpu_handle *h);
+
+/* Number of kernels launched by the last submit. */
+int aisgpu_last_launches(aisgpu_handle *h);
+
+const char *aisgpu_last_error(aisgpu_handle *h); /* h may be NULL: error of the last failed aisgpu_create */
+
+/* == ~Model */
+void aisgpu_destroy(aisgpu_handle *h);
+
+int aisgpu_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
