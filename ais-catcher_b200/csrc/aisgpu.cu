@@ -259,7 +259,42 @@ int carry(aisgpu_handle *h, T *buf, long long stride, int src_begin, int dst_beg
 }
 
 int run_symbols(aisgpu_handle *h, int n_new) {
-	// n_new samples were appended at [HE, HE + n_new) of every row of Ec/Ef; e_left older ones sit just before HE
+	// n_new samples were appended at [HE, HE + n_new) of every row of Ec/Ef.
+	// ModelDefault (ScatterPLL, DSP.h:95-117) only forwards complete groups of 5: e_left older samples sit just
+	// before HE and the incomplete group at the end is carried.  ModelStandard (Deinterleave, DSP.h:65-73)
+	// forwards every sample at once, so partial groups at both ends are walked with a per-phase validity test.
+	if (h->cfg.model == AISGPU_MODEL_STANDARD) {
+		const long long a0 = h->e_abs, a1 = a0 + n_new;
+		const long long g0 = a0 - a0 % 5;
+		const int nslots = (int)((a1 - g0 + 4) / 5);
+		h->last_nsym = nslots;
+		K3Params p;
+		memset(&p, 0, sizeof(p));
+		p.model = h->cfg.model;
+		p.rows = h->rows;
+		p.nsym = nslots;
+		p.e_stride = h->e_stride;
+		p.e_begin = HE - (int)(a0 - g0);
+		p.abs_begin = g0;
+		p.abs_lo = a0;
+		p.abs_hi = a1;
+		p.Ef = h->d_Ef;
+		p.dec = h->d_dec;
+		p.dec_data = h->d_dec_data;
+		p.ring = h->d_ring;
+		p.ring_count = h->d_ring_count;
+		p.ring_cap = h->ring_cap;
+		p.chunk = (int)h->chunk;
+		p.mode_level = (h->cfg.tag_mode & 1) ? 1 : 0;
+		p.tap_dec = h->cfg.enable_taps ? h->d_tap_dec : nullptr;
+		const int warps = (h->rows + K3_GROUPS_PER_WARP - 1) / K3_GROUPS_PER_WARP;
+		const int ctas = (warps + K3_THREADS / 32 - 1) / (K3_THREADS / 32);
+		k_symbols<<<ctas, K3_THREADS, 0, h->stream>>>(p);
+		CU(cudaGetLastError());
+		h->last_launches++;
+		h->e_abs = a1;
+		return 0;
+	}
 	const int total = h->e_left + n_new;
 	const int nsym = total / 5;
 	const int e_begin = HE - h->e_left;
@@ -275,6 +310,8 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.e_stride = h->e_stride;
 		p.e_begin = e_begin;
 		p.abs_begin = h->e_abs;
+		p.abs_lo = h->e_abs;
+		p.abs_hi = h->e_abs + (long long)nsym * 5;
 		p.Ec = h->d_Ec;
 		p.Ef = h->d_Ef;
 		p.ps = h->d_ps;
@@ -300,12 +337,7 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		h->last_launches++;
 	}
 	const int new_left = total - nsym * 5;
-	if (h->cfg.model == AISGPU_MODEL_DEFAULT) {
-		if (carry(h, h->d_Ec, h->e_stride, e_begin + nsym * 5, HE - new_left, new_left)) return AISGPU_ECUDA;
-	}
-	else {
-		if (carry(h, h->d_Ef, h->e_stride, e_begin + nsym * 5, HE - new_left, new_left)) return AISGPU_ECUDA;
-	}
+	if (carry(h, h->d_Ec, h->e_stride, e_begin + nsym * 5, HE - new_left, new_left)) return AISGPU_ECUDA;
 	h->e_left = new_left;
 	h->e_abs += (long long)nsym * 5;
 	return 0;
@@ -496,7 +528,7 @@ int drain_ring(aisgpu_handle *h) {
 		m.ppm = r.ppm;
 		m.chunk = r.chunk;
 		float lvl = r.level;
-		if ((h->cfg.tag_mode & 1) && lvl != 0.0) lvl = (float)(10.0f * log10(lvl)); // AIS.cpp:74-75
+		if ((h->cfg.tag_mode & 1) && lvl != 0.0) lvl = (float)(10.0f * log10((double)lvl)); // AIS.cpp:74-75: the reference resolves to the double log10
 		m.level = lvl;
 		memcpy(m.data, r.data, 140);
 		if (!msg_validate(m.data, m.nbits)) continue; // AIS.cpp:87-93: dropped, siblings were still reset
@@ -576,6 +608,8 @@ static int create_impl(aisgpu_handle *h) {
 	h->seq.assign(B, 0);
 	for (int i = 0; i < 2; i++) {
 		if (int rc = dalloc(h, &h->d_tail[i], (size_t)B * h->P * h->bps)) return rc;
+		if (c.format == AISGPU_FMT_CU8) // the reference's zero initial filter state is byte value 128 in CU8
+			CU(cudaMemsetAsync(h->d_tail[i], 0x80, (size_t)B * h->P * h->bps, h->stream));
 		if (int rc = dalloc(h, &h->d_rot[i], (size_t)h->P96 + (maxN >> k) + 8)) return rc;
 		if (int rc = dalloc(h, &h->d_fir_hist[i], (size_t)h->rows * 16)) return rc;
 	}
@@ -771,6 +805,11 @@ int aisgpu_tap(aisgpu_handle *h, int tap, int stream, int channel, void *dst, si
 		else {
 			src = h->d_tap_dec + (long long)(row * 5 + phase) * h->last_nsym;
 			n = h->last_nsym;
+			if (h->cfg.model == AISGPU_MODEL_STANDARD) { // samples of this phase among the last submit's [a0, a1)
+				const long long a1 = h->e_abs, a0 = a1 - h->last_nE;
+				n = 0;
+				for (long long a = a0; a < a1; a++) n += (a % 5) == phase;
+			}
 		}
 		break;
 	}

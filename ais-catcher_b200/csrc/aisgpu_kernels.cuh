@@ -252,19 +252,13 @@ __global__ void __launch_bounds__(FE_THREADS) k_frontend(const FeParams p) {
 		const int len = (int)min((long long)p.tile, (warm ? seg_start : seg_end) - pos);
 		// ---- load tile into level 0 (converted to float2) ----
 		{
-			const void *src;
-			long long base;
-			if (pos < 0) { // only segment 0 warm-up: previous submit's tail
-				src = p.tail;
-				base = (long long)stream * p.P + (p.P + pos);
-			}
-			else {
-				src = p.in;
-				base = (long long)stream * p.in_stride + pos;
-			}
+			// samples before the submit's first one come from the previous submit's tail (a tile may straddle)
+			const long long tbase = (long long)stream * p.P + p.P + pos;
+			const long long ibase = (long long)stream * p.in_stride + pos;
 			for (int i = tid * 2; i < len; i += FE_THREADS * 2) {
 				float2 a, b;
-				fe_load_pair<FMT>(src, base + i, a, b);
+				if (pos + i < 0) fe_load_pair<FMT>(p.tail, tbase + i, a, b);
+				else fe_load_pair<FMT>(p.in, ibase + i, a, b);
 				*reinterpret_cast<float4 *>(lv0 + i) = make_float4(a.x, a.y, b.x, b.y);
 			}
 		}
@@ -746,10 +740,11 @@ struct K3Params {
 	int model;            // 0 standard, 2 default
 	int ps_ema;
 	int rows;
-	int nsym;             // symbols (groups of 5 samples) to process this submit
+	int nsym;             // symbol slots (groups of 5 samples) to walk this submit
 	long long e_stride;
-	int e_begin;          // index in the row of the first sample of the first group
-	long long abs_begin;  // absolute per-channel index of that sample (TAG::sample_idx, DSP.h:110)
+	int e_begin;          // index in the row of the sample with absolute index abs_begin
+	long long abs_begin;  // absolute per-channel index (TAG::sample_idx, DSP.h:110) of slot 0 / phase 0; multiple of 5
+	long long abs_lo, abs_hi; // samples with abs_lo <= index < abs_hi exist this submit (Deinterleave forwards partial groups)
 	const float2 *Ec;     // ModelDefault: FIR17 output
 	const float *Ef;      // FM models: FIR37 output
 	PsState *ps;
@@ -800,12 +795,14 @@ __global__ void __launch_bounds__(K3_THREADS) k_symbols(const K3Params p) {
 	}
 	const float weight = 0.85f, omw = __fsub_rn(1.0f, 0.85f);
 	const long long e_row = (long long)row * p.e_stride + p.e_begin;
+	int ntap = 0;
 
 	for (int s = 0; s < p.nsym; s++) {
 		float b = 0.0f, sample_lvl = 0.0f;
 		const long long sample_idx = p.abs_begin + (long long)s * 5 + phase;
 		float ppm = 0.0f;
-		if (active) {
+		const bool valid = active && sample_idx >= p.abs_lo && sample_idx < p.abs_hi;
+		if (valid) {
 			if (p.model == 2) {
 				const float2 x = p.Ec[e_row + (long long)s * 5 + phase];
 				// ScatterPLL level: ((((0+n0)+n1)+n2)+n3)+n4, then / 5 (DSP.h:100-106)
@@ -879,13 +876,13 @@ __global__ void __launch_bounds__(K3_THREADS) k_symbols(const K3Params p) {
 			else {
 				b = p.Ef[e_row + (long long)s * 5 + phase];
 			}
-			if (p.tap_dec) p.tap_dec[(long long)sidx * p.nsym + s] = b;
+			if (p.tap_dec) p.tap_dec[(long long)sidx * p.nsym + ntap++] = b;
 		}
 		int fr_len = 0, lastBit_before = 0;
 		float fr_level = 0.0f;
 		const float level_before = d.level;
 		const long long start_before = d.start_idx;
-		bool found = active && dec_step(d, ctx, b, sample_lvl, sample_idx, fr_len, fr_level, lastBit_before);
+		bool found = valid && dec_step(d, ctx, b, sample_lvl, sample_idx, fr_len, fr_level, lastBit_before);
 		const unsigned vote = __ballot_sync(0xffffffffu, found);
 		if (vote) { // rare: FOUNDMESSAGE -> Reset to the four sibling decoders (AIS.cpp:47-49,98-108)
 			const unsigned gv = vote & grp_mask;
@@ -894,7 +891,7 @@ __global__ void __launch_bounds__(K3_THREADS) k_symbols(const K3Params p) {
 				if (lane == winner) {
 					emit_frame(p.ring, p.ring_count, p.ring_cap, p.chunk, ctx, row, phase, fr_len, fr_level, ppm, d.start_idx, sample_idx);
 				}
-				else if (lane < winner) { // already stepped this symbol, then reset
+				else if (lane < winner || !valid) { // already stepped this symbol (or has no sample in this slot), then reset
 					d.state = ST_TRAINING; d.position = 0; d.one_seq = 0;
 				}
 				else { // reset first, then step this symbol from TRAINING/0: only the NRZI memory survives
