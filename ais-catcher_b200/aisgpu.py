@@ -16,7 +16,7 @@ TAP_C, TAP_CGF, TAP_FIR, TAP_ROT, TAP_DEC, TAP_FM = 0, 1, 2, 3, 4, 5
 
 EXPORTS = ["aisgpu_abi_version", "aisgpu_default_config", "aisgpu_create", "aisgpu_submit", "aisgpu_submit_device",
            "aisgpu_sync", "aisgpu_poll", "aisgpu_tap", "aisgpu_counters", "aisgpu_cuda_stream",
-           "aisgpu_last_frontend_ms", "aisgpu_last_launches", "aisgpu_last_error", "aisgpu_destroy"]
+           "aisgpu_last_frontend_ms", "aisgpu_frontend_times", "aisgpu_last_launches", "aisgpu_last_error", "aisgpu_destroy"]
 
 
 class Config(C.Structure):
@@ -80,6 +80,7 @@ def load():
     lib.aisgpu_cuda_stream.restype = C.c_void_p
     lib.aisgpu_last_frontend_ms.argtypes = [C.c_void_p]
     lib.aisgpu_last_frontend_ms.restype = C.c_float
+    lib.aisgpu_frontend_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
     lib.aisgpu_last_launches.argtypes = [C.c_void_p]
     lib.aisgpu_last_error.argtypes = [C.c_void_p]
     lib.aisgpu_last_error.restype = C.c_char_p
@@ -158,6 +159,12 @@ class Engine:
 
     def last_frontend_ms(self):
         return float(self.lib.aisgpu_last_frontend_ms(self.h))
+
+    def frontend_times(self, max_n=128):
+        buf = (C.c_float * max_n)()
+        n = C.c_int(0)
+        self._chk(self.lib.aisgpu_frontend_times(self.h, buf, max_n, C.byref(n)))
+        return [buf[i] for i in range(n.value)]
 
     def last_launches(self):
         return int(self.lib.aisgpu_last_launches(self.h))

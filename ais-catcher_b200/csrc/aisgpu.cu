@@ -62,7 +62,9 @@ struct aisgpu_handle {
 	int rows = 0;
 	int max_n48 = 0;
 	cudaStream_t stream = nullptr, copy_stream = nullptr;
-	cudaEvent_t ev_fe0 = nullptr, ev_fe1 = nullptr, ev_copy[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr };
+	static const int NEV = 128;
+	cudaEvent_t ev_fe0s[128] = { nullptr }, ev_fe1s[128] = { nullptr };
+	cudaEvent_t ev_copy[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr };
 	bool fe_timed = false;
 	// input staging for host submits
 	unsigned char *d_in[2] = { nullptr, nullptr };
@@ -366,9 +368,10 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 		h->last_launches++;
 	}
 	// ---- K1: fused front end ----
-	CU(cudaEventRecord(h->ev_fe0, h->stream));
+	const int evi = (int)(h->chunk % aisgpu_handle::NEV);
+	CU(cudaEventRecord(h->ev_fe0s[evi], h->stream));
 	if (int rc = launch_frontend(h, dev_in, stride, N)) return rc;
-	CU(cudaEventRecord(h->ev_fe1, h->stream));
+	CU(cudaEventRecord(h->ev_fe1s[evi], h->stream));
 	h->fe_timed = true;
 	h->last_launches++;
 	// ---- front-end history for the next submit ----
@@ -592,8 +595,10 @@ static int create_impl(aisgpu_handle *h) {
 	CU(cudaSetDevice(c.device));
 	CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-	CU(cudaEventCreate(&h->ev_fe0));
-	CU(cudaEventCreate(&h->ev_fe1));
+	for (int i = 0; i < aisgpu_handle::NEV; i++) {
+		CU(cudaEventCreate(&h->ev_fe0s[i]));
+		CU(cudaEventCreate(&h->ev_fe1s[i]));
+	}
 	for (int i = 0; i < 2; i++) {
 		CU(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
@@ -838,11 +843,24 @@ int aisgpu_counters(aisgpu_handle *h, uint64_t counters[8]) {
 void *aisgpu_cuda_stream(aisgpu_handle *h) { return h ? (void *)h->stream : nullptr; }
 
 float aisgpu_last_frontend_ms(aisgpu_handle *h) {
-	if (!h || !h->fe_timed) return -1.0f;
-	if (cudaEventSynchronize(h->ev_fe1) != cudaSuccess) return -1.0f;
 	float ms = -1.0f;
-	if (cudaEventElapsedTime(&ms, h->ev_fe0, h->ev_fe1) != cudaSuccess) return -1.0f;
+	int n = 0;
+	if (aisgpu_frontend_times(h, &ms, 1, &n) || n != 1) return -1.0f;
 	return ms;
+}
+
+int aisgpu_frontend_times(aisgpu_handle *h, float *ms_out, int max, int *n) {
+	if (!h || !ms_out || !n) return AISGPU_EINVAL;
+	*n = 0;
+	if (!h->fe_timed) return 0;
+	CU(cudaStreamSynchronize(h->stream));
+	long long cnt = std::min<long long>(std::min<long long>(h->chunk, aisgpu_handle::NEV), max);
+	for (long long i = 0; i < cnt; i++) { // newest first
+		const int evi = (int)((h->chunk - 1 - i) % aisgpu_handle::NEV);
+		CU(cudaEventElapsedTime(&ms_out[i], h->ev_fe0s[evi], h->ev_fe1s[evi]));
+	}
+	*n = (int)cnt;
+	return 0;
 }
 
 int aisgpu_last_launches(aisgpu_handle *h) { return h ? h->last_launches : 0; }
@@ -856,8 +874,10 @@ void aisgpu_destroy(aisgpu_handle *h) {
 					 h->d_ring_count };
 	for (void *p : ptrs)
 		if (p) cudaFree(p);
-	if (h->ev_fe0) cudaEventDestroy(h->ev_fe0);
-	if (h->ev_fe1) cudaEventDestroy(h->ev_fe1);
+	for (int i = 0; i < aisgpu_handle::NEV; i++) {
+		if (h->ev_fe0s[i]) cudaEventDestroy(h->ev_fe0s[i]);
+		if (h->ev_fe1s[i]) cudaEventDestroy(h->ev_fe1s[i]);
+	}
 	for (int i = 0; i < 2; i++) {
 		if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
 		if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);

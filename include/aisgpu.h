@@ -129,6 +129,10 @@ void *aisgpu_cuda_stream(aisgpu_handle *h);
 /* Device time of the front-end kernel of the last submit in ms (CUDA events on the launch stream), <0 if n/a. */
 float aisgpu_last_frontend_ms(aisgpu_handle *h);
 
+/* Device times (ms) of the front-end kernel of the most recent submits, newest first (up to 128 kept).
+ * Implies aisgpu_sync().  This is the live roofline measurement bench.py reports. */
+int aisgpu_frontend_times(aisgpu_handle *h, float *ms_out, int max, int *n);
+
 /* Number of kernels launched by the last submit. */
 int aisgpu_last_launches(aisgpu_handle *h);
 
