@@ -73,11 +73,16 @@ struct aisgpu_handle {
 	unsigned char *d_tail[2] = { nullptr, nullptr };
 	int tail_cur = 0;
 	// Rotate
-	float2 *d_rot[2] = { nullptr, nullptr };
-	int rot_n96[2] = { 0, 0 };
+	// Rotate: table c lives in slot c % 3, rot state after chunk c in d_rot_state[1 + c % 3] (slot 0 = initial state);
+	// tables are produced on side_stream, one submit ahead when the chunk length repeats
+	float2 *d_rot[3] = { nullptr, nullptr, nullptr };
+	int rot_n96[3] = { 0, 0, 0 };
+	long long rot_ready_chunk = -1; // newest chunk whose table has been enqueued on side_stream
 	int rot_cur = 0;
-	bool rot_valid = false;
-	float2 *d_rot_state = nullptr;
+	float2 *d_rot_state = nullptr;  // [4]
+	cudaStream_t side_stream = nullptr;
+	cudaEvent_t ev_rot[3] = { nullptr, nullptr, nullptr }, ev_k1[3] = { nullptr, nullptr, nullptr };
+	bool k1_recorded[3] = { false, false, false };
 	float2 mult;
 	// 48 kHz channel buffer
 	float2 *d_C = nullptr;
@@ -100,6 +105,8 @@ struct aisgpu_handle {
 	long long e_abs = 0;
 	PsState *d_ps = nullptr;
 	float *d_ps_mem = nullptr;
+	uint32_t *d_dbits = nullptr;
+	int dwords = 0;
 	DecState *d_dec = nullptr;
 	uint32_t *d_dec_data = nullptr;
 	PllState *d_pll = nullptr;
@@ -272,7 +279,6 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		h->last_nsym = nslots;
 		K3Params p;
 		memset(&p, 0, sizeof(p));
-		p.model = h->cfg.model;
 		p.rows = h->rows;
 		p.nsym = nslots;
 		p.e_stride = h->e_stride;
@@ -289,9 +295,7 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.chunk = (int)h->chunk;
 		p.mode_level = (h->cfg.tag_mode & 1) ? 1 : 0;
 		p.tap_dec = h->cfg.enable_taps ? h->d_tap_dec : nullptr;
-		const int warps = (h->rows + K3_GROUPS_PER_WARP - 1) / K3_GROUPS_PER_WARP;
-		const int ctas = (warps + K3_THREADS / 32 - 1) / (K3_THREADS / 32);
-		k_symbols<<<ctas, K3_THREADS, 0, h->stream>>>(p);
+		k_decode<0><<<(h->rows + DK_THREADS / 32 - 1) / (DK_THREADS / 32), DK_THREADS, 0, h->stream>>>(p);
 		CU(cudaGetLastError());
 		h->last_launches++;
 		h->e_abs = a1;
@@ -305,7 +309,6 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 	if (nsym > 0) {
 		K3Params p;
 		memset(&p, 0, sizeof(p));
-		p.model = h->cfg.model;
 		p.ps_ema = h->cfg.ps_ema;
 		p.rows = h->rows;
 		p.nsym = nsym;
@@ -332,16 +335,34 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 			p.nblk = n_new / CGF_N;
 		}
 		p.tap_dec = h->cfg.enable_taps ? h->d_tap_dec : nullptr;
-		const int warps = (h->rows + K3_GROUPS_PER_WARP - 1) / K3_GROUPS_PER_WARP;
-		const int ctas = (warps + K3_THREADS / 32 - 1) / (K3_THREADS / 32);
-		k_symbols<<<ctas, K3_THREADS, 0, h->stream>>>(p);
+		p.dbits = h->d_dbits;
+		p.dwords = h->dwords;
+		const long long ps_warps = ((long long)h->rows * 5 + 1) / 2;
+		k_phase_search<<<(unsigned)((ps_warps + PS_THREADS / 32 - 1) / (PS_THREADS / 32)), PS_THREADS, 0, h->stream>>>(p);
 		CU(cudaGetLastError());
-		h->last_launches++;
+		k_decode<2><<<(h->rows + DK_THREADS / 32 - 1) / (DK_THREADS / 32), DK_THREADS, 0, h->stream>>>(p);
+		CU(cudaGetLastError());
+		h->last_launches += 2;
 	}
 	const int new_left = total - nsym * 5;
 	if (carry(h, h->d_Ec, h->e_stride, e_begin + nsym * 5, HE - new_left, new_left)) return AISGPU_ECUDA;
 	h->e_left = new_left;
 	h->e_abs += (long long)nsym * 5;
+	return 0;
+}
+
+// Enqueue the Rotate phasor table of chunk c (n96 samples at 96 kHz) on the side stream.
+int enqueue_rot_table(aisgpu_handle *h, long long c, int n96) {
+	const int slot = (int)(c % 3), prev = (int)((c + 2) % 3);
+	// slot was last read by the front end of chunk c-3
+	if (h->k1_recorded[slot]) CU(cudaStreamWaitEvent(h->side_stream, h->ev_k1[slot], 0));
+	const float2 *prev_tail = c > 0 ? h->d_rot[prev] + h->rot_n96[prev] : nullptr;
+	const float2 *state_in = c > 0 ? h->d_rot_state + 1 + prev : h->d_rot_state;
+	k_rot_table<<<1, 32, 0, h->side_stream>>>(h->d_rot[slot], prev_tail, state_in, h->d_rot_state + 1 + slot, h->mult, h->P96, n96);
+	CU(cudaGetLastError());
+	CU(cudaEventRecord(h->ev_rot[slot], h->side_stream));
+	h->rot_n96[slot] = n96;
+	h->rot_ready_chunk = c;
 	return 0;
 }
 
@@ -356,29 +377,34 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 	h->last_launches = 0;
 	const int k = h->k, B = h->cfg.n_streams;
 	const int n96 = N >> k, n48 = n96 >> 1;
-	// ---- K0: Rotate phasor table ----
+	// ---- K0: Rotate phasor table (side stream; normally already enqueued by the previous submit) ----
 	{
-		const int nxt = h->rot_cur ^ 1;
-		const float2 *prev_tail = h->rot_valid ? h->d_rot[h->rot_cur] + h->rot_n96[h->rot_cur] : nullptr;
-		k_rot_table<<<1, 32, 0, h->stream>>>(h->d_rot[nxt], prev_tail, h->d_rot_state, h->mult, h->P96, n96);
-		CU(cudaGetLastError());
-		h->rot_cur = nxt;
-		h->rot_n96[nxt] = n96;
-		h->rot_valid = true;
-		h->last_launches++;
+		const long long c = h->chunk;
+		const int slot = (int)(c % 3);
+		if (!(h->rot_ready_chunk == c && h->rot_n96[slot] == n96)) {
+			if (int rc = enqueue_rot_table(h, c, n96)) return rc;
+		}
+		CU(cudaStreamWaitEvent(h->stream, h->ev_rot[slot], 0));
+		h->rot_cur = slot;
 	}
 	// ---- K1: fused front end ----
 	const int evi = (int)(h->chunk % aisgpu_handle::NEV);
 	CU(cudaEventRecord(h->ev_fe0s[evi], h->stream));
 	if (int rc = launch_frontend(h, dev_in, stride, N)) return rc;
 	CU(cudaEventRecord(h->ev_fe1s[evi], h->stream));
+	CU(cudaEventRecord(h->ev_k1[h->chunk % 3], h->stream));
+	h->k1_recorded[h->chunk % 3] = true;
 	h->fe_timed = true;
-	h->last_launches++;
+	h->last_launches += 2; // front end + this submit's phasor table
+	// speculate that the next submit has the same length: build its phasor table now, off the critical path
+	if (int rc = enqueue_rot_table(h, h->chunk + 1, n96)) return rc;
 	// ---- front-end history for the next submit ----
 	{
 		const int nxt = h->tail_cur ^ 1;
-		dim3 grid((unsigned)std::min<long long>(64, ((long long)h->P * h->bps + 255) / 256), B);
-		k_tail_update<<<grid, 256, 0, h->stream>>>(h->d_tail[nxt], h->d_tail[h->tail_cur], (const unsigned char *)dev_in, stride, N, h->P, h->bps);
+		const int p_w = h->P * h->bps / 8;
+		dim3 grid((p_w + 127) / 128, B);
+		k_tail_update<<<grid, 128, 0, h->stream>>>((uint2 *)h->d_tail[nxt], (const uint2 *)h->d_tail[h->tail_cur], (const uint2 *)dev_in,
+													stride * h->bps / 8, (long long)N * h->bps / 8, p_w);
 		CU(cudaGetLastError());
 		h->tail_cur = nxt;
 		h->last_launches++;
@@ -595,6 +621,11 @@ static int create_impl(aisgpu_handle *h) {
 	CU(cudaSetDevice(c.device));
 	CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 3; i++) {
+		CU(cudaEventCreateWithFlags(&h->ev_rot[i], cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&h->ev_k1[i], cudaEventDisableTiming));
+	}
 	for (int i = 0; i < aisgpu_handle::NEV; i++) {
 		CU(cudaEventCreate(&h->ev_fe0s[i]));
 		CU(cudaEventCreate(&h->ev_fe1s[i]));
@@ -615,13 +646,14 @@ static int create_impl(aisgpu_handle *h) {
 		if (int rc = dalloc(h, &h->d_tail[i], (size_t)B * h->P * h->bps)) return rc;
 		if (c.format == AISGPU_FMT_CU8) // the reference's zero initial filter state is byte value 128 in CU8
 			CU(cudaMemsetAsync(h->d_tail[i], 0x80, (size_t)B * h->P * h->bps, h->stream));
-		if (int rc = dalloc(h, &h->d_rot[i], (size_t)h->P96 + (maxN >> k) + 8)) return rc;
 		if (int rc = dalloc(h, &h->d_fir_hist[i], (size_t)h->rows * 16)) return rc;
 	}
-	if (int rc = dalloc(h, &h->d_rot_state, 1)) return rc;
+	for (int i = 0; i < 3; i++)
+		if (int rc = dalloc(h, &h->d_rot[i], (size_t)h->P96 + (maxN >> k) + 8)) return rc;
+	if (int rc = dalloc(h, &h->d_rot_state, 4)) return rc;
 	{
 		float2 one = make_float2(1.0f, 0.0f);
-		CU(cudaMemcpyAsync(h->d_rot_state, &one, sizeof(one), cudaMemcpyHostToDevice, h->stream));
+		CU(cudaMemcpyAsync(h->d_rot_state, &one, sizeof(one), cudaMemcpyHostToDevice, h->stream)); // after the memset on the same stream
 		h->mult = polar1((float)(PI_F * 25000.0 / 48000.0)); // Model.cpp:31
 	}
 	h->c_stride = (HC + h->max_n48 + 8 + 1) & ~1LL;
@@ -638,6 +670,8 @@ static int create_impl(aisgpu_handle *h) {
 		if (int rc = dalloc(h, &h->d_cgf_rot, (size_t)h->rows)) return rc;
 		if (int rc = dalloc(h, &h->d_Ec, (size_t)h->rows * h->e_stride)) return rc;
 		if (int rc = dalloc(h, &h->d_ps, (size_t)h->rows * 5)) return rc;
+		h->dwords = (nEmax / 5 + 1 + K3_TS - 1) / K3_TS + 1;
+		if (int rc = dalloc(h, &h->d_dbits, (size_t)h->rows * 5 * h->dwords)) return rc;
 		if (!c.ps_ema)
 			if (int rc = dalloc(h, &h->d_ps_mem, (size_t)h->rows * 5 * 16 * 12)) return rc;
 		if (int rc = dalloc(h, &h->d_steptab, CGF_NIDX)) return rc;
@@ -794,6 +828,7 @@ int aisgpu_tap(aisgpu_handle *h, int tap, int stream, int channel, void *dst, si
 		n = h->last_nE;
 		break;
 	case AISGPU_TAP_ROT:
+		CU(cudaStreamSynchronize(h->side_stream));
 		src = h->d_rot[h->rot_cur] + h->P96;
 		n = h->rot_n96[h->rot_cur];
 		break;
@@ -868,9 +903,9 @@ int aisgpu_last_launches(aisgpu_handle *h) { return h ? h->last_launches : 0; }
 void aisgpu_destroy(aisgpu_handle *h) {
 	if (!h) return;
 	if (h->stream) cudaStreamSynchronize(h->stream);
-	void *ptrs[] = { h->d_in[0], h->d_in[1], h->d_tail[0], h->d_tail[1], h->d_rot[0], h->d_rot[1], h->d_rot_state, h->d_C, h->d_stepidx,
+	void *ptrs[] = { h->d_in[0], h->d_in[1], h->d_tail[0], h->d_tail[1], h->d_rot[0], h->d_rot[1], h->d_rot[2], h->d_rot_state, h->d_C, h->d_stepidx,
 					 h->d_steptab, h->d_omega, h->d_cgf_rot, h->d_rots, h->d_ppmtab, h->d_fir_hist[0], h->d_fir_hist[1], h->d_tap_cgf, h->d_Ec,
-					 h->d_Ef, h->d_ps, h->d_ps_mem, h->d_dec, h->d_dec_data, h->d_pll, h->d_tap_dec, h->d_tap_fm, h->d_tap_cnt, h->d_ring,
+					 h->d_Ef, h->d_ps, h->d_ps_mem, h->d_dbits, h->d_dec, h->d_dec_data, h->d_pll, h->d_tap_dec, h->d_tap_fm, h->d_tap_cnt, h->d_ring,
 					 h->d_ring_count };
 	for (void *p : ptrs)
 		if (p) cudaFree(p);
@@ -882,6 +917,11 @@ void aisgpu_destroy(aisgpu_handle *h) {
 		if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
 		if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
 	}
+	for (int i = 0; i < 3; i++) {
+		if (h->ev_rot[i]) cudaEventDestroy(h->ev_rot[i]);
+		if (h->ev_k1[i]) cudaEventDestroy(h->ev_k1[i]);
+	}
+	if (h->side_stream) { cudaStreamSynchronize(h->side_stream); cudaStreamDestroy(h->side_stream); }
 	if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	delete h;

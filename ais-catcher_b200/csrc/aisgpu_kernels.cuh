@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace aisgpu {
 
@@ -129,17 +130,18 @@ __device__ __forceinline__ float fd_atan2f(float y, float x) {
 // every stream of the batch.  tab[P96 + i] is the phasor that multiplies 96 kHz sample i of this submit;
 // tab[0..P96) repeats the last P96 phasors of the previous submit (warm-up history of the front end).
 // ---------------------------------------------------------------------------------------------
-__global__ void k_rot_table(float2 *__restrict__ tab, const float2 *__restrict__ prev_tail, float2 *__restrict__ rot_state,
-							float2 mult, int P96, int n96) {
-	if (blockIdx.x != 0 || threadIdx.x != 0) return;
-	for (int i = 0; i < P96; i++) tab[i] = prev_tail ? prev_tail[i] : make_float2(1.0f, 0.0f);
-	float2 rot = *rot_state;
+__global__ void k_rot_table(float2 *__restrict__ tab, const float2 *__restrict__ prev_tail, const float2 *__restrict__ state_in,
+							float2 *__restrict__ state_out, float2 mult, int P96, int n96) {
+	if (blockIdx.x != 0) return;
+	for (int i = threadIdx.x; i < P96; i += blockDim.x) tab[i] = prev_tail ? prev_tail[i] : make_float2(1.0f, 0.0f);
+	if (threadIdx.x != 0) return;
+	float2 rot = *state_in;
 	float2 *o = tab + P96;
 	for (int i = 0; i < n96; i++) {
 		o[i] = rot;
 		rot = cmul(rot, mult);
 	}
-	*rot_state = cnormalize(rot);
+	*state_out = cnormalize(rot);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -334,18 +336,14 @@ __global__ void __launch_bounds__(FE_THREADS) k_frontend(const FeParams p) {
 	}
 }
 
-// new_tail[i] = last P samples of (old_tail ++ chunk); works for any N (raw bytes, bps bytes per sample)
-__global__ void k_tail_update(unsigned char *__restrict__ new_tail, const unsigned char *__restrict__ old_tail,
-							  const unsigned char *__restrict__ in, long long in_stride, int N, int P, int bps) {
+// new_tail = last P samples of (old_tail ++ chunk); works for any N.  Copies 8-byte words (P is a multiple of 4
+// samples and every format has >= 2 bytes per sample, so rows and offsets stay 8-byte aligned).
+__global__ void k_tail_update(uint2 *__restrict__ new_tail, const uint2 *__restrict__ old_tail, const uint2 *__restrict__ in,
+							  long long in_stride_w, long long n_w, int p_w) {
 	const int stream = blockIdx.y;
-	const long long nbytes = (long long)P * bps;
-	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += (long long)gridDim.x * blockDim.x) {
-		const long long s = i / bps + (long long)N - P; // sample index relative to chunk start
-		const int b = (int)(i % bps);
-		unsigned char v;
-		if (s >= 0) v = in[((long long)stream * in_stride + s) * bps + b];
-		else v = old_tail[((long long)stream * P + (s + P)) * bps + b];
-		new_tail[(long long)stream * nbytes + i] = v;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p_w; i += gridDim.x * blockDim.x) {
+		const long long s = (long long)i + n_w - p_w; // word index relative to chunk start
+		new_tail[(long long)stream * p_w + i] = s >= 0 ? in[(long long)stream * in_stride_w + s] : old_tail[(long long)stream * p_w + (s + p_w)];
 	}
 }
 
@@ -588,8 +586,7 @@ __global__ void __launch_bounds__(FIRF_TILE) k_fm_fir(const float2 *__restrict__
 enum { ST_TRAINING = 0, ST_STARTFLAG = 1, ST_DATAFCS = 3 };
 constexpr int DEC_WORDS = 35;     // 140 bytes (Message.h:69 data[MAX_AIS_FRAME_BYTES + 4])
 constexpr int MAX_FRAME_BITS = 1087; // MAX_AIS_FRAME_LENGTH (Message.h:41)
-constexpr int K3_THREADS = 128;
-constexpr int K3_GROUPS_PER_WARP = 6;
+constexpr int K3_THREADS = 32; // one warp per CTA: the rows are few, spread them over all SMs
 
 struct DecState { // one per (row, phase); persisted between submits (frame bits live in a separate array)
 	int state, lastBit, prev, position, one_seq;
@@ -737,7 +734,6 @@ __constant__ float c_ps_cos[8];
 __constant__ float c_ps_sin[8];
 
 struct K3Params {
-	int model;            // 0 standard, 2 default
 	int ps_ema;
 	int rows;
 	int nsym;             // symbol slots (groups of 5 samples) to walk this submit
@@ -749,6 +745,8 @@ struct K3Params {
 	const float *Ef;      // FM models: FIR37 output
 	PsState *ps;
 	float *ps_mem;        // PhaseSearch history |t| [16*12][rows*5] (only when !ps_ema)
+	uint32_t *dbits;      // ModelDefault: demodulated bits, [rows*5][dwords], bit (s & 31) of word (s >> 5) = symbol s
+	int dwords;
 	DecState *dec;
 	uint32_t *dec_data;   // [DEC_WORDS][rows*5]
 	FrameRec *ring;
@@ -764,137 +762,270 @@ struct K3Params {
 	float *tap_dec;       // optional: decoder input samples [rows*5][nsym]
 };
 
-__global__ void __launch_bounds__(K3_THREADS) k_symbols(const K3Params p) {
-	__shared__ uint32_t frames[DEC_WORDS * K3_THREADS];
-	__shared__ float ma_s[16 * K3_THREADS];
-	const int tid = threadIdx.x, lane = tid & 31;
-	const int warp_global = blockIdx.x * (K3_THREADS / 32) + (tid >> 5);
-	const int grp = lane / 5, phase = lane - grp * 5;
-	const int row = warp_global * K3_GROUPS_PER_WARP + grp;
-	const bool active = grp < K3_GROUPS_PER_WARP && row < p.rows;
-	const unsigned grp_mask = active ? (0x1fu << (grp * 5)) : 0u;
+constexpr int K3_TS = 32;                 // symbols staged per tile
+constexpr int K3_ROWLEN = K3_TS * 5;      // samples of one row in a tile
+
+__device__ __forceinline__ void cp_async_f(float *smem_dst, const float *gsrc) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_f(float2 *smem_dst, const float2 *gsrc) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// ---------------------------------------------------------------------------------------------
+// K3a: PhaseSearchEMA / PhaseSearch (Demod.cpp:39-170), hypothesis-parallel.  Half a warp per (row, sampling
+// phase): lane h owns hypothesis h (its EMA / 12-sample history and its last 5 sign decisions); the +-1 (+-2)
+// neighbourhood argmax is three (five) shuffles.  The only thing leaving the kernel is one bit per symbol.
+// ---------------------------------------------------------------------------------------------
+constexpr int PS_THREADS = 128;
+__global__ void __launch_bounds__(PS_THREADS) k_phase_search(const K3Params p) {
+	__shared__ float2 tile[PS_THREADS / 32][2][2 * K3_ROWLEN];
+	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+	const int half = lane >> 4, h = lane & 15;
+	const long long ninst = (long long)p.rows * 5;
+	const long long warp_global = (long long)blockIdx.x * (PS_THREADS / 32) + wib;
+	const long long inst = warp_global * 2 + half;
+	const bool active = inst < ninst;
+	const int row = active ? (int)(inst / 5) : 0, phase = active ? (int)(inst - (long long)row * 5) : 0;
+	const unsigned hmask = 0xffffu << (half * 16);
+	const int j = h < 8 ? h : 15 - h;
+	const float cj = c_ps_cos[j];
+	const float sj = h < 8 ? c_ps_sin[j] : -c_ps_sin[j]; // a - b == a + (-b) and im * (-s) == -(im * s), exactly
+	const float weight = 0.85f, omw = __fsub_rn(1.0f, 0.85f);
+
+	float ma = 0.0f, mem[12];
+	uint32_t hist = 0; // bit d = sign decision of this hypothesis d symbols ago (uint8_t bits[] of the reference, low 5 bits)
+	int max_idx = 0, rot = 0, last = 0;
+#pragma unroll
+	for (int l = 0; l < 12; l++) mem[l] = 0.0f;
+	if (active) {
+		const PsState &st = p.ps[inst];
+		ma = st.ma[h];
+#pragma unroll
+		for (int dd = 0; dd < 5; dd++) hist |= ((st.plane[dd] >> h) & 1u) << dd;
+		max_idx = st.max_idx;
+		rot = st.rot;
+		last = st.last;
+		if (!p.ps_ema) {
+#pragma unroll
+			for (int l = 0; l < 12; l++) mem[l] = p.ps_mem[(long long)(h * 12 + l) * ninst + inst];
+		}
+	}
+	const int nsamp = p.nsym * 5;
+	float2(*mytile)[2 * K3_ROWLEN] = tile[wib];
+	// each half stages the samples of its own row
+	auto prefetch = [&](int buf, int s0) {
+		const int base = s0 * 5;
+		if (active) {
+			const float2 *src = p.Ec + (long long)row * p.e_stride + p.e_begin + base;
+			float2 *dst = &mytile[buf][half * K3_ROWLEN];
+			for (int e = h; e < K3_ROWLEN; e += 16)
+				if (base + e < nsamp) cp_async_f(dst + e, src + e);
+		}
+		cp_async_commit();
+	};
+	const int ntiles = (p.nsym + K3_TS - 1) / K3_TS;
+	if (ntiles > 0) prefetch(0, 0);
+	for (int t = 0; t < ntiles; t++) {
+		if (t + 1 < ntiles) {
+			prefetch((t + 1) & 1, (t + 1) * K3_TS);
+			cp_async_wait<1>();
+		}
+		else cp_async_wait<0>();
+		__syncwarp();
+		const float2 *my = &mytile[t & 1][half * K3_ROWLEN + phase];
+		const int s_end = min(K3_TS, p.nsym - t * K3_TS);
+		uint32_t word = 0;
+		for (int sl = 0; sl < s_end; sl++) {
+			const float2 x = my[sl * 5];
+			float re, im; // (1j)^rot pre-rotation (Demod.cpp:44-65)
+			switch (rot) {
+			case 0: re = x.x; im = x.y; break;
+			case 1: im = x.x; re = -x.y; break;
+			case 2: re = -x.x; im = -x.y; break;
+			default: im = -x.x; re = x.y; break;
+			}
+			rot = (rot + 1) & 3;
+			const float tt = __fadd_rn(__fmul_rn(re, cj), __fmul_rn(im, sj));
+			hist = (hist << 1) | (tt > 0.0f ? 1u : 0u);
+			const float at = fabsf(tt);
+			if (p.ps_ema) { // Demod.cpp:67-91
+				ma = __fadd_rn(__fmul_rn(weight, ma), __fmul_rn(omw, at));
+				const int i0 = (max_idx - 1) & 15;
+				const float v0 = __shfl_sync(0xffffffffu, ma, half * 16 + i0);
+				const float v1 = __shfl_sync(0xffffffffu, ma, half * 16 + ((i0 + 1) & 15));
+				const float v2 = __shfl_sync(0xffffffffu, ma, half * 16 + ((i0 + 2) & 15));
+				float mv = v0;
+				int best = i0;
+				if (v1 > mv) { mv = v1; best = (i0 + 1) & 15; }
+				if (v2 > mv) { mv = v2; best = (i0 + 2) & 15; }
+				max_idx = best;
+			}
+			else { // Demod.cpp:129-160: ring slot `last` takes |t|, sums run over slots 0..11 in slot order
+#pragma unroll
+				for (int l = 0; l < 12; l++) mem[l] = (l == last) ? at : mem[l];
+				last = (last + 1) % 12;
+				float avg = mem[0];
+#pragma unroll
+				for (int l = 1; l < 12; l++) avg = __fadd_rn(avg, mem[l]);
+				float mv = 0.0f;
+				const int prev_max = max_idx;
+#pragma unroll
+				for (int q = -2; q <= 2; q++) {
+					const int jj = (prev_max + q) & 15;
+					const float v = __shfl_sync(0xffffffffu, avg, half * 16 + jj);
+					if (v > mv) { mv = v; max_idx = jj; }
+				}
+			}
+			const uint32_t hb = __shfl_sync(0xffffffffu, hist, half * 16 + max_idx);
+			const uint32_t bit = ((hb >> 3) ^ (hb >> 4)) & 1u; // nDelay = 3 (Model.h:219)
+			word |= bit << sl;
+			if (p.tap_dec && active && h == 0) p.tap_dec[inst * p.nsym + t * K3_TS + sl] = bit ? 1.0f : -1.0f;
+		}
+		if (active && h == 0) p.dbits[inst * p.dwords + t] = word;
+		__syncwarp();
+	}
+	if (active) {
+		PsState &st = p.ps[inst];
+		st.ma[h] = ma;
+#pragma unroll
+		for (int dd = 0; dd < 5; dd++) {
+			const uint32_t pl = __ballot_sync(hmask, (hist >> dd) & 1u) >> (half * 16);
+			if (h == 0) st.plane[dd] = pl;
+		}
+		if (h == 0) { st.max_idx = max_idx; st.rot = rot; st.last = last; }
+		if (!p.ps_ema) {
+#pragma unroll
+			for (int l = 0; l < 12; l++) p.ps_mem[(long long)(h * 12 + l) * ninst + inst] = mem[l];
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3b: the five AIS::Decoder instances of one row (AIS.h:91-181) in lanes 0..4 of one warp.  While all five sit
+// in TRAINING / STARTFLAG (the common case on noise) a symbol costs a handful of integer instructions; the full
+// state machine, the ScatterPLL level (DSP.h:100-106) and the Reset vote only run while a frame is being collected.
+// ---------------------------------------------------------------------------------------------
+constexpr int DK_THREADS = 128;
+template <int MODEL>
+__global__ void __launch_bounds__(DK_THREADS) k_decode(const K3Params p) {
+	typedef typename std::conditional<MODEL == 2, float2, float>::type sample_t;
+	__shared__ uint32_t frames_all[DK_THREADS / 32][DEC_WORDS * 32];
+	__shared__ sample_t tile_all[DK_THREADS / 32][2][K3_ROWLEN];
+	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+	const int row = blockIdx.x * (DK_THREADS / 32) + wib;
+	if (row >= p.rows) return; // whole warp
+	const int phase = lane;
+	const bool active = lane < 5;
+	const sample_t *E = MODEL == 2 ? reinterpret_cast<const sample_t *>(p.Ec) : reinterpret_cast<const sample_t *>(p.Ef);
+	sample_t(*tile)[K3_ROWLEN] = tile_all[wib];
 
 	DecCtx ctx;
-	ctx.frame = frames + tid;
+	ctx.frame = frames_all[wib] + lane;
 	ctx.mode_level = p.mode_level;
 	DecState d;
-	PsState ps;
-	float *ma_mine = ma_s + tid;
-	const int sidx = row * 5 + phase;
+	const int sidx = row * 5 + (active ? phase : 0);
 	const long long nthr_total = (long long)p.rows * 5;
 	if (active) {
 		d = p.dec[sidx];
-		for (int w = 0; w < DEC_WORDS; w++) frames[w * K3_THREADS + tid] = p.dec_data[(long long)w * nthr_total + sidx];
-		if (p.model == 2) {
-			ps = p.ps[sidx];
-			for (int h = 0; h < 16; h++) ma_mine[h * K3_THREADS] = ps.ma[h];
-		}
+		for (int w = 0; w < DEC_WORDS; w++) ctx.frame[w * K3_THREADS] = p.dec_data[(long long)w * nthr_total + sidx];
 	}
 	else {
 		d.state = ST_TRAINING; d.lastBit = 0; d.prev = 0; d.position = 0; d.one_seq = 0; d.level = 0.f; d.start_idx = 0;
 	}
-	const float weight = 0.85f, omw = __fsub_rn(1.0f, 0.85f);
-	const long long e_row = (long long)row * p.e_stride + p.e_begin;
 	int ntap = 0;
-
-	for (int s = 0; s < p.nsym; s++) {
-		float b = 0.0f, sample_lvl = 0.0f;
-		const long long sample_idx = p.abs_begin + (long long)s * 5 + phase;
-		float ppm = 0.0f;
-		const bool valid = active && sample_idx >= p.abs_lo && sample_idx < p.abs_hi;
-		if (valid) {
-			if (p.model == 2) {
-				const float2 x = p.Ec[e_row + (long long)s * 5 + phase];
-				// ScatterPLL level: ((((0+n0)+n1)+n2)+n3)+n4, then / 5 (DSP.h:100-106)
+	const int nsamp = p.nsym * 5;
+	auto prefetch = [&](int buf, int s0) {
+		const int base = s0 * 5;
+		const sample_t *src = E + (long long)row * p.e_stride + p.e_begin + base;
+		for (int e = lane; e < K3_ROWLEN; e += 32)
+			if (base + e < nsamp) cp_async_f(&tile[buf][e], src + e);
+		cp_async_commit();
+	};
+	const int ntiles = (p.nsym + K3_TS - 1) / K3_TS;
+	if (ntiles > 0) prefetch(0, 0);
+	for (int t = 0; t < ntiles; t++) {
+		if (t + 1 < ntiles) {
+			prefetch((t + 1) & 1, (t + 1) * K3_TS);
+			cp_async_wait<1>();
+		}
+		else cp_async_wait<0>();
+		__syncwarp();
+		const sample_t *my = &tile[t & 1][active ? phase : 0];
+		uint32_t word = 0;
+		if (MODEL == 2 && active) word = p.dbits[(long long)sidx * p.dwords + t];
+		const int s_end = min(K3_TS, p.nsym - t * K3_TS);
+		for (int sl = 0; sl < s_end; sl++) {
+			const int s = t * K3_TS + sl;
+			const long long sample_idx = p.abs_begin + (long long)s * 5 + phase;
+			bool valid = active;
+			float b;
+			if (MODEL == 2) b = ((word >> sl) & 1u) ? 1.0f : -1.0f;
+			else {
+				valid = active && sample_idx >= p.abs_lo && sample_idx < p.abs_hi;
+				b = *reinterpret_cast<const float *>(&my[sl * 5]);
+				if (p.tap_dec && valid) p.tap_dec[(long long)sidx * p.nsym + ntap++] = b;
+			}
+			const unsigned in_data = __ballot_sync(0xffffffffu, active && d.state == ST_DATAFCS);
+			if (!in_data) { // fast path: nobody collects a frame; TRAINING / STARTFLAG only (AIS.h:103-139)
+				if (valid) {
+					const int dd = b > 0.0f;
+					const int Bit = !(dd ^ d.prev);
+					d.prev = dd;
+					if (d.state == ST_TRAINING) {
+						if (Bit != d.lastBit) d.position++;
+						else if (d.position > 4) { d.start_idx = sample_idx; d.state = ST_STARTFLAG; d.position = Bit ? 3 : 1; }
+						else d.position = 0;
+					}
+					else { // ST_STARTFLAG
+						if (d.position == 7) {
+							if (Bit == 0) {
+								d.state = ST_DATAFCS; d.position = 0; d.one_seq = 0; d.level = 0.0f;
+								for (int w = 0; w < DEC_WORDS; w++) ctx.frame[w * K3_THREADS] = 0u; // msg.clear()
+							}
+							else { d.state = ST_TRAINING; d.position = 0; }
+						}
+						else if (Bit == 1) d.position++;
+						else { d.state = ST_TRAINING; d.position = 0; }
+					}
+					d.lastBit = Bit;
+				}
+				continue;
+			}
+			float sample_lvl = 0.0f;
+			if (MODEL == 2 && p.mode_level) { // ScatterPLL level: ((((0+n0)+n1)+n2)+n3)+n4, then / 5 (DSP.h:100-106)
+				const float2 x = *reinterpret_cast<const float2 *>(&my[sl * 5]);
 				const float nrm = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
 				float acc = 0.0f;
 #pragma unroll
-				for (int j = 0; j < 5; j++) acc = __fadd_rn(acc, __shfl_sync(grp_mask, nrm, grp * 5 + j));
+				for (int jx = 0; jx < 5; jx++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, nrm, jx));
 				sample_lvl = __fdiv_rn(acc, 5.0f);
-				// pre-rotation by (1j)^rot (Demod.cpp:44-65)
-				float re, im;
-				switch (ps.rot) {
-				case 0: re = x.x; im = x.y; break;
-				case 1: im = x.x; re = -x.y; break;
-				case 2: re = -x.x; im = -x.y; break;
-				default: im = -x.x; re = x.y; break;
-				}
-				ps.rot = (ps.rot + 1) & 3;
-				uint32_t dec_mask = 0;
-				float absv[16];
-#pragma unroll
-				for (int j = 0; j < 8; j++) {
-					const float a = __fmul_rn(re, c_ps_cos[j]), bb = __fmul_rn(im, c_ps_sin[j]);
-					const float t1 = __fadd_rn(a, bb), t2 = __fsub_rn(a, bb);
-					dec_mask |= (t1 > 0.0f ? 1u : 0u) << j;
-					dec_mask |= (t2 > 0.0f ? 1u : 0u) << (15 - j);
-					absv[j] = fabsf(t1);
-					absv[15 - j] = fabsf(t2);
-				}
-				ps.plane[4] = ps.plane[3]; ps.plane[3] = ps.plane[2]; ps.plane[2] = ps.plane[1]; ps.plane[1] = ps.plane[0];
-				ps.plane[0] = dec_mask;
-				if (!p.ps_ema) { // PhaseSearch (Demod.cpp:129-160): 12-sample sums, search prev-2..prev+2
-					float *mem = p.ps_mem + sidx;
-#pragma unroll
-					for (int h = 0; h < 16; h++) mem[(long long)(h * 12 + ps.last) * nthr_total] = absv[h];
-					ps.last = (ps.last + 1) % 12;
-					float max_val = 0.0f;
-					const int prev_max = ps.max_idx;
-					for (int q = 16 + prev_max - 2; q <= 16 + prev_max + 2; q++) {
-						const int j = q & 15;
-						float avg = mem[(long long)(j * 12) * nthr_total];
-						for (int l = 1; l < 12; l++) avg = __fadd_rn(avg, mem[(long long)(j * 12 + l) * nthr_total]);
-						if (avg > max_val) { max_val = avg; ps.max_idx = j; }
-					}
-				}
-				else { // PhaseSearchEMA (Demod.cpp:67-91)
-#pragma unroll
-					for (int h = 0; h < 16; h++) {
-						ps.ma[h] = __fadd_rn(__fmul_rn(weight, ps.ma[h]), __fmul_rn(omw, absv[h]));
-						ma_mine[h * K3_THREADS] = ps.ma[h];
-					}
-					int idx = (ps.max_idx - 1) & 15;
-					float max_val = ma_mine[idx * K3_THREADS];
-					int best = idx;
-#pragma unroll
-					for (int q = 0; q < 2; q++) {
-						idx = (idx + 1) & 15;
-						const float v = ma_mine[idx * K3_THREADS];
-						if (v > max_val) { max_val = v; best = idx; }
-					}
-					ps.max_idx = best;
-				}
-				const int b1 = (ps.plane[3] >> ps.max_idx) & 1, b2 = (ps.plane[4] >> ps.max_idx) & 1;
-				b = (b1 ^ b2) ? 1.0f : -1.0f;
-				if (p.ppmtab) {
-					const long long last_of_group = p.abs_begin + (long long)s * 5 + 4;
-					int bi = (int)((last_of_group - p.blk_abs0) >> 9);
-					bi = bi < 0 ? 0 : (bi >= p.nblk ? p.nblk - 1 : bi);
-					ppm = p.ppmtab[p.stepidx[row * p.nblk + bi]];
-				}
 			}
-			else {
-				b = p.Ef[e_row + (long long)s * 5 + phase];
-			}
-			if (p.tap_dec) p.tap_dec[(long long)sidx * p.nsym + ntap++] = b;
-		}
-		int fr_len = 0, lastBit_before = 0;
-		float fr_level = 0.0f;
-		const float level_before = d.level;
-		const long long start_before = d.start_idx;
-		bool found = valid && dec_step(d, ctx, b, sample_lvl, sample_idx, fr_len, fr_level, lastBit_before);
-		const unsigned vote = __ballot_sync(0xffffffffu, found);
-		if (vote) { // rare: FOUNDMESSAGE -> Reset to the four sibling decoders (AIS.cpp:47-49,98-108)
-			const unsigned gv = vote & grp_mask;
-			if (gv) {
-				const int winner = __ffs(gv) - 1; // lowest phase runs first (DSP.h:108-112)
+			int fr_len = 0, lastBit_before = 0;
+			float fr_level = 0.0f;
+			const float level_before = d.level;
+			const long long start_before = d.start_idx;
+			const bool found = valid && dec_step(d, ctx, b, sample_lvl, sample_idx, fr_len, fr_level, lastBit_before);
+			const unsigned vote = __ballot_sync(0xffffffffu, found);
+			if (vote) { // rare: FOUNDMESSAGE -> Reset to the four sibling decoders (AIS.cpp:47-49,98-108)
+				const int winner = __ffs(vote) - 1; // lowest phase runs first (DSP.h:108-112)
 				if (lane == winner) {
+					float ppm = 0.0f;
+					if (MODEL == 2 && p.ppmtab) { // tag.ppm of the CGF block that delivered the group's 5th sample
+						const long long last_of_group = p.abs_begin + (long long)s * 5 + 4;
+						int bi = (int)((last_of_group - p.blk_abs0) >> 9);
+						bi = bi < 0 ? 0 : (bi >= p.nblk ? p.nblk - 1 : bi);
+						ppm = p.ppmtab[p.stepidx[row * p.nblk + bi]];
+					}
 					emit_frame(p.ring, p.ring_count, p.ring_cap, p.chunk, ctx, row, phase, fr_len, fr_level, ppm, d.start_idx, sample_idx);
 				}
-				else if (lane < winner || !valid) { // already stepped this symbol (or has no sample in this slot), then reset
+				else if (active && (lane < winner || !valid)) { // already stepped this symbol (or no sample in this slot), then reset
 					d.state = ST_TRAINING; d.position = 0; d.one_seq = 0;
 				}
-				else { // reset first, then step this symbol from TRAINING/0: only the NRZI memory survives
+				else if (active) { // reset first, then step this symbol from TRAINING/0: only the NRZI memory survives
 					const int Bit = d.lastBit; // dec_step stored the new Bit there
 					d.level = level_before;
 					d.start_idx = start_before;
@@ -904,11 +1035,11 @@ __global__ void __launch_bounds__(K3_THREADS) k_symbols(const K3Params p) {
 				}
 			}
 		}
+		__syncwarp();
 	}
 	if (active) {
-		for (int w = 0; w < DEC_WORDS; w++) p.dec_data[(long long)w * nthr_total + sidx] = frames[w * K3_THREADS + tid];
+		for (int w = 0; w < DEC_WORDS; w++) p.dec_data[(long long)w * nthr_total + sidx] = ctx.frame[w * K3_THREADS];
 		p.dec[sidx] = d;
-		if (p.model == 2) p.ps[sidx] = ps;
 	}
 }
 
