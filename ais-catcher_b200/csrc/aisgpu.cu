@@ -106,6 +106,7 @@ struct aisgpu_handle {
 	PsState *d_ps = nullptr;
 	float *d_ps_mem = nullptr;
 	uint32_t *d_dbits = nullptr;
+	float *d_lvl = nullptr;
 	int dwords = 0;
 	DecState *d_dec = nullptr;
 	uint32_t *d_dec_data = nullptr;
@@ -195,7 +196,12 @@ void layout_frontend(aisgpu_handle *h, int tile) {
 		off += (FE_HIST + n + FE_SLACK + 1) & ~1;
 		return o;
 	};
-	for (int l = 0; l <= k; l++) p.off_lv[l] = take(tile >> l);
+	p.off_in[0] = take(tile);
+	p.off_in[1] = take(tile);
+	p.off_rot[0] = take(tile >> k);
+	p.off_rot[1] = take(tile >> k);
+	p.off_lv[0] = 0;
+	for (int l = 1; l <= k; l++) p.off_lv[l] = take(tile >> l);
 	p.off_up = take(tile >> k);
 	p.off_dn = take(tile >> k);
 	p.off_wa = take(tile >> (k + 1));
@@ -208,12 +214,12 @@ void layout_frontend(aisgpu_handle *h, int tile) {
 int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int N) {
 	FeParams &p = h->fe;
 	const int q = 1 << (h->k + 2);
-	int tile = 2560;
+	int tile = 1280; // per-warp tile: 4 runs of 5 outputs per lane at the first CIC stage
 	if (tile % q) tile = (tile / q + 1) * q;
 	if (tile > N) tile = N;
 	if (tile != p.tile) layout_frontend(h, tile);
 	const int B = h->cfg.n_streams;
-	int n_seg = (6000 + B - 1) / B;
+	int n_seg = (8192 + B - 1) / B; // ~9 waves of warps on 148 SMs x 6 resident warps
 	int tiles_total = (N + tile - 1) / tile;
 	if (n_seg > tiles_total) n_seg = tiles_total;
 	if (n_seg < 1) n_seg = 1;
@@ -295,7 +301,8 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.chunk = (int)h->chunk;
 		p.mode_level = (h->cfg.tag_mode & 1) ? 1 : 0;
 		p.tap_dec = h->cfg.enable_taps ? h->d_tap_dec : nullptr;
-		k_decode<0><<<(h->rows + DK_THREADS / 32 - 1) / (DK_THREADS / 32), DK_THREADS, 0, h->stream>>>(p);
+		if (p.tap_dec) k_decode<0, true><<<(h->rows + DK_THREADS / 32 - 1) / (DK_THREADS / 32), DK_THREADS, 0, h->stream>>>(p);
+		else k_decode<0, false><<<(h->rows + DK_THREADS / 32 - 1) / (DK_THREADS / 32), DK_THREADS, 0, h->stream>>>(p);
 		CU(cudaGetLastError());
 		h->last_launches++;
 		h->e_abs = a1;
@@ -337,10 +344,12 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.tap_dec = h->cfg.enable_taps ? h->d_tap_dec : nullptr;
 		p.dbits = h->d_dbits;
 		p.dwords = h->dwords;
+		p.lvl = h->d_lvl;
+		p.lvl_stride = h->dwords * K3_TS;
 		const long long ps_warps = ((long long)h->rows * 5 + 1) / 2;
 		k_phase_search<<<(unsigned)((ps_warps + PS_THREADS / 32 - 1) / (PS_THREADS / 32)), PS_THREADS, 0, h->stream>>>(p);
 		CU(cudaGetLastError());
-		k_decode<2><<<(h->rows + DK_THREADS / 32 - 1) / (DK_THREADS / 32), DK_THREADS, 0, h->stream>>>(p);
+		k_decode<2, false><<<(h->rows + DK_THREADS / 32 - 1) / (DK_THREADS / 32), DK_THREADS, 0, h->stream>>>(p);
 		CU(cudaGetLastError());
 		h->last_launches += 2;
 	}
@@ -672,6 +681,7 @@ static int create_impl(aisgpu_handle *h) {
 		if (int rc = dalloc(h, &h->d_ps, (size_t)h->rows * 5)) return rc;
 		h->dwords = (nEmax / 5 + 1 + K3_TS - 1) / K3_TS + 1;
 		if (int rc = dalloc(h, &h->d_dbits, (size_t)h->rows * 5 * h->dwords)) return rc;
+		if (int rc = dalloc(h, &h->d_lvl, (size_t)h->rows * h->dwords * K3_TS)) return rc;
 		if (!c.ps_ema)
 			if (int rc = dalloc(h, &h->d_ps_mem, (size_t)h->rows * 5 * 16 * 12)) return rc;
 		if (int rc = dalloc(h, &h->d_steptab, CGF_NIDX)) return rc;
@@ -905,7 +915,7 @@ void aisgpu_destroy(aisgpu_handle *h) {
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	void *ptrs[] = { h->d_in[0], h->d_in[1], h->d_tail[0], h->d_tail[1], h->d_rot[0], h->d_rot[1], h->d_rot[2], h->d_rot_state, h->d_C, h->d_stepidx,
 					 h->d_steptab, h->d_omega, h->d_cgf_rot, h->d_rots, h->d_ppmtab, h->d_fir_hist[0], h->d_fir_hist[1], h->d_tap_cgf, h->d_Ec,
-					 h->d_Ef, h->d_ps, h->d_ps_mem, h->d_dbits, h->d_dec, h->d_dec_data, h->d_pll, h->d_tap_dec, h->d_tap_fm, h->d_tap_cnt, h->d_ring,
+					 h->d_Ef, h->d_ps, h->d_ps_mem, h->d_dbits, h->d_lvl, h->d_dec, h->d_dec_data, h->d_pll, h->d_tap_dec, h->d_tap_fm, h->d_tap_cnt, h->d_ring,
 					 h->d_ring_count };
 	for (void *p : ptrs)
 		if (p) cudaFree(p);

@@ -153,7 +153,7 @@ __global__ void k_rot_table(float2 *__restrict__ tab, const float2 *__restrict__
 // stage's history is exact because each CIC stage is a pure function of its last 6 inputs
 // (u_{s+1}[n] = fl(u_s[n] + u_s[n-1]), y[j] = u_5[2j]/32).
 // ---------------------------------------------------------------------------------------------
-constexpr int FE_THREADS = 256;
+constexpr int FE_THREADS = 32; // one warp per CTA, one CTA per (segment, stream)
 constexpr int FE_HIST = 6;   // >= 5, even so that even sample indices stay 16-byte aligned
 constexpr int FE_SLACK = 12; // over-read room behind each array for partial runs
 constexpr int FE_MAXK = 7;
@@ -169,7 +169,9 @@ struct FeParams {
 	float2 *C;            // [2B][c_stride]
 	long long c_stride;
 	int c_off;
-	int off_lv[FE_MAXK + 1]; // smem offsets (float2 units) of level arrays
+	int off_in[2];           // smem offsets (float2 units) of the two input-ring buffers (level 0, each [HIST | tile])
+	int off_rot[2];          // phasors of the tile
+	int off_lv[FE_MAXK + 1]; // level arrays 1..k (off_lv[0] unused)
 	int off_up, off_dn, off_wa, off_wb;
 	int smem_f2;          // total float2
 };
@@ -199,140 +201,263 @@ __device__ __forceinline__ void fe_load_pair(const void *base, long long idx, fl
 	}
 }
 
+// ---- packed binary32 pairs (SASS FADD2 / FMUL2): one instruction rounds both lanes exactly like two scalar
+// ---- __fadd_rn / __fmul_rn (verified bit-for-bit on 1.6e7 patterns incl. denormals, tools/microbench_f32x2.cu);
+// ---- a complex sample is one 64-bit register pair, so a complex add is ONE issue slot instead of two.
+typedef unsigned long long c64;
+__device__ __forceinline__ c64 padd(c64 a, c64 b) {
+	c64 r;
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+	return r;
+}
+__device__ __forceinline__ c64 pmul(c64 a, c64 b) {
+	c64 r;
+	asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+	return r;
+}
+__device__ __forceinline__ c64 pack2(float x, float y) {
+	c64 r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+	return r;
+}
+__device__ __forceinline__ float2 unpack2(c64 v) {
+	float2 r;
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+	return r;
+}
+
 // R consecutive outputs of one Downsample2CIC5 from 2R+4 inputs held in registers: 9R+6 complex adds.
-// in points at sample 0 of the stage input (history at negative indices); j0 = first output index.
+// sm = the CTA's shared array; in_off / out_off = index of sample 0 of the stage input / output (history at
+// negative indices); j0 = first output index.  Outputs past the valid count land in the arrays' slack.
 template <int R>
-__device__ __forceinline__ void ds2_run(const float2 *__restrict__ in, float2 *__restrict__ out, int j0, int n_out) {
-	float2 v[2 * R + 6];
-	const float4 *p = reinterpret_cast<const float4 *>(in + 2 * j0 - 6);
+__device__ __forceinline__ void ds2_run(float2 *__restrict__ sm, int in_off, int out_off, int j0) {
+	c64 v[2 * R + 6];
+	const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(sm + in_off + 2 * j0 - 6);
 #pragma unroll
-	for (int q = 0; q < R + 3; q++) {
-		float4 t = p[q];
-		v[2 * q] = make_float2(t.x, t.y);
-		v[2 * q + 1] = make_float2(t.z, t.w);
+	for (int q = R + 2; q >= 0; q--) {
+		const ulonglong2 t = p[q];
+		v[2 * q] = t.x;
+		v[2 * q + 1] = t.y;
 	}
 #pragma unroll
 	for (int s = 1; s <= 4; s++) {
 #pragma unroll
-		for (int n = 2 * R + 4; n >= s + 1; n--) v[n] = cadd(v[n], v[n - 1]);
+		for (int n = 2 * R + 4; n >= s + 1; n--) v[n] = padd(v[n], v[n - 1]);
 	}
+	const c64 sc = pack2(0.03125f, 0.03125f);
+	c64 *o = reinterpret_cast<c64 *>(sm + out_off + j0);
 #pragma unroll
 	for (int q = 0; q < R; q++) {
-		int n = 6 + 2 * q;
-		float2 o = cscale(cadd(v[n], v[n - 1]), 0.03125f);
-		if (j0 + q < n_out) out[j0 + q] = o;
+		const int n = 6 + 2 * q;
+		o[q] = pmul(padd(v[n], v[n - 1]), sc);
 	}
 }
 
+// R consecutive outputs of FilterCIC5 (no decimation) from R+5 inputs: 5R+10 complex adds; straight to HBM.
 template <int R>
-__device__ __forceinline__ void ds2_stage(const float2 *__restrict__ in, float2 *__restrict__ out, int n_out) {
-	for (int j0 = threadIdx.x * R; j0 < n_out; j0 += FE_THREADS * R) ds2_run<R>(in, out, j0, n_out);
+__device__ __forceinline__ void fcic_run(const float2 *__restrict__ sm, int in_off, float2 *__restrict__ out, int m0, int n_out) {
+	c64 v[R + 5];
+	const c64 *p = reinterpret_cast<const c64 *>(sm + in_off + m0 - 5);
+#pragma unroll
+	for (int q = 0; q < R + 5; q++) v[q] = p[q];
+#pragma unroll
+	for (int s = 1; s <= 5; s++) {
+#pragma unroll
+		for (int n = R + 4; n >= s; n--) v[n] = padd(v[n], v[n - 1]);
+	}
+	const c64 sc = pack2(0.03125f, 0.03125f);
+	c64 *o = reinterpret_cast<c64 *>(out);
+#pragma unroll
+	for (int q = 0; q < R; q++)
+		if (m0 + q < n_out) o[m0 + q] = pmul(v[5 + q], sc);
 }
 
+// ---- mbarrier + 1-D bulk async copy (TMA, SASS UBLKCP): global -> shared without touching registers ----
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"WAIT_%=:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+		"@p bra DONE_%=;\n\t"
+		"bra WAIT_%=;\n\t"
+		"DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+		"r"(parity)
+		: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+					 (unsigned)__cvta_generic_to_shared(smem_dst)),
+				 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+				 : "memory");
+}
+
+// Work list of one segment: tile t covers input samples [pos, pos+len) (relative to the submit's first sample).
+__device__ __forceinline__ void fe_tile_of(const FeParams &p, long long seg_start, long long seg_end, int t, int n_warm, long long &pos, int &len,
+										   bool &warm) {
+	if (t < n_warm) {
+		pos = seg_start - p.P + (long long)t * p.tile;
+		len = (int)min((long long)p.tile, seg_start - pos);
+		warm = true;
+	}
+	else {
+		pos = seg_start + (long long)(t - n_warm) * p.tile;
+		len = (int)min((long long)p.tile, seg_end - pos);
+		warm = false;
+	}
+}
+
+// One WARP owns (segment, stream): no block-wide barriers anywhere.  Lane 0 keeps a two-deep ring of bulk
+// async copies (input tile + its Rotate phasors) in flight; all 32 lanes then run the stages of the tile back to
+// back out of the warp's private shared-memory arrays, separated only by __syncwarp().
 template <int FMT>
 __global__ void __launch_bounds__(FE_THREADS) k_frontend(const FeParams p) {
 	extern __shared__ __align__(16) float2 sm[];
-	const int tid = threadIdx.x;
+	__shared__ __align__(8) uint64_t mbar[2];
+	const int lane = threadIdx.x;
 	const int stream = blockIdx.y;
 	const int k = p.k;
 	const long long seg_start = (long long)blockIdx.x * p.seg_len;
 	if (seg_start >= p.N) return;
 	const long long seg_end = min((long long)p.N, seg_start + p.seg_len);
-
-	for (int i = tid; i < p.smem_f2; i += FE_THREADS) sm[i] = make_float2(0.f, 0.f);
-	__syncthreads();
-
-	float2 *lv0 = sm + p.off_lv[0] + FE_HIST;
-	float2 *d = sm + p.off_lv[k] + FE_HIST;
-	float2 *up = sm + p.off_up + FE_HIST, *dn = sm + p.off_dn + FE_HIST;
-	float2 *wa = sm + p.off_wa + FE_HIST, *wb = sm + p.off_wb + FE_HIST;
+	const int n_warm = (p.P + p.tile - 1) / p.tile;
+	const int n_tiles = n_warm + (int)((seg_end - seg_start + p.tile - 1) / p.tile);
 	const int P96 = p.P >> k;
 
-	long long pos = seg_start - p.P;
-	while (pos < seg_end) {
-		const bool warm = pos < seg_start;
-		const int len = (int)min((long long)p.tile, (warm ? seg_start : seg_end) - pos);
-		// ---- load tile into level 0 (converted to float2) ----
-		{
-			// samples before the submit's first one come from the previous submit's tail (a tile may straddle)
-			const long long tbase = (long long)stream * p.P + p.P + pos;
-			const long long ibase = (long long)stream * p.in_stride + pos;
-			for (int i = tid * 2; i < len; i += FE_THREADS * 2) {
-				float2 a, b;
-				if (pos + i < 0) fe_load_pair<FMT>(p.tail, tbase + i, a, b);
-				else fe_load_pair<FMT>(p.in, ibase + i, a, b);
-				*reinterpret_cast<float4 *>(lv0 + i) = make_float4(a.x, a.y, b.x, b.y);
+	// zero only what acts as history or may be read before written (whole array is small enough to clear)
+	for (int i = lane; i < p.smem_f2; i += 32) sm[i] = make_float2(0.f, 0.f);
+	if (lane == 0) {
+		mbar_init(&mbar[0], 1);
+		mbar_init(&mbar[1], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncwarp();
+
+	auto issue = [&](int t) {
+		long long pos;
+		int len;
+		bool warm;
+		fe_tile_of(p, seg_start, seg_end, t, n_warm, pos, len, warm);
+		const int b = t & 1;
+		const int n96 = len >> k;
+		unsigned bytes = (unsigned)n96 * 8u;
+		if (FMT == 0) bytes += (unsigned)len * 8u;
+		mbar_expect_tx(&mbar[b], bytes);
+		bulk_g2s(sm + p.off_rot[b], p.rot + (pos >> k) + P96, (unsigned)n96 * 8u, &mbar[b]);
+		if (FMT == 0) {
+			float2 *dst = sm + p.off_in[b] + FE_HIST;
+			const float2 *in = reinterpret_cast<const float2 *>(p.in) + (long long)stream * p.in_stride;
+			const float2 *tl = reinterpret_cast<const float2 *>(p.tail) + (long long)stream * p.P + p.P;
+			if (pos >= 0) bulk_g2s(dst, in + pos, (unsigned)len * 8u, &mbar[b]);
+			else if (pos + len <= 0) bulk_g2s(dst, tl + pos, (unsigned)len * 8u, &mbar[b]);
+			else { // the tile straddles the first sample of the submit
+				const int nt = (int)(-pos);
+				bulk_g2s(dst, tl + pos, (unsigned)nt * 8u, &mbar[b]);
+				bulk_g2s(dst + nt, in, (unsigned)(len - nt) * 8u, &mbar[b]);
 			}
 		}
-		__syncthreads();
+	};
+	if (lane == 0) issue(0);
+
+	const int off_up = p.off_up + FE_HIST, off_dn = p.off_dn + FE_HIST, off_wa = p.off_wa + FE_HIST, off_wb = p.off_wb + FE_HIST;
+	for (int t = 0; t < n_tiles; t++) {
+		long long pos;
+		int len;
+		bool warm;
+		fe_tile_of(p, seg_start, seg_end, t, n_warm, pos, len, warm);
+		const int b = t & 1;
+		if (lane == 0 && t + 1 < n_tiles) issue(t + 1); // ring slot b^1 was released by the __syncwarp closing tile t-1
+		const int off_in = (b ? p.off_in[1] : p.off_in[0]) + FE_HIST;
+		if (FMT != 0) { // integer formats: convert while loading (registers), no bulk copy
+			const long long tbase = (long long)stream * p.P + p.P + pos;
+			const long long ibase = (long long)stream * p.in_stride + pos;
+			for (int i = lane * 2; i < len; i += 64) {
+				float2 x, y;
+				if (pos + i < 0) fe_load_pair<FMT>(p.tail, tbase + i, x, y);
+				else fe_load_pair<FMT>(p.in, ibase + i, x, y);
+				*reinterpret_cast<float4 *>(sm + off_in + i) = make_float4(x.x, x.y, y.x, y.y);
+			}
+			__syncwarp();
+		}
+		mbar_wait(&mbar[b], (unsigned)((t >> 1) & 1));
 		// ---- k cascaded Downsample2CIC5 at the input rate ----
+		int src = off_in;
 		for (int l = 0; l < k; l++) {
-			ds2_stage<5>(sm + p.off_lv[l] + FE_HIST, sm + p.off_lv[l + 1] + FE_HIST, len >> (l + 1));
-			__syncthreads();
+			const int dst = p.off_lv[l + 1] + FE_HIST;
+			const int n_out = len >> (l + 1);
+			for (int j0 = lane * 5; j0 < n_out; j0 += 160) ds2_run<5>(sm, src, dst, j0);
+			__syncwarp();
+			src = dst;
 		}
 		// ---- FilterComplex3Tap + Rotate at 96 kHz ----
 		const int n96 = len >> k;
-		const long long i96 = (pos >> k) + P96; // table index of 96 kHz sample 0 of this tile
-		for (int i = tid; i < n96; i += FE_THREADS) {
-			float2 x = d[i];
+		const int off_rt = b ? p.off_rot[1] : p.off_rot[0];
+		for (int i = lane; i < n96; i += 32) {
+			float2 x = sm[src + i];
 			if (p.use_fdc) { // alpha * (h1 + data[i]) + h2 * beta
-				float2 t = cadd(d[i - 2], x);
-				float2 h2 = d[i - 1];
-				x = make_float2(__fadd_rn(__fmul_rn(p.fdc_alpha, t.x), __fmul_rn(h2.x, p.fdc_beta)),
-								__fadd_rn(__fmul_rn(p.fdc_alpha, t.y), __fmul_rn(h2.y, p.fdc_beta)));
+				const float2 tt = cadd(sm[src + i - 2], x);
+				const float2 h2 = sm[src + i - 1];
+				x = make_float2(__fadd_rn(__fmul_rn(p.fdc_alpha, tt.x), __fmul_rn(h2.x, p.fdc_beta)),
+								__fadd_rn(__fmul_rn(p.fdc_alpha, tt.y), __fmul_rn(h2.y, p.fdc_beta)));
 			}
-			float2 r = __ldg(p.rot + i96 + i);
-			float RR = __fmul_rn(x.x, r.x), II = __fmul_rn(x.y, r.y), RI = __fmul_rn(x.x, r.y), IR = __fmul_rn(x.y, r.x);
-			up[i] = make_float2(__fsub_rn(RR, II), __fadd_rn(IR, RI));
-			dn[i] = make_float2(__fadd_rn(RR, II), __fsub_rn(IR, RI));
+			const float2 r = sm[off_rt + i];
+			const float RR = __fmul_rn(x.x, r.x), II = __fmul_rn(x.y, r.y), RI = __fmul_rn(x.x, r.y), IR = __fmul_rn(x.y, r.x);
+			sm[off_up + i] = make_float2(__fsub_rn(RR, II), __fadd_rn(IR, RI));
+			sm[off_dn + i] = make_float2(__fadd_rn(RR, II), __fsub_rn(IR, RI));
 		}
-		__syncthreads();
+		__syncwarp();
 		// ---- per channel Downsample2CIC5 96k -> 48k ----
 		const int n48 = n96 >> 1;
-		for (int j = tid; j < 2 * n48; j += FE_THREADS) {
-			if (j < n48) ds2_run<1>(up, wa, j, n48);
-			else ds2_run<1>(dn, wb, j - n48, n48);
+		const int runs = (n48 + 4) / 5;
+		for (int r = lane; r < 2 * runs; r += 32) {
+			if (r < runs) ds2_run<5>(sm, off_up, off_wa, r * 5);
+			else ds2_run<5>(sm, off_dn, off_wb, (r - runs) * 5);
 		}
-		__syncthreads();
+		__syncwarp();
 		// ---- per channel FilterCIC5 at 48k, straight to HBM ----
 		if (!warm) {
 			const long long m0 = pos >> (k + 1);
-			for (int j = tid; j < 2 * n48; j += FE_THREADS) {
-				const int ch = j >= n48;
-				const int m = ch ? j - n48 : j;
-				const float2 *w = ch ? wb : wa;
-				float2 v[6];
-#pragma unroll
-				for (int q = 0; q < 6; q++) v[q] = w[m - 5 + q];
-#pragma unroll
-				for (int s = 1; s <= 5; s++) {
-#pragma unroll
-					for (int n = 5; n >= s; n--) v[n] = cadd(v[n], v[n - 1]);
-				}
-				p.C[(long long)(stream * 2 + ch) * p.c_stride + p.c_off + m0 + m] = cscale(v[5], 0.03125f);
+			for (int r = lane; r < 2 * runs; r += 32) {
+				const int ch = r >= runs;
+				const int mm = (ch ? r - runs : r) * 5;
+				fcic_run<5>(sm, ch ? off_wb : off_wa, p.C + (long long)(stream * 2 + ch) * p.c_stride + p.c_off + m0, mm, n48);
 			}
 		}
-		__syncthreads();
-		// ---- carry the last HIST entries of every stage array to its front ----
+		__syncwarp();
+		// ---- carry the last HIST entries of every stage array to the front of the array the next tile reads ----
 		{
-			const int narr = k + 1 + 4;
-			const int w = tid >> 5, lane = tid & 31;
-			for (int a = w; a < narr; a += FE_THREADS / 32) {
-				float2 *arr;
-				int n;
-				if (a <= k) { arr = sm + p.off_lv[a]; n = len >> a; }
-				else if (a == k + 1) { arr = sm + p.off_up; n = n96; }
-				else if (a == k + 2) { arr = sm + p.off_dn; n = n96; }
-				else if (a == k + 3) { arr = sm + p.off_wa; n = n48; }
-				else { arr = sm + p.off_wb; n = n48; }
-				float2 t = make_float2(0.f, 0.f);
-				if (lane < FE_HIST) t = arr[n + lane];
-				__syncwarp();
-				if (lane < FE_HIST) arr[lane] = t;
+			// arrays: 0 = input ring (this slot -> other slot), 1..k = levels, then up, dn, wa, wb
+			const int narr = k + 5;
+			float2 val[3];
+			int dsti[3];
+#pragma unroll
+			for (int it = 0; it < 3; it++) {
+				const int item = lane + 32 * it;
+				const int a = item / FE_HIST, e = item - a * FE_HIST;
+				dsti[it] = -1;
+				if (a < narr) {
+					int so, dof, n;
+					if (a == 0) { so = b ? p.off_in[1] : p.off_in[0]; dof = b ? p.off_in[0] : p.off_in[1]; n = len; }
+					else if (a <= k) { so = dof = p.off_lv[a]; n = len >> a; }
+					else if (a == k + 1) { so = dof = p.off_up; n = n96; }
+					else if (a == k + 2) { so = dof = p.off_dn; n = n96; }
+					else if (a == k + 3) { so = dof = p.off_wa; n = n48; }
+					else { so = dof = p.off_wb; n = n48; }
+					val[it] = sm[so + n + e];
+					dsti[it] = dof + e;
+				}
 			}
+			__syncwarp();
+#pragma unroll
+			for (int it = 0; it < 3; it++)
+				if (dsti[it] >= 0) sm[dsti[it]] = val[it];
 		}
-		__syncthreads();
-		pos += len;
+		__syncwarp();
 	}
 }
 
@@ -747,6 +872,8 @@ struct K3Params {
 	float *ps_mem;        // PhaseSearch history |t| [16*12][rows*5] (only when !ps_ema)
 	uint32_t *dbits;      // ModelDefault: demodulated bits, [rows*5][dwords], bit (s & 31) of word (s >> 5) = symbol s
 	int dwords;
+	float *lvl;           // ModelDefault: ScatterPLL level of symbol s (TAG::sample_lvl, DSP.h:100-106), [rows][lvl_stride]
+	int lvl_stride;
 	DecState *dec;
 	uint32_t *dec_data;   // [DEC_WORDS][rows*5]
 	FrameRec *ring;
@@ -886,6 +1013,18 @@ __global__ void __launch_bounds__(PS_THREADS) k_phase_search(const K3Params p) {
 			if (p.tap_dec && active && h == 0) p.tap_dec[inst * p.nsym + t * K3_TS + sl] = bit ? 1.0f : -1.0f;
 		}
 		if (active && h == 0) p.dbits[inst * p.dwords + t] = word;
+		if (active && phase == 0 && p.mode_level) { // ScatterPLL level: ((((0+n0)+n1)+n2)+n3)+n4, then / 5
+			const float2 *rowt = &mytile[t & 1][half * K3_ROWLEN];
+			for (int sl = h; sl < s_end; sl += 16) {
+				float acc = 0.0f;
+#pragma unroll
+				for (int jx = 0; jx < 5; jx++) {
+					const float2 x = rowt[sl * 5 + jx];
+					acc = __fadd_rn(acc, __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y)));
+				}
+				p.lvl[(long long)row * p.lvl_stride + t * K3_TS + sl] = __fdiv_rn(acc, 5.0f);
+			}
+		}
 		__syncwarp();
 	}
 	if (active) {
@@ -910,18 +1049,49 @@ __global__ void __launch_bounds__(PS_THREADS) k_phase_search(const K3Params p) {
 // state machine, the ScatterPLL level (DSP.h:100-106) and the Reset vote only run while a frame is being collected.
 // ---------------------------------------------------------------------------------------------
 constexpr int DK_THREADS = 128;
-template <int MODEL>
+
+// The DATAFCS branch of Decoder::Run (AIS.h:141-175) for one lane; returns true on a frame with good CRC.
+__device__ __forceinline__ bool dec_data_step(DecState &d, const DecCtx &c, int Bit, float sample_lvl, int &fr_len, float &fr_level) {
+	bool found = false;
+	const int pos = d.position++;
+	if (pos < MAX_FRAME_BITS) { // Message::setBit (Message.h:264-273)
+		uint32_t *wp = &c.frame[(pos >> 5) * K3_THREADS];
+		const uint32_t m = 1u << (pos & 31);
+		const uint32_t w = *wp;
+		*wp = Bit ? (w | m) : (w & ~m);
+	}
+	if (c.mode_level) d.level = __fadd_rn(d.level, sample_lvl);
+	if (Bit) {
+		if (d.one_seq == 5) {
+			fr_level = c.mode_level ? __fdiv_rn(d.level, (float)d.position) : 0.0f;
+			const int len = d.position - 7;
+			if (len >= 16 && dec_crc16(c, len)) {
+				found = true;
+				fr_len = len;
+			}
+			d.state = ST_TRAINING; d.position = 0; d.one_seq = 0;
+		}
+		else d.one_seq++;
+	}
+	else {
+		if (d.one_seq == 5) d.position--;
+		d.one_seq = 0;
+	}
+	const int q = d.position;
+	if (q >= 30 && (q == MAX_FRAME_BITS || dec_cannot_be_valid(c, q))) { d.state = ST_TRAINING; d.position = 0; d.one_seq = 0; }
+	return found;
+}
+
+template <int MODEL, bool TAPS>
 __global__ void __launch_bounds__(DK_THREADS) k_decode(const K3Params p) {
-	typedef typename std::conditional<MODEL == 2, float2, float>::type sample_t;
 	__shared__ uint32_t frames_all[DK_THREADS / 32][DEC_WORDS * 32];
-	__shared__ sample_t tile_all[DK_THREADS / 32][2][K3_ROWLEN];
+	__shared__ float tile_all[DK_THREADS / 32][2][K3_ROWLEN]; // MODEL 0: the row's FIR37 samples; MODEL 2: its 32 symbol levels
 	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
 	const int row = blockIdx.x * (DK_THREADS / 32) + wib;
 	if (row >= p.rows) return; // whole warp
 	const int phase = lane;
 	const bool active = lane < 5;
-	const sample_t *E = MODEL == 2 ? reinterpret_cast<const sample_t *>(p.Ec) : reinterpret_cast<const sample_t *>(p.Ef);
-	sample_t(*tile)[K3_ROWLEN] = tile_all[wib];
+	float(*tile)[K3_ROWLEN] = tile_all[wib];
 
 	DecCtx ctx;
 	ctx.frame = frames_all[wib] + lane;
@@ -937,12 +1107,17 @@ __global__ void __launch_bounds__(DK_THREADS) k_decode(const K3Params p) {
 		d.state = ST_TRAINING; d.lastBit = 0; d.prev = 0; d.position = 0; d.one_seq = 0; d.level = 0.f; d.start_idx = 0;
 	}
 	int ntap = 0;
-	const int nsamp = p.nsym * 5;
+	// slots in which this phase has a sample (Deinterleave forwards partial groups at both ends of a submit)
+	const int lo_rel = (int)(p.abs_lo - p.abs_begin), hi_rel = (int)(p.abs_hi - p.abs_begin);
+	const int slot_lo = phase >= lo_rel ? 0 : 1;
+	const int slot_hi = (hi_rel - phase + 4) / 5;
+	const int per_sym = MODEL == 2 ? 1 : 5;
+	const int nelem = p.nsym * per_sym;
+	const float *src_row = MODEL == 2 ? p.lvl + (long long)row * p.lvl_stride : p.Ef + (long long)row * p.e_stride + p.e_begin;
 	auto prefetch = [&](int buf, int s0) {
-		const int base = s0 * 5;
-		const sample_t *src = E + (long long)row * p.e_stride + p.e_begin + base;
-		for (int e = lane; e < K3_ROWLEN; e += 32)
-			if (base + e < nsamp) cp_async_f(&tile[buf][e], src + e);
+		const int base = s0 * per_sym;
+		for (int e = lane; e < K3_TS * per_sym; e += 32)
+			if (base + e < nelem) cp_async_f(&tile[buf][e], src_row + base + e);
 		cp_async_commit();
 	};
 	const int ntiles = (p.nsym + K3_TS - 1) / K3_TS;
@@ -954,79 +1129,71 @@ __global__ void __launch_bounds__(DK_THREADS) k_decode(const K3Params p) {
 		}
 		else cp_async_wait<0>();
 		__syncwarp();
-		const sample_t *my = &tile[t & 1][active ? phase : 0];
+		const float *my = &tile[t & 1][MODEL == 2 ? 0 : (active ? phase : 0)];
 		uint32_t word = 0;
 		if (MODEL == 2 && active) word = p.dbits[(long long)sidx * p.dwords + t];
 		const int s_end = min(K3_TS, p.nsym - t * K3_TS);
 		for (int sl = 0; sl < s_end; sl++) {
-			const int s = t * K3_TS + sl;
-			const long long sample_idx = p.abs_begin + (long long)s * 5 + phase;
+			const int slot = t * K3_TS + sl;
+			const int rel = slot * 5 + phase;
 			bool valid = active;
-			float b;
-			if (MODEL == 2) b = ((word >> sl) & 1u) ? 1.0f : -1.0f;
+			int dd;
+			if (MODEL == 2) dd = (word >> sl) & 1u;
 			else {
-				valid = active && sample_idx >= p.abs_lo && sample_idx < p.abs_hi;
-				b = *reinterpret_cast<const float *>(&my[sl * 5]);
-				if (p.tap_dec && valid) p.tap_dec[(long long)sidx * p.nsym + ntap++] = b;
+				valid = active && slot >= slot_lo && slot < slot_hi;
+				const float bsmp = my[sl * 5];
+				dd = bsmp > 0.0f;
+				if (TAPS && valid) p.tap_dec[(long long)sidx * p.nsym + ntap++] = bsmp;
 			}
-			const unsigned in_data = __ballot_sync(0xffffffffu, active && d.state == ST_DATAFCS);
-			if (!in_data) { // fast path: nobody collects a frame; TRAINING / STARTFLAG only (AIS.h:103-139)
-				if (valid) {
-					const int dd = b > 0.0f;
-					const int Bit = !(dd ^ d.prev);
-					d.prev = dd;
-					if (d.state == ST_TRAINING) {
-						if (Bit != d.lastBit) d.position++;
-						else if (d.position > 4) { d.start_idx = sample_idx; d.state = ST_STARTFLAG; d.position = Bit ? 3 : 1; }
-						else d.position = 0;
-					}
-					else { // ST_STARTFLAG
-						if (d.position == 7) {
-							if (Bit == 0) {
-								d.state = ST_DATAFCS; d.position = 0; d.one_seq = 0; d.level = 0.0f;
-								for (int w = 0; w < DEC_WORDS; w++) ctx.frame[w * K3_THREADS] = 0u; // msg.clear()
-							}
-							else { d.state = ST_TRAINING; d.position = 0; }
-						}
-						else if (Bit == 1) d.position++;
-						else { d.state = ST_TRAINING; d.position = 0; }
-					}
-					d.lastBit = Bit;
-				}
-				continue;
-			}
-			float sample_lvl = 0.0f;
-			if (MODEL == 2 && p.mode_level) { // ScatterPLL level: ((((0+n0)+n1)+n2)+n3)+n4, then / 5 (DSP.h:100-106)
-				const float2 x = *reinterpret_cast<const float2 *>(&my[sl * 5]);
-				const float nrm = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
-				float acc = 0.0f;
-#pragma unroll
-				for (int jx = 0; jx < 5; jx++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, nrm, jx));
-				sample_lvl = __fdiv_rn(acc, 5.0f);
-			}
-			int fr_len = 0, lastBit_before = 0;
-			float fr_level = 0.0f;
+			// NRZI (AIS.h:93-96), then the TRAINING / STARTFLAG transitions (AIS.h:103-139) as straight-line selects
+			const int Bit = !(dd ^ d.prev);
+			const int lastBit_before = d.lastBit;
+			const int st = d.state, pos = d.position;
+			const bool was_data = valid && st == ST_DATAFCS;
 			const float level_before = d.level;
 			const long long start_before = d.start_idx;
-			const bool found = valid && dec_step(d, ctx, b, sample_lvl, sample_idx, fr_len, fr_level, lastBit_before);
+			const bool upd = valid && st != ST_DATAFCS;
+			const bool tr = st == ST_TRAINING;
+			const bool alt = Bit != lastBit_before;
+			const bool to_sf = upd && tr && !alt && pos > 4;                 // 01010|1 1 or 0 0 -> look for the flag
+			const bool sf_run = !tr && pos != 7 && Bit;                        // still inside 0111111
+			const bool to_data = upd && !tr && pos == 7 && !Bit;               // 0111111|0 -> frame starts
+			const int pos_tr = alt ? pos + 1 : (to_sf ? (Bit ? 3 : 1) : 0);
+			const int pos_sf = sf_run ? pos + 1 : 0;
+			const int st_tr = to_sf ? ST_STARTFLAG : ST_TRAINING;
+			const int st_sf = to_data ? ST_DATAFCS : (sf_run ? ST_STARTFLAG : ST_TRAINING);
+			d.position = upd ? (tr ? pos_tr : pos_sf) : pos;
+			d.state = upd ? (tr ? st_tr : st_sf) : st;
+			d.prev = valid ? dd : d.prev;
+			d.lastBit = valid ? Bit : lastBit_before;
+			if (to_sf) d.start_idx = p.abs_begin + rel;
+			if (to_data) {
+				d.one_seq = 0;
+				d.level = 0.0f;
+				for (int w = 0; w < DEC_WORDS; w++) ctx.frame[w * K3_THREADS] = 0u; // msg.clear()
+			}
+			if (!__ballot_sync(0xffffffffu, was_data)) continue; // nobody is collecting a frame
+			int fr_len = 0;
+			float fr_level = 0.0f;
+			bool found = false;
+			if (was_data) found = dec_data_step(d, ctx, Bit, MODEL == 2 ? my[sl] : 0.0f, fr_len, fr_level);
 			const unsigned vote = __ballot_sync(0xffffffffu, found);
 			if (vote) { // rare: FOUNDMESSAGE -> Reset to the four sibling decoders (AIS.cpp:47-49,98-108)
 				const int winner = __ffs(vote) - 1; // lowest phase runs first (DSP.h:108-112)
 				if (lane == winner) {
 					float ppm = 0.0f;
 					if (MODEL == 2 && p.ppmtab) { // tag.ppm of the CGF block that delivered the group's 5th sample
-						const long long last_of_group = p.abs_begin + (long long)s * 5 + 4;
+						const long long last_of_group = p.abs_begin + (long long)(t * K3_TS + sl) * 5 + 4;
 						int bi = (int)((last_of_group - p.blk_abs0) >> 9);
 						bi = bi < 0 ? 0 : (bi >= p.nblk ? p.nblk - 1 : bi);
 						ppm = p.ppmtab[p.stepidx[row * p.nblk + bi]];
 					}
-					emit_frame(p.ring, p.ring_count, p.ring_cap, p.chunk, ctx, row, phase, fr_len, fr_level, ppm, d.start_idx, sample_idx);
+					emit_frame(p.ring, p.ring_count, p.ring_cap, p.chunk, ctx, row, phase, fr_len, fr_level, ppm, d.start_idx, p.abs_begin + rel);
 				}
 				else if (active && (lane < winner || !valid)) { // already stepped this symbol (or no sample in this slot), then reset
 					d.state = ST_TRAINING; d.position = 0; d.one_seq = 0;
 				}
 				else if (active) { // reset first, then step this symbol from TRAINING/0: only the NRZI memory survives
-					const int Bit = d.lastBit; // dec_step stored the new Bit there
 					d.level = level_before;
 					d.start_idx = start_before;
 					d.state = ST_TRAINING;
