@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -61,7 +62,11 @@ struct aisgpu_handle {
 	float fdc_alpha = 0, fdc_beta = 1;
 	int rows = 0;
 	int max_n48 = 0;
-	cudaStream_t stream = nullptr, copy_stream = nullptr;
+	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
+	// for timing).  The front end of submit c+1 overlaps the back end of submit c; Cbuf is double buffered for that.
+	cudaStream_t stream = nullptr, copy_stream = nullptr, fe_stream = nullptr;
+	cudaEvent_t ev_fe_done[2] = { nullptr, nullptr }, ev_be_done[2] = { nullptr, nullptr };
+	bool be_recorded[2] = { false, false };
 	static const int NEV = 128;
 	cudaEvent_t ev_fe0s[128] = { nullptr }, ev_fe1s[128] = { nullptr };
 	cudaEvent_t ev_copy[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr };
@@ -85,7 +90,8 @@ struct aisgpu_handle {
 	bool k1_recorded[3] = { false, false, false };
 	float2 mult;
 	// 48 kHz channel buffer
-	float2 *d_C = nullptr;
+	float2 *d_C2[2] = { nullptr, nullptr };
+	int c_last = 0; // buffer the last submit's front end wrote
 	long long c_stride = 0;
 	int c_hist = 0; // samples kept in front of HC
 	// CGF
@@ -105,6 +111,7 @@ struct aisgpu_handle {
 	long long e_abs = 0;
 	PsState *d_ps = nullptr;
 	float *d_ps_mem = nullptr;
+	long long *d_dbg = nullptr; // AISGPU_DEBUG=1: per-row decoder counters (tap 6)
 	uint32_t *d_dbits = nullptr;
 	float *d_lvl = nullptr;
 	int dwords = 0;
@@ -237,7 +244,7 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 	p.fdc_alpha = h->fdc_alpha;
 	p.fdc_beta = h->fdc_beta;
 	p.rot = h->d_rot[h->rot_cur];
-	p.C = h->d_C;
+	p.C = h->d_C2[h->chunk & 1];
 	p.c_stride = h->c_stride;
 	p.c_off = HC;
 	const size_t smem = (size_t)p.smem_f2 * sizeof(float2);
@@ -245,19 +252,19 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 	switch (h->cfg.format) {
 	case AISGPU_FMT_CF32:
 		CU(cudaFuncSetAttribute(k_frontend<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		k_frontend<0><<<grid, FE_THREADS, smem, h->stream>>>(p);
+		k_frontend<0><<<grid, FE_THREADS, smem, h->fe_stream>>>(p);
 		break;
 	case AISGPU_FMT_CU8:
 		CU(cudaFuncSetAttribute(k_frontend<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		k_frontend<1><<<grid, FE_THREADS, smem, h->stream>>>(p);
+		k_frontend<1><<<grid, FE_THREADS, smem, h->fe_stream>>>(p);
 		break;
 	case AISGPU_FMT_CS8:
 		CU(cudaFuncSetAttribute(k_frontend<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		k_frontend<2><<<grid, FE_THREADS, smem, h->stream>>>(p);
+		k_frontend<2><<<grid, FE_THREADS, smem, h->fe_stream>>>(p);
 		break;
 	default:
 		CU(cudaFuncSetAttribute(k_frontend<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		k_frontend<3><<<grid, FE_THREADS, smem, h->stream>>>(p);
+		k_frontend<3><<<grid, FE_THREADS, smem, h->fe_stream>>>(p);
 		break;
 	}
 	CU(cudaGetLastError());
@@ -268,6 +275,15 @@ template <typename T>
 int carry(aisgpu_handle *h, T *buf, long long stride, int src_begin, int dst_begin, int cnt) {
 	if (cnt <= 0 || src_begin == dst_begin) return 0;
 	k_carry<T><<<h->rows, 128, cnt * sizeof(T), h->stream>>>(buf, stride, src_begin, dst_begin, cnt);
+	CU(cudaGetLastError());
+	h->last_launches++;
+	return 0;
+}
+
+template <typename T>
+int carry2(aisgpu_handle *h, const T *src, T *dst, long long stride, int src_begin, int dst_begin, int cnt) {
+	if (cnt <= 0) return 0;
+	k_carry2<T><<<h->rows, 128, 0, h->stream>>>(src, dst, stride, src_begin, dst_begin, cnt);
 	CU(cudaGetLastError());
 	h->last_launches++;
 	return 0;
@@ -301,6 +317,7 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.chunk = (int)h->chunk;
 		p.mode_level = (h->cfg.tag_mode & 1) ? 1 : 0;
 		p.tap_dec = h->cfg.enable_taps ? h->d_tap_dec : nullptr;
+		p.dbg = h->d_dbg;
 		if (p.tap_dec) k_decode<0, true><<<(h->rows + DK_THREADS / 32 - 1) / (DK_THREADS / 32), DK_THREADS, 0, h->stream>>>(p);
 		else k_decode<0, false><<<(h->rows + DK_THREADS / 32 - 1) / (DK_THREADS / 32), DK_THREADS, 0, h->stream>>>(p);
 		CU(cudaGetLastError());
@@ -342,6 +359,7 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 			p.nblk = n_new / CGF_N;
 		}
 		p.tap_dec = h->cfg.enable_taps ? h->d_tap_dec : nullptr;
+		p.dbg = h->d_dbg;
 		p.dbits = h->d_dbits;
 		p.dwords = h->dwords;
 		p.lvl = h->d_lvl;
@@ -393,15 +411,19 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 		if (!(h->rot_ready_chunk == c && h->rot_n96[slot] == n96)) {
 			if (int rc = enqueue_rot_table(h, c, n96)) return rc;
 		}
-		CU(cudaStreamWaitEvent(h->stream, h->ev_rot[slot], 0));
+		CU(cudaStreamWaitEvent(h->fe_stream, h->ev_rot[slot], 0));
 		h->rot_cur = slot;
 	}
-	// ---- K1: fused front end ----
+	const int cb = (int)(h->chunk & 1);
+	float2 *Ccur = h->d_C2[cb], *Cnext = h->d_C2[cb ^ 1];
+	h->c_last = cb;
+	// ---- K1: fused front end (its own stream: overlaps the back end of the previous submit) ----
+	if (h->be_recorded[cb]) CU(cudaStreamWaitEvent(h->fe_stream, h->ev_be_done[cb], 0)); // back end of submit c-2 still reads Cbuf[cb]
 	const int evi = (int)(h->chunk % aisgpu_handle::NEV);
-	CU(cudaEventRecord(h->ev_fe0s[evi], h->stream));
+	CU(cudaEventRecord(h->ev_fe0s[evi], h->fe_stream));
 	if (int rc = launch_frontend(h, dev_in, stride, N)) return rc;
-	CU(cudaEventRecord(h->ev_fe1s[evi], h->stream));
-	CU(cudaEventRecord(h->ev_k1[h->chunk % 3], h->stream));
+	CU(cudaEventRecord(h->ev_fe1s[evi], h->fe_stream));
+	CU(cudaEventRecord(h->ev_k1[h->chunk % 3], h->fe_stream));
 	h->k1_recorded[h->chunk % 3] = true;
 	h->fe_timed = true;
 	h->last_launches += 2; // front end + this submit's phasor table
@@ -412,12 +434,14 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 		const int nxt = h->tail_cur ^ 1;
 		const int p_w = h->P * h->bps / 8;
 		dim3 grid((p_w + 127) / 128, B);
-		k_tail_update<<<grid, 128, 0, h->stream>>>((uint2 *)h->d_tail[nxt], (const uint2 *)h->d_tail[h->tail_cur], (const uint2 *)dev_in,
+		k_tail_update<<<grid, 128, 0, h->fe_stream>>>((uint2 *)h->d_tail[nxt], (const uint2 *)h->d_tail[h->tail_cur], (const uint2 *)dev_in,
 													stride * h->bps / 8, (long long)N * h->bps / 8, p_w);
 		CU(cudaGetLastError());
 		h->tail_cur = nxt;
 		h->last_launches++;
 	}
+	CU(cudaEventRecord(h->ev_fe_done[cb], h->fe_stream));
+	CU(cudaStreamWaitEvent(h->stream, h->ev_fe_done[cb], 0));
 	h->last_n = N;
 	h->last_n48 = n48;
 	h->last_nE = 0;
@@ -432,14 +456,14 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 			const int total_blocks = h->rows * nblk;
 			const int ctas = (total_blocks + CGF_BLK_PER_CTA - 1) / CGF_BLK_PER_CTA;
 			const size_t smem = 4096 + 2 * (size_t)CGF_BLK_PER_CTA * CGF_ROWP * 4;
-			k_cgf_estimate<<<ctas, CGF_THREADS, smem, h->stream>>>(h->d_C, h->c_stride, c_begin, nblk, total_blocks, h->d_omega,
+			k_cgf_estimate<<<ctas, CGF_THREADS, smem, h->stream>>>(Ccur, h->c_stride, c_begin, nblk, total_blocks, h->d_omega,
 																	 h->cfg.afc_wide, h->d_stepidx);
 			CU(cudaGetLastError());
 			k_cgf_rot<<<(h->rows + 31) / 32, 32, 0, h->stream>>>(h->d_stepidx, h->d_steptab, h->d_cgf_rot, h->d_rots, h->r_stride, nblk, h->rows);
 			CU(cudaGetLastError());
 			const int nE = nblk * CGF_N;
 			dim3 grid((nE + FIRC_TILE - 1) / FIRC_TILE, h->rows);
-			k_cgf_derot_fir<<<grid, FIRC_TILE, 0, h->stream>>>(h->d_C, h->c_stride, c_begin, h->d_rots, h->r_stride, nE, h->d_fir_hist[h->fir_cur],
+			k_cgf_derot_fir<<<grid, FIRC_TILE, 0, h->stream>>>(Ccur, h->c_stride, c_begin, h->d_rots, h->r_stride, nE, h->d_fir_hist[h->fir_cur],
 																 h->d_fir_hist[h->fir_cur ^ 1], h->d_Ec, h->e_stride, HE,
 																 h->cfg.enable_taps ? h->d_tap_cgf : nullptr, h->r_stride);
 			CU(cudaGetLastError());
@@ -450,17 +474,17 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 			h->cgf_abs += nE;
 		}
 		const int newcnt = total - nblk * CGF_N;
-		if (int rc = carry(h, h->d_C, h->c_stride, c_begin + nblk * CGF_N, HC - newcnt, newcnt)) return rc;
+		if (int rc = carry2(h, Ccur, Cnext, h->c_stride, c_begin + nblk * CGF_N, HC - newcnt, newcnt)) return rc;
 		h->c_hist = newcnt;
 	}
 	else {
 		dim3 grid((n48 + FIRF_TILE - 1) / FIRF_TILE, h->rows);
-		k_fm_fir<<<grid, FIRF_TILE, 0, h->stream>>>(h->d_C, h->c_stride, HC, n48, h->d_Ef, h->e_stride, HE,
+		k_fm_fir<<<grid, FIRF_TILE, 0, h->stream>>>(Ccur, h->c_stride, HC, n48, h->d_Ef, h->e_stride, HE,
 													 h->cfg.enable_taps ? h->d_tap_fm : nullptr, h->r_stride);
 		CU(cudaGetLastError());
 		h->last_launches++;
 		h->last_nE = n48;
-		if (int rc = carry(h, h->d_C, h->c_stride, HC + n48 - FIRF_T, HC - FIRF_T, FIRF_T)) return rc;
+		if (int rc = carry2(h, Ccur, Cnext, h->c_stride, HC + n48 - FIRF_T, HC - FIRF_T, FIRF_T)) return rc;
 		if (h->cfg.model == AISGPU_MODEL_STANDARD) {
 			if (int rc = run_symbols(h, n48)) return rc;
 		}
@@ -472,6 +496,8 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 			h->last_launches++;
 		}
 	}
+	CU(cudaEventRecord(h->ev_be_done[cb], h->stream));
+	h->be_recorded[cb] = true;
 	h->counters[2] += (uint64_t)N;
 	h->counters[3] += 1;
 	h->chunk++;
@@ -628,9 +654,18 @@ static int create_impl(aisgpu_handle *h) {
 		return AISGPU_ENODEV;
 	}
 	CU(cudaSetDevice(c.device));
-	CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+	// Back-end kernels are small and latency bound; give them priority so that their CTAs are dispatched as soon as the
+	// (large-grid) front end of the next submit frees a slot, instead of queueing behind all of its CTAs.
+	int prio_lo = 0, prio_hi = 0;
+	CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+	CU(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
 	CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithPriority(&h->fe_stream, cudaStreamNonBlocking, prio_lo));
+	for (int i = 0; i < 2; i++) {
+		CU(cudaEventCreateWithFlags(&h->ev_fe_done[i], cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&h->ev_be_done[i], cudaEventDisableTiming));
+	}
 	for (int i = 0; i < 3; i++) {
 		CU(cudaEventCreateWithFlags(&h->ev_rot[i], cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&h->ev_k1[i], cudaEventDisableTiming));
@@ -666,7 +701,8 @@ static int create_impl(aisgpu_handle *h) {
 		h->mult = polar1((float)(PI_F * 25000.0 / 48000.0)); // Model.cpp:31
 	}
 	h->c_stride = (HC + h->max_n48 + 8 + 1) & ~1LL;
-	if (int rc = dalloc(h, &h->d_C, (size_t)h->rows * h->c_stride)) return rc;
+	for (int i = 0; i < 2; i++)
+		if (int rc = dalloc(h, &h->d_C2[i], (size_t)h->rows * h->c_stride)) return rc;
 	const int nEmax = HC + h->max_n48;
 	h->e_stride = (HE + nEmax + 8 + 1) & ~1LL;
 	h->r_stride = nEmax;
@@ -727,10 +763,18 @@ static int create_impl(aisgpu_handle *h) {
 	}
 	if (c.enable_taps)
 		if (int rc = dalloc(h, &h->d_tap_dec, (size_t)h->rows * 5 * (nEmax / 5 + 2))) return rc;
+	if (getenv("AISGPU_DEBUG"))
+		if (int rc = dalloc(h, &h->d_dbg, (size_t)h->rows * 4)) return rc;
 	CU(cudaMemcpyToSymbol(c_taps_coherent, H_TAPS_COHERENT, sizeof(H_TAPS_COHERENT)));
 	CU(cudaMemcpyToSymbol(c_taps_receiver, H_TAPS_RECEIVER, sizeof(H_TAPS_RECEIVER)));
 	CU(cudaMemcpyToSymbol(c_ps_cos, H_PS_COS, sizeof(H_PS_COS)));
 	CU(cudaMemcpyToSymbol(c_ps_sin, H_PS_SIN, sizeof(H_PS_SIN)));
+	{
+		uint32_t ab[35] = { 0 };
+		const int pos[] = { 30, 62, 96, 168, 184, 192, 336, 385, 448, MAX_FRAME_BITS }; // AIS.cpp:111-142, AIS.h:172
+		for (int q : pos) ab[q >> 5] |= 1u << (q & 31);
+		CU(cudaMemcpyToSymbol(c_abort_bits, ab, sizeof(ab)));
+	}
 	h->ring_cap = c.max_frames > 0 ? c.max_frames : std::max(4096, B * 64);
 	if (int rc = dalloc(h, &h->d_ring, (size_t)h->ring_cap)) return rc;
 	if (int rc = dalloc(h, &h->d_ring_count, 1)) return rc;
@@ -784,10 +828,10 @@ int aisgpu_submit(aisgpu_handle *h, const void *host_samples, int n_samples) {
 	if (h->in_used[cur]) CU(cudaStreamWaitEvent(h->copy_stream, h->ev_done[cur], 0));
 	CU(cudaMemcpyAsync(h->d_in[cur], host_samples, bytes, cudaMemcpyHostToDevice, h->copy_stream));
 	CU(cudaEventRecord(h->ev_copy[cur], h->copy_stream));
-	CU(cudaStreamWaitEvent(h->stream, h->ev_copy[cur], 0));
+	CU(cudaStreamWaitEvent(h->fe_stream, h->ev_copy[cur], 0));
 	int rc = submit_common(h, h->d_in[cur], n_samples, n_samples);
 	if (rc) return rc;
-	CU(cudaEventRecord(h->ev_done[cur], h->stream));
+	CU(cudaEventRecord(h->ev_done[cur], h->fe_stream)); // the front end is the only reader of the staging buffer
 	h->in_used[cur] = true;
 	h->in_cur ^= 1;
 	// the caller's buffer is only borrowed for the call (Stream.h:41 semantics): wait for the copy, not for the kernels
@@ -797,6 +841,7 @@ int aisgpu_submit(aisgpu_handle *h, const void *host_samples, int n_samples) {
 
 int aisgpu_sync(aisgpu_handle *h) {
 	if (!h) return AISGPU_EINVAL;
+	CU(cudaStreamSynchronize(h->fe_stream));
 	CU(cudaStreamSynchronize(h->stream));
 	return 0;
 }
@@ -818,13 +863,14 @@ int aisgpu_poll(aisgpu_handle *h, aisgpu_msg *out, int max, int *n) {
 int aisgpu_tap(aisgpu_handle *h, int tap, int stream, int channel, void *dst, size_t dst_bytes, size_t *n_out) {
 	if (!h || !n_out || stream < 0 || stream >= h->cfg.n_streams || channel < 0 || channel > 9) return AISGPU_EINVAL;
 	CU(cudaSetDevice(h->cfg.device));
+	CU(cudaStreamSynchronize(h->fe_stream));
 	CU(cudaStreamSynchronize(h->stream));
 	const int row = stream * 2 + (channel & 1);
 	const void *src = nullptr;
 	size_t n = 0, esz = 8;
 	switch (tap) {
 	case AISGPU_TAP_C:
-		src = h->d_C + (long long)row * h->c_stride + HC; // note: valid until the next submit only for [0, n48)
+		src = h->d_C2[h->c_last] + (long long)row * h->c_stride + HC; // note: valid until the next submit only for [0, n48)
 		n = h->last_n48;
 		break;
 	case AISGPU_TAP_CGF:
@@ -863,6 +909,11 @@ int aisgpu_tap(aisgpu_handle *h, int tap, int stream, int channel, void *dst, si
 		}
 		break;
 	}
+	case 6: // debug counters of the decoder kernel, 4 x int64 per row (stream/channel ignored, all rows)
+		if (!h->d_dbg) { h->err = "AISGPU_DEBUG not set"; return AISGPU_EINVAL; }
+		src = h->d_dbg;
+		n = (size_t)h->rows * 4;
+		break;
 	case 5:
 		if (!h->d_tap_fm) { h->err = "taps not enabled or not an FM engine"; return AISGPU_EINVAL; }
 		src = h->d_tap_fm + (long long)row * h->r_stride;
@@ -898,6 +949,7 @@ int aisgpu_frontend_times(aisgpu_handle *h, float *ms_out, int max, int *n) {
 	if (!h || !ms_out || !n) return AISGPU_EINVAL;
 	*n = 0;
 	if (!h->fe_timed) return 0;
+	CU(cudaStreamSynchronize(h->fe_stream));
 	CU(cudaStreamSynchronize(h->stream));
 	long long cnt = std::min<long long>(std::min<long long>(h->chunk, aisgpu_handle::NEV), max);
 	for (long long i = 0; i < cnt; i++) { // newest first
@@ -912,10 +964,11 @@ int aisgpu_last_launches(aisgpu_handle *h) { return h ? h->last_launches : 0; }
 
 void aisgpu_destroy(aisgpu_handle *h) {
 	if (!h) return;
+	if (h->fe_stream) cudaStreamSynchronize(h->fe_stream);
 	if (h->stream) cudaStreamSynchronize(h->stream);
-	void *ptrs[] = { h->d_in[0], h->d_in[1], h->d_tail[0], h->d_tail[1], h->d_rot[0], h->d_rot[1], h->d_rot[2], h->d_rot_state, h->d_C, h->d_stepidx,
+	void *ptrs[] = { h->d_in[0], h->d_in[1], h->d_tail[0], h->d_tail[1], h->d_rot[0], h->d_rot[1], h->d_rot[2], h->d_rot_state, h->d_C2[0], h->d_C2[1], h->d_stepidx,
 					 h->d_steptab, h->d_omega, h->d_cgf_rot, h->d_rots, h->d_ppmtab, h->d_fir_hist[0], h->d_fir_hist[1], h->d_tap_cgf, h->d_Ec,
-					 h->d_Ef, h->d_ps, h->d_ps_mem, h->d_dbits, h->d_lvl, h->d_dec, h->d_dec_data, h->d_pll, h->d_tap_dec, h->d_tap_fm, h->d_tap_cnt, h->d_ring,
+					 h->d_Ef, h->d_ps, h->d_ps_mem, h->d_dbits, h->d_lvl, h->d_dbg, h->d_dec, h->d_dec_data, h->d_pll, h->d_tap_dec, h->d_tap_fm, h->d_tap_cnt, h->d_ring,
 					 h->d_ring_count };
 	for (void *p : ptrs)
 		if (p) cudaFree(p);
@@ -932,6 +985,11 @@ void aisgpu_destroy(aisgpu_handle *h) {
 		if (h->ev_k1[i]) cudaEventDestroy(h->ev_k1[i]);
 	}
 	if (h->side_stream) { cudaStreamSynchronize(h->side_stream); cudaStreamDestroy(h->side_stream); }
+	for (int i = 0; i < 2; i++) {
+		if (h->ev_fe_done[i]) cudaEventDestroy(h->ev_fe_done[i]);
+		if (h->ev_be_done[i]) cudaEventDestroy(h->ev_be_done[i]);
+	}
+	if (h->fe_stream) cudaStreamDestroy(h->fe_stream);
 	if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	delete h;

@@ -486,6 +486,15 @@ __global__ void k_carry(T *__restrict__ buf, long long stride, int src_begin, in
 	for (int i = threadIdx.x; i < cnt; i += blockDim.x) row[dst_begin + i] = tmp[i];
 }
 
+// copy `cnt` elements of each row from one buffer to another (unconsumed samples / filter history handed to the
+// buffer the next submit's front end writes into)
+template <typename T>
+__global__ void k_carry2(const T *__restrict__ src, T *__restrict__ dst, long long stride, int src_begin, int dst_begin, int cnt) {
+	const T *srow = src + (long long)blockIdx.x * stride + src_begin;
+	T *drow = dst + (long long)blockIdx.x * stride + dst_begin;
+	for (int i = threadIdx.x; i < cnt; i += blockDim.x) drow[i] = srow[i];
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2a: SquareFreqOffsetCorrection, estimation half (DSP.cpp:417-455, FFT.h:93-130).
 // One warp per 512-sample block: x^2 in bit-reversed order, the reference's radix-2 DIT butterflies stage by
@@ -887,6 +896,7 @@ struct K3Params {
 	long long blk_abs0;
 	int nblk;
 	float *tap_dec;       // optional: decoder input samples [rows*5][nsym]
+	long long *dbg;       // optional per-row counters [rows][4]: cycles, frame-collecting steps, CRC runs, CRC bits
 };
 
 constexpr int K3_TS = 32;                 // symbols staged per tile
@@ -1043,55 +1053,46 @@ __global__ void __launch_bounds__(PS_THREADS) k_phase_search(const K3Params p) {
 	}
 }
 
-// ---------------------------------------------------------------------------------------------
-// K3b: the five AIS::Decoder instances of one row (AIS.h:91-181) in lanes 0..4 of one warp.  While all five sit
-// in TRAINING / STARTFLAG (the common case on noise) a symbol costs a handful of integer instructions; the full
-// state machine, the ScatterPLL level (DSP.h:100-106) and the Reset vote only run while a frame is being collected.
-// ---------------------------------------------------------------------------------------------
-constexpr int DK_THREADS = 128;
+// positions at which Decoder::cannotBeValid (AIS.cpp:111-142) can fire: 30 62 96 168 184 192 336 385 448,
+// plus MAX_FRAME_BITS (AIS.h:172) -- one bit per frame position
+__constant__ uint32_t c_abort_bits[35];
 
-// The DATAFCS branch of Decoder::Run (AIS.h:141-175) for one lane; returns true on a frame with good CRC.
-__device__ __forceinline__ bool dec_data_step(DecState &d, const DecCtx &c, int Bit, float sample_lvl, int &fr_len, float &fr_level) {
-	bool found = false;
-	const int pos = d.position++;
-	if (pos < MAX_FRAME_BITS) { // Message::setBit (Message.h:264-273)
-		uint32_t *wp = &c.frame[(pos >> 5) * K3_THREADS];
-		const uint32_t m = 1u << (pos & 31);
-		const uint32_t w = *wp;
-		*wp = Bit ? (w | m) : (w & ~m);
-	}
-	if (c.mode_level) d.level = __fadd_rn(d.level, sample_lvl);
-	if (Bit) {
-		if (d.one_seq == 5) {
-			fr_level = c.mode_level ? __fdiv_rn(d.level, (float)d.position) : 0.0f;
-			const int len = d.position - 7;
-			if (len >= 16 && dec_crc16(c, len)) {
-				found = true;
-				fr_len = len;
-			}
-			d.state = ST_TRAINING; d.position = 0; d.one_seq = 0;
-		}
-		else d.one_seq++;
-	}
-	else {
-		if (d.one_seq == 5) d.position--;
-		d.one_seq = 0;
-	}
-	const int q = d.position;
-	if (q >= 30 && (q == MAX_FRAME_BITS || dec_cannot_be_valid(c, q))) { d.state = ST_TRAINING; d.position = 0; d.one_seq = 0; }
-	return found;
+// Outside a frame the decoder is a tiny automaton; q encodes it in one register:
+//   q = 0..5   TRAINING with min(position, 5) alternations seen (only "position > 4" is ever tested, AIS.h:105-113)
+//   q = 8..14  STARTFLAG with position = q - 7 (AIS.h:116-137)
+__device__ __forceinline__ int dec_q_from_state(const DecState &d) {
+	return d.state == ST_TRAINING ? min(d.position, 5) : (d.state == ST_STARTFLAG ? 7 + d.position : 0);
 }
 
+// K3b: the five AIS::Decoder instances of one row (AIS.h:91-181) in lanes 0..4 of one warp, one symbol per
+// iteration for all of them.  Every lane runs the same straight-line code each symbol -- the out-of-frame automaton
+// (one table lookup) and the in-frame bit collector (bits gathered in a register, flushed to shared memory once per
+// 32) are both evaluated and masked -- so a row costs the same whether or not it is collecting a frame; only the
+// rare events (frame start, word flush, abort positions, closing flag + CRC + Reset vote) branch.
+constexpr int DK_THREADS = 128;
 template <int MODEL, bool TAPS>
 __global__ void __launch_bounds__(DK_THREADS) k_decode(const K3Params p) {
 	__shared__ uint32_t frames_all[DK_THREADS / 32][DEC_WORDS * 32];
 	__shared__ float tile_all[DK_THREADS / 32][2][K3_ROWLEN]; // MODEL 0: the row's FIR37 samples; MODEL 2: its 32 symbol levels
+	__shared__ uint8_t lut_all[DK_THREADS / 32][64];
 	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
 	const int row = blockIdx.x * (DK_THREADS / 32) + wib;
 	if (row >= p.rows) return; // whole warp
 	const int phase = lane;
 	const bool active = lane < 5;
 	float(*tile)[K3_ROWLEN] = tile_all[wib];
+	// transition table of the out-of-frame automaton, index (q << 2) | (alt << 1) | Bit:
+	// bits 0-3 next q, bit 4 TRAINING->STARTFLAG (start_idx is taken), bit 5 0111111|0 seen: the frame starts
+	uint8_t *lut = lut_all[wib];
+	for (int i = lane; i < 64; i += 32) {
+		const int qq = i >> 2, al = (i >> 1) & 1, bt = i & 1;
+		int qn;
+		if (qq < 8) qn = al ? min(qq + 1, 5) : (qq == 5 ? 8 + 2 * bt : 0);  // TRAINING (AIS.h:103-114)
+		else qn = qq == 14 ? (bt ? 0 : 15) : (bt ? qq + 1 : 0);             // STARTFLAG (AIS.h:116-137)
+		const int to_sf = qq < 8 && qn >= 8, enter = qn == 15;
+		lut[i] = (uint8_t)((enter ? 0 : qn) | (to_sf << 4) | (enter << 5));
+	}
+	__syncwarp();
 
 	DecCtx ctx;
 	ctx.frame = frames_all[wib] + lane;
@@ -1106,6 +1107,15 @@ __global__ void __launch_bounds__(DK_THREADS) k_decode(const K3Params p) {
 	else {
 		d.state = ST_TRAINING; d.lastBit = 0; d.prev = 0; d.position = 0; d.one_seq = 0; d.level = 0.f; d.start_idx = 0;
 	}
+	const long long clk0 = clock64();
+	int n_slow = 0, n_crc = 0, n_crcbits = 0;
+	int in_data = active && d.state == ST_DATAFCS;
+	int q = dec_q_from_state(d);
+	int prev = d.prev, lastBit = d.lastBit;
+	int pos = in_data ? d.position : 0, ones = in_data ? d.one_seq : 0;
+	float level = d.level;
+	uint32_t cur = in_data ? ctx.frame[(pos >> 5) * K3_THREADS] : 0u; // the partially filled frame word
+	int start_rel = -1; // slot*5+phase of the most recent TRAINING -> STARTFLAG transition in this submit
 	int ntap = 0;
 	// slots in which this phase has a sample (Deinterleave forwards partial groups at both ends of a submit)
 	const int lo_rel = (int)(p.abs_lo - p.abs_begin), hi_rel = (int)(p.abs_hi - p.abs_begin);
@@ -1129,57 +1139,96 @@ __global__ void __launch_bounds__(DK_THREADS) k_decode(const K3Params p) {
 		}
 		else cp_async_wait<0>();
 		__syncwarp();
-		const float *my = &tile[t & 1][MODEL == 2 ? 0 : (active ? phase : 0)];
-		uint32_t word = 0;
-		if (MODEL == 2 && active) word = p.dbits[(long long)sidx * p.dwords + t];
 		const int s_end = min(K3_TS, p.nsym - t * K3_TS);
-		for (int sl = 0; sl < s_end; sl++) {
-			const int slot = t * K3_TS + sl;
-			const int rel = slot * 5 + phase;
-			bool valid = active;
-			int dd;
-			if (MODEL == 2) dd = (word >> sl) & 1u;
-			else {
-				valid = active && slot >= slot_lo && slot < slot_hi;
+		// decision bits and validity of this lane's 32 slots
+		uint32_t dword = 0, vword = 0;
+		if (MODEL == 2) {
+			if (active) {
+				dword = p.dbits[(long long)sidx * p.dwords + t];
+				vword = s_end >= 32 ? 0xffffffffu : ((1u << s_end) - 1u);
+			}
+		}
+		else if (active) {
+			const float *my = &tile[t & 1][phase];
+			for (int sl = 0; sl < s_end; sl++) {
+				const int slot = t * K3_TS + sl;
 				const float bsmp = my[sl * 5];
-				dd = bsmp > 0.0f;
+				const bool valid = slot >= slot_lo && slot < slot_hi;
+				dword |= (bsmp > 0.0f ? 1u : 0u) << sl;
+				vword |= (valid ? 1u : 0u) << sl;
 				if (TAPS && valid) p.tap_dec[(long long)sidx * p.nsym + ntap++] = bsmp;
 			}
-			// NRZI (AIS.h:93-96), then the TRAINING / STARTFLAG transitions (AIS.h:103-139) as straight-line selects
-			const int Bit = !(dd ^ d.prev);
-			const int lastBit_before = d.lastBit;
-			const int st = d.state, pos = d.position;
-			const bool was_data = valid && st == ST_DATAFCS;
-			const float level_before = d.level;
-			const long long start_before = d.start_idx;
-			const bool upd = valid && st != ST_DATAFCS;
-			const bool tr = st == ST_TRAINING;
-			const bool alt = Bit != lastBit_before;
-			const bool to_sf = upd && tr && !alt && pos > 4;                 // 01010|1 1 or 0 0 -> look for the flag
-			const bool sf_run = !tr && pos != 7 && Bit;                        // still inside 0111111
-			const bool to_data = upd && !tr && pos == 7 && !Bit;               // 0111111|0 -> frame starts
-			const int pos_tr = alt ? pos + 1 : (to_sf ? (Bit ? 3 : 1) : 0);
-			const int pos_sf = sf_run ? pos + 1 : 0;
-			const int st_tr = to_sf ? ST_STARTFLAG : ST_TRAINING;
-			const int st_sf = to_data ? ST_DATAFCS : (sf_run ? ST_STARTFLAG : ST_TRAINING);
-			d.position = upd ? (tr ? pos_tr : pos_sf) : pos;
-			d.state = upd ? (tr ? st_tr : st_sf) : st;
-			d.prev = valid ? dd : d.prev;
-			d.lastBit = valid ? Bit : lastBit_before;
-			if (to_sf) d.start_idx = p.abs_begin + rel;
-			if (to_data) {
-				d.one_seq = 0;
-				d.level = 0.0f;
-				for (int w = 0; w < DEC_WORDS; w++) ctx.frame[w * K3_THREADS] = 0u; // msg.clear()
+		}
+		for (int sl = 0; sl < s_end; sl++) {
+			const int dd = (dword >> sl) & 1u;
+			const int valid = (vword >> sl) & 1u;
+			const int Bit = 1 ^ dd ^ prev; // NRZI (AIS.h:93-96)
+			const int lastBit_before = lastBit;
+			const int alt = Bit ^ lastBit_before;
+			const int tv = lut[(q << 2) | (alt << 1) | Bit];
+			const int upd = valid & (in_data ^ 1), dat = valid & in_data;
+			const int start_before = start_rel;
+			const float level_before = level;
+			// ---- out of frame: TRAINING / STARTFLAG automaton ----
+			const int ev = upd ? (tv >> 4) : 0; // bit 0: start_idx taken, bit 1: the frame starts
+			start_rel = (ev & 1) ? (t * K3_TS + sl) * 5 + phase : start_rel;
+			q = upd ? (tv & 15) : q;
+			// ---- in frame: DATAFCS (AIS.h:141-175) ----
+			const int five = ones == 5;
+			const int append = dat & ((five & (Bit ^ 1)) ^ 1); // a 0 after five 1s is a stuffing bit and is dropped
+			cur |= (uint32_t)(append & Bit) << (pos & 31);
+			const int pos_n = pos + append;
+			if (MODEL == 2) {
+				const float lv = tile[t & 1][sl];
+				level = (dat && ctx.mode_level) ? __fadd_rn(level, lv) : level;
 			}
-			if (!__ballot_sync(0xffffffffu, was_data)) continue; // nobody is collecting a frame
+			ones = dat ? (Bit ? ones + 1 : 0) : ones;
+			const int closing = dat & Bit & five; // sixth 1 in a row: closing flag (AIS.h:151-161)
+			const int full = append & ((pos_n & 31) == 0);
+			const int abortpos = dat & ((c_abort_bits[pos_n >> 5] >> (pos_n & 31)) & 1u);
+			pos = pos_n;
+			prev = valid ? dd : prev;
+			lastBit = valid ? Bit : lastBit;
+			if ((ev >> 1) | full | abortpos) { // lane-local rare events
+				if (ev >> 1) { // 0111111|0: the frame starts (AIS.h:120-124)
+					in_data = 1;
+					q = 0;
+					pos = 0; ones = 0; level = 0.0f; cur = 0u;
+					d.start_idx = start_rel >= 0 ? p.abs_begin + start_rel : d.start_idx;
+					for (int w = 0; w < DEC_WORDS; w++) ctx.frame[w * K3_THREADS] = 0u; // msg.clear()
+				}
+				if (full) {
+					ctx.frame[((pos >> 5) - 1) * K3_THREADS] = cur;
+					cur = 0u;
+				}
+				if (abortpos && !closing) { // position == MaxBits || cannotBeValid(position) (AIS.h:172)
+					if (pos & 31) ctx.frame[(pos >> 5) * K3_THREADS] = cur;
+					if (pos == MAX_FRAME_BITS || dec_cannot_be_valid(ctx, pos)) { in_data = 0; q = 0; }
+				}
+			}
+			const unsigned closers = __ballot_sync(0xffffffffu, closing);
+			if (!closers) continue;
+			// ---- some decoder of the row saw a closing flag: CRC, frame emission, Reset of the siblings ----
+			n_slow++;
 			int fr_len = 0;
 			float fr_level = 0.0f;
 			bool found = false;
-			if (was_data) found = dec_data_step(d, ctx, Bit, MODEL == 2 ? my[sl] : 0.0f, fr_len, fr_level);
+			if (closing) {
+				if (pos & 31) ctx.frame[(pos >> 5) * K3_THREADS] = cur;
+				fr_level = ctx.mode_level ? __fdiv_rn(level, (float)pos) : 0.0f;
+				const int len = pos - 7;
+				if (len >= 16 && dec_crc16(ctx, len)) {
+					found = true;
+					fr_len = len;
+				}
+				in_data = 0;
+				q = 0;
+				if (p.dbg) { n_crc++; n_crcbits += len > 0 ? len : 0; }
+			}
 			const unsigned vote = __ballot_sync(0xffffffffu, found);
-			if (vote) { // rare: FOUNDMESSAGE -> Reset to the four sibling decoders (AIS.cpp:47-49,98-108)
+			if (vote) { // FOUNDMESSAGE -> Reset to the four sibling decoders (AIS.cpp:47-49,98-108)
 				const int winner = __ffs(vote) - 1; // lowest phase runs first (DSP.h:108-112)
+				const int rel = (t * K3_TS + sl) * 5 + phase;
 				if (lane == winner) {
 					float ppm = 0.0f;
 					if (MODEL == 2 && p.ppmtab) { // tag.ppm of the CGF block that delivered the group's 5th sample
@@ -1191,20 +1240,45 @@ __global__ void __launch_bounds__(DK_THREADS) k_decode(const K3Params p) {
 					emit_frame(p.ring, p.ring_count, p.ring_cap, p.chunk, ctx, row, phase, fr_len, fr_level, ppm, d.start_idx, p.abs_begin + rel);
 				}
 				else if (active && (lane < winner || !valid)) { // already stepped this symbol (or no sample in this slot), then reset
-					d.state = ST_TRAINING; d.position = 0; d.one_seq = 0;
+					in_data = 0;
+					q = 0;
 				}
 				else if (active) { // reset first, then step this symbol from TRAINING/0: only the NRZI memory survives
-					d.level = level_before;
-					d.start_idx = start_before;
-					d.state = ST_TRAINING;
-					d.one_seq = 0;
-					d.position = (Bit != lastBit_before) ? 1 : 0;
+					in_data = 0;
+					level = level_before;
+					start_rel = start_before;
+					q = alt ? 1 : 0;
 				}
 			}
 		}
 		__syncwarp();
 	}
+	if (p.dbg) {
+		const long long dt = clock64() - clk0;
+		for (int o = 16; o > 0; o >>= 1) {
+			n_crc += __shfl_xor_sync(0xffffffffu, n_crc, o);
+			n_crcbits += __shfl_xor_sync(0xffffffffu, n_crcbits, o);
+		}
+		if (lane == 0) {
+			p.dbg[row * 4 + 0] = dt;
+			p.dbg[row * 4 + 1] = n_slow;
+			p.dbg[row * 4 + 2] = n_crc;
+			p.dbg[row * 4 + 3] = n_crcbits;
+		}
+	}
 	if (active) {
+		if (in_data) {
+			d.state = ST_DATAFCS;
+			d.position = pos;
+			d.one_seq = ones;
+			if (pos & 31) ctx.frame[(pos >> 5) * K3_THREADS] = cur; // keep the partial word with the persisted frame
+		}
+		else if (q < 8) { d.state = ST_TRAINING; d.position = q; d.one_seq = 0; }
+		else { d.state = ST_STARTFLAG; d.position = q - 7; d.one_seq = 0; }
+		if (!in_data && q >= 8 && start_rel >= 0) d.start_idx = p.abs_begin + start_rel;
+		d.level = level;
+		d.prev = prev;
+		d.lastBit = lastBit;
 		for (int w = 0; w < DEC_WORDS; w++) p.dec_data[(long long)w * nthr_total + sidx] = ctx.frame[w * K3_THREADS];
 		p.dec[sidx] = d;
 	}
