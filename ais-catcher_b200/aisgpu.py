@@ -16,7 +16,8 @@ TAP_C, TAP_CGF, TAP_FIR, TAP_ROT, TAP_DEC, TAP_FM = 0, 1, 2, 3, 4, 5
 
 EXPORTS = ["aisgpu_abi_version", "aisgpu_default_config", "aisgpu_create", "aisgpu_submit", "aisgpu_submit_device",
            "aisgpu_sync", "aisgpu_poll", "aisgpu_tap", "aisgpu_counters", "aisgpu_cuda_stream",
-           "aisgpu_last_frontend_ms", "aisgpu_frontend_times", "aisgpu_last_launches", "aisgpu_last_error", "aisgpu_destroy"]
+           "aisgpu_last_frontend_ms", "aisgpu_frontend_times", "aisgpu_last_launches", "aisgpu_last_error", "aisgpu_destroy",
+           "aisgpu_validate", "aisgpu_build_nmea", "aisgpu_chunk_granule"]
 
 
 class Config(C.Structure):
@@ -30,7 +31,8 @@ class Config(C.Structure):
 class MsgStruct(C.Structure):
     _fields_ = [("stream", C.c_int32), ("channel", C.c_char), ("nbits", C.c_int32), ("start_idx", C.c_int64),
                 ("end_idx", C.c_int64), ("level", C.c_float), ("ppm", C.c_float), ("chunk", C.c_int64),
-                ("data", C.c_uint8 * 140), ("n_sentences", C.c_int32), ("nmea", (C.c_char * 100) * 4)]
+                ("data", C.c_uint8 * 140), ("n_sentences", C.c_int32), ("nmea", (C.c_char * 100) * 4),
+                ("nmea_len", C.c_int32 * 4)]
 
 
 class Msg:
@@ -46,7 +48,7 @@ class Msg:
         self.ppm = m.ppm
         self.chunk = m.chunk
         self.payload = bytes(m.data[:(m.nbits + 7) // 8])
-        self.nmea = [m.nmea[i].value.decode() for i in range(min(m.n_sentences, 4))]
+        self.nmea = [m.nmea[i].raw[:m.nmea_len[i]].decode("latin-1") for i in range(min(m.n_sentences, 4))]
 
     def key(self):
         return (self.channel, self.nbits, self.payload, tuple(self.nmea))
@@ -84,10 +86,40 @@ def load():
     lib.aisgpu_last_launches.argtypes = [C.c_void_p]
     lib.aisgpu_last_error.argtypes = [C.c_void_p]
     lib.aisgpu_last_error.restype = C.c_char_p
+    lib.aisgpu_chunk_granule.argtypes = [C.POINTER(Config)]
+    lib.aisgpu_validate.argtypes = [C.c_char_p, C.c_int]
+    lib.aisgpu_build_nmea.argtypes = [C.POINTER(MsgStruct), C.c_int, C.POINTER(C.c_int)]
     lib.aisgpu_destroy.argtypes = [C.c_void_p]
     lib.aisgpu_destroy.restype = None
     _lib = lib
     return lib
+
+
+def chunk_granule(sample_rate, model=MODEL_DEFAULT):
+    """Granule (samples) every submit length must be a multiple of; raises with the reference's wording if unsupported."""
+    lib = load()
+    cfg = Config()
+    lib.aisgpu_default_config(C.byref(cfg))
+    cfg.sample_rate, cfg.model = sample_rate, model
+    g = lib.aisgpu_chunk_granule(C.byref(cfg))
+    if g <= 0:
+        raise AisGpuError("rc=%d: %s" % (g, lib.aisgpu_last_error(None).decode()))
+    return g
+
+
+def build_nmea(payload_bytes, nbits, channel="A", own_mmsi=-1, seq=0):
+    """Host-only: (sentences, next seq) for a frame, through aisgpu_build_nmea (reference Message.cpp:569-631)."""
+    lib = load()
+    m = MsgStruct()
+    m.nbits = nbits
+    m.channel = channel.encode()
+    for i, b in enumerate(payload_bytes[:140]):
+        m.data[i] = b
+    s = C.c_int(seq)
+    rc = lib.aisgpu_build_nmea(C.byref(m), own_mmsi, C.byref(s))
+    if rc:
+        raise AisGpuError("aisgpu_build_nmea rc=%d" % rc)
+    return Msg(m).nmea, s.value
 
 
 class AisGpuError(RuntimeError):

@@ -525,17 +525,17 @@ bool msg_validate(const uint8_t *d, int length) { // Message.cpp:398-413
 	return length >= ml[t - 1];
 }
 
-void build_nmea(aisgpu_handle *h, aisgpu_msg &m) { // Message.cpp:569-631
+void build_nmea(aisgpu_msg &m, int own_mmsi, int *seq_counter) { // Message.cpp:569-631
 	static const char hex[] = "0123456789ABCDEF";
 	const uint8_t *data = m.data;
 	const int length = m.nbits;
 	const unsigned mmsi = ((unsigned)data[1] << 22) | (data[2] << 14) | (data[3] << 6) | (data[4] >> 2);
 	int nletters = (length + 5) / 6;
 	int nsent = nletters == 0 ? 1 : (nletters + 55) / 56;
-	char own = (h->cfg.own_mmsi == (int)mmsi) ? 'O' : 'M';
+	char own = (own_mmsi == (int)mmsi) ? 'O' : 'M';
 	char seq = 0;
-	if (nsent > 1) {
-		int &s = h->seq[m.stream];
+	if (nsent > 1) { // Message::nextSeqId (Message.cpp:28-39), one counter per stream instead of per process
+		int &s = *seq_counter;
 		seq = (char)(s + '0');
 		s = (s + 1) % 10;
 	}
@@ -562,6 +562,7 @@ void build_nmea(aisgpu_handle *h, aisgpu_msg &m) { // Message.cpp:569-631
 		p[i++] = hex[(c >> 4) & 0xF];
 		p[i++] = hex[c & 0xF];
 		p[i] = 0;
+		m.nmea_len[s] = i; // a 1064-bit message ends in a NUL letter (Message.cpp:646-647), so strlen() is not enough
 	}
 }
 
@@ -596,7 +597,7 @@ int drain_ring(aisgpu_handle *h) {
 		m.level = lvl;
 		memcpy(m.data, r.data, 140);
 		if (!msg_validate(m.data, m.nbits)) continue; // AIS.cpp:87-93: dropped, siblings were still reset
-		build_nmea(h, m);
+		build_nmea(m, h->cfg.own_mmsi, &h->seq[m.stream]);
 		h->counters[1]++;
 		h->counters[(r.row & 1) ? 6 : 5]++;
 		h->out_queue.push_back(m);
@@ -961,6 +962,31 @@ int aisgpu_frontend_times(aisgpu_handle *h, float *ms_out, int max, int *n) {
 }
 
 int aisgpu_last_launches(aisgpu_handle *h) { return h ? h->last_launches : 0; }
+
+int aisgpu_chunk_granule(const aisgpu_config *cfg) {
+	if (!cfg || cfg->struct_size != sizeof(aisgpu_config)) {
+		g_create_error = "aisgpu_chunk_granule: null argument or struct_size mismatch";
+		return AISGPU_EINVAL;
+	}
+	aisgpu_handle tmp;
+	tmp.cfg = *cfg;
+	if (int rc = plan_frontend(&tmp)) {
+		g_create_error = tmp.err;
+		return rc;
+	}
+	return 1 << (tmp.k + 2);
+}
+
+int aisgpu_validate(const uint8_t *data, int nbits) {
+	if (!data || nbits < 0) return 0;
+	return msg_validate(data, nbits) ? 1 : 0;
+}
+
+int aisgpu_build_nmea(aisgpu_msg *m, int own_mmsi, int *seq) {
+	if (!m || !seq || m->nbits < 0 || m->nbits > 1064 || *seq < 0 || *seq > 9) return AISGPU_EINVAL;
+	build_nmea(*m, own_mmsi, seq);
+	return 0;
+}
 
 void aisgpu_destroy(aisgpu_handle *h) {
 	if (!h) return;

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define AISGPU_ABI_VERSION 1
+#define AISGPU_ABI_VERSION 2
 
 /* model kinds: the reference's "-m" numbers (Source/Application/Receiver.cpp:155-195) */
 #define AISGPU_MODEL_STANDARD 0 /* FM -> FIR37 -> 5-phase deinterleave -> 5 decoders (Model.cpp:484-518) */
@@ -89,6 +89,8 @@ typedef struct aisgpu_msg {
 	uint8_t data[140];          /* Message::data (Message.h:69), payload bytes, MSB-first fields */
 	int32_t n_sentences;        /* Message::sentences().size() */
 	char nmea[4][100];          /* NUL-terminated !AIVDM sentences (Message.cpp:569-631) */
+	int32_t nmea_len[4];        /* their lengths: the last letter of a 1064-bit message is a NUL byte in the reference
+	                               (Message::getLetter returns 0 when the letter crosses bit 1064, Message.cpp:646-647) */
 } aisgpu_msg;
 
 typedef struct aisgpu_handle aisgpu_handle;
@@ -98,6 +100,11 @@ void aisgpu_default_config(aisgpu_config *cfg);
 
 /* == AIS::Model::buildModel(CH1, CH2, sample_rate, timerOn, device) (Model.h:94, Model.cpp:27,520). */
 int aisgpu_create(const aisgpu_config *cfg, aisgpu_handle **out);
+
+/* Checks the rate -> chain table of ModelFrontend::buildModel (Model.cpp:109-338) without touching the GPU and returns
+ * the granule every n_samples passed to aisgpu_submit must be a multiple of (> 0), or AISGPU_EINVAL with the
+ * reference's wording in aisgpu_last_error(NULL). */
+int aisgpu_chunk_granule(const aisgpu_config *cfg);
 
 /* == StreamIn<RAW>::Receive(const RAW*, 1, TAG&) for every stream of the batch (Stream.h:41; Model.cpp:33).
  * host_samples: n_streams contiguous runs of n_samples samples (stream-major), borrowed for the call only
@@ -135,6 +142,15 @@ int aisgpu_frontend_times(aisgpu_handle *h, float *ms_out, int max, int *n);
 
 /* Number of kernels launched by the last submit. */
 int aisgpu_last_launches(aisgpu_handle *h);
+
+/* Host-only pieces of the per-frame tail of AIS::Decoder::processData (AIS.cpp:66-96), exported so that they can be
+ * checked without a GPU:
+ *   aisgpu_validate   == AIS::Message::validate (Message.cpp:398-413): 1 if the frame would be published.
+ *   aisgpu_build_nmea == AIS::Message::buildNMEA (Message.cpp:569-631): fills n_sentences / nmea / nmea_len of *m from
+ *                        m->data, m->nbits, m->channel.  *seq (0..9) is the multi-sentence sequence id and is advanced
+ *                        exactly like Message::nextSeqId (Message.cpp:28-39). */
+int aisgpu_validate(const uint8_t *data, int nbits);
+int aisgpu_build_nmea(aisgpu_msg *m, int own_mmsi, int *seq);
 
 const char *aisgpu_last_error(aisgpu_handle *h); /* h may be NULL: error of the last failed aisgpu_create */
 
