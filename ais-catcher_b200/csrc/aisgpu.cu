@@ -62,6 +62,7 @@ struct aisgpu_handle {
 	float fdc_alpha = 0, fdc_beta = 1;
 	int rows = 0;
 	int max_n48 = 0;
+	int fe_warps = 4, fe_tile = 0, fe_ctas = 8192; // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
 	// for timing).  The front end of submit c+1 overlaps the back end of submit c; Cbuf is double buffered for that.
 	cudaStream_t stream = nullptr, copy_stream = nullptr, fe_stream = nullptr;
@@ -218,15 +219,34 @@ void layout_frontend(aisgpu_handle *h, int tile) {
 	h->tile = tile;
 }
 
+template <int FMT, int NW>
+int launch_fe(aisgpu_handle *h, dim3 grid, size_t smem) {
+	CU(cudaFuncSetAttribute(k_frontend<FMT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_frontend<FMT, NW><<<grid, NW * 32, smem, h->fe_stream>>>(h->fe);
+	CU(cudaGetLastError());
+	return 0;
+}
+
+template <int FMT>
+int launch_fe_nw(aisgpu_handle *h, dim3 grid, size_t smem) {
+	switch (h->fe_warps) {
+	case 1: return launch_fe<FMT, 1>(h, grid, smem);
+	case 2: return launch_fe<FMT, 2>(h, grid, smem);
+	case 8: return launch_fe<FMT, 8>(h, grid, smem);
+	default: return launch_fe<FMT, 4>(h, grid, smem);
+	}
+}
+
 int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int N) {
 	FeParams &p = h->fe;
 	const int q = 1 << (h->k + 2);
-	int tile = 1280; // per-warp tile: 4 runs of 5 outputs per lane at the first CIC stage
+	// per-CTA tile: one run of 5 outputs per thread at the first CIC stage (2 x 5 x threads input samples)
+	int tile = h->fe_tile > 0 ? h->fe_tile : 320 * h->fe_warps;
 	if (tile % q) tile = (tile / q + 1) * q;
 	if (tile > N) tile = N;
 	if (tile != p.tile) layout_frontend(h, tile);
 	const int B = h->cfg.n_streams;
-	int n_seg = (8192 + B - 1) / B; // ~9 waves of warps on 148 SMs x 6 resident warps
+	int n_seg = (h->fe_ctas + B - 1) / B; // enough CTAs for several waves over 148 SMs
 	int tiles_total = (N + tile - 1) / tile;
 	if (n_seg > tiles_total) n_seg = tiles_total;
 	if (n_seg < 1) n_seg = 1;
@@ -250,25 +270,11 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 	const size_t smem = (size_t)p.smem_f2 * sizeof(float2);
 	dim3 grid(n_seg, B);
 	switch (h->cfg.format) {
-	case AISGPU_FMT_CF32:
-		CU(cudaFuncSetAttribute(k_frontend<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		k_frontend<0><<<grid, FE_THREADS, smem, h->fe_stream>>>(p);
-		break;
-	case AISGPU_FMT_CU8:
-		CU(cudaFuncSetAttribute(k_frontend<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		k_frontend<1><<<grid, FE_THREADS, smem, h->fe_stream>>>(p);
-		break;
-	case AISGPU_FMT_CS8:
-		CU(cudaFuncSetAttribute(k_frontend<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		k_frontend<2><<<grid, FE_THREADS, smem, h->fe_stream>>>(p);
-		break;
-	default:
-		CU(cudaFuncSetAttribute(k_frontend<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		k_frontend<3><<<grid, FE_THREADS, smem, h->fe_stream>>>(p);
-		break;
+	case AISGPU_FMT_CF32: return launch_fe_nw<0>(h, grid, smem);
+	case AISGPU_FMT_CU8: return launch_fe_nw<1>(h, grid, smem);
+	case AISGPU_FMT_CS8: return launch_fe_nw<2>(h, grid, smem);
+	default: return launch_fe_nw<3>(h, grid, smem);
 	}
-	CU(cudaGetLastError());
-	return 0;
 }
 
 template <typename T>
@@ -645,6 +651,10 @@ static int create_impl(aisgpu_handle *h) {
 		return AISGPU_EINVAL;
 	}
 	if (int rc = plan_frontend(h)) return rc;
+	if (const char *e = getenv("AISGPU_FE_WARPS")) h->fe_warps = atoi(e);
+	if (h->fe_warps != 1 && h->fe_warps != 2 && h->fe_warps != 8) h->fe_warps = 4;
+	if (const char *e = getenv("AISGPU_FE_TILE")) h->fe_tile = atoi(e);
+	if (const char *e = getenv("AISGPU_FE_CTAS")) h->fe_ctas = std::max(1, atoi(e));
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
 		h->err = "no CUDA device (the B200 path has no CPU fallback)";

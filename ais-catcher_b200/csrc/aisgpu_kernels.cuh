@@ -153,7 +153,6 @@ __global__ void k_rot_table(float2 *__restrict__ tab, const float2 *__restrict__
 // stage's history is exact because each CIC stage is a pure function of its last 6 inputs
 // (u_{s+1}[n] = fl(u_s[n] + u_s[n-1]), y[j] = u_5[2j]/32).
 // ---------------------------------------------------------------------------------------------
-constexpr int FE_THREADS = 32; // one warp per CTA, one CTA per (segment, stream)
 constexpr int FE_HIST = 6;   // >= 5, even so that even sample indices stay 16-byte aligned
 constexpr int FE_SLACK = 12; // over-read room behind each array for partial runs
 constexpr int FE_MAXK = 7;
@@ -255,7 +254,7 @@ __device__ __forceinline__ void ds2_run(float2 *__restrict__ sm, int in_off, int
 
 // R consecutive outputs of FilterCIC5 (no decimation) from R+5 inputs: 5R+10 complex adds; straight to HBM.
 template <int R>
-__device__ __forceinline__ void fcic_run(const float2 *__restrict__ sm, int in_off, float2 *__restrict__ out, int m0, int n_out) {
+__device__ __forceinline__ void fcic_run(const float2 *__restrict__ sm, int in_off, float2 *__restrict__ out, int m0, int m_lo, int n_out) {
 	c64 v[R + 5];
 	const c64 *p = reinterpret_cast<const c64 *>(sm + in_off + m0 - 5);
 #pragma unroll
@@ -269,7 +268,7 @@ __device__ __forceinline__ void fcic_run(const float2 *__restrict__ sm, int in_o
 	c64 *o = reinterpret_cast<c64 *>(out);
 #pragma unroll
 	for (int q = 0; q < R; q++)
-		if (m0 + q < n_out) o[m0 + q] = pmul(v[5 + q], sc);
+		if (m0 + q >= m_lo && m0 + q < n_out) o[m0 + q] = pmul(v[5 + q], sc);
 }
 
 // ---- mbarrier + 1-D bulk async copy (TMA, SASS UBLKCP): global -> shared without touching registers ----
@@ -297,59 +296,70 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsig
 				 : "memory");
 }
 
-// Work list of one segment: tile t covers input samples [pos, pos+len) (relative to the submit's first sample).
-__device__ __forceinline__ void fe_tile_of(const FeParams &p, long long seg_start, long long seg_end, int t, int n_warm, long long &pos, int &len,
-										   bool &warm) {
-	if (t < n_warm) {
-		pos = seg_start - p.P + (long long)t * p.tile;
-		len = (int)min((long long)p.tile, seg_start - pos);
-		warm = true;
-	}
-	else {
-		pos = seg_start + (long long)(t - n_warm) * p.tile;
-		len = (int)min((long long)p.tile, seg_end - pos);
-		warm = false;
+// One CTA of NW warps owns (segment, stream) and walks [seg_start - P, seg_end) in tiles of p.tile input samples,
+// starting from zero history: after P >= h_k samples every stage's history is exact, so only 48 kHz outputs that
+// belong to [seg_start, seg_end) are written.  Thread 0 keeps a two-deep ring of bulk async copies (input tile + its
+// Rotate phasors) in flight; all threads then run the stages of the tile back to back out of the CTA's shared-memory
+// arrays ([HIST history | tile] each).  The arrays of one CTA serve NW warps, so the shared-memory footprint per
+// resident warp -- what capped the one-warp version at 6 warps per SM -- drops NW-fold; the deeper (shorter) stages
+// simply occupy fewer warps.  After the barrier that ends a stage, three threads move the last HIST inputs of that
+// stage to the front of the array the next tile will read (the reference's h0..h4 / h1,h2 carried state).
+template <int NW>
+__device__ __forceinline__ void fe_sync() {
+	if (NW == 1) __syncwarp();
+	else __syncthreads();
+}
+
+// history for the next tile: dst[-HIST .. 0) = src[n - HIST .. n); n even, may be < HIST (then part of the old history
+// moves up).  One warp instruction loads all six entries before any is stored, so src == dst is fine.
+template <int NW>
+__device__ __forceinline__ void fe_carry(float2 *__restrict__ sm, int src_off, int dst_off, int n, int tid) {
+	constexpr int T0 = (NW - 1) * 32; // the last warp: it has the least work in the short stages
+	if (tid >= T0 && tid < T0 + FE_HIST / 2) {
+		const int e = 2 * (tid - T0);
+		const float4 v = *reinterpret_cast<const float4 *>(sm + src_off + n - FE_HIST + e);
+		*reinterpret_cast<float4 *>(sm + dst_off - FE_HIST + e) = v;
 	}
 }
 
-// One WARP owns (segment, stream): no block-wide barriers anywhere.  Lane 0 keeps a two-deep ring of bulk
-// async copies (input tile + its Rotate phasors) in flight; all 32 lanes then run the stages of the tile back to
-// back out of the warp's private shared-memory arrays, separated only by __syncwarp().
-template <int FMT>
-__global__ void __launch_bounds__(FE_THREADS) k_frontend(const FeParams p) {
+template <int FMT, int NW>
+__global__ void __launch_bounds__(NW * 32) k_frontend(const FeParams p) {
+	constexpr int NT = NW * 32;
 	extern __shared__ __align__(16) float2 sm[];
 	__shared__ __align__(8) uint64_t mbar[2];
-	const int lane = threadIdx.x;
+	const int tid = threadIdx.x;
 	const int stream = blockIdx.y;
 	const int k = p.k;
 	const long long seg_start = (long long)blockIdx.x * p.seg_len;
 	if (seg_start >= p.N) return;
-	const long long seg_end = min((long long)p.N, seg_start + p.seg_len);
-	const int n_warm = (p.P + p.tile - 1) / p.tile;
-	const int n_tiles = n_warm + (int)((seg_end - seg_start + p.tile - 1) / p.tile);
-	const int P96 = p.P >> k;
+	const int seg_n = (int)min((long long)p.seg_len, (long long)p.N - seg_start); // samples of this segment
+	const int span = seg_n + p.P;                                                  // samples walked, warm-up included
+	const int n_tiles = (span + p.tile - 1) / p.tile;
+	const long long base = seg_start - p.P; // first sample walked, relative to the submit (negative: previous submit's tail)
+	const float2 *rot_g = p.rot + (p.P >> k) + (base >> k);
+	float2 *Cg = p.C + (long long)(stream * 2) * p.c_stride + p.c_off + (base >> (k + 1));
+	const int m_first = p.P >> (k + 1); // first 48 kHz output (relative to base) that belongs to the segment
 
-	// zero only what acts as history or may be read before written (whole array is small enough to clear)
-	for (int i = lane; i < p.smem_f2; i += 32) sm[i] = make_float2(0.f, 0.f);
-	if (lane == 0) {
+	// zero what acts as history or may be read before written (the whole array is small enough to clear)
+	for (int i = tid; i < p.smem_f2; i += NT) sm[i] = make_float2(0.f, 0.f);
+	if (tid == 0) {
 		mbar_init(&mbar[0], 1);
 		mbar_init(&mbar[1], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	__syncwarp();
+	fe_sync<NW>();
 
 	auto issue = [&](int t) {
-		long long pos;
-		int len;
-		bool warm;
-		fe_tile_of(p, seg_start, seg_end, t, n_warm, pos, len, warm);
+		const int rel = t * p.tile;
+		const int len = min(p.tile, span - rel);
 		const int b = t & 1;
 		const int n96 = len >> k;
 		unsigned bytes = (unsigned)n96 * 8u;
 		if (FMT == 0) bytes += (unsigned)len * 8u;
 		mbar_expect_tx(&mbar[b], bytes);
-		bulk_g2s(sm + p.off_rot[b], p.rot + (pos >> k) + P96, (unsigned)n96 * 8u, &mbar[b]);
+		bulk_g2s(sm + p.off_rot[b], rot_g + (rel >> k), (unsigned)n96 * 8u, &mbar[b]);
 		if (FMT == 0) {
+			const long long pos = base + rel;
 			float2 *dst = sm + p.off_in[b] + FE_HIST;
 			const float2 *in = reinterpret_cast<const float2 *>(p.in) + (long long)stream * p.in_stride;
 			const float2 *tl = reinterpret_cast<const float2 *>(p.tail) + (long long)stream * p.P + p.P;
@@ -362,42 +372,43 @@ __global__ void __launch_bounds__(FE_THREADS) k_frontend(const FeParams p) {
 			}
 		}
 	};
-	if (lane == 0) issue(0);
+	if (tid == 0) issue(0);
 
 	const int off_up = p.off_up + FE_HIST, off_dn = p.off_dn + FE_HIST, off_wa = p.off_wa + FE_HIST, off_wb = p.off_wb + FE_HIST;
 	for (int t = 0; t < n_tiles; t++) {
-		long long pos;
-		int len;
-		bool warm;
-		fe_tile_of(p, seg_start, seg_end, t, n_warm, pos, len, warm);
+		const int rel = t * p.tile;
+		const int len = min(p.tile, span - rel);
 		const int b = t & 1;
-		if (lane == 0 && t + 1 < n_tiles) issue(t + 1); // ring slot b^1 was released by the __syncwarp closing tile t-1
+		if (tid == 0 && t + 1 < n_tiles) issue(t + 1); // ring slot b^1 was released by the barriers of tile t-1
 		const int off_in = (b ? p.off_in[1] : p.off_in[0]) + FE_HIST;
+		const int off_in_next = (b ? p.off_in[0] : p.off_in[1]) + FE_HIST;
 		if (FMT != 0) { // integer formats: convert while loading (registers), no bulk copy
+			const long long pos = base + rel;
 			const long long tbase = (long long)stream * p.P + p.P + pos;
 			const long long ibase = (long long)stream * p.in_stride + pos;
-			for (int i = lane * 2; i < len; i += 64) {
+			for (int i = tid * 2; i < len; i += 2 * NT) {
 				float2 x, y;
 				if (pos + i < 0) fe_load_pair<FMT>(p.tail, tbase + i, x, y);
 				else fe_load_pair<FMT>(p.in, ibase + i, x, y);
 				*reinterpret_cast<float4 *>(sm + off_in + i) = make_float4(x.x, x.y, y.x, y.y);
 			}
-			__syncwarp();
+			fe_sync<NW>();
 		}
 		mbar_wait(&mbar[b], (unsigned)((t >> 1) & 1));
 		// ---- k cascaded Downsample2CIC5 at the input rate ----
-		int src = off_in;
+		int src = off_in, src_next = off_in_next;
 		for (int l = 0; l < k; l++) {
 			const int dst = p.off_lv[l + 1] + FE_HIST;
 			const int n_out = len >> (l + 1);
-			for (int j0 = lane * 5; j0 < n_out; j0 += 160) ds2_run<5>(sm, src, dst, j0);
-			__syncwarp();
-			src = dst;
+			for (int j0 = tid * 5; j0 < n_out; j0 += 5 * NT) ds2_run<5>(sm, src, dst, j0);
+			fe_sync<NW>();
+			fe_carry<NW>(sm, src, src_next, 2 * n_out, tid);
+			src = src_next = dst;
 		}
 		// ---- FilterComplex3Tap + Rotate at 96 kHz ----
 		const int n96 = len >> k;
 		const int off_rt = b ? p.off_rot[1] : p.off_rot[0];
-		for (int i = lane; i < n96; i += 32) {
+		for (int i = tid; i < n96; i += NT) {
 			float2 x = sm[src + i];
 			if (p.use_fdc) { // alpha * (h1 + data[i]) + h2 * beta
 				const float2 tt = cadd(sm[src + i - 2], x);
@@ -410,54 +421,30 @@ __global__ void __launch_bounds__(FE_THREADS) k_frontend(const FeParams p) {
 			sm[off_up + i] = make_float2(__fsub_rn(RR, II), __fadd_rn(IR, RI));
 			sm[off_dn + i] = make_float2(__fadd_rn(RR, II), __fsub_rn(IR, RI));
 		}
-		__syncwarp();
+		fe_sync<NW>();
+		fe_carry<NW>(sm, src, src_next, n96, tid);
 		// ---- per channel Downsample2CIC5 96k -> 48k ----
 		const int n48 = n96 >> 1;
 		const int runs = (n48 + 4) / 5;
-		for (int r = lane; r < 2 * runs; r += 32) {
-			if (r < runs) ds2_run<5>(sm, off_up, off_wa, r * 5);
-			else ds2_run<5>(sm, off_dn, off_wb, (r - runs) * 5);
+		for (int r = tid; r < 2 * runs; r += NT) {
+			const int ch = r >= runs;
+			ds2_run<5>(sm, ch ? off_dn : off_up, ch ? off_wb : off_wa, (ch ? r - runs : r) * 5);
 		}
-		__syncwarp();
+		fe_sync<NW>();
+		fe_carry<NW>(sm, off_up, off_up, n96, tid);
+		fe_carry<NW>(sm, off_dn, off_dn, n96, tid);
 		// ---- per channel FilterCIC5 at 48k, straight to HBM ----
-		if (!warm) {
-			const long long m0 = pos >> (k + 1);
-			for (int r = lane; r < 2 * runs; r += 32) {
+		const int m_rel = rel >> (k + 1); // 48 kHz index of the tile's first output, relative to base
+		if (m_rel + n48 > m_first) {
+			const int m_lo = m_first - m_rel; // outputs before it are warm-up
+			for (int r = tid; r < 2 * runs; r += NT) {
 				const int ch = r >= runs;
-				const int mm = (ch ? r - runs : r) * 5;
-				fcic_run<5>(sm, ch ? off_wb : off_wa, p.C + (long long)(stream * 2 + ch) * p.c_stride + p.c_off + m0, mm, n48);
+				fcic_run<5>(sm, ch ? off_wb : off_wa, Cg + (ch ? p.c_stride : 0) + m_rel, (ch ? r - runs : r) * 5, m_lo, n48);
 			}
 		}
-		__syncwarp();
-		// ---- carry the last HIST entries of every stage array to the front of the array the next tile reads ----
-		{
-			// arrays: 0 = input ring (this slot -> other slot), 1..k = levels, then up, dn, wa, wb
-			const int narr = k + 5;
-			float2 val[3];
-			int dsti[3];
-#pragma unroll
-			for (int it = 0; it < 3; it++) {
-				const int item = lane + 32 * it;
-				const int a = item / FE_HIST, e = item - a * FE_HIST;
-				dsti[it] = -1;
-				if (a < narr) {
-					int so, dof, n;
-					if (a == 0) { so = b ? p.off_in[1] : p.off_in[0]; dof = b ? p.off_in[0] : p.off_in[1]; n = len; }
-					else if (a <= k) { so = dof = p.off_lv[a]; n = len >> a; }
-					else if (a == k + 1) { so = dof = p.off_up; n = n96; }
-					else if (a == k + 2) { so = dof = p.off_dn; n = n96; }
-					else if (a == k + 3) { so = dof = p.off_wa; n = n48; }
-					else { so = dof = p.off_wb; n = n48; }
-					val[it] = sm[so + n + e];
-					dsti[it] = dof + e;
-				}
-			}
-			__syncwarp();
-#pragma unroll
-			for (int it = 0; it < 3; it++)
-				if (dsti[it] >= 0) sm[dsti[it]] = val[it];
-		}
-		__syncwarp();
+		fe_sync<NW>();
+		fe_carry<NW>(sm, off_wa, off_wa, n48, tid);
+		fe_carry<NW>(sm, off_wb, off_wb, n48, tid);
 	}
 }
 
