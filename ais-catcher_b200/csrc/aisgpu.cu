@@ -62,7 +62,7 @@ struct aisgpu_handle {
 	float fdc_alpha = 0, fdc_beta = 1;
 	int rows = 0;
 	int max_n48 = 0;
-	int fe_warps = 4, fe_tile = 0, fe_ctas = 8192; // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
+	int fe_warps = 4, fe_tile = 0, fe_ctas = 4096; // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
 	// for timing).  The front end of submit c+1 overlaps the back end of submit c; Cbuf is double buffered for that.
 	cudaStream_t stream = nullptr, copy_stream = nullptr, fe_stream = nullptr;
@@ -219,22 +219,38 @@ void layout_frontend(aisgpu_handle *h, int tile) {
 	h->tile = tile;
 }
 
-template <int FMT, int NW>
+template <int FMT, int NW, int K>
 int launch_fe(aisgpu_handle *h, dim3 grid, size_t smem) {
-	CU(cudaFuncSetAttribute(k_frontend<FMT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	k_frontend<FMT, NW><<<grid, NW * 32, smem, h->fe_stream>>>(h->fe);
+	CU(cudaFuncSetAttribute(k_frontend<FMT, NW, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_frontend<FMT, NW, K><<<grid, NW * 32, smem, h->fe_stream>>>(h->fe);
 	CU(cudaGetLastError());
 	return 0;
 }
 
+template <int FMT, int NW>
+int launch_fe_k(aisgpu_handle *h, dim3 grid, size_t smem) {
+	switch (h->k) {
+	case 0: return launch_fe<FMT, NW, 0>(h, grid, smem);
+	case 1: return launch_fe<FMT, NW, 1>(h, grid, smem);
+	case 2: return launch_fe<FMT, NW, 2>(h, grid, smem);
+	case 3: return launch_fe<FMT, NW, 3>(h, grid, smem);
+	case 4: return launch_fe<FMT, NW, 4>(h, grid, smem);
+	case 5: return launch_fe<FMT, NW, 5>(h, grid, smem);
+	case 6: return launch_fe<FMT, NW, 6>(h, grid, smem);
+	default: return launch_fe<FMT, NW, 7>(h, grid, smem);
+	}
+}
+
 template <int FMT>
 int launch_fe_nw(aisgpu_handle *h, dim3 grid, size_t smem) {
+#ifdef AISGPU_FE_ALL_WARP_COUNTS
 	switch (h->fe_warps) {
-	case 1: return launch_fe<FMT, 1>(h, grid, smem);
-	case 2: return launch_fe<FMT, 2>(h, grid, smem);
-	case 8: return launch_fe<FMT, 8>(h, grid, smem);
-	default: return launch_fe<FMT, 4>(h, grid, smem);
+	case 2: return launch_fe_k<FMT, 2>(h, grid, smem);
+	case 8: return launch_fe_k<FMT, 8>(h, grid, smem);
+	default: break;
 	}
+#endif
+	return launch_fe_k<FMT, 4>(h, grid, smem);
 }
 
 int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int N) {
@@ -652,7 +668,11 @@ static int create_impl(aisgpu_handle *h) {
 	}
 	if (int rc = plan_frontend(h)) return rc;
 	if (const char *e = getenv("AISGPU_FE_WARPS")) h->fe_warps = atoi(e);
-	if (h->fe_warps != 1 && h->fe_warps != 2 && h->fe_warps != 8) h->fe_warps = 4;
+#ifdef AISGPU_FE_ALL_WARP_COUNTS
+	if (h->fe_warps != 2 && h->fe_warps != 8) h->fe_warps = 4;
+#else
+	h->fe_warps = 4;
+#endif
 	if (const char *e = getenv("AISGPU_FE_TILE")) h->fe_tile = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_CTAS")) h->fe_ctas = std::max(1, atoi(e));
 	int ndev = 0;

@@ -310,35 +310,38 @@ __device__ __forceinline__ void fe_sync() {
 	else __syncthreads();
 }
 
-// history for the next tile: dst[-HIST .. 0) = src[n - HIST .. n); n even, may be < HIST (then part of the old history
-// moves up).  One warp instruction loads all six entries before any is stored, so src == dst is fine.
-template <int NW>
-__device__ __forceinline__ void fe_carry(float2 *__restrict__ sm, int src_off, int dst_off, int n, int tid) {
-	constexpr int T0 = (NW - 1) * 32; // the last warp: it has the least work in the short stages
-	if (tid >= T0 && tid < T0 + FE_HIST / 2) {
-		const int e = 2 * (tid - T0);
-		const float4 v = *reinterpret_cast<const float4 *>(sm + src_off + n - FE_HIST + e);
-		*reinterpret_cast<float4 *>(sm + dst_off - FE_HIST + e) = v;
+// History for the next tile: dst[-HIST .. 0) = src[n - HIST .. n) for a group of stage arrays, n = len >> shift (even;
+// when n < HIST part of the old history moves up -- one warp instruction loads all entries before any is stored).
+// Array descriptors (src offset, dst offset, shift) sit in shared memory; three threads of warp 0 serve one array.
+struct FeCarryDesc { int src, dst, shift, pad; };
+__device__ __forceinline__ void fe_carry_group(float2 *__restrict__ sm, const FeCarryDesc *__restrict__ desc, int first, int count, int len, int tid) {
+	if (tid < 3 * count) {
+		const int a = tid / 3, e = 2 * (tid - 3 * a);
+		const FeCarryDesc d = desc[first + a];
+		const int n = len >> d.shift;
+		const float4 v = *reinterpret_cast<const float4 *>(sm + d.src + n - FE_HIST + e);
+		*reinterpret_cast<float4 *>(sm + d.dst - FE_HIST + e) = v;
 	}
 }
 
-template <int FMT, int NW>
+template <int FMT, int NW, int K>
 __global__ void __launch_bounds__(NW * 32) k_frontend(const FeParams p) {
 	constexpr int NT = NW * 32;
 	extern __shared__ __align__(16) float2 sm[];
 	__shared__ __align__(8) uint64_t mbar[2];
+	__shared__ FeCarryDesc cdesc[2][FE_MAXK + 6]; // [parity of the tile][array]: input ring, levels 1..K, up, dn | wa, wb
 	const int tid = threadIdx.x;
 	const int stream = blockIdx.y;
-	const int k = p.k;
 	const long long seg_start = (long long)blockIdx.x * p.seg_len;
 	if (seg_start >= p.N) return;
 	const int seg_n = (int)min((long long)p.seg_len, (long long)p.N - seg_start); // samples of this segment
 	const int span = seg_n + p.P;                                                  // samples walked, warm-up included
 	const int n_tiles = (span + p.tile - 1) / p.tile;
 	const long long base = seg_start - p.P; // first sample walked, relative to the submit (negative: previous submit's tail)
-	const float2 *rot_g = p.rot + (p.P >> k) + (base >> k);
-	float2 *Cg = p.C + (long long)(stream * 2) * p.c_stride + p.c_off + (base >> (k + 1));
-	const int m_first = p.P >> (k + 1); // first 48 kHz output (relative to base) that belongs to the segment
+	const float2 *rot_g = p.rot + (p.P >> K) + (base >> K);
+	float2 *Cg = p.C + (long long)(stream * 2) * p.c_stride + p.c_off + (base >> (K + 1));
+	const int m_first = p.P >> (K + 1); // first 48 kHz output (relative to base) that belongs to the segment
+	const int off_up = p.off_up + FE_HIST, off_dn = p.off_dn + FE_HIST, off_wa = p.off_wa + FE_HIST, off_wb = p.off_wb + FE_HIST;
 
 	// zero what acts as history or may be read before written (the whole array is small enough to clear)
 	for (int i = tid; i < p.smem_f2; i += NT) sm[i] = make_float2(0.f, 0.f);
@@ -347,17 +350,29 @@ __global__ void __launch_bounds__(NW * 32) k_frontend(const FeParams p) {
 		mbar_init(&mbar[1], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
+	if (tid < 2 * (K + 5)) {
+		const int par = tid / (K + 5), a = tid - par * (K + 5);
+		FeCarryDesc d;
+		d.pad = 0;
+		if (a == 0) { d.src = p.off_in[par] + FE_HIST; d.dst = p.off_in[par ^ 1] + FE_HIST; d.shift = 0; }
+		else if (a <= K) { d.src = d.dst = p.off_lv[a] + FE_HIST; d.shift = a; }
+		else if (a == K + 1) { d.src = d.dst = off_up; d.shift = K; }
+		else if (a == K + 2) { d.src = d.dst = off_dn; d.shift = K; }
+		else if (a == K + 3) { d.src = d.dst = off_wa; d.shift = K + 1; }
+		else { d.src = d.dst = off_wb; d.shift = K + 1; }
+		cdesc[par][a] = d;
+	}
 	fe_sync<NW>();
 
 	auto issue = [&](int t) {
 		const int rel = t * p.tile;
 		const int len = min(p.tile, span - rel);
 		const int b = t & 1;
-		const int n96 = len >> k;
+		const int n96 = len >> K;
 		unsigned bytes = (unsigned)n96 * 8u;
 		if (FMT == 0) bytes += (unsigned)len * 8u;
 		mbar_expect_tx(&mbar[b], bytes);
-		bulk_g2s(sm + p.off_rot[b], rot_g + (rel >> k), (unsigned)n96 * 8u, &mbar[b]);
+		bulk_g2s(sm + p.off_rot[b], rot_g + (rel >> K), (unsigned)n96 * 8u, &mbar[b]);
 		if (FMT == 0) {
 			const long long pos = base + rel;
 			float2 *dst = sm + p.off_in[b] + FE_HIST;
@@ -374,14 +389,12 @@ __global__ void __launch_bounds__(NW * 32) k_frontend(const FeParams p) {
 	};
 	if (tid == 0) issue(0);
 
-	const int off_up = p.off_up + FE_HIST, off_dn = p.off_dn + FE_HIST, off_wa = p.off_wa + FE_HIST, off_wb = p.off_wb + FE_HIST;
 	for (int t = 0; t < n_tiles; t++) {
 		const int rel = t * p.tile;
 		const int len = min(p.tile, span - rel);
 		const int b = t & 1;
 		if (tid == 0 && t + 1 < n_tiles) issue(t + 1); // ring slot b^1 was released by the barriers of tile t-1
 		const int off_in = (b ? p.off_in[1] : p.off_in[0]) + FE_HIST;
-		const int off_in_next = (b ? p.off_in[0] : p.off_in[1]) + FE_HIST;
 		if (FMT != 0) { // integer formats: convert while loading (registers), no bulk copy
 			const long long pos = base + rel;
 			const long long tbase = (long long)stream * p.P + p.P + pos;
@@ -395,18 +408,19 @@ __global__ void __launch_bounds__(NW * 32) k_frontend(const FeParams p) {
 			fe_sync<NW>();
 		}
 		mbar_wait(&mbar[b], (unsigned)((t >> 1) & 1));
-		// ---- k cascaded Downsample2CIC5 at the input rate ----
-		int src = off_in, src_next = off_in_next;
-		for (int l = 0; l < k; l++) {
+		// ---- K cascaded Downsample2CIC5 at the input rate ----
+		int src = off_in;
+#pragma unroll
+		for (int l = 0; l < K; l++) {
 			const int dst = p.off_lv[l + 1] + FE_HIST;
 			const int n_out = len >> (l + 1);
 			for (int j0 = tid * 5; j0 < n_out; j0 += 5 * NT) ds2_run<5>(sm, src, dst, j0);
 			fe_sync<NW>();
-			fe_carry<NW>(sm, src, src_next, 2 * n_out, tid);
-			src = src_next = dst;
+			if (l == 0) fe_carry_group(sm, cdesc[b], K + 3, 2, p.tile, tid); // wa, wb of the previous (always full) tile; its FilterCIC5 pass is two barriers back
+			src = dst;
 		}
 		// ---- FilterComplex3Tap + Rotate at 96 kHz ----
-		const int n96 = len >> k;
+		const int n96 = len >> K;
 		const int off_rt = b ? p.off_rot[1] : p.off_rot[0];
 		for (int i = tid; i < n96; i += NT) {
 			float2 x = sm[src + i];
@@ -422,19 +436,20 @@ __global__ void __launch_bounds__(NW * 32) k_frontend(const FeParams p) {
 			sm[off_dn + i] = make_float2(__fadd_rn(RR, II), __fsub_rn(IR, RI));
 		}
 		fe_sync<NW>();
-		fe_carry<NW>(sm, src, src_next, n96, tid);
+		if (K == 0) fe_carry_group(sm, cdesc[b], K + 3, 2, p.tile, tid);
 		// ---- per channel Downsample2CIC5 96k -> 48k ----
 		const int n48 = n96 >> 1;
 		const int runs = (n48 + 4) / 5;
+		if (K == 0) fe_sync<NW>(); // the wa/wb history move above reads what this pass overwrites
 		for (int r = tid; r < 2 * runs; r += NT) {
 			const int ch = r >= runs;
 			ds2_run<5>(sm, ch ? off_dn : off_up, ch ? off_wb : off_wa, (ch ? r - runs : r) * 5);
 		}
 		fe_sync<NW>();
-		fe_carry<NW>(sm, off_up, off_up, n96, tid);
-		fe_carry<NW>(sm, off_dn, off_dn, n96, tid);
+		// every stage that reads the input ring, the level arrays, up and dn has run: move their histories
+		fe_carry_group(sm, cdesc[b], 0, K + 3, len, tid);
 		// ---- per channel FilterCIC5 at 48k, straight to HBM ----
-		const int m_rel = rel >> (k + 1); // 48 kHz index of the tile's first output, relative to base
+		const int m_rel = rel >> (K + 1); // 48 kHz index of the tile's first output, relative to base
 		if (m_rel + n48 > m_first) {
 			const int m_lo = m_first - m_rel; // outputs before it are warm-up
 			for (int r = tid; r < 2 * runs; r += NT) {
@@ -443,8 +458,6 @@ __global__ void __launch_bounds__(NW * 32) k_frontend(const FeParams p) {
 			}
 		}
 		fe_sync<NW>();
-		fe_carry<NW>(sm, off_wa, off_wa, n48, tid);
-		fe_carry<NW>(sm, off_wb, off_wb, n48, tid);
 	}
 }
 
