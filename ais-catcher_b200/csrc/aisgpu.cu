@@ -62,7 +62,8 @@ struct aisgpu_handle {
 	float fdc_alpha = 0, fdc_beta = 1;
 	int rows = 0;
 	int max_n48 = 0;
-	int fe_warps = 4, fe_tile = 0, fe_ctas = 4096; // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
+	int fe_warps = 4, fe_tile = 0, fe_ctas = 4096;
+	int dec_rpw = 6; // rows per warp in the event-driven decoder kernel // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
 	// for timing).  The front end of submit c+1 overlaps the back end of submit c; Cbuf is double buffered for that.
 	cudaStream_t stream = nullptr, copy_stream = nullptr, fe_stream = nullptr;
@@ -311,6 +312,34 @@ int carry2(aisgpu_handle *h, const T *src, T *dst, long long stride, int src_beg
 	return 0;
 }
 
+// Five AIS::Decoder instances per row.  dec_rpw rows share a warp in the event-driven kernel (AISGPU_DEC_RPW = 1, 3, 6);
+// AISGPU_DEC_RPW=0 selects the plain bit-serial kernel (one row per warp), kept as the in-tree cross-check.
+template <int MODEL>
+int launch_decode(aisgpu_handle *h, const K3Params &p) {
+	const bool taps = MODEL == 0 && p.tap_dec;
+	if (h->dec_rpw == 0) {
+		const int grid = (h->rows + DK_THREADS / 32 - 1) / (DK_THREADS / 32);
+		if (taps) k_decode<MODEL, true><<<grid, DK_THREADS, 0, h->stream>>>(p);
+		else k_decode<MODEL, false><<<grid, DK_THREADS, 0, h->stream>>>(p);
+	}
+	else {
+		const int rpw = h->dec_rpw;
+		const int grid = (h->rows + rpw * DK2_WARPS - 1) / (rpw * DK2_WARPS);
+		if (taps) {
+			if (rpw == 1) k_decode2<MODEL, true, 1><<<grid, DK2_WARPS * 32, 0, h->stream>>>(p);
+			else if (rpw == 3) k_decode2<MODEL, true, 3><<<grid, DK2_WARPS * 32, 0, h->stream>>>(p);
+			else k_decode2<MODEL, true, 6><<<grid, DK2_WARPS * 32, 0, h->stream>>>(p);
+		}
+		else {
+			if (rpw == 1) k_decode2<MODEL, false, 1><<<grid, DK2_WARPS * 32, 0, h->stream>>>(p);
+			else if (rpw == 3) k_decode2<MODEL, false, 3><<<grid, DK2_WARPS * 32, 0, h->stream>>>(p);
+			else k_decode2<MODEL, false, 6><<<grid, DK2_WARPS * 32, 0, h->stream>>>(p);
+		}
+	}
+	CU(cudaGetLastError());
+	return 0;
+}
+
 int run_symbols(aisgpu_handle *h, int n_new) {
 	// n_new samples were appended at [HE, HE + n_new) of every row of Ec/Ef.
 	// ModelDefault (ScatterPLL, DSP.h:95-117) only forwards complete groups of 5: e_left older samples sit just
@@ -340,8 +369,7 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.mode_level = (h->cfg.tag_mode & 1) ? 1 : 0;
 		p.tap_dec = h->cfg.enable_taps ? h->d_tap_dec : nullptr;
 		p.dbg = h->d_dbg;
-		if (p.tap_dec) k_decode<0, true><<<(h->rows + DK_THREADS / 32 - 1) / (DK_THREADS / 32), DK_THREADS, 0, h->stream>>>(p);
-		else k_decode<0, false><<<(h->rows + DK_THREADS / 32 - 1) / (DK_THREADS / 32), DK_THREADS, 0, h->stream>>>(p);
+		if (int rc = launch_decode<0>(h, p)) return rc;
 		CU(cudaGetLastError());
 		h->last_launches++;
 		h->e_abs = a1;
@@ -389,8 +417,7 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		const long long ps_warps = ((long long)h->rows * 5 + 1) / 2;
 		k_phase_search<<<(unsigned)((ps_warps + PS_THREADS / 32 - 1) / (PS_THREADS / 32)), PS_THREADS, 0, h->stream>>>(p);
 		CU(cudaGetLastError());
-		k_decode<2, false><<<(h->rows + DK_THREADS / 32 - 1) / (DK_THREADS / 32), DK_THREADS, 0, h->stream>>>(p);
-		CU(cudaGetLastError());
+		if (int rc = launch_decode<2>(h, p)) return rc;
 		h->last_launches += 2;
 	}
 	const int new_left = total - nsym * 5;
@@ -673,6 +700,10 @@ static int create_impl(aisgpu_handle *h) {
 #else
 	h->fe_warps = 4;
 #endif
+	if (const char *e = getenv("AISGPU_DEC_RPW")) {
+		h->dec_rpw = atoi(e);
+		if (h->dec_rpw != 0 && h->dec_rpw != 1 && h->dec_rpw != 3) h->dec_rpw = 6;
+	}
 	if (const char *e = getenv("AISGPU_FE_TILE")) h->fe_tile = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_CTAS")) h->fe_ctas = std::max(1, atoi(e));
 	int ndev = 0;

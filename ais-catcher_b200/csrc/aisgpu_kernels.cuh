@@ -1284,6 +1284,316 @@ __global__ void __launch_bounds__(DK_THREADS) k_decode(const K3Params p) {
 	}
 }
 
+// K3b': the same decoders, event driven.  RPW rows per warp (lane = row_in_warp * 5 + phase).  Outside a frame the
+// decoder is a regular-expression matcher on the NRZI-decoded bit stream -- ">= 5 alternations, a repeat, the rest of
+// 0111 1110" (AIS.h:103-137) -- so a word of 32 symbols is handled with a handful of bitwise operations: the positions
+// where TRAINING would enter STARTFLAG are  ~alt & alt<<1 & ... & alt<<5 , and for each of them (about one every other
+// word on noise) the outcome of STARTFLAG is read off the following bits.  A failed STARTFLAG at bit f only leaves
+// "alternations are counted from f" behind (variable e).  Only when a row has a decoder inside a frame, or a start
+// flag completes, or at the first (FM model) / last word of a submit, the row's five decoders drop to the exact
+// bit-serial machine of k_decode for that word -- which is where CRC, frame emission and the Reset broadcast
+// (AIS.cpp:47-49, Model.cpp:566-573) happen.
+constexpr int DK2_WARPS = 2;
+template <int MODEL, bool TAPS, int RPW>
+__global__ void __launch_bounds__(DK2_WARPS * 32) k_decode2(const K3Params p) {
+	constexpr int PER_SYM = MODEL == 2 ? 1 : 5;
+	constexpr int ROWEL = K3_TS * PER_SYM; // elements of one row in a tile: 32 levels (MODEL 2) / 160 FIR37 samples (MODEL 0)
+	__shared__ uint32_t frames_all[DK2_WARPS][DEC_WORDS * 32];
+	__shared__ float tile_all[DK2_WARPS][RPW][3][ROWEL];
+	__shared__ uint8_t lut_all[DK2_WARPS][64];
+	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+	const int g = lane / 5, phase = lane - 5 * g;
+	const int row0 = (blockIdx.x * DK2_WARPS + wib) * RPW;
+	if (row0 >= p.rows) return; // whole warp
+	const int row = row0 + g;
+	const bool active = g < RPW && row < p.rows;
+	const unsigned gsh = 5 * (g < RPW ? g : 0);
+	float(*tile)[3][ROWEL] = tile_all[wib];
+	uint8_t *lut = lut_all[wib];
+	for (int i = lane; i < 64; i += 32) { // same transition table as k_decode
+		const int qq = i >> 2, al = (i >> 1) & 1, bt = i & 1;
+		int qn;
+		if (qq < 8) qn = al ? min(qq + 1, 5) : (qq == 5 ? 8 + 2 * bt : 0);
+		else qn = qq == 14 ? (bt ? 0 : 15) : (bt ? qq + 1 : 0);
+		const int to_sf = qq < 8 && qn >= 8, enter = qn == 15;
+		lut[i] = (uint8_t)((enter ? 0 : qn) | (to_sf << 4) | (enter << 5));
+	}
+	__syncwarp();
+
+	DecCtx ctx;
+	ctx.frame = frames_all[wib] + lane;
+	ctx.mode_level = p.mode_level;
+	DecState d;
+	const int sidx = active ? row * 5 + phase : 0;
+	const long long nthr_total = (long long)p.rows * 5;
+	if (active) {
+		d = p.dec[sidx];
+		for (int w = 0; w < DEC_WORDS; w++) ctx.frame[w * K3_THREADS] = p.dec_data[(long long)w * nthr_total + sidx];
+	}
+	else {
+		d.state = ST_TRAINING; d.lastBit = 0; d.prev = 0; d.position = 0; d.one_seq = 0; d.level = 0.f; d.start_idx = 0;
+	}
+	int in_data = active && d.state == ST_DATAFCS;
+	int q = dec_q_from_state(d);
+	int prev = d.prev, lastBit = d.lastBit;
+	int pos = in_data ? d.position : 0, ones = in_data ? d.one_seq : 0;
+	float level = d.level;
+	uint32_t cur = in_data ? ctx.frame[(pos >> 5) * K3_THREADS] : 0u;
+	int start_rel = -1;
+	int ntap = 0;
+	// scan representation of a decoder in TRAINING: alternations are counted for bit indices > e_w (relative to the
+	// current word), altprev = alternation flags of the previous word, q_carry = STARTFLAG state a failing flag is in at
+	// the word boundary
+	bool scanrep = !in_data && q < 8;
+	int e_w = -1 - q, q_carry = 0;
+	uint32_t altprev = q ? (0xffffffffu << (32 - q)) : 0u;
+
+	const int lo_rel = (int)(p.abs_lo - p.abs_begin), hi_rel = (int)(p.abs_hi - p.abs_begin);
+	const int slot_lo = phase >= lo_rel ? 0 : 1;
+	const int slot_hi = (hi_rel - phase + 4) / 5;
+	const int nelem = p.nsym * PER_SYM;
+	auto prefetch = [&](int buf, int s0) {
+		const int base = s0 * PER_SYM;
+#pragma unroll
+		for (int g2 = 0; g2 < RPW; g2++) {
+			const int r2 = row0 + g2;
+			if (r2 < p.rows) {
+				const float *src_row = MODEL == 2 ? p.lvl + (long long)r2 * p.lvl_stride : p.Ef + (long long)r2 * p.e_stride + p.e_begin;
+				for (int e = lane; e < ROWEL; e += 32)
+					if (base + e < nelem) cp_async_f(&tile[g2][buf][e], src_row + base + e);
+			}
+		}
+		cp_async_commit();
+	};
+	const int ntiles = (p.nsym + K3_TS - 1) / K3_TS;
+	// decision bits (sample > 0) and slot validity of word t for this lane
+	auto get_word = [&](int t, uint32_t &dword, uint32_t &vword) {
+		dword = 0;
+		vword = 0;
+		if (!active) return;
+		const int s_end = min(K3_TS, p.nsym - t * K3_TS);
+		if (MODEL == 2) {
+			dword = p.dbits[(long long)sidx * p.dwords + t];
+			vword = s_end >= 32 ? 0xffffffffu : ((1u << s_end) - 1u);
+		}
+		else {
+			const float *my = &tile[g][t % 3][phase];
+			for (int sl = 0; sl < s_end; sl++) {
+				const int slot = t * K3_TS + sl;
+				const float bsmp = my[sl * 5];
+				const bool valid = slot >= slot_lo && slot < slot_hi;
+				dword |= (bsmp > 0.0f ? 1u : 0u) << sl;
+				vword |= (valid ? 1u : 0u) << sl;
+				if (TAPS && valid) p.tap_dec[(long long)sidx * p.nsym + ntap++] = bsmp;
+			}
+		}
+	};
+	uint32_t dword = 0, vword = 0, dnext = 0, vnext = 0;
+	uint32_t pre1 = 0, pre2 = 0; // MODEL 2: decision words t+1 and t+2, loaded two iterations before their first use
+	auto load_dbits = [&](int t) -> uint32_t { return (active && t < ntiles) ? p.dbits[(long long)sidx * p.dwords + t] : 0u; };
+	if (ntiles > 0) {
+		prefetch(0, 0);
+		if (ntiles > 1) prefetch(1, K3_TS);
+		else cp_async_commit();
+		cp_async_wait<1>();
+		__syncwarp();
+		get_word(0, dword, vword);
+		if (MODEL == 2) { pre1 = load_dbits(1); pre2 = load_dbits(2); }
+	}
+	for (int t = 0; t < ntiles; t++) {
+		if (t + 2 < ntiles) prefetch((t + 2) % 3, (t + 2) * K3_TS);
+		else cp_async_commit();
+		cp_async_wait<1>(); // tiles <= t+1 have landed
+		__syncwarp();
+		dnext = 0;
+		vnext = 0;
+		if (MODEL == 2) {
+			if (active && t + 1 < ntiles) {
+				const int se = min(K3_TS, p.nsym - (t + 1) * K3_TS);
+				dnext = pre1;
+				vnext = se >= 32 ? 0xffffffffu : ((1u << se) - 1u);
+			}
+			pre1 = pre2;
+			pre2 = load_dbits(t + 3);
+		}
+		else if (t + 1 < ntiles) get_word(t + 1, dnext, vnext);
+		const int s_end = min(K3_TS, p.nsym - t * K3_TS);
+		const bool last = t == ntiles - 1;
+		// ---------------- fast path: all five decoders of the row are in TRAINING ----------------
+		bool ser_lane = active && (!scanrep || last || (MODEL != 2 && t == 0));
+		bool ser_row = ((__ballot_sync(0xffffffffu, ser_lane) >> gsh) & 31u) != 0;
+		uint32_t Bitw = 0, alt = 0;
+		int e_new = e_w, qc_new = 0;
+		if (active && !ser_row) {
+			Bitw = ~(dword ^ ((dword << 1) | (uint32_t)prev));
+			alt = Bitw ^ ((Bitw << 1) | (uint32_t)lastBit);
+			uint32_t run5 = __funnelshift_l(altprev, alt, 1);
+			run5 &= __funnelshift_l(altprev, alt, 2);
+			run5 &= __funnelshift_l(altprev, alt, 3);
+			run5 &= __funnelshift_l(altprev, alt, 4);
+			run5 &= __funnelshift_l(altprev, alt, 5);
+			uint32_t E = ~alt & run5; // a repeat after >= 5 alternations: TRAINING -> STARTFLAG if the alternations count
+			if (E) {
+				const uint32_t Bn = ~(dnext ^ ((dnext << 1) | (dword >> 31)));
+				const int avail_next = __popc(vnext); // valid slots are a prefix of the next word
+				while (E) {
+					const int j = __ffs(E) - 1;
+					E &= E - 1;
+					if (j - 5 <= e_new) continue; // some of the five alternations precede the last reset
+					const int b = (Bitw >> j) & 1;
+					const int need = b ? 4 : 6; // ones still to come before the closing 0 of the flag
+					unsigned long long U = (((unsigned long long)Bn << 32) | Bitw) >> (j + 1);
+					const int avail = 31 - j + avail_next;
+					if (avail < 64) U |= ~0ull << avail; // unknown bits must not look like a 0
+					const int t1 = ~U ? __ffsll((long long)~U) - 1 : 64; // ones that follow bit j
+					const int decide = j + 1 + min(t1, need);   // index of the bit that decides the flag
+					if (decide - 32 >= avail_next || t1 == need) { // undecidable here, or 0111 1110 complete: exact machine
+						ser_lane = true;
+						break;
+					}
+					e_new = decide; // STARTFLAG failed there: NextState(TRAINING, 0)
+					qc_new = decide >= 32 ? 7 + (b ? 3 : 1) + (31 - j) : 0;
+				}
+			}
+		}
+		ser_row = ((__ballot_sync(0xffffffffu, ser_lane) >> gsh) & 31u) != 0;
+		if (active && !ser_row) { // commit the fast path
+			altprev = alt;
+			lastBit = (int)(Bitw >> 31);
+			prev = (int)(dword >> 31);
+			e_w = max(e_new - 32, -64);
+			q_carry = qc_new;
+		}
+		// ---------------- exact path: bit-serial for the rows that need it ----------------
+		if (__any_sync(0xffffffffu, active && ser_row)) {
+			const bool ser = active && ser_row;
+			if (ser && scanrep) { // scan representation -> automaton state at the first bit of the word
+				if (q_carry) q = q_carry;
+				else {
+					const int n_alt = __clz((int)~altprev);
+					q = max(0, min(min(5, n_alt), -1 - e_w));
+				}
+				scanrep = false;
+			}
+			const uint32_t vw = ser ? vword : 0u;
+			for (int sl = 0; sl < s_end; sl++) {
+				const int dd = (dword >> sl) & 1u;
+				const int valid = (vw >> sl) & 1u;
+				const int Bit = 1 ^ dd ^ prev; // NRZI (AIS.h:93-96)
+				const int lastBit_before = lastBit;
+				const int altb = Bit ^ lastBit_before;
+				const int tv = lut[(q << 2) | (altb << 1) | Bit];
+				const int upd = valid & (in_data ^ 1), dat = valid & in_data;
+				const int start_before = start_rel;
+				const float level_before = level;
+				const int ev = upd ? (tv >> 4) : 0; // bit 0: start_idx taken, bit 1: the frame starts
+				start_rel = (ev & 1) ? (t * K3_TS + sl) * 5 + phase : start_rel;
+				q = upd ? (tv & 15) : q;
+				const int five = ones == 5;
+				const int append = dat & ((five & (Bit ^ 1)) ^ 1); // a 0 after five 1s is a stuffing bit and is dropped
+				cur |= (uint32_t)(append & Bit) << (pos & 31);
+				const int pos_n = pos + append;
+				if (MODEL == 2) {
+					const float lv = tile[g < RPW ? g : 0][t % 3][sl];
+					level = (dat && ctx.mode_level) ? __fadd_rn(level, lv) : level;
+				}
+				ones = dat ? (Bit ? ones + 1 : 0) : ones;
+				const int closing = dat & Bit & five; // sixth 1 in a row: closing flag (AIS.h:151-161)
+				const int full = append & ((pos_n & 31) == 0);
+				const int abortpos = dat & ((c_abort_bits[pos_n >> 5] >> (pos_n & 31)) & 1u);
+				pos = pos_n;
+				prev = valid ? dd : prev;
+				lastBit = valid ? Bit : lastBit;
+				if ((ev >> 1) | full | abortpos) { // lane-local rare events
+					if (ev >> 1) { // 0111111|0: the frame starts (AIS.h:120-124)
+						in_data = 1;
+						q = 0;
+						pos = 0; ones = 0; level = 0.0f; cur = 0u;
+						d.start_idx = start_rel >= 0 ? p.abs_begin + start_rel : d.start_idx;
+						for (int w = 0; w < DEC_WORDS; w++) ctx.frame[w * K3_THREADS] = 0u; // msg.clear()
+					}
+					if (full) {
+						ctx.frame[((pos >> 5) - 1) * K3_THREADS] = cur;
+						cur = 0u;
+					}
+					if (abortpos && !closing) { // position == MaxBits || cannotBeValid(position) (AIS.h:172)
+						if (pos & 31) ctx.frame[(pos >> 5) * K3_THREADS] = cur;
+						if (pos == MAX_FRAME_BITS || dec_cannot_be_valid(ctx, pos)) { in_data = 0; q = 0; }
+					}
+				}
+				const unsigned closers = __ballot_sync(0xffffffffu, closing);
+				if (!closers) continue;
+				// ---- some decoder saw a closing flag: CRC, frame emission, Reset of the siblings ----
+				int fr_len = 0;
+				float fr_level = 0.0f;
+				bool found = false;
+				if (closing) {
+					if (pos & 31) ctx.frame[(pos >> 5) * K3_THREADS] = cur;
+					fr_level = ctx.mode_level ? __fdiv_rn(level, (float)pos) : 0.0f;
+					const int len = pos - 7;
+					if (len >= 16 && dec_crc16(ctx, len)) {
+						found = true;
+						fr_len = len;
+					}
+					in_data = 0;
+					q = 0;
+				}
+				const unsigned vote = (__ballot_sync(0xffffffffu, found) >> gsh) & 31u; // my row's decoders
+				if (vote && ser) { // FOUNDMESSAGE -> Reset to the four sibling decoders (AIS.cpp:47-49,98-108)
+					const int winner = __ffs(vote) - 1; // lowest phase runs first (DSP.h:108-112)
+					const int rel = (t * K3_TS + sl) * 5 + phase;
+					if (phase == winner) {
+						float ppm = 0.0f;
+						if (MODEL == 2 && p.ppmtab) { // tag.ppm of the CGF block that delivered the group's 5th sample
+							const long long last_of_group = p.abs_begin + (long long)(t * K3_TS + sl) * 5 + 4;
+							int bi = (int)((last_of_group - p.blk_abs0) >> 9);
+							bi = bi < 0 ? 0 : (bi >= p.nblk ? p.nblk - 1 : bi);
+							ppm = p.ppmtab[p.stepidx[row * p.nblk + bi]];
+						}
+						emit_frame(p.ring, p.ring_count, p.ring_cap, p.chunk, ctx, row, phase, fr_len, fr_level, ppm, d.start_idx, p.abs_begin + rel);
+					}
+					else if (phase < winner || !valid) { // already stepped this symbol (or no sample in this slot), then reset
+						in_data = 0;
+						q = 0;
+					}
+					else { // reset first, then step this symbol from TRAINING/0: only the NRZI memory survives
+						in_data = 0;
+						level = level_before;
+						start_rel = start_before;
+						q = altb ? 1 : 0;
+					}
+				}
+			}
+			if (ser && !in_data && q < 8) { // back to the scan representation
+				scanrep = true;
+				e_w = -1 - q;
+				altprev = q ? (0xffffffffu << (32 - q)) : 0u;
+				q_carry = 0;
+			}
+		}
+		dword = dnext;
+		vword = vnext;
+		__syncwarp();
+	}
+	if (active) {
+		// the last word of a submit always runs on the exact machine, so q is current here
+		if (in_data) {
+			d.state = ST_DATAFCS;
+			d.position = pos;
+			d.one_seq = ones;
+			if (pos & 31) ctx.frame[(pos >> 5) * K3_THREADS] = cur;
+		}
+		else if (q < 8) { d.state = ST_TRAINING; d.position = q; d.one_seq = 0; }
+		else { d.state = ST_STARTFLAG; d.position = q - 7; d.one_seq = 0; }
+		if (!in_data && q >= 8 && start_rel >= 0) d.start_idx = p.abs_begin + start_rel;
+		d.level = level;
+		d.prev = prev;
+		d.lastBit = lastBit;
+		for (int w = 0; w < DEC_WORDS; w++) p.dec_data[(long long)w * nthr_total + sidx] = ctx.frame[w * K3_THREADS];
+		p.dec[sidx] = d;
+	}
+}
+
 // ModelBase: SimplePLL (DSP.cpp:28-57) + one Decoder per row; strictly sequential per row.
 struct PllState { int prev; float pll; int fast; };
 __global__ void __launch_bounds__(K3_THREADS) k_base(const float *__restrict__ Ef, long long e_stride, int e_begin, int n, int rows,

@@ -21,12 +21,20 @@ x = torch.empty((R, B, N, 2), dtype=torch.float32, device=dev)
 for b0 in range(0, B, 16):
     nb = min(16, B - b0)
     x[:, b0:b0 + nb] = ud[:nb].view(nb, R, N, 2).permute(1, 0, 2, 3)
+torch.manual_seed(7)
 x += torch.randn_like(x) * 0.005
 torch.cuda.synchronize()
 
-settings = [s.split(",") for s in (sys.argv[1:] or ["4,0,8192"])]
-for w, tile, ctas in settings:
+torch.manual_seed(7)
+settings = [s.split(",") for s in (sys.argv[1:] or ["4,0,4096"])]
+for st in settings:
+    w, tile, ctas = st[:3]
     os.environ["AISGPU_FE_WARPS"], os.environ["AISGPU_FE_TILE"], os.environ["AISGPU_FE_CTAS"] = w, tile, ctas
+    extra = {}
+    for kv in st[3:]:  # further KEY=VALUE environment settings, e.g. AISGPU_DEC_RPW=3
+        k_, v_ = kv.split("=")
+        os.environ[k_] = v_
+        extra[k_] = v_
     eng = aisgpu.Engine(model=model, sample_rate=FS, n_streams=B, max_chunk=N, max_frames=1 << 20)
     for i in range(3):
         eng.submit_device(x[i % R].data_ptr(), N, N)
@@ -47,6 +55,6 @@ for w, tile, ctas in settings:
     e1.synchronize()
     step = e0.elapsed_time(e1) / K
     nm = len(eng.poll())
-    print(json.dumps({"warps": int(w), "tile": int(tile), "ctas": int(ctas), "model": model, "B": B, "fe_iso_ms": round(min(iso), 4),
+    print(json.dumps({"extra": extra, "warps": int(w), "tile": int(tile), "ctas": int(ctas), "model": model, "B": B, "fe_iso_ms": round(min(iso), 4),
                       "fe_iso_GBs": round(B * N * 8 / min(iso) / 1e6, 1), "step_ms": round(step, 4), "step_GBs": round(B * N * 8 / step / 1e6, 1), "msgs": nm}), flush=True)
     eng.close()
