@@ -367,8 +367,10 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.ring_cap = h->ring_cap;
 		p.chunk = (int)h->chunk;
 		p.mode_level = (h->cfg.tag_mode & 1) ? 1 : 0;
-		p.tap_dec = h->cfg.enable_taps ? h->d_tap_dec : nullptr;
+		p.tap_dec = nullptr; // the decoder input samples are recorded by the FM/FIR kernel
 		p.dbg = h->d_dbg;
+		p.dbits = h->d_dbits;
+		p.dwords = h->dwords;
 		if (int rc = launch_decode<0>(h, p)) return rc;
 		CU(cudaGetLastError());
 		h->last_launches++;
@@ -527,9 +529,30 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 		h->c_hist = newcnt;
 	}
 	else {
-		dim3 grid((n48 + FIRF_TILE - 1) / FIRF_TILE, h->rows);
-		k_fm_fir<<<grid, FIRF_TILE, 0, h->stream>>>(Ccur, h->c_stride, HC, n48, h->d_Ef, h->e_stride, HE,
-													 h->cfg.enable_taps ? h->d_tap_fm : nullptr, h->r_stride);
+		{
+			// the 5-phase deinterleaver's slots are aligned to absolute sample indices (DSP.h:65-73)
+			const long long a0 = h->e_abs, a1 = a0 + n48;
+			const long long g0 = a0 - a0 % 5;
+			const int nslots = (int)((a1 - g0 + 4) / 5);
+			Fm5Params f;
+			memset(&f, 0, sizeof(f));
+			f.Cbuf = Ccur;
+			f.c_stride = h->c_stride;
+			f.c_new = HC;
+			f.n = n48;
+			f.r0 = h->cfg.model == AISGPU_MODEL_STANDARD ? (int)(a0 - g0) : 0;
+			f.nslots = nslots;
+			f.Fbuf = h->d_Ef;
+			f.f_stride = h->e_stride;
+			f.f_off = HE;
+			f.dbits = h->d_dbits;
+			f.dwords = h->dwords;
+			f.tap_fm = h->cfg.enable_taps ? h->d_tap_fm : nullptr;
+			f.tap_stride = h->r_stride;
+			f.tap_dec = (h->cfg.enable_taps && h->cfg.model == AISGPU_MODEL_STANDARD) ? h->d_tap_dec : nullptr;
+			dim3 grid((nslots + FM5_THREADS - 1) / FM5_THREADS, h->rows);
+			k_fm_fir5<<<grid, FM5_THREADS, 0, h->stream>>>(f);
+		}
 		CU(cudaGetLastError());
 		h->last_launches++;
 		h->last_nE = n48;
@@ -811,6 +834,8 @@ static int create_impl(aisgpu_handle *h) {
 	else {
 		h->c_hist = FIRF_T;
 		if (int rc = dalloc(h, &h->d_Ef, (size_t)h->rows * h->e_stride)) return rc;
+		h->dwords = (nEmax / 5 + 2 + K3_TS - 1) / K3_TS + 1;
+		if (int rc = dalloc(h, &h->d_dbits, (size_t)h->rows * 5 * h->dwords)) return rc;
 		if (c.model == AISGPU_MODEL_BASE) {
 			if (int rc = dalloc(h, &h->d_pll, (size_t)h->rows)) return rc;
 			std::vector<PllState> pl(h->rows);

@@ -709,6 +709,71 @@ __global__ void __launch_bounds__(FIRF_TILE) k_fm_fir(const float2 *__restrict__
 	}
 }
 
+// K2-FM': the same FM + FIR37, five outputs (one symbol slot of the 5-phase deinterleaver, DSP.h:65-73) per thread:
+// 41 discriminator values are read once into registers and reused by the five 37-tap sums (each still accumulated
+// in the reference's order, k = 0..36 from 0.0f).  Besides the filtered samples the kernel emits what the decoders
+// actually consume: one sign bit per (row, sampling phase, slot), packed 32 slots per word by warp ballots.
+constexpr int FM5_THREADS = 128; // slots per CTA
+constexpr int FM5_SAMPLES = FM5_THREADS * 5;
+struct Fm5Params {
+	const float2 *Cbuf;
+	long long c_stride;
+	int c_new, n;        // new samples start at Cbuf[row][c_new], n of them
+	int r0;              // abs index of new sample 0 modulo 5: slot 0 starts r0 samples before it
+	int nslots;
+	float *Fbuf;         // FIR37 output, [rows][f_stride], new sample m at f_off + m
+	long long f_stride;
+	int f_off;
+	uint32_t *dbits;     // [rows*5][dwords]
+	int dwords;
+	float *tap_fm;       // optional
+	long long tap_stride;
+	float *tap_dec;      // optional: decoder input samples [rows*5][nslots], valid ones only, packed per phase
+};
+__global__ void __launch_bounds__(FM5_THREADS) k_fm_fir5(const Fm5Params p) {
+	__shared__ float fm[FM5_SAMPLES + FIRF_T - 1 + 3];
+	const int row = blockIdx.y, tid = threadIdx.x;
+	const int S0 = blockIdx.x * FM5_THREADS;
+	const int M0 = 5 * S0 - p.r0; // new-sample index of the first sample of slot S0
+	const float2 *c = p.Cbuf + (long long)row * p.c_stride + p.c_new;
+	for (int i = tid; i < FM5_SAMPLES + FIRF_T - 1; i += FM5_THREADS) {
+		const int m = M0 + i - (FIRF_T - 1);
+		float v = 0.0f;
+		if (m < p.n && m >= -(FIRF_T - 1) - 4) {
+			const float2 a = c[m], pv = c[m - 1];
+			const float re = __fsub_rn(__fmul_rn(a.x, pv.x), __fmul_rn(a.y, -pv.y));
+			const float im = __fadd_rn(__fmul_rn(a.x, -pv.y), __fmul_rn(a.y, pv.x));
+			v = __fdiv_rn(fd_atan2f(im, re), 3.14159265358979323846f);
+			if (p.tap_fm && m >= 0 && i >= FIRF_T - 1) p.tap_fm[(long long)row * p.tap_stride + m] = v;
+		}
+		fm[i] = v;
+	}
+	__syncthreads();
+	float x[FIRF_T + 4];
+#pragma unroll
+	for (int i = 0; i < FIRF_T + 4; i++) x[i] = fm[5 * tid + i];
+	float y[5];
+#pragma unroll
+	for (int j = 0; j < 5; j++) {
+		float acc = 0.0f;
+#pragma unroll
+		for (int k = 0; k < FIRF_T; k++) acc = __fadd_rn(acc, __fmul_rn(c_taps_receiver[k], x[j + k]));
+		y[j] = acc;
+	}
+	const int slot = S0 + tid;
+	const int m0 = M0 + 5 * tid;
+#pragma unroll
+	for (int j = 0; j < 5; j++) {
+		const int m = m0 + j;
+		if (m >= 0 && m < p.n) {
+			p.Fbuf[(long long)row * p.f_stride + p.f_off + m] = y[j];
+			if (p.tap_dec) p.tap_dec[(long long)(row * 5 + j) * p.nslots + slot - (j >= p.r0 ? 0 : 1)] = y[j];
+		}
+		const unsigned w = __ballot_sync(0xffffffffu, y[j] > 0.0f);
+		if ((tid & 31) == j && (slot >> 5) < p.dwords) p.dbits[(long long)(row * 5 + j) * p.dwords + (slot >> 5)] = w;
+	}
+}
+
 // ---------------------------------------------------------------------------------------------
 // K3: symbol timing + demodulation + bit decoder.
 //   ModelDefault : ScatterPLL (DSP.h:95-117) -> 5 x PhaseSearchEMA / PhaseSearch (Demod.cpp:39-170) -> 5 x Decoder
@@ -1296,8 +1361,8 @@ __global__ void __launch_bounds__(DK_THREADS) k_decode(const K3Params p) {
 constexpr int DK2_WARPS = 2;
 template <int MODEL, bool TAPS, int RPW>
 __global__ void __launch_bounds__(DK2_WARPS * 32) k_decode2(const K3Params p) {
-	constexpr int PER_SYM = MODEL == 2 ? 1 : 5;
-	constexpr int ROWEL = K3_TS * PER_SYM; // elements of one row in a tile: 32 levels (MODEL 2) / 160 FIR37 samples (MODEL 0)
+	constexpr int PER_SYM = 1;
+	constexpr int ROWEL = K3_TS; // elements of one row in a tile: the 32 symbol levels (MODEL 2 only)
 	__shared__ uint32_t frames_all[DK2_WARPS][DEC_WORDS * 32];
 	__shared__ float tile_all[DK2_WARPS][RPW][3][ROWEL];
 	__shared__ uint8_t lut_all[DK2_WARPS][64];
@@ -1357,8 +1422,8 @@ __global__ void __launch_bounds__(DK2_WARPS * 32) k_decode2(const K3Params p) {
 #pragma unroll
 		for (int g2 = 0; g2 < RPW; g2++) {
 			const int r2 = row0 + g2;
-			if (r2 < p.rows) {
-				const float *src_row = MODEL == 2 ? p.lvl + (long long)r2 * p.lvl_stride : p.Ef + (long long)r2 * p.e_stride + p.e_begin;
+			if (MODEL == 2 && r2 < p.rows) {
+				const float *src_row = p.lvl + (long long)r2 * p.lvl_stride;
 				for (int e = lane; e < ROWEL; e += 32)
 					if (base + e < nelem) cp_async_f(&tile[g2][buf][e], src_row + base + e);
 			}
@@ -1372,20 +1437,12 @@ __global__ void __launch_bounds__(DK2_WARPS * 32) k_decode2(const K3Params p) {
 		vword = 0;
 		if (!active) return;
 		const int s_end = min(K3_TS, p.nsym - t * K3_TS);
-		if (MODEL == 2) {
-			dword = p.dbits[(long long)sidx * p.dwords + t];
-			vword = s_end >= 32 ? 0xffffffffu : ((1u << s_end) - 1u);
-		}
-		else {
-			const float *my = &tile[g][t % 3][phase];
-			for (int sl = 0; sl < s_end; sl++) {
-				const int slot = t * K3_TS + sl;
-				const float bsmp = my[sl * 5];
-				const bool valid = slot >= slot_lo && slot < slot_hi;
-				dword |= (bsmp > 0.0f ? 1u : 0u) << sl;
-				vword |= (valid ? 1u : 0u) << sl;
-				if (TAPS && valid) p.tap_dec[(long long)sidx * p.nsym + ntap++] = bsmp;
-			}
+		dword = p.dbits[(long long)sidx * p.dwords + t];
+		vword = s_end >= 32 ? 0xffffffffu : ((1u << s_end) - 1u);
+		if (MODEL != 2) { // Deinterleave forwards partial groups at both ends of a submit
+			const int lo = slot_lo - t * K3_TS, hi = slot_hi - t * K3_TS;
+			if (lo > 0) vword &= lo >= 32 ? 0u : (0xffffffffu << lo);
+			if (hi < 32) vword &= hi <= 0 ? 0u : ((1u << hi) - 1u);
 		}
 	};
 	uint32_t dword = 0, vword = 0, dnext = 0, vnext = 0;
@@ -1417,6 +1474,7 @@ __global__ void __launch_bounds__(DK2_WARPS * 32) k_decode2(const K3Params p) {
 			pre2 = load_dbits(t + 3);
 		}
 		else if (t + 1 < ntiles) get_word(t + 1, dnext, vnext);
+		(void)ntap;
 		const int s_end = min(K3_TS, p.nsym - t * K3_TS);
 		const bool last = t == ntiles - 1;
 		// ---------------- fast path: all five decoders of the row are in TRAINING ----------------
