@@ -63,7 +63,7 @@ struct aisgpu_handle {
 	int rows = 0;
 	int max_n48 = 0;
 	int fe_warps = 4, fe_tile = 0, fe_ctas = 4096;
-	int dec_rpw = 6; // rows per warp in the event-driven decoder kernel // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
+	int dec_rpw = 6, decoder = 3; // rows per warp / which decoder kernel // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
 	// for timing).  The front end of submit c+1 overlaps the back end of submit c; Cbuf is double buffered for that.
 	cudaStream_t stream = nullptr, copy_stream = nullptr, fe_stream = nullptr;
@@ -312,29 +312,27 @@ int carry2(aisgpu_handle *h, const T *src, T *dst, long long stride, int src_beg
 	return 0;
 }
 
-// Five AIS::Decoder instances per row.  dec_rpw rows share a warp in the event-driven kernel (AISGPU_DEC_RPW = 1, 3, 6);
-// AISGPU_DEC_RPW=0 selects the plain bit-serial kernel (one row per warp), kept as the in-tree cross-check.
+// Five AIS::Decoder instances per row.  decoder = 3: word-parallel kernel (default), 2: event-driven kernel with the
+// bit-serial machine inside frames, 1: plain bit-serial kernel (one row per warp) -- the older ones stay in the tree as
+// cross-checks (AISGPU_DECODER).  dec_rpw rows share a warp (AISGPU_DEC_RPW = 1, 3, 6).
 template <int MODEL>
 int launch_decode(aisgpu_handle *h, const K3Params &p) {
-	const bool taps = MODEL == 0 && p.tap_dec;
-	if (h->dec_rpw == 0) {
+	const int rpw = h->dec_rpw;
+	if (h->decoder == 1) {
 		const int grid = (h->rows + DK_THREADS / 32 - 1) / (DK_THREADS / 32);
-		if (taps) k_decode<MODEL, true><<<grid, DK_THREADS, 0, h->stream>>>(p);
-		else k_decode<MODEL, false><<<grid, DK_THREADS, 0, h->stream>>>(p);
+		k_decode<MODEL, false><<<grid, DK_THREADS, 0, h->stream>>>(p);
+	}
+	else if (h->decoder == 2) {
+		const int grid = (h->rows + rpw * DK2_WARPS - 1) / (rpw * DK2_WARPS);
+		if (rpw == 1) k_decode2<MODEL, false, 1><<<grid, DK2_WARPS * 32, 0, h->stream>>>(p);
+		else if (rpw == 3) k_decode2<MODEL, false, 3><<<grid, DK2_WARPS * 32, 0, h->stream>>>(p);
+		else k_decode2<MODEL, false, 6><<<grid, DK2_WARPS * 32, 0, h->stream>>>(p);
 	}
 	else {
-		const int rpw = h->dec_rpw;
-		const int grid = (h->rows + rpw * DK2_WARPS - 1) / (rpw * DK2_WARPS);
-		if (taps) {
-			if (rpw == 1) k_decode2<MODEL, true, 1><<<grid, DK2_WARPS * 32, 0, h->stream>>>(p);
-			else if (rpw == 3) k_decode2<MODEL, true, 3><<<grid, DK2_WARPS * 32, 0, h->stream>>>(p);
-			else k_decode2<MODEL, true, 6><<<grid, DK2_WARPS * 32, 0, h->stream>>>(p);
-		}
-		else {
-			if (rpw == 1) k_decode2<MODEL, false, 1><<<grid, DK2_WARPS * 32, 0, h->stream>>>(p);
-			else if (rpw == 3) k_decode2<MODEL, false, 3><<<grid, DK2_WARPS * 32, 0, h->stream>>>(p);
-			else k_decode2<MODEL, false, 6><<<grid, DK2_WARPS * 32, 0, h->stream>>>(p);
-		}
+		const int grid = (h->rows + rpw * DK3_WARPS - 1) / (rpw * DK3_WARPS);
+		if (rpw == 1) k_decode3<MODEL, 1><<<grid, DK3_WARPS * 32, 0, h->stream>>>(p);
+		else if (rpw == 3) k_decode3<MODEL, 3><<<grid, DK3_WARPS * 32, 0, h->stream>>>(p);
+		else k_decode3<MODEL, 6><<<grid, DK3_WARPS * 32, 0, h->stream>>>(p);
 	}
 	CU(cudaGetLastError());
 	return 0;
@@ -725,7 +723,11 @@ static int create_impl(aisgpu_handle *h) {
 #endif
 	if (const char *e = getenv("AISGPU_DEC_RPW")) {
 		h->dec_rpw = atoi(e);
-		if (h->dec_rpw != 0 && h->dec_rpw != 1 && h->dec_rpw != 3) h->dec_rpw = 6;
+		if (h->dec_rpw != 1 && h->dec_rpw != 3) h->dec_rpw = 6;
+	}
+	if (const char *e = getenv("AISGPU_DECODER")) {
+		h->decoder = atoi(e);
+		if (h->decoder != 1 && h->decoder != 2) h->decoder = 3;
 	}
 	if (const char *e = getenv("AISGPU_FE_TILE")) h->fe_tile = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_CTAS")) h->fe_ctas = std::max(1, atoi(e));

@@ -1652,6 +1652,360 @@ __global__ void __launch_bounds__(DK2_WARPS * 32) k_decode2(const K3Params p) {
 	}
 }
 
+// K3c: the five decoders of a row, fully word-parallel.  Every state of AIS::Decoder::Run (AIS.h:91-181) consumes a
+// run of bits of the 32-symbol word with bitwise operations instead of one step per bit:
+//   TRAINING  : candidate TRAINING->STARTFLAG transitions are  E = ~alt & alt<<1 & .. & alt<<5  (a repeat after five
+//               alternations); one counts only if its five alternations come after the last reset (index e).  What
+//               STARTFLAG does with it is read off the next bits (count of ones that follow) in the same iteration.
+//   STARTFLAG : only when a flag straddles a word boundary: position so far in sfP.
+//   DATAFCS   : closing flag = first run of six ones (carry-in `ones` prepended), stuffing bits = zeros after five
+//               ones, both by shifted ANDs; the surviving bits are squeezed together and appended to the frame;
+//               the cannotBeValid()/MaxBits exits (AIS.cpp:111-142) are evaluated only when the position crosses one
+//               of their lengths; the signal level is summed bit by bit in the reference's order.
+// A CRC-valid frame is rare; when one closes in a word, the row rolls back to the state at the start of the word
+// section, replays it up to that bit (its siblings one bit less if they come later in the round-robin order of
+// DSP.h:108-112), applies the Reset broadcast (AIS.cpp:47-49, Model.cpp:566-573) and carries on.
+struct Dk3 {
+	int mode;        // 0 TRAINING, 1 STARTFLAG, 2 DATAFCS
+	int sfP;         // STARTFLAG: position (1..7)
+	int pos, ones;   // DATAFCS: position, one_seq_count
+	float level;
+	uint32_t cur;    // partially filled frame word
+	int e;           // TRAINING: alternations count only at bit indices > e (relative to the current word)
+	int start_rel;   // slot*5+phase of the latest TRAINING->STARTFLAG transition of this submit, -1 if none
+};
+
+__device__ __forceinline__ uint32_t lowmask(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
+
+// Consumes bits [i0, i1) of the word.  Returns 32, or the index of the bit at which a CRC-valid frame closed (the
+// state is then TRAINING with e = that bit, the frame bits are complete in shared memory, fr_len / fr_level set).
+template <bool LEVEL>
+__device__ __forceinline__ int dk3_run(Dk3 &st, const DecCtx &ctx, uint32_t Bitw, uint32_t E, int i0, int i1, const float *__restrict__ lvl,
+									   int slot0, int phase, int &fr_len, float &fr_level) {
+	int i = i0;
+	while (i < i1) {
+		if (st.mode == 0) {
+			uint32_t Em = E & ~lowmask(i) & lowmask(i1);
+			bool done = true;
+			while (Em) {
+				const int j = __ffs(Em) - 1;
+				Em &= Em - 1;
+				if (j - 5 <= st.e) continue; // some of the five alternations precede the last reset
+				// TRAINING -> STARTFLAG at bit j (AIS.h:107-111); position = Bit ? 3 : 1
+				st.start_rel = (slot0 + j) * 5 + phase;
+				const int b = (Bitw >> j) & 1;
+				const int need = b ? 4 : 6; // ones still to come before the 0 that ends the flag
+				const int n = i1 - (j + 1);
+				const uint32_t W = n > 0 ? ((Bitw >> (j + 1)) | ~lowmask(n)) : 0xffffffffu; // j + 1 may be 32
+				const int t1 = ~W ? __ffs(~W) - 1 : 32; // ones that follow
+				const int m = min(t1, need);
+				if (m >= n) { // the word ends inside the flag
+					st.mode = 1;
+					st.sfP = (b ? 3 : 1) + n;
+					i = i1;
+					done = false;
+					break;
+				}
+				const int decide = j + 1 + m;
+				if (t1 == need) { // 0111111|0: the frame starts (AIS.h:120-124)
+					st.mode = 2;
+					st.pos = 0; st.ones = 0; st.level = 0.0f; st.cur = 0u;
+					i = decide + 1;
+					done = false;
+					break;
+				}
+				st.e = decide; // the flag failed there: NextState(TRAINING, 0)
+			}
+			if (done) i = i1;
+		}
+		else if (st.mode == 1) {
+			const int n = i1 - i;
+			const uint32_t W = (Bitw >> i) | ~lowmask(n);
+			const int t1 = ~W ? __ffs(~W) - 1 : 32;
+			const int need = 7 - st.sfP;
+			const int m = min(t1, need);
+			if (m >= n) {
+				st.sfP += n;
+				i = i1;
+			}
+			else {
+				const int decide = i + m;
+				if (t1 == need) {
+					st.mode = 2;
+					st.pos = 0; st.ones = 0; st.level = 0.0f; st.cur = 0u;
+				}
+				else {
+					st.mode = 0;
+					st.e = decide;
+				}
+				i = decide + 1;
+			}
+		}
+		else {
+			const int n = i1 - i;
+			const uint32_t W = (Bitw >> i) & lowmask(n);
+			const unsigned long long X = ((unsigned long long)W << st.ones) | ((1ull << st.ones) - 1ull); // carried-in ones first
+			const unsigned long long R5 = X & (X << 1) & (X << 2) & (X << 3) & (X << 4);
+			const unsigned long long R6 = R5 & (X << 5);
+			const int c = R6 ? (__ffsll((long long)R6) - 1 - st.ones) : 64; // closing flag: the sixth 1 in a row (AIS.h:151-161)
+			const int endb = c < n ? c : n - 1;                              // last bit consumed if no early exit
+			const uint32_t Sw = (uint32_t)((~X & (R5 << 1)) >> st.ones) & lowmask(endb + 1); // stuffing zeros
+			uint32_t bits = W & lowmask(endb + 1);
+			for (uint32_t tmp = Sw; tmp;) { // squeeze the stuffing bits out, highest first
+				const int sb = 31 - __clz((int)tmp);
+				tmp &= ~(1u << sb);
+				bits = (bits & lowmask(sb)) | ((sb >= 31 ? 0u : (bits >> (sb + 1))) << sb);
+			}
+			const int cnt = endb + 1 - __popc(Sw);
+			const int pos0 = st.pos;
+			const int sh = pos0 & 31;
+			uint32_t cur = st.cur | (bits << sh);
+			if (sh + cnt >= 32) {
+				ctx.frame[(pos0 >> 5) * K3_THREADS] = cur;
+				cur = sh ? (bits >> (32 - sh)) : 0u;
+			}
+			const int newpos = pos0 + cnt;
+			// exits by length: position == MaxBits || cannotBeValid(position), tested after every bit (AIS.h:172)
+			int exit_m = -1;
+			{
+				const int w0 = (pos0 + 1) >> 5, w1 = newpos >> 5;
+				bool any = false;
+				for (int w = w0; w <= w1 && w < 35; w++) {
+					uint32_t ab = c_abort_bits[w];
+					if (w == w0) ab &= ~lowmask((pos0 + 1) & 31);
+					if (w == w1) ab &= lowmask((newpos & 31) + 1);
+					any |= ab != 0;
+				}
+				if (any) {
+					ctx.frame[(newpos >> 5) * K3_THREADS] = cur; // type / mmsi fields must be readable
+					for (int Pa = pos0 + 1; Pa <= newpos; Pa++) {
+						if (!((c_abort_bits[Pa >> 5] >> (Pa & 31)) & 1u)) continue;
+						const int r = Pa - pos0 - 1; // ordinal of the appended bit that makes position == Pa
+						int m = r;
+						for (;;) {
+							const int m2 = r + __popc(Sw & lowmask(m + 1));
+							if (m2 == m) break;
+							m = m2;
+						}
+						if (m == c) break; // closing flag on the same bit: NextState(TRAINING) came first
+						if (Pa == MAX_FRAME_BITS || dec_cannot_be_valid(ctx, Pa)) {
+							exit_m = m;
+							break;
+						}
+					}
+				}
+			}
+			if (exit_m >= 0) {
+				st.mode = 0;
+				st.e = i + exit_m;
+				i += exit_m + 1;
+				continue;
+			}
+			if (LEVEL && ctx.mode_level) {
+				float lv = st.level;
+				for (int m = 0; m <= endb; m++) lv = __fadd_rn(lv, lvl[i + m]);
+				st.level = lv;
+			}
+			if (c < n) { // closing flag
+				if (newpos & 31) ctx.frame[(newpos >> 5) * K3_THREADS] = cur;
+				st.mode = 0;
+				st.e = i + c;
+				i += c + 1;
+				const int len = newpos - 7;
+				if (len >= 16 && dec_crc16(ctx, len)) {
+					fr_len = len;
+					fr_level = ctx.mode_level ? __fdiv_rn(st.level, (float)newpos) : 0.0f;
+					st.pos = newpos;
+					return i - 1;
+				}
+			}
+			else {
+				st.pos = newpos;
+				st.cur = cur;
+				const int tot = n + st.ones; // trailing ones of the consumed bits (a stuffing zero resets the count)
+				const unsigned long long Y = ~(X << (64 - tot));
+				st.ones = Y ? __clzll((long long)Y) : tot;
+				i = i1;
+			}
+		}
+	}
+	return 32;
+}
+
+constexpr int DK3_WARPS = 2;
+template <int MODEL, int RPW>
+__global__ void __launch_bounds__(DK3_WARPS * 32) k_decode3(const K3Params p) {
+	__shared__ uint32_t frames_all[DK3_WARPS][DEC_WORDS * 32];
+	__shared__ float tile_all[DK3_WARPS][RPW][3][K3_TS];
+	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+	const int g = lane / 5, phase = lane - 5 * g;
+	const int row0 = (blockIdx.x * DK3_WARPS + wib) * RPW;
+	if (row0 >= p.rows) return; // whole warp
+	const int row = row0 + g;
+	const bool active = g < RPW && row < p.rows;
+	const int gbase = 5 * (g < RPW ? g : 0);
+	float(*tile)[3][K3_TS] = tile_all[wib];
+
+	DecCtx ctx;
+	ctx.frame = frames_all[wib] + lane;
+	ctx.mode_level = p.mode_level;
+	DecState d;
+	const int sidx = active ? row * 5 + phase : 0;
+	const long long nthr_total = (long long)p.rows * 5;
+	Dk3 st;
+	st.mode = 0; st.sfP = 0; st.pos = 0; st.ones = 0; st.level = 0.0f; st.cur = 0u; st.e = -1; st.start_rel = -1;
+	int prev = 0, lastBit = 0;
+	uint32_t altprev = 0u;
+	if (active) {
+		d = p.dec[sidx];
+		prev = d.prev;
+		lastBit = d.lastBit;
+		if (d.state == ST_DATAFCS) {
+			st.mode = 2;
+			st.pos = d.position;
+			st.ones = d.one_seq;
+			st.level = d.level;
+			const int nw = (d.position >> 5) + 1;
+			for (int w = 0; w < nw && w < DEC_WORDS; w++) ctx.frame[w * K3_THREADS] = p.dec_data[(long long)w * nthr_total + sidx];
+			st.cur = (d.position & 31) ? ctx.frame[(d.position >> 5) * K3_THREADS] : 0u;
+		}
+		else if (d.state == ST_STARTFLAG) {
+			st.mode = 1;
+			st.sfP = d.position;
+		}
+		else { // TRAINING with `position` alternations counted so far (only "> 4" is ever tested)
+			const int q = min(d.position, 5);
+			st.e = -1 - q;
+			altprev = q ? (0xffffffffu << (32 - q)) : 0u;
+		}
+	}
+	const int lo_rel = (int)(p.abs_lo - p.abs_begin), hi_rel = (int)(p.abs_hi - p.abs_begin);
+	const int slot_lo = phase >= lo_rel ? 0 : 1; // Deinterleave forwards partial groups at both ends of a submit
+	const int slot_hi = (hi_rel - phase + 4) / 5;
+	const int ntiles = (p.nsym + K3_TS - 1) / K3_TS;
+	auto prefetch = [&](int buf, int s0) {
+		if (MODEL == 2) {
+#pragma unroll
+			for (int g2 = 0; g2 < RPW; g2++) {
+				const int r2 = row0 + g2;
+				if (r2 < p.rows && s0 + lane < p.nsym) cp_async_f(&tile[g2][buf][lane], p.lvl + (long long)r2 * p.lvl_stride + s0 + lane);
+			}
+		}
+		cp_async_commit();
+	};
+	auto load_dbits = [&](int t) -> uint32_t { return (active && t < ntiles) ? p.dbits[(long long)sidx * p.dwords + t] : 0u; };
+	uint32_t pre0 = load_dbits(0), pre1 = load_dbits(1), pre2 = load_dbits(2);
+	if (ntiles > 0) {
+		prefetch(0, 0);
+		if (ntiles > 1) prefetch(1, K3_TS);
+		else cp_async_commit();
+	}
+	int nbits_total = 0; // valid bits seen by this lane in this submit
+	for (int t = 0; t < ntiles; t++) {
+		if (t + 2 < ntiles) prefetch((t + 2) % 3, (t + 2) * K3_TS);
+		else cp_async_commit();
+		cp_async_wait<2>(); // tile t has landed
+		__syncwarp();
+		uint32_t dword = pre0;
+		pre0 = pre1;
+		pre1 = pre2;
+		pre2 = load_dbits(t + 3);
+		// valid slots of this word for this lane: [lo, hi)
+		int lo = max(0, slot_lo - t * K3_TS), hi = min(K3_TS, min(p.nsym, slot_hi) - t * K3_TS);
+		if (!active) hi = 0;
+		const int nb = max(0, hi - lo);
+		const int slot0 = t * K3_TS + lo;
+		dword >>= lo;
+		const uint32_t Bitw = ~(dword ^ ((dword << 1) | (uint32_t)prev)); // NRZI (AIS.h:93-96)
+		const uint32_t alt = Bitw ^ ((Bitw << 1) | (uint32_t)lastBit);
+		uint32_t run5 = __funnelshift_l(altprev, alt, 1);
+		run5 &= __funnelshift_l(altprev, alt, 2);
+		run5 &= __funnelshift_l(altprev, alt, 3);
+		run5 &= __funnelshift_l(altprev, alt, 4);
+		run5 &= __funnelshift_l(altprev, alt, 5);
+		const uint32_t E = ~alt & run5 & lowmask(nb);
+		const float *lvl = &tile[g < RPW ? g : 0][t % 3][lo];
+		int i = 0;
+		for (;;) {
+			const Dk3 saved = st;
+			const int i_saved = i;
+			int fr_len = 0;
+			float fr_level = 0.0f;
+			const int x = dk3_run<MODEL == 2>(st, ctx, Bitw, E, i, nb, lvl, slot0, phase, fr_len, fr_level);
+			i = x < 32 ? x + 1 : nb;
+			if (!__any_sync(0xffffffffu, x < 32)) break;
+			// a frame with a good CRC closed somewhere in the warp: per row, the first one in (bit, phase) order wins
+			const int key = x < 32 ? (x + lo) * 8 + phase : 0x7fffffff; // bit index in slot units (lanes of a row may differ in lo)
+			int rowmin = 0x7fffffff;
+#pragma unroll
+			for (int k2 = 0; k2 < 5; k2++) rowmin = min(rowmin, __shfl_sync(0xffffffffu, key, gbase + k2));
+			if (rowmin == 0x7fffffff || !active) continue; // nothing in this row: its lanes have finished the word already
+			const int xs = rowmin >> 3, pw = rowmin & 7; // slot (relative to the word) and phase of the winner
+			if (key == rowmin) { // FOUNDMESSAGE: publish, Reset goes to the four siblings (AIS.cpp:47-49,98-108)
+				float ppm = 0.0f;
+				const int slot = t * K3_TS + xs;
+				if (MODEL == 2 && p.ppmtab) { // tag.ppm of the CGF block that delivered the group's 5th sample
+					const long long last_of_group = p.abs_begin + (long long)slot * 5 + 4;
+					int bi = (int)((last_of_group - p.blk_abs0) >> 9);
+					bi = bi < 0 ? 0 : (bi >= p.nblk ? p.nblk - 1 : bi);
+					ppm = p.ppmtab[p.stepidx[row * p.nblk + bi]];
+				}
+				const long long sidx0 = st.start_rel >= 0 ? p.abs_begin + st.start_rel : d.start_idx;
+				const int slotw = atomicAdd(p.ring_count, 1);
+				if (slotw < p.ring_cap) {
+					FrameRec &r = p.ring[slotw];
+					r.row = row; r.phase = phase; r.nbits = fr_len - 16; r.level = fr_level; r.ppm = ppm; r.chunk = p.chunk;
+					r.start_idx = sidx0;
+					r.end_idx = p.abs_begin + (long long)slot * 5 + phase;
+					const int nw = (st.pos + 31) >> 5;
+					for (int w = 0; w < DEC_WORDS; w++) r.data[w] = w < nw ? frame_word(ctx, w) : 0u; // msg.clear() left the rest zero
+				}
+			}
+			else { // sibling: replay up to the winner's bit, then Reset -> NextState(TRAINING, 0)
+				st = saved;
+				const int xl = xs - lo; // the winner's slot as a bit index of this lane's word (may be -1 when lo = 1)
+				const int stop = max(i_saved, min(nb, phase < pw ? xl + 1 : xl)); // earlier phases have already stepped that symbol
+				int fl = 0;
+				float fv = 0.0f;
+				if (stop > i_saved) dk3_run<MODEL == 2>(st, ctx, Bitw, E, i_saved, stop, lvl, slot0, phase, fl, fv);
+				st.mode = 0;
+				st.e = stop - 1;
+				i = stop;
+			}
+		}
+		if (nb > 0) {
+			altprev = nb >= 32 ? alt : ((alt << (32 - nb)) | (altprev >> nb)); // keep "bit 31 = latest alternation flag"
+			lastBit = (int)((Bitw >> (nb - 1)) & 1u);
+			prev = (int)((dword >> (nb - 1)) & 1u);
+			st.e = max(st.e - nb, -64);
+			nbits_total += nb;
+		}
+		__syncwarp();
+	}
+	if (active) {
+		if (st.mode == 2) {
+			d.state = ST_DATAFCS;
+			d.position = st.pos;
+			d.one_seq = st.ones;
+			if (st.pos & 31) ctx.frame[(st.pos >> 5) * K3_THREADS] = st.cur;
+			const int nw = (st.pos >> 5) + 1;
+			for (int w = 0; w < nw && w < DEC_WORDS; w++) p.dec_data[(long long)w * nthr_total + sidx] = ctx.frame[w * K3_THREADS];
+		}
+		else if (st.mode == 1) { d.state = ST_STARTFLAG; d.position = st.sfP; d.one_seq = 0; }
+		else { // TRAINING: alternations counted = trailing alternation flags that come after the last reset
+			const int n_alt = __clz((int)~altprev);
+			d.state = ST_TRAINING;
+			d.position = max(0, min(min(5, n_alt), -1 - st.e));
+			d.one_seq = 0;
+		}
+		if (st.mode != 0 && st.start_rel >= 0) d.start_idx = p.abs_begin + st.start_rel;
+		d.level = st.level;
+		d.prev = prev;
+		d.lastBit = lastBit;
+		p.dec[sidx] = d;
+	}
+}
+
 // ModelBase: SimplePLL (DSP.cpp:28-57) + one Decoder per row; strictly sequential per row.
 struct PllState { int prev; float pll; int fast; };
 __global__ void __launch_bounds__(K3_THREADS) k_base(const float *__restrict__ Ef, long long e_stride, int e_begin, int n, int rows,
