@@ -44,39 +44,35 @@ __device__ __forceinline__ float2 cnormalize(float2 r) { // rot /= std::abs(rot)
 
 // fdlibm atanf/atan2f (the algorithm behind glibc 2.39 __ieee754_atan2f; verified bit-identical on 5e7 inputs)
 __device__ __forceinline__ float fd_atanf(float x) {
-	const float atanhi[4] = { 4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f };
-	const float atanlo[4] = { 5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f };
 	const float aT[11] = { 3.3333334327e-01f, -2.0000000298e-01f, 1.4285714924e-01f, -1.1111110449e-01f, 9.0908870101e-02f,
 						   -7.6918758452e-02f, 6.6610731184e-02f, -5.8335702866e-02f, 4.9768779427e-02f, -3.6531571299e-02f, 1.6285819933e-02f };
-	int hx = __float_as_int(x), ix = hx & 0x7fffffff, id;
-	float hi = 0.f, lo = 0.f;
-	if (ix >= 0x4c000000) {
+	const int hx = __float_as_int(x), ix = hx & 0x7fffffff;
+	if (ix >= 0x4c000000) { // |x| >= 2^25 (rare)
 		if (ix > 0x7f800000) return __fadd_rn(x, x);
-		float r = __fadd_rn(atanhi[3], atanlo[3]);
+		const float r = __fadd_rn(1.5707962513e+00f, 7.5497894159e-08f);
 		return hx > 0 ? r : -r;
 	}
-	if (ix < 0x3ee00000) {
-		if (ix < 0x31000000) return x;
-		id = -1;
-	}
-	else {
-		x = fabsf(x);
-		if (ix < 0x3f980000) {
-			if (ix < 0x3f300000) { id = 0; hi = atanhi[0]; lo = atanlo[0]; x = __fdiv_rn(__fsub_rn(__fmul_rn(2.0f, x), 1.0f), __fadd_rn(2.0f, x)); }
-			else { id = 1; hi = atanhi[1]; lo = atanlo[1]; x = __fdiv_rn(__fsub_rn(x, 1.0f), __fadd_rn(x, 1.0f)); }
-		}
-		else {
-			if (ix < 0x401c0000) { id = 2; hi = atanhi[2]; lo = atanlo[2]; x = __fdiv_rn(__fsub_rn(x, 1.5f), __fadd_rn(1.0f, __fmul_rn(1.5f, x))); }
-			else { id = 3; hi = atanhi[3]; lo = atanlo[3]; x = __fdiv_rn(-1.0f, x); }
-		}
-	}
-	float z = __fmul_rn(x, x), w = __fmul_rn(z, z);
-	float s1 = __fmul_rn(z, __fadd_rn(aT[0], __fmul_rn(w, __fadd_rn(aT[2], __fmul_rn(w, __fadd_rn(aT[4], __fmul_rn(w, __fadd_rn(aT[6], __fmul_rn(w, __fadd_rn(aT[8], __fmul_rn(w, aT[10])))))))))));
-	float s2 = __fmul_rn(w, __fadd_rn(aT[1], __fmul_rn(w, __fadd_rn(aT[3], __fmul_rn(w, __fadd_rn(aT[5], __fmul_rn(w, __fadd_rn(aT[7], __fmul_rn(w, aT[9])))))))));
-	float xs = __fmul_rn(x, __fadd_rn(s1, s2));
-	if (id < 0) return __fsub_rn(x, xs);
-	z = __fsub_rn(hi, __fsub_rn(__fsub_rn(xs, lo), x));
-	return hx < 0 ? -z : z;
+	if (ix < 0x31000000) return x; // |x| < 2^-29 (rare)
+	// The four argument reductions of fdlibm are evaluated side by side and selected, so a warp does not serialise
+	// over them; the operations on the selected path are exactly the library's.
+	const bool small = ix < 0x3ee00000; // |x| < 0.4375: no reduction, x keeps its sign
+	const float ax = fabsf(x);
+	const int id = ix < 0x3f300000 ? 0 : (ix < 0x3f980000 ? 1 : (ix < 0x401c0000 ? 2 : 3));
+	const float n0 = __fsub_rn(__fmul_rn(2.0f, ax), 1.0f), d0 = __fadd_rn(2.0f, ax);
+	const float n1 = __fsub_rn(ax, 1.0f), d1 = __fadd_rn(ax, 1.0f);
+	const float n2 = __fsub_rn(ax, 1.5f), d2 = __fadd_rn(1.0f, __fmul_rn(1.5f, ax));
+	const float num = id == 0 ? n0 : (id == 1 ? n1 : (id == 2 ? n2 : -1.0f));
+	const float den = id == 0 ? d0 : (id == 1 ? d1 : (id == 2 ? d2 : ax));
+	const float hi = id == 0 ? 4.6364760399e-01f : (id == 1 ? 7.8539812565e-01f : (id == 2 ? 9.8279368877e-01f : 1.5707962513e+00f));
+	const float lo = id == 0 ? 5.0121582440e-09f : (id == 1 ? 3.7748947079e-08f : (id == 2 ? 3.4473217170e-08f : 7.5497894159e-08f));
+	const float xr = small ? x : __fdiv_rn(num, den);
+	const float z = __fmul_rn(xr, xr), w = __fmul_rn(z, z);
+	const float s1 = __fmul_rn(z, __fadd_rn(aT[0], __fmul_rn(w, __fadd_rn(aT[2], __fmul_rn(w, __fadd_rn(aT[4], __fmul_rn(w, __fadd_rn(aT[6], __fmul_rn(w, __fadd_rn(aT[8], __fmul_rn(w, aT[10])))))))))));
+	const float s2 = __fmul_rn(w, __fadd_rn(aT[1], __fmul_rn(w, __fadd_rn(aT[3], __fmul_rn(w, __fadd_rn(aT[5], __fmul_rn(w, __fadd_rn(aT[7], __fmul_rn(w, aT[9])))))))));
+	const float xs = __fmul_rn(xr, __fadd_rn(s1, s2));
+	if (small) return __fsub_rn(xr, xs);
+	const float r = __fsub_rn(hi, __fsub_rn(__fsub_rn(xs, lo), xr));
+	return hx < 0 ? -r : r;
 }
 __device__ __forceinline__ float fd_atan2f(float y, float x) {
 	const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
@@ -834,6 +830,24 @@ __device__ __forceinline__ bool dec_cannot_be_valid(const DecCtx &c, int len) { 
 	case 448: return t == 5;
 	}
 	return false;
+}
+// Same CRC (AIS.cpp:55-64: reflected 0x8408, init 0xFFFF, good residue 0xF0B8), eight bits per step: the frame words
+// hold the bits LSB first, which is the order the reflected CRC consumes them.
+__device__ __forceinline__ bool dec_crc16_bytes(const DecCtx &c, int len) {
+	unsigned crc = 0xFFFF;
+	const int nbytes = len >> 3;
+	uint32_t w = 0;
+	for (int k = 0; k < nbytes; k++) {
+		if ((k & 3) == 0) w = frame_word(c, k >> 2);
+		unsigned dta = ((w >> ((k & 3) * 8)) ^ crc) & 0xffu;
+		dta ^= (dta << 4) & 0xffu;
+		crc = (((dta << 8) | (crc >> 8)) ^ (dta >> 4) ^ (dta << 3)) & 0xffffu;
+	}
+	for (int i = nbytes * 8; i < len; i++) {
+		const unsigned bit = (frame_word(c, i >> 5) >> (i & 31)) & 1u;
+		crc = ((bit ^ crc) & 1u) ? ((crc >> 1) ^ 0x8408u) : (crc >> 1);
+	}
+	return crc == 0xF0B8u;
 }
 __device__ __forceinline__ bool dec_crc16(const DecCtx &c, int len) { // AIS.cpp:55-64
 	unsigned crc = 0xFFFF;
@@ -1801,9 +1815,13 @@ __device__ __forceinline__ int dk3_run(Dk3 &st, const DecCtx &ctx, uint32_t Bitw
 				i += exit_m + 1;
 				continue;
 			}
-			if (LEVEL && ctx.mode_level) {
+			if (LEVEL && ctx.mode_level) { // level += tag.sample_lvl for every bit in DATAFCS, in order (AIS.h:146-147)
 				float lv = st.level;
-				for (int m = 0; m <= endb; m++) lv = __fadd_rn(lv, lvl[i + m]);
+#pragma unroll
+				for (int m = 0; m < 32; m++) {
+					const float v = lvl[min(i + m, 31)];
+					lv = m <= endb ? __fadd_rn(lv, v) : lv;
+				}
 				st.level = lv;
 			}
 			if (c < n) { // closing flag
@@ -1812,7 +1830,7 @@ __device__ __forceinline__ int dk3_run(Dk3 &st, const DecCtx &ctx, uint32_t Bitw
 				st.e = i + c;
 				i += c + 1;
 				const int len = newpos - 7;
-				if (len >= 16 && dec_crc16(ctx, len)) {
+				if (len >= 16 && dec_crc16_bytes(ctx, len)) {
 					fr_len = len;
 					fr_level = ctx.mode_level ? __fdiv_rn(st.level, (float)newpos) : 0.0f;
 					st.pos = newpos;
