@@ -43,6 +43,12 @@ const float H_TAPS_COHERENT[17] = { // DSP/Filters.h:35-41
 	2.06995719e-06f, 3.18610148e-05f, 3.40605309e-04f, 2.52892989e-03f, 1.30411453e-02f, 4.67076746e-02f,
 	1.16186141e-01f, 2.00730781e-01f, 2.40861391e-01f, 2.00730781e-01f, 1.16186141e-01f, 4.67076746e-02f,
 	1.30411453e-02f, 2.52892989e-03f, 3.40605309e-04f, 3.18610148e-05f, 2.06995719e-06f };
+const float H_TAPS_BH28_3[26] = { // DSP/Filters.h:43-53
+	6.32542387e-05f, -2.90015252e-04f, -1.54206250e-03f, -1.64972455e-03f, 3.12793899e-03f, 1.09494413e-02f,
+	9.04975801e-03f, -1.43685846e-02f, -4.45615933e-02f, -3.44883647e-02f, 5.53474269e-02f, 2.01827915e-01f,
+	3.16534610e-01f, 3.16534610e-01f, 2.01827915e-01f, 5.53474269e-02f, -3.44883647e-02f, -4.45615933e-02f,
+	-1.43685846e-02f, 9.04975801e-03f, 1.09494413e-02f, 3.12793899e-03f, -1.64972455e-03f, -1.54206250e-03f,
+	-2.90015252e-04f, 6.32542387e-05f };
 const float H_PS_COS[8] = { 9.9518472640441780e-01f, 9.5694033335306883e-01f, 8.8192125790916542e-01f, 7.7301044123076901e-01f,
 							6.3439326515712957e-01f, 4.7139671032286945e-01f, 2.9028464326824349e-01f, 9.8017099547459546e-02f }; // Demod.h:29-31
 const float H_PS_SIN[8] = { 9.8017143048367339e-02f, 2.9028468509743588e-01f, 4.7139674887287397e-01f, 6.3439329894649099e-01f,
@@ -58,6 +64,34 @@ int bytes_per_sample(int fmt) { return fmt == AISGPU_FMT_CF32 ? 8 : (fmt == AISG
 struct aisgpu_handle {
 	aisgpu_config cfg;
 	int k = 0, P = 0, P96 = 0, tile = 0, bps = 8;
+	// Rates the reference serves through DSP::Upsample (non-bucket rates, Model.cpp:134-149) or DSP::DownsampleKFilter
+	// (288 kS/s, Model.cpp:308-313) get a pre-stage that fills a ring of whole reference blocks (d_S); the front end
+	// proper then runs once per block with k = the CIC stages behind the resampler ("inner" submits).
+	int pre = 0;          // 0 none, 1 = [kA x Downsample2CIC5 ->] Upsample, 2 = DownsampleKFilter / 3
+	int kA = 0, PA = 0;   // pre-stage: CIC stages in front of the resampler and their warm-up history (input samples)
+	int in_fmt = 0;       // sample format the front end proper reads (CF32 behind a pre-stage)
+	int outer_N = 0;      // submit length of a pre-stage engine (must not change: the reference's block sizes depend on it)
+	int blk = 0;          // reference block length entering the front end proper (L_us or 8192)
+	int s_cap = 0;        // ring capacity in samples (whole blocks)
+	long long s_stride = 0, d0_stride = 0;
+	long long s_produced = 0, s_consumed = 0; // ring samples written / handed to the front end proper
+	float us_alpha = 0.0f, us_inc = 1.0f;     // Upsample::alpha / increment (DSP.h:165)
+	int dsk_first = 0;                         // DownsampleKFilter::idx_in
+	unsigned char *d_ptail[2] = { nullptr, nullptr };
+	int ptail_cur = 0;
+	float2 *d_D0 = nullptr, *d_S = nullptr, *d_S2 = nullptr; // d_S2: the 96 kS/s ring behind Upsample -> DownsampleKFilter
+	float2 *d_ptail2[2] = { nullptr, nullptr };
+	int ptail2_cur = 0, us_blk = 0, s2_cap = 0;
+	long long s2_stride = 0, s2_produced = 0, s2_consumed = 0;
+	int *d_us_src = nullptr;
+	float *d_us_alpha = nullptr;
+	std::vector<int> h_us_src;
+	std::vector<float> h_us_alpha;
+	FeParams fe_pre;
+	int pre_tile = 0;
+	long long msg_chunk = 0; // ordinal of the caller's submit (what frames are tagged with)
+	int obps = 8;            // bytes per sample of the caller's format (bps: of what the front end proper reads)
+	int inner_max = 0;       // longest block the front end proper can be handed
 	int use_fdc = 0;
 	float fdc_alpha = 0, fdc_beta = 1;
 	int rows = 0;
@@ -67,8 +101,9 @@ struct aisgpu_handle {
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
 	// for timing).  The front end of submit c+1 overlaps the back end of submit c; Cbuf is double buffered for that.
 	cudaStream_t stream = nullptr, copy_stream = nullptr, fe_stream = nullptr;
-	cudaEvent_t ev_fe_done[2] = { nullptr, nullptr }, ev_be_done[2] = { nullptr, nullptr };
-	bool be_recorded[2] = { false, false };
+	static const int NC = 3; // ring of 48 kHz buffers: the front end may run two submits ahead of the back end
+	cudaEvent_t ev_fe_done[3] = { nullptr, nullptr, nullptr }, ev_be_done[3] = { nullptr, nullptr, nullptr };
+	bool be_recorded[3] = { false, false, false };
 	static const int NEV = 128;
 	cudaEvent_t ev_fe0s[128] = { nullptr }, ev_fe1s[128] = { nullptr };
 	cudaEvent_t ev_copy[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr };
@@ -92,7 +127,7 @@ struct aisgpu_handle {
 	bool k1_recorded[3] = { false, false, false };
 	float2 mult;
 	// 48 kHz channel buffer
-	float2 *d_C2[2] = { nullptr, nullptr };
+	float2 *d_C2[3] = { nullptr, nullptr, nullptr };
 	int c_last = 0; // buffer the last submit's front end wrote
 	long long c_stride = 0;
 	int c_hist = 0; // samples kept in front of HC
@@ -159,25 +194,50 @@ int dalloc(aisgpu_handle *h, T **p, size_t n) {
 	return 0;
 }
 
-// Model.cpp:129-338: which bucket, how many CIC stages, droop taps.  Returns <0 when unsupported.
+// Model.cpp:129-338: which bucket, how many CIC stages, droop taps, resampler.  Returns <0 when unsupported.
 int plan_frontend(aisgpu_handle *h) {
 	const int sr = h->cfg.sample_rate;
 	if (sr < 96000 || sr > 12288000) {
 		h->err = "Model: sample rate must be between 96K and 12288K (inclusive).";
 		return AISGPU_EINVAL;
 	}
-	int k = -1;
-	for (int i = 0; i <= 7; i++)
-		if ((96000 << i) == sr) k = i;
-	if (k < 0) {
-		h->err = "sample rate is not one of the 96k*2^k buckets; the interpolated (Upsample) and /3 (DownsampleKFilter) "
-				 "front ends are not built yet";
-		return AISGPU_EINVAL;
+	static const int buckets[9] = { 96000, 192000, 288000, 384000, 768000, 1536000, 3072000, 6144000, 12288000 }; // Model.cpp:129
+	int bucket = 0;
+	for (int b : buckets)
+		if (b >= sr) { bucket = b; break; }
+	const bool interp = bucket != sr; // "sample rate ...K upsampled to ...K." (Model.cpp:146-147)
+	h->pre = 0;
+	h->kA = 0;
+	h->in_fmt = h->cfg.format;
+	int k_total = 0;
+	if (bucket == 288000) { // [US ->] DSK(BlackmanHarris_28_3, 3) -> ROT, no droop filter (Model.cpp:308-313)
+		h->pre = interp ? 3 : 2; // 3: Upsample to 288K first (Model.cpp:308-313 with `interpolated`)
+		if (interp) {
+			h->us_inc = (float)sr / (float)bucket;
+			h->PA = 4;
+		}
+		h->k = 0;
+		h->blk = 8192; // DownsampleKFilter::outputSize (DSP.h:193)
+		h->in_fmt = AISGPU_FMT_CF32;
 	}
-	h->k = k;
-	h->use_fdc = (h->cfg.droop && k > 0) ? 1 : 0;
+	else {
+		for (int b = bucket; b > 96000; b >>= 1) k_total++;
+		if (interp) { // Upsample sits in front of the last min(k, 2) CIC stages (Model.cpp:183-189 and siblings)
+			const int post = k_total < 2 ? k_total : 2;
+			h->pre = 1;
+			h->kA = k_total - post;
+			h->k = post;
+			h->in_fmt = AISGPU_FMT_CF32;
+			h->us_inc = (float)sr / (float)bucket; // Upsample::setParams (DSP.h:174-178)
+			int pa = 5 * ((1 << h->kA) - 1);       // history a kA-stage CIC cascade needs (input samples)
+			const int g = std::max(4, 2 << h->kA);    // every level of a tile must hold an even number of samples
+			h->PA = std::max(g, (pa + g - 1) / g * g);
+		}
+		else h->k = k_total;
+	}
+	h->use_fdc = (h->cfg.droop && k_total > 0) ? 1 : 0;
 	float a = 0.0f;
-	switch (sr) {
+	switch (bucket) {
 	case 12288000: case 6144000: a = -2.0f; break;
 	case 3072000: a = -1.5f; break;
 	case 1536000: case 768000: a = -1.2f; break;
@@ -188,6 +248,7 @@ int plan_frontend(aisgpu_handle *h) {
 	h->fdc_alpha = a;
 	h->fdc_beta = 1 - 2 * a; // DSP.h:293-297
 	// history needed in input samples: h_0 = 17 (FDC 2 + DS2 5 + FCIC5 2*5), h_l = 2 h_{l-1} + 5
+	const int k = h->k;
 	int hk = 17;
 	for (int i = 0; i < k; i++) hk = 2 * hk + 5;
 	const int q = 1 << (k + 2);
@@ -196,9 +257,10 @@ int plan_frontend(aisgpu_handle *h) {
 	return 0;
 }
 
-void layout_frontend(aisgpu_handle *h, int tile) {
-	FeParams &p = h->fe;
-	const int k = h->k;
+// granule of the caller's submit length: every CIC stage needs an even block (DSP.cpp:94,135)
+int outer_granule(const aisgpu_handle *h) { return h->pre >= 2 ? 64 : (1 << (h->k + h->kA + 2)); }
+
+void layout_frontend(FeParams &p, int k, int tile) {
 	int off = 0;
 	auto take = [&](int n) {
 		int o = off;
@@ -217,7 +279,6 @@ void layout_frontend(aisgpu_handle *h, int tile) {
 	p.off_wb = take(tile >> (k + 1));
 	p.smem_f2 = off;
 	p.tile = tile;
-	h->tile = tile;
 }
 
 template <int FMT, int NW, int K>
@@ -226,6 +287,26 @@ int launch_fe(aisgpu_handle *h, dim3 grid, size_t smem) {
 	k_frontend<FMT, NW, K><<<grid, NW * 32, smem, h->fe_stream>>>(h->fe);
 	CU(cudaGetLastError());
 	return 0;
+}
+
+// decimation in front of DSP::Upsample: kA <= 5 CIC stages, level-kA samples to HBM
+template <int FMT, int K>
+int launch_pre(aisgpu_handle *h, dim3 grid, size_t smem) {
+	CU(cudaFuncSetAttribute(k_frontend<FMT, 4, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_frontend<FMT, 4, K, true><<<grid, 128, smem, h->fe_stream>>>(h->fe_pre);
+	CU(cudaGetLastError());
+	return 0;
+}
+template <int FMT>
+int launch_pre_k(aisgpu_handle *h, dim3 grid, size_t smem) {
+	switch (h->kA) {
+	case 0: return launch_pre<FMT, 0>(h, grid, smem);
+	case 1: return launch_pre<FMT, 1>(h, grid, smem);
+	case 2: return launch_pre<FMT, 2>(h, grid, smem);
+	case 3: return launch_pre<FMT, 3>(h, grid, smem);
+	case 4: return launch_pre<FMT, 4>(h, grid, smem);
+	default: return launch_pre<FMT, 5>(h, grid, smem);
+	}
 }
 
 template <int FMT, int NW>
@@ -261,7 +342,8 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 	int tile = h->fe_tile > 0 ? h->fe_tile : 320 * h->fe_warps;
 	if (tile % q) tile = (tile / q + 1) * q;
 	if (tile > N) tile = N;
-	if (tile != p.tile) layout_frontend(h, tile);
+	if (tile != p.tile) layout_frontend(p, h->k, tile);
+	h->tile = tile;
 	const int B = h->cfg.n_streams;
 	int n_seg = (h->fe_ctas + B - 1) / B; // enough CTAs for several waves over 148 SMs
 	int tiles_total = (N + tile - 1) / tile;
@@ -273,7 +355,7 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 	p.in = dev_in;
 	p.tail = h->d_tail[h->tail_cur];
 	p.in_stride = stride;
-	p.format = h->cfg.format;
+	p.format = h->in_fmt;
 	p.k = h->k;
 	p.N = N;
 	p.P = h->P;
@@ -281,12 +363,12 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 	p.fdc_alpha = h->fdc_alpha;
 	p.fdc_beta = h->fdc_beta;
 	p.rot = h->d_rot[h->rot_cur];
-	p.C = h->d_C2[h->chunk & 1];
+	p.C = h->d_C2[h->chunk % aisgpu_handle::NC];
 	p.c_stride = h->c_stride;
 	p.c_off = HC;
 	const size_t smem = (size_t)p.smem_f2 * sizeof(float2);
 	dim3 grid(n_seg, B);
-	switch (h->cfg.format) {
+	switch (h->in_fmt) {
 	case AISGPU_FMT_CF32: return launch_fe_nw<0>(h, grid, smem);
 	case AISGPU_FMT_CU8: return launch_fe_nw<1>(h, grid, smem);
 	case AISGPU_FMT_CS8: return launch_fe_nw<2>(h, grid, smem);
@@ -363,7 +445,8 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.ring = h->d_ring;
 		p.ring_count = h->d_ring_count;
 		p.ring_cap = h->ring_cap;
-		p.chunk = (int)h->chunk;
+		p.chunk = (int)h->msg_chunk;
+		p.blk = (int)h->chunk;
 		p.mode_level = (h->cfg.tag_mode & 1) ? 1 : 0;
 		p.tap_dec = nullptr; // the decoder input samples are recorded by the FM/FIR kernel
 		p.dbg = h->d_dbg;
@@ -400,7 +483,8 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.ring = h->d_ring;
 		p.ring_count = h->d_ring_count;
 		p.ring_cap = h->ring_cap;
-		p.chunk = (int)h->chunk;
+		p.chunk = (int)h->msg_chunk;
+		p.blk = (int)h->chunk;
 		p.mode_level = (h->cfg.tag_mode & 1) ? 1 : 0;
 		if (h->cfg.model == AISGPU_MODEL_DEFAULT) {
 			p.stepidx = h->d_stepidx;
@@ -442,15 +526,15 @@ int enqueue_rot_table(aisgpu_handle *h, long long c, int n96) {
 	return 0;
 }
 
+// One Receive() of the front end proper: N samples per stream (a whole reference block) -> frames.
 int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N) {
 	const int q = 1 << (h->k + 2);
-	if (N <= 0 || N > h->cfg.max_chunk_samples || (N % q) != 0) {
+	if (N <= 0 || N > h->inner_max || (N % q) != 0) {
 		char b[160];
-		snprintf(b, sizeof(b), "n_samples=%d must be a positive multiple of %d and <= max_chunk_samples=%d", N, q, h->cfg.max_chunk_samples);
+		snprintf(b, sizeof(b), "block of %d samples must be a positive multiple of %d and <= %d", N, q, h->inner_max);
 		h->err = b;
 		return AISGPU_EINVAL;
 	}
-	h->last_launches = 0;
 	const int k = h->k, B = h->cfg.n_streams;
 	const int n96 = N >> k, n48 = n96 >> 1;
 	// ---- K0: Rotate phasor table (side stream; normally already enqueued by the previous submit) ----
@@ -463,11 +547,11 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 		CU(cudaStreamWaitEvent(h->fe_stream, h->ev_rot[slot], 0));
 		h->rot_cur = slot;
 	}
-	const int cb = (int)(h->chunk & 1);
-	float2 *Ccur = h->d_C2[cb], *Cnext = h->d_C2[cb ^ 1];
+	const int cb = (int)(h->chunk % aisgpu_handle::NC);
+	float2 *Ccur = h->d_C2[cb], *Cnext = h->d_C2[(cb + 1) % aisgpu_handle::NC];
 	h->c_last = cb;
 	// ---- K1: fused front end (its own stream: overlaps the back end of the previous submit) ----
-	if (h->be_recorded[cb]) CU(cudaStreamWaitEvent(h->fe_stream, h->ev_be_done[cb], 0)); // back end of submit c-2 still reads Cbuf[cb]
+	if (h->be_recorded[cb]) CU(cudaStreamWaitEvent(h->fe_stream, h->ev_be_done[cb], 0)); // back end of submit c-3 still reads Cbuf[cb]
 	const int evi = (int)(h->chunk % aisgpu_handle::NEV);
 	CU(cudaEventRecord(h->ev_fe0s[evi], h->fe_stream));
 	if (int rc = launch_frontend(h, dev_in, stride, N)) return rc;
@@ -560,7 +644,7 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 		}
 		else {
 			k_base<<<(h->rows + K3_THREADS - 1) / K3_THREADS, K3_THREADS, 0, h->stream>>>(
-				h->d_Ef, h->e_stride, HE, n48, h->rows, h->d_pll, h->d_dec, h->d_dec_data, h->d_ring, h->d_ring_count, h->ring_cap, (int)h->chunk,
+				h->d_Ef, h->e_stride, HE, n48, h->rows, h->d_pll, h->d_dec, h->d_dec_data, h->d_ring, h->d_ring_count, h->ring_cap, (int)h->msg_chunk, (int)h->chunk,
 				h->cfg.enable_taps ? h->d_tap_dec : nullptr, h->cfg.enable_taps ? h->d_tap_cnt : nullptr);
 			CU(cudaGetLastError());
 			h->last_launches++;
@@ -568,9 +652,169 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 	}
 	CU(cudaEventRecord(h->ev_be_done[cb], h->stream));
 	h->be_recorded[cb] = true;
+	h->chunk++;
+	return 0;
+}
+
+__global__ void k_d0_carry(float2 *__restrict__ D0, long long d0_stride, int d0_off, int L, int rows) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r < rows) D0[(long long)r * d0_stride + d0_off - 1] = D0[(long long)r * d0_stride + d0_off + L - 1]; // Upsample::a = b
+}
+
+// DownsampleKFilter over N input samples per stream (any format) -> ring of 96 kS/s samples
+int run_dsk(aisgpu_handle *h, const void *in, long long stride, int fmt, int N, const void *tail, float2 *S, long long s_stride, long long &produced, int cap) {
+	const int B = h->cfg.n_streams;
+	const int first = h->dsk_first;
+	const int n_out = first < N ? (N - first + 2) / 3 : 0;
+	if (n_out > 0) {
+		dim3 grid((n_out + DSK_THREADS - 1) / DSK_THREADS, B);
+		switch (fmt) {
+		case AISGPU_FMT_CF32: k_dsk<0><<<grid, DSK_THREADS, 0, h->fe_stream>>>(in, stride, tail, 32, first, n_out, S, s_stride, produced, cap); break;
+		case AISGPU_FMT_CU8: k_dsk<1><<<grid, DSK_THREADS, 0, h->fe_stream>>>(in, stride, tail, 32, first, n_out, S, s_stride, produced, cap); break;
+		case AISGPU_FMT_CS8: k_dsk<2><<<grid, DSK_THREADS, 0, h->fe_stream>>>(in, stride, tail, 32, first, n_out, S, s_stride, produced, cap); break;
+		default: k_dsk<3><<<grid, DSK_THREADS, 0, h->fe_stream>>>(in, stride, tail, 32, first, n_out, S, s_stride, produced, cap); break;
+		}
+		CU(cudaGetLastError());
+		h->last_launches++;
+	}
+	h->dsk_first = first + 3 * n_out - N;
+	produced += n_out;
+	return 0;
+}
+
+int check_outer(aisgpu_handle *h, int N) {
+	const int q = outer_granule(h);
+	if (N <= 0 || N > h->cfg.max_chunk_samples || (N % q) != 0) {
+		char b[160];
+		snprintf(b, sizeof(b), "n_samples=%d must be a positive multiple of %d and <= max_chunk_samples=%d", N, q, h->cfg.max_chunk_samples);
+		h->err = b;
+		return AISGPU_EINVAL;
+	}
+	if ((h->pre == 1 || h->pre == 3) && h->outer_N && N != h->outer_N) {
+		h->err = "at an interpolated sample rate every submit must have the same length (DSP::Upsample re-blocks by it, DSP.cpp:203)";
+		return AISGPU_EINVAL;
+	}
+	return 0;
+}
+
+// The caller's Receive(): N samples per stream in the caller's format.
+int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) {
+	if (int rc = check_outer(h, N)) return rc;
+	h->last_launches = 0;
+	h->msg_chunk = (long long)h->counters[3];
+	const int B = h->cfg.n_streams;
+	int rc = 0;
+	if (h->pre == 0) rc = submit_common(h, dev_in, stride, N);
+	else {
+		const int cur = h->ptail_cur, nxt = cur ^ 1;
+		int tail_len = 0;
+		if (h->pre == 1 || h->pre == 3) { // [kA x Downsample2CIC5 ->] Upsample (Model.cpp:183-189; DSP.cpp:192-212)
+			const int L = N >> h->kA;
+			if (!h->outer_N) {
+				h->outer_N = N;
+				h->us_blk = L;
+				if (h->pre == 1) h->blk = L;
+				h->s_cap = 4 * L;
+			}
+			FeParams &pp = h->fe_pre;
+			int tile = 1280;
+			if (tile > N) tile = N;
+			if (tile != pp.tile) layout_frontend(pp, h->kA, tile);
+			int n_seg = (h->fe_ctas + B - 1) / B;
+			const int tiles_total = (N + tile - 1) / tile;
+			n_seg = std::max(1, std::min(n_seg, tiles_total));
+			pp.seg_len = (tiles_total + n_seg - 1) / n_seg * tile;
+			n_seg = (N + pp.seg_len - 1) / pp.seg_len;
+			pp.in = dev_in;
+			pp.tail = h->d_ptail[cur];
+			pp.in_stride = stride;
+			pp.format = h->cfg.format;
+			pp.k = h->kA;
+			pp.N = N;
+			pp.P = h->PA;
+			pp.use_fdc = 0;
+			pp.rot = nullptr;
+			pp.C = nullptr;
+			pp.D0 = h->d_D0;
+			pp.d0_stride = h->d0_stride;
+			pp.d0_off = 2;
+			const size_t smem = (size_t)pp.smem_f2 * sizeof(float2);
+			dim3 grid(n_seg, B);
+			switch (h->cfg.format) {
+			case AISGPU_FMT_CF32: rc = launch_pre_k<0>(h, grid, smem); break;
+			case AISGPU_FMT_CU8: rc = launch_pre_k<1>(h, grid, smem); break;
+			case AISGPU_FMT_CS8: rc = launch_pre_k<2>(h, grid, smem); break;
+			default: rc = launch_pre_k<3>(h, grid, smem); break;
+			}
+			if (rc) return rc;
+			tail_len = h->PA;
+			// replay Upsample's float accumulator: one (input index, alpha) pair per output (DSP.cpp:196-209)
+			h->h_us_src.clear();
+			h->h_us_alpha.clear();
+			float alpha = h->us_alpha;
+			const float inc = h->us_inc;
+			for (int i = 0; i < L; i++) {
+				do {
+					h->h_us_src.push_back(i);
+					h->h_us_alpha.push_back(alpha);
+					alpha += inc;
+				} while (alpha < 1.0f);
+				alpha -= 1.0f;
+			}
+			h->us_alpha = alpha;
+			const int M = (int)h->h_us_src.size();
+			CU(cudaMemcpyAsync(h->d_us_src, h->h_us_src.data(), (size_t)M * sizeof(int), cudaMemcpyHostToDevice, h->fe_stream));
+			CU(cudaMemcpyAsync(h->d_us_alpha, h->h_us_alpha.data(), (size_t)M * sizeof(float), cudaMemcpyHostToDevice, h->fe_stream));
+			k_upsample<<<dim3((M + 255) / 256, B), 256, 0, h->fe_stream>>>(h->d_D0, h->d0_stride, 2, h->d_us_src, h->d_us_alpha, M, h->d_S, h->s_stride,
+																			  h->s_produced, h->s_cap);
+			CU(cudaGetLastError());
+			k_d0_carry<<<(B + 127) / 128, 128, 0, h->fe_stream>>>(h->d_D0, h->d0_stride, 2, L, B);
+			CU(cudaGetLastError());
+			h->s_produced += M;
+			h->last_launches += 3;
+		}
+		else { // DownsampleKFilter(BlackmanHarris_28_3, 3) (Model.cpp:308-313; DSP.cpp:160-189)
+			tail_len = 32;
+			if ((rc = run_dsk(h, dev_in, stride, h->cfg.format, N, h->d_ptail[cur], h->d_S, h->s_stride, h->s_produced, h->s_cap))) return rc;
+		}
+		{ // raw-format history of the pre-stage for the next submit
+			const int p_w = tail_len * h->obps / 8;
+			dim3 grid((p_w + 127) / 128, B);
+			k_tail_update<<<grid, 128, 0, h->fe_stream>>>((uint2 *)h->d_ptail[nxt], (const uint2 *)h->d_ptail[cur], (const uint2 *)dev_in,
+														stride * h->obps / 8, (long long)N * h->obps / 8, p_w);
+			CU(cudaGetLastError());
+			h->ptail_cur = nxt;
+			h->last_launches++;
+		}
+		if (h->pre == 3) { // every complete Upsample block goes through DownsampleKFilter into the 96 kS/s ring
+			while (h->s_produced - h->s_consumed >= h->us_blk) {
+				const int slot = (int)(h->s_consumed % h->s_cap);
+				const int c2 = h->ptail2_cur;
+				if ((rc = run_dsk(h, h->d_S + slot, h->s_stride, AISGPU_FMT_CF32, h->us_blk, h->d_ptail2[c2], h->d_S2, h->s2_stride, h->s2_produced, h->s2_cap))) return rc;
+				k_tail_update<<<dim3(1, B), 128, 0, h->fe_stream>>>((uint2 *)h->d_ptail2[c2 ^ 1], (const uint2 *)h->d_ptail2[c2], (const uint2 *)(h->d_S + slot),
+																	 h->s_stride, (long long)h->us_blk, 32);
+				CU(cudaGetLastError());
+				h->ptail2_cur = c2 ^ 1;
+				h->s_consumed += h->us_blk;
+			}
+			while (h->s2_produced - h->s2_consumed >= h->blk) {
+				const int slot = (int)(h->s2_consumed % h->s2_cap);
+				if ((rc = submit_common(h, h->d_S2 + slot, h->s2_stride, h->blk))) return rc;
+				h->s2_consumed += h->blk;
+			}
+		}
+		else {
+			// hand every complete reference block to the front end proper
+			while (h->s_produced - h->s_consumed >= h->blk) {
+				const int slot = (int)(h->s_consumed % h->s_cap);
+				if ((rc = submit_common(h, h->d_S + slot, h->s_stride, h->blk))) return rc;
+				h->s_consumed += h->blk;
+			}
+		}
+	}
+	if (rc) return rc;
 	h->counters[2] += (uint64_t)N;
 	h->counters[3] += 1;
-	h->chunk++;
 	return 0;
 }
 
@@ -649,6 +893,7 @@ int drain_ring(aisgpu_handle *h) {
 	// reference emission order: per submit, stream-major, channel A (ROT.up) before B (DSP.cpp:312-313), then time
 	std::stable_sort(h->h_ring.begin(), h->h_ring.end(), [](const FrameRec &a, const FrameRec &b) {
 		if (a.chunk != b.chunk) return a.chunk < b.chunk;
+		if (a.blk != b.blk) return a.blk < b.blk; // Rotate sends whole blocks: A then B per block (DSP.cpp:312-313)
 		return a.row < b.row;
 	});
 	for (const FrameRec &r : h->h_ring) {
@@ -749,7 +994,7 @@ static int create_impl(aisgpu_handle *h) {
 	CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithPriority(&h->fe_stream, cudaStreamNonBlocking, prio_lo));
-	for (int i = 0; i < 2; i++) {
+	for (int i = 0; i < aisgpu_handle::NC; i++) {
 		CU(cudaEventCreateWithFlags(&h->ev_fe_done[i], cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&h->ev_be_done[i], cudaEventDisableTiming));
 	}
@@ -766,21 +1011,55 @@ static int create_impl(aisgpu_handle *h) {
 		CU(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
 	}
 	const int B = c.n_streams, k = h->k;
-	const int q = 1 << (k + 2);
+	const int q = outer_granule(h);
 	const int maxN = (c.max_chunk_samples + q - 1) / q * q;
 	h->cfg.max_chunk_samples = maxN;
 	h->rows = 2 * B;
-	h->bps = bytes_per_sample(c.format);
-	h->max_n48 = maxN >> (k + 1);
+	h->obps = bytes_per_sample(c.format);
+	h->bps = bytes_per_sample(h->in_fmt);
+	h->inner_max = h->pre == 1 ? (maxN >> h->kA) : (h->pre >= 2 ? h->blk : maxN);
+	h->max_n48 = h->inner_max >> (k + 1);
 	h->seq.assign(B, 0);
+	if (h->pre) { // resampler pre-stage: raw-format history, decimated stream, schedule tables, ring of reference blocks
+		const int tl = h->pre == 2 ? 32 : h->PA;
+		for (int i = 0; i < 2; i++) {
+			if (int rc = dalloc(h, &h->d_ptail[i], (size_t)B * tl * h->obps)) return rc;
+			if (c.format == AISGPU_FMT_CU8) CU(cudaMemsetAsync(h->d_ptail[i], 0x80, (size_t)B * tl * h->obps, h->stream));
+		}
+		if (h->pre == 1 || h->pre == 3) {
+			const int Lmax = maxN >> h->kA;
+			h->d0_stride = (Lmax + 4 + 1) & ~1LL;
+			if (int rc = dalloc(h, &h->d_D0, (size_t)B * h->d0_stride)) return rc;
+			if (int rc = dalloc(h, &h->d_us_src, (size_t)2 * Lmax + 8)) return rc;
+			if (int rc = dalloc(h, &h->d_us_alpha, (size_t)2 * Lmax + 8)) return rc;
+			h->s_stride = 4LL * Lmax;
+			memset(&h->fe_pre, 0, sizeof(h->fe_pre));
+		}
+		if (h->pre >= 2) {
+			const int cap96 = ((2 * maxN / 3 + 1 + h->blk + h->blk - 1) / h->blk + 1) * h->blk; // behind Upsample up to 2x the samples
+			CU(cudaMemcpyToSymbol(c_taps_bh28_3, H_TAPS_BH28_3, sizeof(H_TAPS_BH28_3)));
+			if (h->pre == 2) {
+				h->s_cap = cap96;
+				h->s_stride = cap96;
+			}
+			else {
+				h->s2_cap = cap96;
+				h->s2_stride = cap96;
+				if (int rc = dalloc(h, &h->d_S2, (size_t)B * h->s2_stride)) return rc;
+				for (int i = 0; i < 2; i++)
+					if (int rc = dalloc(h, &h->d_ptail2[i], (size_t)B * 32)) return rc;
+			}
+		}
+		if (int rc = dalloc(h, &h->d_S, (size_t)B * h->s_stride)) return rc;
+	}
 	for (int i = 0; i < 2; i++) {
 		if (int rc = dalloc(h, &h->d_tail[i], (size_t)B * h->P * h->bps)) return rc;
-		if (c.format == AISGPU_FMT_CU8) // the reference's zero initial filter state is byte value 128 in CU8
+		if (h->in_fmt == AISGPU_FMT_CU8) // the reference's zero initial filter state is byte value 128 in CU8
 			CU(cudaMemsetAsync(h->d_tail[i], 0x80, (size_t)B * h->P * h->bps, h->stream));
 		if (int rc = dalloc(h, &h->d_fir_hist[i], (size_t)h->rows * 16)) return rc;
 	}
 	for (int i = 0; i < 3; i++)
-		if (int rc = dalloc(h, &h->d_rot[i], (size_t)h->P96 + (maxN >> k) + 8)) return rc;
+		if (int rc = dalloc(h, &h->d_rot[i], (size_t)h->P96 + (h->inner_max >> k) + 8)) return rc;
 	if (int rc = dalloc(h, &h->d_rot_state, 4)) return rc;
 	{
 		float2 one = make_float2(1.0f, 0.0f);
@@ -790,6 +1069,7 @@ static int create_impl(aisgpu_handle *h) {
 	h->c_stride = (HC + h->max_n48 + 8 + 1) & ~1LL;
 	for (int i = 0; i < 2; i++)
 		if (int rc = dalloc(h, &h->d_C2[i], (size_t)h->rows * h->c_stride)) return rc;
+	if (int rc = dalloc(h, &h->d_C2[2], (size_t)h->rows * h->c_stride)) return rc;
 	const int nEmax = HC + h->max_n48;
 	h->e_stride = (HE + nEmax + 8 + 1) & ~1LL;
 	h->r_stride = nEmax;
@@ -897,28 +1177,22 @@ int aisgpu_submit_device(aisgpu_handle *h, const void *dev_samples, int64_t stri
 		h->err = "stride_samples must be even and >= n_samples";
 		return AISGPU_EINVAL;
 	}
-	return submit_common(h, dev_samples, stride_samples, n_samples);
+	return submit_outer(h, dev_samples, stride_samples, n_samples);
 }
 
 int aisgpu_submit(aisgpu_handle *h, const void *host_samples, int n_samples) {
 	if (!h || !host_samples) return AISGPU_EINVAL;
 	CU(cudaSetDevice(h->cfg.device));
-	const int q = 1 << (h->k + 2);
-	if (n_samples <= 0 || n_samples > h->cfg.max_chunk_samples || (n_samples % q) != 0) {
-		char b[160];
-		snprintf(b, sizeof(b), "n_samples=%d must be a positive multiple of %d and <= max_chunk_samples=%d", n_samples, q, h->cfg.max_chunk_samples);
-		h->err = b;
-		return AISGPU_EINVAL;
-	}
-	const size_t bytes = (size_t)h->cfg.n_streams * n_samples * h->bps;
+	if (int rc = check_outer(h, n_samples)) return rc;
+	const size_t bytes = (size_t)h->cfg.n_streams * n_samples * h->obps;
 	const int cur = h->in_cur;
-	if (!h->d_in[cur]) CU(cudaMalloc((void **)&h->d_in[cur], (size_t)h->cfg.n_streams * h->cfg.max_chunk_samples * h->bps));
+	if (!h->d_in[cur]) CU(cudaMalloc((void **)&h->d_in[cur], (size_t)h->cfg.n_streams * h->cfg.max_chunk_samples * h->obps));
 	// the staging buffer may still be read by the kernels of the submit before last
 	if (h->in_used[cur]) CU(cudaStreamWaitEvent(h->copy_stream, h->ev_done[cur], 0));
 	CU(cudaMemcpyAsync(h->d_in[cur], host_samples, bytes, cudaMemcpyHostToDevice, h->copy_stream));
 	CU(cudaEventRecord(h->ev_copy[cur], h->copy_stream));
 	CU(cudaStreamWaitEvent(h->fe_stream, h->ev_copy[cur], 0));
-	int rc = submit_common(h, h->d_in[cur], n_samples, n_samples);
+	int rc = submit_outer(h, h->d_in[cur], n_samples, n_samples);
 	if (rc) return rc;
 	CU(cudaEventRecord(h->ev_done[cur], h->fe_stream)); // the front end is the only reader of the staging buffer
 	h->in_used[cur] = true;
@@ -1062,7 +1336,7 @@ int aisgpu_chunk_granule(const aisgpu_config *cfg) {
 		g_create_error = tmp.err;
 		return rc;
 	}
-	return 1 << (tmp.k + 2);
+	return outer_granule(&tmp);
 }
 
 int aisgpu_validate(const uint8_t *data, int nbits) {
@@ -1080,7 +1354,7 @@ void aisgpu_destroy(aisgpu_handle *h) {
 	if (!h) return;
 	if (h->fe_stream) cudaStreamSynchronize(h->fe_stream);
 	if (h->stream) cudaStreamSynchronize(h->stream);
-	void *ptrs[] = { h->d_in[0], h->d_in[1], h->d_tail[0], h->d_tail[1], h->d_rot[0], h->d_rot[1], h->d_rot[2], h->d_rot_state, h->d_C2[0], h->d_C2[1], h->d_stepidx,
+	void *ptrs[] = { h->d_ptail[0], h->d_ptail[1], h->d_ptail2[0], h->d_ptail2[1], h->d_S2, h->d_D0, h->d_S, h->d_us_src, h->d_us_alpha, h->d_in[0], h->d_in[1], h->d_tail[0], h->d_tail[1], h->d_rot[0], h->d_rot[1], h->d_rot[2], h->d_rot_state, h->d_C2[0], h->d_C2[1], h->d_C2[2], h->d_stepidx,
 					 h->d_steptab, h->d_omega, h->d_cgf_rot, h->d_rots, h->d_ppmtab, h->d_fir_hist[0], h->d_fir_hist[1], h->d_tap_cgf, h->d_Ec,
 					 h->d_Ef, h->d_ps, h->d_ps_mem, h->d_dbits, h->d_lvl, h->d_dbg, h->d_dec, h->d_dec_data, h->d_pll, h->d_tap_dec, h->d_tap_fm, h->d_tap_cnt, h->d_ring,
 					 h->d_ring_count };
@@ -1099,7 +1373,7 @@ void aisgpu_destroy(aisgpu_handle *h) {
 		if (h->ev_k1[i]) cudaEventDestroy(h->ev_k1[i]);
 	}
 	if (h->side_stream) { cudaStreamSynchronize(h->side_stream); cudaStreamDestroy(h->side_stream); }
-	for (int i = 0; i < 2; i++) {
+	for (int i = 0; i < aisgpu_handle::NC; i++) {
 		if (h->ev_fe_done[i]) cudaEventDestroy(h->ev_fe_done[i]);
 		if (h->ev_be_done[i]) cudaEventDestroy(h->ev_be_done[i]);
 	}

