@@ -35,6 +35,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Exactly ONE line may reach stdout (the JSON result): libraries that print there (NCCL's version banner, ...) are
+# diverted to stderr by pointing fd 1 at fd 2 for the lifetime of the process; emit() writes to the saved stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -166,7 +176,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": v, "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(args):
@@ -355,7 +365,7 @@ def main():
         }
         if also:
             line["also"] = also
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
