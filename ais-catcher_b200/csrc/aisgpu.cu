@@ -97,6 +97,9 @@ struct aisgpu_handle {
 	int rows = 0;
 	int max_n48 = 0;
 	int fe_warps = 4, fe_tile = 0, fe_ctas = 4096;
+	int fe_ws = 0;               // AISGPU_FE_WS=1: warp-specialised stage pipeline instead of the barrier-synchronised kernel
+	int fe_st = 1, st_S = 0;     // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane
+	bool fe_ws_laidout = false;
 	int dec_rpw = 6, decoder = 3; // rows per warp / which decoder kernel // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
 	// for timing).  The front end of submit c+1 overlaps the back end of submit c; Cbuf is double buffered for that.
@@ -281,6 +284,64 @@ void layout_frontend(FeParams &p, int k, int tile) {
 	p.tile = tile;
 }
 
+// shared-memory layout of the warp-specialised kernel: level 1 and level 3 are double buffered (hand-offs between warps)
+void layout_frontend_ws(FeParams &p, int k, int tile) {
+	int off = 0;
+	auto take = [&](int n) {
+		int o = off;
+		off += (FE_HIST + n + FE_SLACK + 1) & ~1;
+		return o;
+	};
+	p.off_in[0] = take(tile);
+	p.off_in[1] = take(tile);
+	p.off_rot[0] = p.off_rot[1] = 0;
+	p.off_lv[0] = 0;
+	for (int l = 1; l <= k; l++) p.off_lv[l] = take(tile >> l);
+	p.off_l1b = take(tile >> 1);
+	p.off_l3b = take(tile >> 3);
+	p.off_up = take(tile >> k);
+	p.off_dn = take(tile >> k);
+	p.off_wa = take(tile >> (k + 1));
+	p.off_wb = take(tile >> (k + 1));
+	p.smem_f2 = off;
+	p.tile = tile;
+}
+
+template <int FMT, int K>
+int launch_fe_ws(aisgpu_handle *h, dim3 grid, size_t smem) {
+	CU(cudaFuncSetAttribute(k_frontend_ws<FMT, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_frontend_ws<FMT, K><<<grid, WS_THREADS, smem, h->fe_stream>>>(h->fe);
+	CU(cudaGetLastError());
+	return 0;
+}
+template <int FMT>
+int launch_fe_ws_k(aisgpu_handle *h, dim3 grid, size_t smem) {
+	switch (h->k) {
+	case 3: return launch_fe_ws<FMT, 3>(h, grid, smem);
+	case 4: return launch_fe_ws<FMT, 4>(h, grid, smem);
+	case 5: return launch_fe_ws<FMT, 5>(h, grid, smem);
+	case 6: return launch_fe_ws<FMT, 6>(h, grid, smem);
+	default: return launch_fe_ws<FMT, 7>(h, grid, smem);
+	}
+}
+
+template <int FMT, int K>
+int launch_fe_st(aisgpu_handle *h, int ctas) {
+	const size_t smem = (size_t)ST_WARPS * ST_NB * 32 * StFmt<FMT>::SLOT;
+	CU(cudaFuncSetAttribute(k_frontend_st<FMT, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_frontend_st<FMT, K><<<ctas, ST_WARPS * 32, smem, h->fe_stream>>>(h->fe);
+	CU(cudaGetLastError());
+	return 0;
+}
+template <int FMT>
+int launch_fe_st_k(aisgpu_handle *h, int ctas) {
+	switch (h->k) {
+	case 3: return launch_fe_st<FMT, 3>(h, ctas);
+	case 4: return launch_fe_st<FMT, 4>(h, ctas);
+	default: return launch_fe_st<FMT, 5>(h, ctas);
+	}
+}
+
 template <int FMT, int NW, int K>
 int launch_fe(aisgpu_handle *h, dim3 grid, size_t smem) {
 	CU(cudaFuncSetAttribute(k_frontend<FMT, NW, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -342,7 +403,12 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 	int tile = h->fe_tile > 0 ? h->fe_tile : 320 * h->fe_warps;
 	if (tile % q) tile = (tile / q + 1) * q;
 	if (tile > N) tile = N;
-	if (tile != p.tile) layout_frontend(p, h->k, tile);
+	const bool ws = h->fe_ws && h->k >= 3; // warp-specialised stage pipeline for the high-rate front ends
+	if (tile != p.tile || ws != h->fe_ws_laidout) {
+		if (ws) layout_frontend_ws(p, h->k, tile);
+		else layout_frontend(p, h->k, tile);
+		h->fe_ws_laidout = ws;
+	}
 	h->tile = tile;
 	const int B = h->cfg.n_streams;
 	int n_seg = (h->fe_ctas + B - 1) / B; // enough CTAs for several waves over 148 SMs
@@ -366,8 +432,40 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 	p.C = h->d_C2[h->chunk % aisgpu_handle::NC];
 	p.c_stride = h->c_stride;
 	p.c_off = HC;
+	// 768 kS/s .. 3072 kS/s: per-thread streaming pipeline (state in registers) when the rows are 16-byte aligned
+	if (h->fe_st && h->k >= 3 && h->k <= 5 && ((stride * h->bps) % 16) == 0 && (((size_t)dev_in) % 16) == 0) {
+		// every lane of a warp gets S samples, S a multiple of a super-step; N must split into whole warps of lanes
+		const int SS = 1 << (h->k + 2);
+		int S = h->st_S > 0 ? h->st_S / SS * SS : 0;
+		if (S <= 0) {
+			S = 4096;
+			while (S >= 2 * SS && S / 2 >= 4 * h->P && N % (32 * S) != 0) S /= 2; // longer sub-segments = smaller warm-up share
+		}
+		if (S >= SS && N % (32 * S) == 0) {
+			p.in = dev_in;
+			p.st_S = S;
+			p.st_wps = N / (32 * S);
+			p.st_B = B;
+			const long long warps = (long long)B * p.st_wps;
+			const int ctas = (int)((warps + ST_WARPS - 1) / ST_WARPS);
+			switch (h->in_fmt) {
+			case AISGPU_FMT_CF32: return launch_fe_st_k<0>(h, ctas);
+			case AISGPU_FMT_CU8: return launch_fe_st_k<1>(h, ctas);
+			case AISGPU_FMT_CS8: return launch_fe_st_k<2>(h, ctas);
+			default: return launch_fe_st_k<3>(h, ctas);
+			}
+		}
+	}
 	const size_t smem = (size_t)p.smem_f2 * sizeof(float2);
 	dim3 grid(n_seg, B);
+	if (ws) {
+		switch (h->in_fmt) {
+		case AISGPU_FMT_CF32: return launch_fe_ws_k<0>(h, grid, smem);
+		case AISGPU_FMT_CU8: return launch_fe_ws_k<1>(h, grid, smem);
+		case AISGPU_FMT_CS8: return launch_fe_ws_k<2>(h, grid, smem);
+		default: return launch_fe_ws_k<3>(h, grid, smem);
+		}
+	}
 	switch (h->in_fmt) {
 	case AISGPU_FMT_CF32: return launch_fe_nw<0>(h, grid, smem);
 	case AISGPU_FMT_CU8: return launch_fe_nw<1>(h, grid, smem);
@@ -975,6 +1073,9 @@ static int create_impl(aisgpu_handle *h) {
 		if (h->decoder != 1 && h->decoder != 2) h->decoder = 3;
 	}
 	if (const char *e = getenv("AISGPU_FE_TILE")) h->fe_tile = atoi(e);
+	if (const char *e = getenv("AISGPU_FE_WS")) h->fe_ws = atoi(e) ? 1 : 0;
+	if (const char *e = getenv("AISGPU_FE_ST")) h->fe_st = atoi(e) ? 1 : 0;
+	if (const char *e = getenv("AISGPU_ST_S")) h->st_S = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_CTAS")) h->fe_ctas = std::max(1, atoi(e));
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {

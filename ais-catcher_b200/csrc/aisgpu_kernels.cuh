@@ -168,6 +168,8 @@ struct FeParams {
 	int off_rot[2];          // phasors of the tile
 	int off_lv[FE_MAXK + 1]; // level arrays 1..k (off_lv[0] unused)
 	int off_up, off_dn, off_wa, off_wb;
+	int off_l1b, off_l3b; // warp-specialised kernel: second buffers of the level-1 and level-3 arrays
+	int st_S, st_wps, st_B; // streaming kernel: samples per lane sub-segment, warps per stream, streams
 	int smem_f2;          // total float2
 	float2 *D0;           // PRE mode (decimation in front of DSP::Upsample): level-K samples, [B][d0_stride], sample i at d0_off + i
 	long long d0_stride;
@@ -407,13 +409,19 @@ __global__ void __launch_bounds__(NW * 32) k_frontend(const FeParams p) {
 			fe_sync<NW>();
 		}
 		mbar_wait(&mbar[b], (unsigned)((t >> 1) & 1));
+		// The deeper stages only have work for one or two warps.  Warp w of every CTA sits on scheduler w % 4, so a fixed
+		// assignment would pile all of that work on one of the SM's four schedulers; the work index vt is therefore
+		// rotated by one warp per stage and per tile, which spreads it evenly (CTAs are at different tiles).
+		int rotw = t + blockIdx.x;
+#define FE_VT() ((tid + 32 * ((rotw++) & (NW - 1))) & (NT - 1))
 		// ---- K cascaded Downsample2CIC5 at the input rate ----
 		int src = off_in;
 #pragma unroll
 		for (int l = 0; l < K; l++) {
 			const int dst = p.off_lv[l + 1] + FE_HIST;
 			const int n_out = len >> (l + 1);
-			for (int j0 = tid * 5; j0 < n_out; j0 += 5 * NT) ds2_run<5>(sm, src, dst, j0);
+			const int vt = FE_VT();
+			for (int j0 = vt * 5; j0 < n_out; j0 += 5 * NT) ds2_run<5>(sm, src, dst, j0);
 			fe_sync<NW>();
 			if (l == 0 && !PRE) fe_carry_group(sm, cdesc[b], K + 3, 2, p.tile, tid); // wa, wb of the previous (always full) tile; its FilterCIC5 pass is two barriers back
 			src = dst;
@@ -421,7 +429,8 @@ __global__ void __launch_bounds__(NW * 32) k_frontend(const FeParams p) {
 		if (PRE) { // decimation in front of DSP::Upsample (Model.cpp:183-189): the level-K samples go to HBM
 			const int nK = len >> K, iK = rel >> K, firstK = p.P >> K; // samples before firstK are warm-up
 			float2 *o = p.D0 + (long long)stream * p.d0_stride + p.d0_off + (base >> K) + iK;
-			for (int i = tid; i < nK; i += NT)
+			const int vt_o = FE_VT();
+			for (int i = vt_o; i < nK; i += NT)
 				if (iK + i >= firstK) o[i] = sm[src + i];
 			fe_sync<NW>();
 			fe_carry_group(sm, cdesc[b], 0, K + 1, len, tid);
@@ -431,7 +440,8 @@ __global__ void __launch_bounds__(NW * 32) k_frontend(const FeParams p) {
 		// ---- FilterComplex3Tap + Rotate at 96 kHz ----
 		const int n96 = len >> K;
 		const int off_rt = b ? p.off_rot[1] : p.off_rot[0];
-		for (int i = tid; i < n96; i += NT) {
+		const int vt_r = FE_VT();
+		for (int i = vt_r; i < n96; i += NT) {
 			float2 x = sm[src + i];
 			if (p.use_fdc) { // alpha * (h1 + data[i]) + h2 * beta
 				const float2 tt = cadd(sm[src + i - 2], x);
@@ -450,7 +460,8 @@ __global__ void __launch_bounds__(NW * 32) k_frontend(const FeParams p) {
 		const int n48 = n96 >> 1;
 		const int runs = (n48 + 4) / 5;
 		if (K == 0) fe_sync<NW>(); // the wa/wb history move above reads what this pass overwrites
-		for (int r = tid; r < 2 * runs; r += NT) {
+		const int vt_c = FE_VT();
+		for (int r = vt_c; r < 2 * runs; r += NT) {
 			const int ch = r >= runs;
 			ds2_run<5>(sm, ch ? off_dn : off_up, ch ? off_wb : off_wa, (ch ? r - runs : r) * 5);
 		}
@@ -461,13 +472,423 @@ __global__ void __launch_bounds__(NW * 32) k_frontend(const FeParams p) {
 		const int m_rel = rel >> (K + 1); // 48 kHz index of the tile's first output, relative to base
 		if (m_rel + n48 > m_first) {
 			const int m_lo = m_first - m_rel; // outputs before it are warm-up
-			for (int r = tid; r < 2 * runs; r += NT) {
+			const int vt_f = FE_VT();
+			for (int r = vt_f; r < 2 * runs; r += NT) {
 				const int ch = r >= runs;
 				fcic_run<5>(sm, ch ? off_wb : off_wa, Cg + (ch ? p.c_stride : 0) + m_rel, (ch ? r - runs : r) * 5, m_lo, n48);
 			}
 		}
 		fe_sync<NW>();
 	}
+}
+#undef FE_VT
+
+// ---------------------------------------------------------------------------------------------
+// K1': the same front end as a three-stage software pipeline of specialised warps (K >= 3, i.e. >= 768 kS/s).
+// In k_frontend the deeper stages keep one warp busy while the other three wait at the CTA barrier, so an SM rarely
+// has more than one runnable warp per resident CTA.  Here every warp owns a group of stages and the groups work on
+// different tiles at the same time:
+//   warp 0: input tile (TMA ring)            -> Downsample2CIC5 level 1                -> L1[t & 1]
+//   warp 1: L1[t & 1]                        -> levels 2, 3                             -> L3[t & 1]
+//   warp 2: L3[t & 1] -> levels 4..K -> FilterComplex3Tap -> Rotate -> 2 x (Downsample2CIC5, FilterCIC5) -> HBM
+// hand-offs through mbarriers (full/empty per double buffer); inside a warp the stages are ordered by __syncwarp.
+// The arithmetic (ds2_run / fcic_run, operation order) is exactly that of k_frontend.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+// history for the next tile, moved by three lanes of the calling warp (see fe_carry_group); n even
+__device__ __forceinline__ void ws_carry(float2 *__restrict__ sm, int src, int dst, int n, int lane) {
+	if (lane < FE_HIST / 2) {
+		const float4 v = *reinterpret_cast<const float4 *>(sm + src + n - FE_HIST + 2 * lane);
+		*reinterpret_cast<float4 *>(sm + dst - FE_HIST + 2 * lane) = v;
+	}
+}
+constexpr int WS_THREADS = 96;
+template <int FMT, int K>
+__global__ void __launch_bounds__(WS_THREADS) k_frontend_ws(const FeParams p) {
+	static_assert(K >= 3, "the warp-specialised front end needs at least three CIC stages");
+	extern __shared__ __align__(16) float2 sm[];
+	__shared__ __align__(8) uint64_t bar_in[2], bar_f1[2], bar_e1[2], bar_f3[2], bar_e3[2];
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int stream = blockIdx.y;
+	const long long seg_start = (long long)blockIdx.x * p.seg_len;
+	if (seg_start >= p.N) return;
+	const int seg_n = (int)min((long long)p.seg_len, (long long)p.N - seg_start);
+	const int span = seg_n + p.P;
+	const int n_tiles = (span + p.tile - 1) / p.tile;
+	const long long base = seg_start - p.P;
+	for (int i = tid; i < p.smem_f2; i += WS_THREADS) sm[i] = make_float2(0.f, 0.f);
+	if (tid == 0) {
+		for (int b = 0; b < 2; b++) {
+			mbar_init(&bar_in[b], 1);
+			mbar_init(&bar_f1[b], 1);
+			mbar_init(&bar_e1[b], 1);
+			mbar_init(&bar_f3[b], 1);
+			mbar_init(&bar_e3[b], 1);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	const int L1_0 = p.off_lv[1] + FE_HIST, L1_1 = p.off_l1b + FE_HIST, L3_0 = p.off_lv[3] + FE_HIST, L3_1 = p.off_l3b + FE_HIST;
+#define L1(bb) ((bb) ? L1_1 : L1_0)
+#define L3(bb) ((bb) ? L3_1 : L3_0)
+
+	if (warp == 0) {
+		// ---------------- input ring -> level 1 ----------------
+		auto issue = [&](int t) {
+			const int rel = t * p.tile;
+			const int len = min(p.tile, span - rel);
+			const int b = t & 1;
+			mbar_expect_tx(&bar_in[b], (unsigned)len * 8u);
+			const long long pos = base + rel;
+			float2 *dst = sm + p.off_in[b] + FE_HIST;
+			const float2 *in = reinterpret_cast<const float2 *>(p.in) + (long long)stream * p.in_stride;
+			const float2 *tl = reinterpret_cast<const float2 *>(p.tail) + (long long)stream * p.P + p.P;
+			if (pos >= 0) bulk_g2s(dst, in + pos, (unsigned)len * 8u, &bar_in[b]);
+			else if (pos + len <= 0) bulk_g2s(dst, tl + pos, (unsigned)len * 8u, &bar_in[b]);
+			else {
+				const int nt = (int)(-pos);
+				bulk_g2s(dst, tl + pos, (unsigned)nt * 8u, &bar_in[b]);
+				bulk_g2s(dst + nt, in, (unsigned)(len - nt) * 8u, &bar_in[b]);
+			}
+		};
+		if (FMT == 0 && lane == 0) issue(0);
+		for (int t = 0; t < n_tiles; t++) {
+			const int rel = t * p.tile;
+			const int len = min(p.tile, span - rel);
+			const int b = t & 1;
+			const int off_in = p.off_in[b] + FE_HIST, off_in_next = p.off_in[b ^ 1] + FE_HIST;
+			if (FMT == 0) {
+				if (lane == 0 && t + 1 < n_tiles) issue(t + 1); // slot b^1 was released when this warp finished tile t-1
+				mbar_wait(&bar_in[b], (unsigned)((t >> 1) & 1));
+			}
+			else {
+				const long long pos = base + rel;
+				const long long tbase = (long long)stream * p.P + p.P + pos;
+				const long long ibase = (long long)stream * p.in_stride + pos;
+				for (int i = lane * 2; i < len; i += 64) {
+					float2 x, y;
+					if (pos + i < 0) fe_load_pair<FMT>(p.tail, tbase + i, x, y);
+					else fe_load_pair<FMT>(p.in, ibase + i, x, y);
+					*reinterpret_cast<float4 *>(sm + off_in + i) = make_float4(x.x, x.y, y.x, y.y);
+				}
+				__syncwarp();
+			}
+			if (t >= 2) mbar_wait(&bar_e1[b], (unsigned)(((t >> 1) + 1) & 1)); // warp 1 is done with L1(b) of tile t-2
+			const int n_out = len >> 1;
+			for (int j0 = lane * 5; j0 < n_out; j0 += 160) ds2_run<5>(sm, off_in, L1(b), j0);
+			__syncwarp();
+			ws_carry(sm, off_in, off_in_next, len, lane);
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&bar_f1[b]);
+		}
+	}
+	else if (warp == 1) {
+		// ---------------- level 1 -> levels 2, 3 ----------------
+		const int L2 = p.off_lv[2] + FE_HIST;
+		for (int t = 0; t < n_tiles; t++) {
+			const int len = min(p.tile, span - t * p.tile);
+			const int b = t & 1;
+			mbar_wait(&bar_f1[b], (unsigned)((t >> 1) & 1));
+			const int n2 = len >> 2;
+			for (int j0 = lane * 5; j0 < n2; j0 += 160) ds2_run<5>(sm, L1(b), L2, j0);
+			__syncwarp();
+			ws_carry(sm, L1(b), L1(b ^ 1), len >> 1, lane); // history of level 1 for the next tile (other buffer)
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&bar_e1[b]);
+			if (t >= 2) mbar_wait(&bar_e3[b], (unsigned)(((t >> 1) + 1) & 1)); // warp 2 is done with L3(b) of tile t-2
+			const int n3 = len >> 3;
+			for (int j0 = lane * 5; j0 < n3; j0 += 160) ds2_run<5>(sm, L2, L3(b), j0);
+			__syncwarp();
+			ws_carry(sm, L2, L2, n2, lane);
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&bar_f3[b]);
+		}
+	}
+	else {
+		// ---------------- level 3 -> levels 4..K -> 96 kHz -> 48 kHz -> HBM ----------------
+		const float2 *rot_g = p.rot + (p.P >> K) + (base >> K);
+		float2 *Cg = p.C + (long long)(stream * 2) * p.c_stride + p.c_off + (base >> (K + 1));
+		const int m_first = p.P >> (K + 1);
+		const int off_up = p.off_up + FE_HIST, off_dn = p.off_dn + FE_HIST, off_wa = p.off_wa + FE_HIST, off_wb = p.off_wb + FE_HIST;
+		for (int t = 0; t < n_tiles; t++) {
+			const int rel = t * p.tile;
+			const int len = min(p.tile, span - rel);
+			const int b = t & 1;
+			mbar_wait(&bar_f3[b], (unsigned)((t >> 1) & 1));
+			int src = L3(b);
+#pragma unroll
+			for (int l = 3; l < K; l++) {
+				const int dst = p.off_lv[l + 1] + FE_HIST;
+				const int n_out = len >> (l + 1);
+				for (int j0 = lane * 5; j0 < n_out; j0 += 160) ds2_run<5>(sm, src, dst, j0);
+				__syncwarp();
+				if (l == 3) {
+					ws_carry(sm, L3(b), L3(b ^ 1), len >> 3, lane);
+					__syncwarp();
+					if (lane == 0) mbar_arrive(&bar_e3[b]);
+				}
+				else ws_carry(sm, src, src, len >> l, lane);
+				src = dst;
+			}
+			const int n96 = len >> K;
+			const float2 *rg = rot_g + (rel >> K);
+			for (int i = lane; i < n96; i += 32) {
+				float2 x = sm[src + i];
+				if (p.use_fdc) { // alpha * (h1 + data[i]) + h2 * beta
+					const float2 tt = cadd(sm[src + i - 2], x);
+					const float2 h2 = sm[src + i - 1];
+					x = make_float2(__fadd_rn(__fmul_rn(p.fdc_alpha, tt.x), __fmul_rn(h2.x, p.fdc_beta)),
+									__fadd_rn(__fmul_rn(p.fdc_alpha, tt.y), __fmul_rn(h2.y, p.fdc_beta)));
+				}
+				const float2 r = __ldg(rg + i);
+				const float RR = __fmul_rn(x.x, r.x), II = __fmul_rn(x.y, r.y), RI = __fmul_rn(x.x, r.y), IR = __fmul_rn(x.y, r.x);
+				sm[off_up + i] = make_float2(__fsub_rn(RR, II), __fadd_rn(IR, RI));
+				sm[off_dn + i] = make_float2(__fadd_rn(RR, II), __fsub_rn(IR, RI));
+			}
+			__syncwarp();
+			if (K == 3) { // level 3 fed the 96 kHz stage directly
+				ws_carry(sm, L3(b), L3(b ^ 1), n96, lane);
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&bar_e3[b]);
+			}
+			else ws_carry(sm, src, src, n96, lane);
+			const int n48 = n96 >> 1;
+			const int runs = (n48 + 4) / 5;
+			for (int r = lane; r < 2 * runs; r += 32) {
+				const int ch = r >= runs;
+				ds2_run<5>(sm, ch ? off_dn : off_up, ch ? off_wb : off_wa, (ch ? r - runs : r) * 5);
+			}
+			__syncwarp();
+			ws_carry(sm, off_up, off_up, n96, lane);
+			ws_carry(sm, off_dn, off_dn, n96, lane);
+			const int m_rel = rel >> (K + 1);
+			if (m_rel + n48 > m_first) {
+				const int m_lo = m_first - m_rel;
+				for (int r = lane; r < 2 * runs; r += 32) {
+					const int ch = r >= runs;
+					fcic_run<5>(sm, ch ? off_wb : off_wa, Cg + (ch ? p.c_stride : 0) + m_rel, (ch ? r - runs : r) * 5, m_lo, n48);
+				}
+			}
+			__syncwarp();
+			ws_carry(sm, off_wa, off_wa, n48, lane);
+			ws_carry(sm, off_wb, off_wb, n48, lane);
+			__syncwarp();
+		}
+	}
+}
+#undef L1
+#undef L3
+
+// ---------------------------------------------------------------------------------------------
+// K1'': the front end as the reference writes it -- a per-sample streaming pipeline with its state in registers --
+// run by every THREAD on its own sub-segment of a stream.  A lane walks [a - P, a + S): the first P samples only warm
+// the state up from zero (each CIC stage is a pure function of its last six inputs, see k_frontend), after that every
+// 2^(K+1) inputs yield one 48 kHz sample per channel.  Per input pair a Downsample2CIC5 stage costs 9 packed adds and
+// one packed multiply (DSP.cpp:93-117, literally: r_k = z; z += h_k / h_k = z; z += r_k) and nothing goes through shared
+// memory between stages (ptxas fuses the exact 1/32 scaling of a stage with the first add of the next one into FFMA2;
+// a power-of-two factor makes that bit-identical to the separate multiply unless a value is subnormal); shared memory only stages the input: the warp fetches the next 16 samples of all 32 lanes with
+// coalesced 16-byte cp.async copies (raw format, converted when read) into a ring, four chunks ahead.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+struct Cic5 { c64 h0, h1, h2, h3, h4; };
+__device__ __forceinline__ void cic5_zero(Cic5 &s) { s.h0 = s.h1 = s.h2 = s.h3 = s.h4 = 0ull; }
+// one even/odd input pair of Downsample2CIC5 -> one output
+__device__ __forceinline__ c64 ds2_pair(Cic5 &s, c64 xe, c64 xo, c64 sc) {
+	c64 z = xe;
+	const c64 r0 = z; z = padd(z, s.h0);
+	const c64 r1 = z; z = padd(z, s.h1);
+	const c64 r2 = z; z = padd(z, s.h2);
+	const c64 r3 = z; z = padd(z, s.h3);
+	const c64 r4 = z; z = padd(z, s.h4);
+	const c64 out = pmul(z, sc);
+	z = xo;
+	s.h0 = z; z = padd(z, r0);
+	s.h1 = z; z = padd(z, r1);
+	s.h2 = z; z = padd(z, r2);
+	s.h3 = z; z = padd(z, r3);
+	s.h4 = z;
+	(void)r4;
+	return out;
+}
+// one even/odd input pair of FilterCIC5 -> two outputs (DSP.cpp:132-157)
+__device__ __forceinline__ void fcic_pair(Cic5 &s, c64 xe, c64 xo, c64 sc, c64 &oe, c64 &oo) {
+	c64 z = xe;
+	const c64 r0 = z; z = padd(z, s.h0);
+	const c64 r1 = z; z = padd(z, s.h1);
+	const c64 r2 = z; z = padd(z, s.h2);
+	const c64 r3 = z; z = padd(z, s.h3);
+	const c64 r4 = z; z = padd(z, s.h4);
+	oe = pmul(z, sc);
+	z = xo;
+	s.h0 = z; z = padd(z, r0);
+	s.h1 = z; z = padd(z, r1);
+	s.h2 = z; z = padd(z, r2);
+	s.h3 = z; z = padd(z, r3);
+	s.h4 = z; z = padd(z, r4);
+	oo = pmul(z, sc);
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+
+constexpr int ST_WARPS = 4;  // warps per CTA (independent of each other)
+constexpr int ST_G = 16;     // samples per lane per staged chunk
+constexpr int ST_NB = 4;     // chunks in the ring
+template <int FMT>
+struct StFmt {
+	static constexpr int BPS = FMT == 0 ? 8 : (FMT == 3 ? 4 : 2);
+	static constexpr int CHUNK = ST_G * BPS;      // bytes of one lane's chunk: 128 / 32 / 32 / 64
+	static constexpr int PIECES = CHUNK / 16;     // 16-byte pieces per lane chunk = cp.async instructions per warp chunk
+	static constexpr int SLOT = CHUNK + 16;       // lane stride in the ring (odd multiple of 16 bytes: conflict-free 16-byte reads)
+};
+// sample pair j (samples 2j, 2j+1) of a staged chunk
+template <int FMT>
+__device__ __forceinline__ void st_read_pair(const unsigned char *slot, int j, c64 &xe, c64 &xo) {
+	if (FMT == 0) {
+		const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(slot + j * 16);
+		xe = v.x;
+		xo = v.y;
+	}
+	else if (FMT == 1) {
+		const uchar4 v = *reinterpret_cast<const uchar4 *>(slot + j * 4);
+		xe = pack2(__fmul_rn((float)((int)v.x - 128), 0.0078125f), __fmul_rn((float)((int)v.y - 128), 0.0078125f));
+		xo = pack2(__fmul_rn((float)((int)v.z - 128), 0.0078125f), __fmul_rn((float)((int)v.w - 128), 0.0078125f));
+	}
+	else if (FMT == 2) {
+		const char4 v = *reinterpret_cast<const char4 *>(slot + j * 4);
+		xe = pack2(__fmul_rn((float)v.x, 0.0078125f), __fmul_rn((float)v.y, 0.0078125f));
+		xo = pack2(__fmul_rn((float)v.z, 0.0078125f), __fmul_rn((float)v.w, 0.0078125f));
+	}
+	else {
+		const short4 v = *reinterpret_cast<const short4 *>(slot + j * 8);
+		xe = pack2(__fmul_rn((float)v.x, 3.0517578125e-05f), __fmul_rn((float)v.y, 3.0517578125e-05f));
+		xo = pack2(__fmul_rn((float)v.z, 3.0517578125e-05f), __fmul_rn((float)v.w, 3.0517578125e-05f));
+	}
+}
+
+template <int FMT, int K>
+__global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p) {
+	static_assert(K >= 3 && K <= 5, "streaming front end: 768 kS/s .. 3072 kS/s");
+	typedef StFmt<FMT> F;
+	constexpr int SS = 1 << (K + 2);     // inputs per super-step: two 48 kHz samples per channel
+	constexpr int NCH = SS / ST_G;       // chunks per super-step
+	constexpr int N96 = SS >> K;         // 96 kHz samples per super-step (4)
+	extern __shared__ __align__(16) unsigned char st_ring[]; // [ST_WARPS][ST_NB][32 * SLOT]
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const long long wg = (long long)blockIdx.x * ST_WARPS + wib;
+	const int stream = (int)(wg / p.st_wps);
+	if (stream >= p.st_B) return; // whole warp
+	const int sub0 = (int)(wg - (long long)stream * p.st_wps) * 32;
+	const int S = p.st_S;
+	unsigned char(*ring)[32 * F::SLOT] = reinterpret_cast<unsigned char(*)[32 * F::SLOT]>(st_ring + (size_t)wib * ST_NB * 32 * F::SLOT);
+	// every lane owns S samples [a, a + S) (the host only picks this kernel when N is a multiple of 32 * S * st_wps)
+	const long long a = (long long)(sub0 + lane) * S;
+	const int warp_chunks = (S + p.P) / ST_G; // warm-up included
+	const unsigned char *in_b = reinterpret_cast<const unsigned char *>(p.in) + (long long)stream * p.in_stride * F::BPS;
+	const unsigned char *tl_b = reinterpret_cast<const unsigned char *>(p.tail) + ((long long)stream * p.P + p.P) * F::BPS;
+	// staging: in instruction `it` lane j fetches 16-byte piece (j % PIECES) of the chunk of owner it*(32/PIECES) + j / PIECES
+	constexpr int OWN_PER_IT = 32 / F::PIECES;
+	const int o0 = lane / F::PIECES, q0 = lane % F::PIECES;
+	const long long lane_off = ((long long)(sub0 + o0) * S - p.P) * F::BPS + q0 * 16; // byte offset of chunk 0, piece q0, owner o0
+	const long long it_step = (long long)OWN_PER_IT * S * F::BPS;                        // next instruction: next group of owners
+	const int dst_off = o0 * F::SLOT + q0 * 16;
+	const bool from_tail = sub0 == 0 && o0 == 0; // only the first sub-segment of a stream starts in the previous submit
+	auto prefetch = [&](int c) {
+		if (c < warp_chunks) {
+			const long long coff = lane_off + (long long)c * (ST_G * F::BPS);
+			unsigned char *dst = &ring[c % ST_NB][dst_off];
+#pragma unroll
+			for (int it = 0; it < F::PIECES; it++) {
+				const unsigned char *src = ((it == 0 && from_tail && c * ST_G < p.P) ? tl_b : in_b) + coff + it * it_step;
+				cp_async16(dst + it * OWN_PER_IT * F::SLOT, src);
+			}
+		}
+		cp_async_commit();
+	};
+	const c64 sc = pack2(0.03125f, 0.03125f);
+	Cic5 lv[K], chA, chB, fA, fB;
+#pragma unroll
+	for (int l = 0; l < K; l++) cic5_zero(lv[l]);
+	cic5_zero(chA); cic5_zero(chB); cic5_zero(fA); cic5_zero(fB);
+	c64 fd1 = 0ull, fd2 = 0ull; // FilterComplex3Tap h1, h2
+	const float2 *rot_g = p.rot + (p.P >> K) + ((a - p.P) >> K);
+	float2 *Cg = p.C + (long long)(stream * 2) * p.c_stride + p.c_off + ((a - p.P) >> (K + 1));
+	const int n_super = warp_chunks / NCH;
+	const int warm_super = p.P / SS;
+#pragma unroll
+	for (int c = 0; c < ST_NB - 1; c++) prefetch(c);
+	for (int ss = 0; ss < n_super; ss++) {
+		float2 rt[N96];
+#pragma unroll
+		for (int i = 0; i < N96; i++) rt[i] = __ldg(rot_g + ss * N96 + i);
+		c64 pend[K + 1];  // pend[l]: even-indexed input waiting at level l+1 (l = 1..K-1), pend[K]: unused
+		c64 upE = 0ull, dnE = 0ull, waE = 0ull, wbE = 0ull;
+		c64 outA0 = 0ull, outA1 = 0ull, outB0 = 0ull, outB1 = 0ull;
+#pragma unroll
+		for (int cc = 0; cc < NCH; cc++) {
+			const int c = ss * NCH + cc;
+			prefetch(c + ST_NB - 1);
+			cp_async_wait<ST_NB - 1>(); // chunk c has landed
+			__syncwarp();
+			{
+				const unsigned char *slot = &ring[c % ST_NB][lane * F::SLOT];
+#pragma unroll
+				for (int j = 0; j < ST_G / 2; j++) {
+					const int n1 = cc * (ST_G / 2) + j; // index of this pair's output at level 1 within the super-step
+					c64 xe, xo;
+					st_read_pair<FMT>(slot, j, xe, xo);
+					c64 y = ds2_pair(lv[0], xe, xo, sc);
+					// ripple through the deeper levels: an output with an odd index completes a pair one level down
+					int idx = n1;
+					bool live = true;
+#pragma unroll
+					for (int l = 1; l < K; l++) {
+						if (live) {
+							if ((idx & 1) == 0) { pend[l] = y; live = false; }
+							else { y = ds2_pair(lv[l], pend[l], y, sc); idx >>= 1; }
+						}
+					}
+					if (live) { // y is 96 kHz sample idx (0..N96-1) of the super-step
+						c64 x = y;
+						if (p.use_fdc) { // FilterComplex3Tap: alpha * (h1 + x) + h2 * beta (DSP.cpp:283-293)
+							// scalar intrinsics: ptxas would contract a packed mul + add pair into FFMA2 here, and these products are not exact
+							const float2 h1 = unpack2(fd1), h2 = unpack2(fd2), yv = unpack2(y);
+							const float tx = __fadd_rn(h1.x, yv.x), ty = __fadd_rn(h1.y, yv.y);
+							x = pack2(__fadd_rn(__fmul_rn(p.fdc_alpha, tx), __fmul_rn(h2.x, p.fdc_beta)),
+									  __fadd_rn(__fmul_rn(p.fdc_alpha, ty), __fmul_rn(h2.y, p.fdc_beta)));
+							fd1 = fd2;
+							fd2 = y;
+						}
+						const float2 xv = unpack2(x);
+						const float2 r = rt[idx];
+						const float RR = __fmul_rn(xv.x, r.x), II = __fmul_rn(xv.y, r.y), RI = __fmul_rn(xv.x, r.y), IR = __fmul_rn(xv.y, r.x);
+						const c64 up = pack2(__fsub_rn(RR, II), __fadd_rn(IR, RI));
+						const c64 dn = pack2(__fadd_rn(RR, II), __fsub_rn(IR, RI));
+						if ((idx & 1) == 0) { upE = up; dnE = dn; }
+						else {
+							const c64 wa = ds2_pair(chA, upE, up, sc), wb = ds2_pair(chB, dnE, dn, sc);
+							if ((idx & 2) == 0) { waE = wa; wbE = wb; }
+							else {
+								fcic_pair(fA, waE, wa, sc, outA0, outA1);
+								fcic_pair(fB, wbE, wb, sc, outB0, outB1);
+							}
+						}
+					}
+				}
+			}
+			__syncwarp(); // the ring slot may be refilled by a later prefetch
+		}
+		if (ss >= warm_super) { // two 48 kHz samples per channel
+			float2 *o = Cg + ss * 2;
+			*reinterpret_cast<ulonglong2 *>(o) = make_ulonglong2(outA0, outA1);
+			*reinterpret_cast<ulonglong2 *>(o + p.c_stride) = make_ulonglong2(outB0, outB1);
+		}
+	}
+	cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1071,9 +1492,6 @@ __device__ __forceinline__ void cp_async_f(float *smem_dst, const float *gsrc) {
 __device__ __forceinline__ void cp_async_f(float2 *smem_dst, const float2 *gsrc) {
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
 // ---------------------------------------------------------------------------------------------
 // K3a: PhaseSearchEMA / PhaseSearch (Demod.cpp:39-170), hypothesis-parallel.  Half a warp per (row, sampling
