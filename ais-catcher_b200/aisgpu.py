@@ -17,7 +17,7 @@ TAP_C, TAP_CGF, TAP_FIR, TAP_ROT, TAP_DEC, TAP_FM = 0, 1, 2, 3, 4, 5
 EXPORTS = ["aisgpu_abi_version", "aisgpu_default_config", "aisgpu_create", "aisgpu_submit", "aisgpu_submit_device",
            "aisgpu_sync", "aisgpu_poll", "aisgpu_tap", "aisgpu_counters", "aisgpu_cuda_stream",
            "aisgpu_last_frontend_ms", "aisgpu_frontend_times", "aisgpu_last_launches", "aisgpu_last_error", "aisgpu_destroy",
-           "aisgpu_validate", "aisgpu_build_nmea", "aisgpu_chunk_granule"]
+           "aisgpu_validate", "aisgpu_build_nmea", "aisgpu_chunk_granule", "aisgpu_join"]
 
 
 class Config(C.Structure):
@@ -78,6 +78,7 @@ def load():
     lib.aisgpu_poll.argtypes = [C.c_void_p, C.POINTER(MsgStruct), C.c_int, C.POINTER(C.c_int)]
     lib.aisgpu_tap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.aisgpu_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.aisgpu_join.argtypes = [C.c_void_p]
     lib.aisgpu_cuda_stream.argtypes = [C.c_void_p]
     lib.aisgpu_cuda_stream.restype = C.c_void_p
     lib.aisgpu_last_frontend_ms.argtypes = [C.c_void_p]
@@ -185,6 +186,9 @@ class Engine:
         c = (C.c_uint64 * 8)()
         self._chk(self.lib.aisgpu_counters(self.h, c))
         return list(c)
+
+    def join(self):
+        self._chk(self.lib.aisgpu_join(self.h))
 
     def cuda_stream(self):
         return self.lib.aisgpu_cuda_stream(self.h)

@@ -104,6 +104,15 @@ struct aisgpu_handle {
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
 	// for timing).  The front end of submit c+1 overlaps the back end of submit c; Cbuf is double buffered for that.
 	cudaStream_t stream = nullptr, copy_stream = nullptr, fe_stream = nullptr;
+	// Back-end stages of consecutive submits are pipelined: submit c runs on be_streams[c & 1] (be_streams[0] == stream);
+	// stage s of submit c waits for stage s of submit c-1 (its carried state) through ev_stage[s][(c-1) & 1]; the buffers
+	// between stages are double buffered (index c & 1).  With taps enabled everything stays on one stream.
+	cudaStream_t be_streams[2] = { nullptr, nullptr }, bs = nullptr;
+	static const int NSTAGE = 6; // 0 estimate / fm+fir, 1 cgf_rot, 2 derot+fir (+Ec carry), 3 phase search, 4 decode, 5 carry of Cbuf
+	cudaEvent_t ev_stage[6][2] = {};
+	bool stage_rec[6][2] = {};
+	cudaEvent_t ev_join = nullptr;
+	int pb = 0; // buffer parity of the submit being enqueued
 	static const int NC = 3; // ring of 48 kHz buffers: the front end may run two submits ahead of the back end
 	cudaEvent_t ev_fe_done[3] = { nullptr, nullptr, nullptr }, ev_be_done[3] = { nullptr, nullptr, nullptr };
 	bool be_recorded[3] = { false, false, false };
@@ -136,24 +145,24 @@ struct aisgpu_handle {
 	int c_hist = 0; // samples kept in front of HC
 	// CGF
 	long long cgf_abs = 0;
-	int *d_stepidx = nullptr;
-	float2 *d_steptab = nullptr, *d_omega = nullptr, *d_cgf_rot = nullptr, *d_rots = nullptr;
+	int *d_stepidx2[2] = { nullptr, nullptr };
+	float2 *d_steptab = nullptr, *d_omega = nullptr, *d_cgf_rot = nullptr, *d_rots2[2] = { nullptr, nullptr };
 	float *d_ppmtab = nullptr;
 	long long r_stride = 0;
 	float2 *d_fir_hist[2] = { nullptr, nullptr };
 	int fir_cur = 0;
 	float2 *d_tap_cgf = nullptr;
 	// symbol stage
-	float2 *d_Ec = nullptr;
-	float *d_Ef = nullptr;
+	float2 *d_Ec2[2] = { nullptr, nullptr };
+	float *d_Ef2[2] = { nullptr, nullptr };
 	long long e_stride = 0;
 	int e_left = 0;
 	long long e_abs = 0;
 	PsState *d_ps = nullptr;
 	float *d_ps_mem = nullptr;
 	long long *d_dbg = nullptr; // AISGPU_DEBUG=1: per-row decoder counters (tap 6)
-	uint32_t *d_dbits = nullptr;
-	float *d_lvl = nullptr;
+	uint32_t *d_dbits2[2] = { nullptr, nullptr };
+	float *d_lvl2[2] = { nullptr, nullptr };
 	int dwords = 0;
 	DecState *d_dec = nullptr;
 	uint32_t *d_dec_data = nullptr;
@@ -474,10 +483,24 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 	}
 }
 
+// stage s of this submit may start when stage s of the previous submit (other stream) has finished
+int stage_begin(aisgpu_handle *h, int s) {
+	const int prev = h->pb ^ 1;
+	if (h->be_streams[1] != h->be_streams[0] && h->stage_rec[s][prev]) CU(cudaStreamWaitEvent(h->bs, h->ev_stage[s][prev], 0));
+	return 0;
+}
+int stage_end(aisgpu_handle *h, int s) {
+	if (h->be_streams[1] != h->be_streams[0]) {
+		CU(cudaEventRecord(h->ev_stage[s][h->pb], h->bs));
+		h->stage_rec[s][h->pb] = true;
+	}
+	return 0;
+}
+
 template <typename T>
 int carry(aisgpu_handle *h, T *buf, long long stride, int src_begin, int dst_begin, int cnt) {
 	if (cnt <= 0 || src_begin == dst_begin) return 0;
-	k_carry<T><<<h->rows, 128, cnt * sizeof(T), h->stream>>>(buf, stride, src_begin, dst_begin, cnt);
+	k_carry<T><<<h->rows, 128, cnt * sizeof(T), h->bs>>>(buf, stride, src_begin, dst_begin, cnt);
 	CU(cudaGetLastError());
 	h->last_launches++;
 	return 0;
@@ -486,7 +509,7 @@ int carry(aisgpu_handle *h, T *buf, long long stride, int src_begin, int dst_beg
 template <typename T>
 int carry2(aisgpu_handle *h, const T *src, T *dst, long long stride, int src_begin, int dst_begin, int cnt) {
 	if (cnt <= 0) return 0;
-	k_carry2<T><<<h->rows, 128, 0, h->stream>>>(src, dst, stride, src_begin, dst_begin, cnt);
+	k_carry2<T><<<h->rows, 128, 0, h->bs>>>(src, dst, stride, src_begin, dst_begin, cnt);
 	CU(cudaGetLastError());
 	h->last_launches++;
 	return 0;
@@ -500,19 +523,19 @@ int launch_decode(aisgpu_handle *h, const K3Params &p) {
 	const int rpw = h->dec_rpw;
 	if (h->decoder == 1) {
 		const int grid = (h->rows + DK_THREADS / 32 - 1) / (DK_THREADS / 32);
-		k_decode<MODEL, false><<<grid, DK_THREADS, 0, h->stream>>>(p);
+		k_decode<MODEL, false><<<grid, DK_THREADS, 0, h->bs>>>(p);
 	}
 	else if (h->decoder == 2) {
 		const int grid = (h->rows + rpw * DK2_WARPS - 1) / (rpw * DK2_WARPS);
-		if (rpw == 1) k_decode2<MODEL, false, 1><<<grid, DK2_WARPS * 32, 0, h->stream>>>(p);
-		else if (rpw == 3) k_decode2<MODEL, false, 3><<<grid, DK2_WARPS * 32, 0, h->stream>>>(p);
-		else k_decode2<MODEL, false, 6><<<grid, DK2_WARPS * 32, 0, h->stream>>>(p);
+		if (rpw == 1) k_decode2<MODEL, false, 1><<<grid, DK2_WARPS * 32, 0, h->bs>>>(p);
+		else if (rpw == 3) k_decode2<MODEL, false, 3><<<grid, DK2_WARPS * 32, 0, h->bs>>>(p);
+		else k_decode2<MODEL, false, 6><<<grid, DK2_WARPS * 32, 0, h->bs>>>(p);
 	}
 	else {
 		const int grid = (h->rows + rpw * DK3_WARPS - 1) / (rpw * DK3_WARPS);
-		if (rpw == 1) k_decode3<MODEL, 1><<<grid, DK3_WARPS * 32, 0, h->stream>>>(p);
-		else if (rpw == 3) k_decode3<MODEL, 3><<<grid, DK3_WARPS * 32, 0, h->stream>>>(p);
-		else k_decode3<MODEL, 6><<<grid, DK3_WARPS * 32, 0, h->stream>>>(p);
+		if (rpw == 1) k_decode3<MODEL, 1><<<grid, DK3_WARPS * 32, 0, h->bs>>>(p);
+		else if (rpw == 3) k_decode3<MODEL, 3><<<grid, DK3_WARPS * 32, 0, h->bs>>>(p);
+		else k_decode3<MODEL, 6><<<grid, DK3_WARPS * 32, 0, h->bs>>>(p);
 	}
 	CU(cudaGetLastError());
 	return 0;
@@ -537,7 +560,7 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.abs_begin = g0;
 		p.abs_lo = a0;
 		p.abs_hi = a1;
-		p.Ef = h->d_Ef;
+		p.Ef = h->d_Ef2[0];
 		p.dec = h->d_dec;
 		p.dec_data = h->d_dec_data;
 		p.ring = h->d_ring;
@@ -548,10 +571,11 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.mode_level = (h->cfg.tag_mode & 1) ? 1 : 0;
 		p.tap_dec = nullptr; // the decoder input samples are recorded by the FM/FIR kernel
 		p.dbg = h->d_dbg;
-		p.dbits = h->d_dbits;
+		p.dbits = h->d_dbits2[h->pb];
 		p.dwords = h->dwords;
+		if (int rc = stage_begin(h, 4)) return rc;
 		if (int rc = launch_decode<0>(h, p)) return rc;
-		CU(cudaGetLastError());
+		if (int rc = stage_end(h, 4)) return rc;
 		h->last_launches++;
 		h->e_abs = a1;
 		return 0;
@@ -572,8 +596,8 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.abs_begin = h->e_abs;
 		p.abs_lo = h->e_abs;
 		p.abs_hi = h->e_abs + (long long)nsym * 5;
-		p.Ec = h->d_Ec;
-		p.Ef = h->d_Ef;
+		p.Ec = h->d_Ec2[0];
+		p.Ef = h->d_Ef2[0];
 		p.ps = h->d_ps;
 		p.ps_mem = h->d_ps_mem;
 		p.dec = h->d_dec;
@@ -585,25 +609,37 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.blk = (int)h->chunk;
 		p.mode_level = (h->cfg.tag_mode & 1) ? 1 : 0;
 		if (h->cfg.model == AISGPU_MODEL_DEFAULT) {
-			p.stepidx = h->d_stepidx;
+			p.stepidx = h->d_stepidx2[h->pb];
 			p.ppmtab = h->d_ppmtab;
 			p.blk_abs0 = h->cgf_abs;
 			p.nblk = n_new / CGF_N;
 		}
 		p.tap_dec = h->cfg.enable_taps ? h->d_tap_dec : nullptr;
 		p.dbg = h->d_dbg;
-		p.dbits = h->d_dbits;
+		p.dbits = h->d_dbits2[h->pb];
 		p.dwords = h->dwords;
-		p.lvl = h->d_lvl;
+		p.lvl = h->d_lvl2[h->pb];
 		p.lvl_stride = h->dwords * K3_TS;
 		const long long ps_warps = ((long long)h->rows * 5 + 1) / 2;
-		k_phase_search<<<(unsigned)((ps_warps + PS_THREADS / 32 - 1) / (PS_THREADS / 32)), PS_THREADS, 0, h->stream>>>(p);
+		if (int rc = stage_begin(h, 3)) return rc;
+		k_phase_search<<<(unsigned)((ps_warps + PS_THREADS / 32 - 1) / (PS_THREADS / 32)), PS_THREADS, 0, h->bs>>>(p);
 		CU(cudaGetLastError());
+		// the incomplete group of 5 at the end moves to the front for the next submit (Ec is single buffered: the next
+		// submit's derotation waits for this stage)
+		const int nl = total - nsym * 5;
+		if (carry(h, h->d_Ec2[0], h->e_stride, e_begin + nsym * 5, HE - nl, nl)) return AISGPU_ECUDA;
+		if (int rc = stage_end(h, 3)) return rc;
+		if (int rc = stage_begin(h, 4)) return rc;
 		if (int rc = launch_decode<2>(h, p)) return rc;
+		if (int rc = stage_end(h, 4)) return rc;
 		h->last_launches += 2;
 	}
 	const int new_left = total - nsym * 5;
-	if (carry(h, h->d_Ec, h->e_stride, e_begin + nsym * 5, HE - new_left, new_left)) return AISGPU_ECUDA;
+	if (nsym == 0) {
+		if (int rc = stage_begin(h, 3)) return rc;
+		if (carry(h, h->d_Ec2[0], h->e_stride, e_begin + nsym * 5, HE - new_left, new_left)) return AISGPU_ECUDA;
+		if (int rc = stage_end(h, 3)) return rc;
+	}
 	h->e_left = new_left;
 	h->e_abs += (long long)nsym * 5;
 	return 0;
@@ -672,43 +708,63 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 		h->last_launches++;
 	}
 	CU(cudaEventRecord(h->ev_fe_done[cb], h->fe_stream));
-	CU(cudaStreamWaitEvent(h->stream, h->ev_fe_done[cb], 0));
+	h->pb = (int)(h->chunk & 1);
+	h->bs = h->be_streams[h->pb];
+	CU(cudaStreamWaitEvent(h->bs, h->ev_fe_done[cb], 0));
 	h->last_n = N;
 	h->last_n48 = n48;
 	h->last_nE = 0;
 	h->last_nsym = 0;
-	// ---- back end ----
+	// ---- back end (stage-pipelined over consecutive submits, see aisgpu_handle::be_streams) ----
 	if (h->cfg.model == AISGPU_MODEL_DEFAULT) {
 		const int cnt = h->c_hist; // unconsumed samples in front of HC
 		const int total = cnt + n48;
 		const int nblk = total / CGF_N;
 		const int c_begin = HC - cnt;
+		const int newcnt = total - nblk * CGF_N;
+		// samples that do not fill a 512-block go to the front of the next submit's buffer; the estimator of the next
+		// submit only has to wait for this copy (and this one for the copy of the previous submit)
+		if (int rc = stage_begin(h, 5)) return rc;
+		if (int rc = carry2(h, Ccur, Cnext, h->c_stride, c_begin + nblk * CGF_N, HC - newcnt, newcnt)) return rc;
+		if (int rc = stage_end(h, 5)) return rc;
+		h->c_hist = newcnt;
 		if (nblk > 0) {
 			const int total_blocks = h->rows * nblk;
 			const int ctas = (total_blocks + CGF_BLK_PER_CTA - 1) / CGF_BLK_PER_CTA;
 			const size_t smem = 4096 + 2 * (size_t)CGF_BLK_PER_CTA * CGF_ROWP * 4;
-			k_cgf_estimate<<<ctas, CGF_THREADS, smem, h->stream>>>(Ccur, h->c_stride, c_begin, nblk, total_blocks, h->d_omega,
-																	 h->cfg.afc_wide, h->d_stepidx);
+			int *stepidx = h->d_stepidx2[h->pb];
+			float2 *rots = h->d_rots2[h->pb];
+			// stepidx / rots / dbits / lvl are double buffered by submit parity == stream, so stream order protects them
+			k_cgf_estimate<<<ctas, CGF_THREADS, smem, h->bs>>>(Ccur, h->c_stride, c_begin, nblk, total_blocks, h->d_omega, h->cfg.afc_wide, stepidx);
 			CU(cudaGetLastError());
-			k_cgf_rot<<<(h->rows + 31) / 32, 32, 0, h->stream>>>(h->d_stepidx, h->d_steptab, h->d_cgf_rot, h->d_rots, h->r_stride, nblk, h->rows);
+			if (int rc = stage_begin(h, 1)) return rc;
+			k_cgf_rot<<<(h->rows + 31) / 32, 32, 0, h->bs>>>(stepidx, h->d_steptab, h->d_cgf_rot, rots, h->r_stride, nblk, h->rows);
 			CU(cudaGetLastError());
+			if (int rc = stage_end(h, 1)) return rc;
 			const int nE = nblk * CGF_N;
 			dim3 grid((nE + FIRC_TILE - 1) / FIRC_TILE, h->rows);
-			k_cgf_derot_fir<<<grid, FIRC_TILE, 0, h->stream>>>(Ccur, h->c_stride, c_begin, h->d_rots, h->r_stride, nE, h->d_fir_hist[h->fir_cur],
-																 h->d_fir_hist[h->fir_cur ^ 1], h->d_Ec, h->e_stride, HE,
-																 h->cfg.enable_taps ? h->d_tap_cgf : nullptr, h->r_stride);
+			if (int rc = stage_begin(h, 2)) return rc;
+			if (int rc = stage_begin(h, 3)) return rc; // Ec is free once the previous submit's phase search has read it
+			k_cgf_derot_fir<<<grid, FIRC_TILE, 0, h->bs>>>(Ccur, h->c_stride, c_begin, rots, h->r_stride, nE, h->d_fir_hist[h->fir_cur],
+															 h->d_fir_hist[h->fir_cur ^ 1], h->d_Ec2[0], h->e_stride, HE,
+															 h->cfg.enable_taps ? h->d_tap_cgf : nullptr, h->r_stride);
 			CU(cudaGetLastError());
+			if (int rc = stage_end(h, 2)) return rc;
 			h->fir_cur ^= 1;
 			h->last_launches += 3;
 			h->last_nE = nE;
-			if (int rc = run_symbols(h, nE)) return rc;
-			h->cgf_abs += nE;
 		}
-		const int newcnt = total - nblk * CGF_N;
-		if (int rc = carry2(h, Ccur, Cnext, h->c_stride, c_begin + nblk * CGF_N, HC - newcnt, newcnt)) return rc;
-		h->c_hist = newcnt;
+		CU(cudaEventRecord(h->ev_be_done[cb], h->bs)); // last reader of Cbuf[cb]
+		h->be_recorded[cb] = true;
+		if (nblk > 0) {
+			if (int rc = run_symbols(h, nblk * CGF_N)) return rc;
+			h->cgf_abs += nblk * CGF_N;
+		}
 	}
 	else {
+		if (int rc = stage_begin(h, 5)) return rc;
+		if (int rc = carry2(h, Ccur, Cnext, h->c_stride, HC + n48 - FIRF_T, HC - FIRF_T, FIRF_T)) return rc; // FM + FIR history
+		if (int rc = stage_end(h, 5)) return rc;
 		{
 			// the 5-phase deinterleaver's slots are aligned to absolute sample indices (DSP.h:65-73)
 			const long long a0 = h->e_abs, a1 = a0 + n48;
@@ -722,34 +778,35 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 			f.n = n48;
 			f.r0 = h->cfg.model == AISGPU_MODEL_STANDARD ? (int)(a0 - g0) : 0;
 			f.nslots = nslots;
-			f.Fbuf = h->d_Ef;
+			f.Fbuf = h->d_Ef2[0];
 			f.f_stride = h->e_stride;
 			f.f_off = HE;
-			f.dbits = h->d_dbits;
+			f.dbits = h->d_dbits2[h->pb];
 			f.dwords = h->dwords;
 			f.tap_fm = h->cfg.enable_taps ? h->d_tap_fm : nullptr;
 			f.tap_stride = h->r_stride;
 			f.tap_dec = (h->cfg.enable_taps && h->cfg.model == AISGPU_MODEL_STANDARD) ? h->d_tap_dec : nullptr;
 			dim3 grid((nslots + FM5_THREADS - 1) / FM5_THREADS, h->rows);
-			k_fm_fir5<<<grid, FM5_THREADS, 0, h->stream>>>(f);
+			if (int rc = stage_begin(h, 0)) return rc; // Ef (single buffered) is only read by taps / k_base, which do not pipeline
+			k_fm_fir5<<<grid, FM5_THREADS, 0, h->bs>>>(f);
+			CU(cudaGetLastError());
+			if (int rc = stage_end(h, 0)) return rc;
 		}
-		CU(cudaGetLastError());
+		CU(cudaEventRecord(h->ev_be_done[cb], h->bs));
+		h->be_recorded[cb] = true;
 		h->last_launches++;
 		h->last_nE = n48;
-		if (int rc = carry2(h, Ccur, Cnext, h->c_stride, HC + n48 - FIRF_T, HC - FIRF_T, FIRF_T)) return rc;
 		if (h->cfg.model == AISGPU_MODEL_STANDARD) {
 			if (int rc = run_symbols(h, n48)) return rc;
 		}
 		else {
-			k_base<<<(h->rows + K3_THREADS - 1) / K3_THREADS, K3_THREADS, 0, h->stream>>>(
-				h->d_Ef, h->e_stride, HE, n48, h->rows, h->d_pll, h->d_dec, h->d_dec_data, h->d_ring, h->d_ring_count, h->ring_cap, (int)h->msg_chunk, (int)h->chunk,
+			k_base<<<(h->rows + K3_THREADS - 1) / K3_THREADS, K3_THREADS, 0, h->bs>>>(
+				h->d_Ef2[0], h->e_stride, HE, n48, h->rows, h->d_pll, h->d_dec, h->d_dec_data, h->d_ring, h->d_ring_count, h->ring_cap, (int)h->msg_chunk, (int)h->chunk,
 				h->cfg.enable_taps ? h->d_tap_dec : nullptr, h->cfg.enable_taps ? h->d_tap_cnt : nullptr);
 			CU(cudaGetLastError());
 			h->last_launches++;
 		}
 	}
-	CU(cudaEventRecord(h->ev_be_done[cb], h->stream));
-	h->be_recorded[cb] = true;
 	h->chunk++;
 	return 0;
 }
@@ -777,6 +834,12 @@ int run_dsk(aisgpu_handle *h, const void *in, long long stride, int fmt, int N, 
 	}
 	h->dsk_first = first + 3 * n_out - N;
 	produced += n_out;
+	return 0;
+}
+
+int sync_backend(aisgpu_handle *h) {
+	CU(cudaStreamSynchronize(h->be_streams[0]));
+	if (h->be_streams[1] != h->be_streams[0]) CU(cudaStreamSynchronize(h->be_streams[1]));
 	return 0;
 }
 
@@ -979,7 +1042,7 @@ void build_nmea(aisgpu_msg &m, int own_mmsi, int *seq_counter) { // Message.cpp:
 }
 
 int drain_ring(aisgpu_handle *h) {
-	CU(cudaStreamSynchronize(h->stream));
+	if (int rc = sync_backend(h)) return rc;
 	int count = 0;
 	CU(cudaMemcpy(&count, h->d_ring_count, sizeof(int), cudaMemcpyDeviceToHost));
 	if (count <= 0) return 0;
@@ -1092,6 +1155,17 @@ static int create_impl(aisgpu_handle *h) {
 	int prio_lo = 0, prio_hi = 0;
 	CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
 	CU(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
+	h->be_streams[0] = h->be_streams[1] = h->stream;
+	{
+		const char *e = getenv("AISGPU_BE_PIPE");
+		// measured: overlapping the stages of consecutive submits pays for the FM chain (+6 %), not for the coherent one
+		const bool pipe = (e ? atoi(e) != 0 : c.model == AISGPU_MODEL_STANDARD) && !c.enable_taps && c.model != AISGPU_MODEL_BASE;
+		if (pipe) CU(cudaStreamCreateWithPriority(&h->be_streams[1], cudaStreamNonBlocking, prio_hi));
+	}
+	h->bs = h->stream;
+	for (int st = 0; st < aisgpu_handle::NSTAGE; st++)
+		for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&h->ev_stage[st][i], cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
 	CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithPriority(&h->fe_stream, cudaStreamNonBlocking, prio_lo));
@@ -1178,14 +1252,18 @@ static int create_impl(aisgpu_handle *h) {
 	if (int rc = dalloc(h, &h->d_dec_data, (size_t)h->rows * 5 * DEC_WORDS)) return rc;
 	if (c.model == AISGPU_MODEL_DEFAULT) {
 		h->c_hist = 0;
-		if (int rc = dalloc(h, &h->d_stepidx, (size_t)h->rows * (nEmax / CGF_N + 1))) return rc;
-		if (int rc = dalloc(h, &h->d_rots, (size_t)h->rows * h->r_stride)) return rc;
+		for (int i = 0; i < 2; i++) {
+			if (int rc = dalloc(h, &h->d_stepidx2[i], (size_t)h->rows * (nEmax / CGF_N + 1))) return rc;
+			if (int rc = dalloc(h, &h->d_rots2[i], (size_t)h->rows * h->r_stride)) return rc;
+		}
 		if (int rc = dalloc(h, &h->d_cgf_rot, (size_t)h->rows)) return rc;
-		if (int rc = dalloc(h, &h->d_Ec, (size_t)h->rows * h->e_stride)) return rc;
+		if (int rc = dalloc(h, &h->d_Ec2[0], (size_t)h->rows * h->e_stride)) return rc;
 		if (int rc = dalloc(h, &h->d_ps, (size_t)h->rows * 5)) return rc;
 		h->dwords = (nEmax / 5 + 1 + K3_TS - 1) / K3_TS + 1;
-		if (int rc = dalloc(h, &h->d_dbits, (size_t)h->rows * 5 * h->dwords)) return rc;
-		if (int rc = dalloc(h, &h->d_lvl, (size_t)h->rows * h->dwords * K3_TS)) return rc;
+		for (int i = 0; i < 2; i++) {
+			if (int rc = dalloc(h, &h->d_dbits2[i], (size_t)h->rows * 5 * h->dwords)) return rc;
+			if (int rc = dalloc(h, &h->d_lvl2[i], (size_t)h->rows * h->dwords * K3_TS)) return rc;
+		}
 		if (!c.ps_ema)
 			if (int rc = dalloc(h, &h->d_ps_mem, (size_t)h->rows * 5 * 16 * 12)) return rc;
 		if (int rc = dalloc(h, &h->d_steptab, CGF_NIDX)) return rc;
@@ -1216,9 +1294,10 @@ static int create_impl(aisgpu_handle *h) {
 	}
 	else {
 		h->c_hist = FIRF_T;
-		if (int rc = dalloc(h, &h->d_Ef, (size_t)h->rows * h->e_stride)) return rc;
+		if (int rc = dalloc(h, &h->d_Ef2[0], (size_t)h->rows * h->e_stride)) return rc;
 		h->dwords = (nEmax / 5 + 2 + K3_TS - 1) / K3_TS + 1;
-		if (int rc = dalloc(h, &h->d_dbits, (size_t)h->rows * 5 * h->dwords)) return rc;
+		for (int i = 0; i < 2; i++)
+			if (int rc = dalloc(h, &h->d_dbits2[i], (size_t)h->rows * 5 * h->dwords)) return rc;
 		if (c.model == AISGPU_MODEL_BASE) {
 			if (int rc = dalloc(h, &h->d_pll, (size_t)h->rows)) return rc;
 			std::vector<PllState> pl(h->rows);
@@ -1306,7 +1385,7 @@ int aisgpu_submit(aisgpu_handle *h, const void *host_samples, int n_samples) {
 int aisgpu_sync(aisgpu_handle *h) {
 	if (!h) return AISGPU_EINVAL;
 	CU(cudaStreamSynchronize(h->fe_stream));
-	CU(cudaStreamSynchronize(h->stream));
+	if (int rc = sync_backend(h)) return rc;
 	return 0;
 }
 
@@ -1328,7 +1407,7 @@ int aisgpu_tap(aisgpu_handle *h, int tap, int stream, int channel, void *dst, si
 	if (!h || !n_out || stream < 0 || stream >= h->cfg.n_streams || channel < 0 || channel > 9) return AISGPU_EINVAL;
 	CU(cudaSetDevice(h->cfg.device));
 	CU(cudaStreamSynchronize(h->fe_stream));
-	CU(cudaStreamSynchronize(h->stream));
+	if (int rc = sync_backend(h)) return rc;
 	const int row = stream * 2 + (channel & 1);
 	const void *src = nullptr;
 	size_t n = 0, esz = 8;
@@ -1343,8 +1422,8 @@ int aisgpu_tap(aisgpu_handle *h, int tap, int stream, int channel, void *dst, si
 		n = h->last_nE;
 		break;
 	case AISGPU_TAP_FIR:
-		if (h->cfg.model == AISGPU_MODEL_DEFAULT) src = h->d_Ec + (long long)row * h->e_stride + HE;
-		else { src = h->d_Ef + (long long)row * h->e_stride + HE; esz = 4; }
+		if (h->cfg.model == AISGPU_MODEL_DEFAULT) src = h->d_Ec2[0] + (long long)row * h->e_stride + HE;
+		else { src = h->d_Ef2[0] + (long long)row * h->e_stride + HE; esz = 4; }
 		n = h->last_nE;
 		break;
 	case AISGPU_TAP_ROT:
@@ -1402,6 +1481,15 @@ int aisgpu_counters(aisgpu_handle *h, uint64_t counters[8]) {
 
 void *aisgpu_cuda_stream(aisgpu_handle *h) { return h ? (void *)h->stream : nullptr; }
 
+int aisgpu_join(aisgpu_handle *h) {
+	if (!h) return AISGPU_EINVAL;
+	if (h->be_streams[1] != h->be_streams[0]) {
+		CU(cudaEventRecord(h->ev_join, h->be_streams[1]));
+		CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+	}
+	return 0;
+}
+
 float aisgpu_last_frontend_ms(aisgpu_handle *h) {
 	float ms = -1.0f;
 	int n = 0;
@@ -1414,7 +1502,7 @@ int aisgpu_frontend_times(aisgpu_handle *h, float *ms_out, int max, int *n) {
 	*n = 0;
 	if (!h->fe_timed) return 0;
 	CU(cudaStreamSynchronize(h->fe_stream));
-	CU(cudaStreamSynchronize(h->stream));
+	if (int rc = sync_backend(h)) return rc;
 	long long cnt = std::min<long long>(std::min<long long>(h->chunk, aisgpu_handle::NEV), max);
 	for (long long i = 0; i < cnt; i++) { // newest first
 		const int evi = (int)((h->chunk - 1 - i) % aisgpu_handle::NEV);
@@ -1455,9 +1543,14 @@ void aisgpu_destroy(aisgpu_handle *h) {
 	if (!h) return;
 	if (h->fe_stream) cudaStreamSynchronize(h->fe_stream);
 	if (h->stream) cudaStreamSynchronize(h->stream);
-	void *ptrs[] = { h->d_ptail[0], h->d_ptail[1], h->d_ptail2[0], h->d_ptail2[1], h->d_S2, h->d_D0, h->d_S, h->d_us_src, h->d_us_alpha, h->d_in[0], h->d_in[1], h->d_tail[0], h->d_tail[1], h->d_rot[0], h->d_rot[1], h->d_rot[2], h->d_rot_state, h->d_C2[0], h->d_C2[1], h->d_C2[2], h->d_stepidx,
-					 h->d_steptab, h->d_omega, h->d_cgf_rot, h->d_rots, h->d_ppmtab, h->d_fir_hist[0], h->d_fir_hist[1], h->d_tap_cgf, h->d_Ec,
-					 h->d_Ef, h->d_ps, h->d_ps_mem, h->d_dbits, h->d_lvl, h->d_dbg, h->d_dec, h->d_dec_data, h->d_pll, h->d_tap_dec, h->d_tap_fm, h->d_tap_cnt, h->d_ring,
+	if (h->be_streams[1] && h->be_streams[1] != h->stream) { cudaStreamSynchronize(h->be_streams[1]); cudaStreamDestroy(h->be_streams[1]); }
+	for (int st = 0; st < aisgpu_handle::NSTAGE; st++)
+		for (int i = 0; i < 2; i++)
+			if (h->ev_stage[st][i]) cudaEventDestroy(h->ev_stage[st][i]);
+	if (h->ev_join) cudaEventDestroy(h->ev_join);
+	void *ptrs[] = { h->d_ptail[0], h->d_ptail[1], h->d_ptail2[0], h->d_ptail2[1], h->d_S2, h->d_D0, h->d_S, h->d_us_src, h->d_us_alpha, h->d_in[0], h->d_in[1], h->d_tail[0], h->d_tail[1], h->d_rot[0], h->d_rot[1], h->d_rot[2], h->d_rot_state, h->d_C2[0], h->d_C2[1], h->d_C2[2],
+					 h->d_steptab, h->d_omega, h->d_cgf_rot, h->d_rots2[0], h->d_rots2[1], h->d_stepidx2[0], h->d_stepidx2[1], h->d_ppmtab, h->d_fir_hist[0], h->d_fir_hist[1], h->d_tap_cgf, h->d_Ec2[0],
+					 h->d_Ef2[0], h->d_ps, h->d_ps_mem, h->d_dbits2[0], h->d_dbits2[1], h->d_lvl2[0], h->d_lvl2[1], h->d_dbg, h->d_dec, h->d_dec_data, h->d_pll, h->d_tap_dec, h->d_tap_fm, h->d_tap_cnt, h->d_ring,
 					 h->d_ring_count };
 	for (void *p : ptrs)
 		if (p) cudaFree(p);

@@ -821,10 +821,17 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p)
 	const int warm_super = p.P / SS;
 #pragma unroll
 	for (int c = 0; c < ST_NB - 1; c++) prefetch(c);
+	float2 rt_next[N96]; // Rotate phasors of the next super-step: loaded one super-step ahead of their use
+#pragma unroll
+	for (int i = 0; i < N96; i++) rt_next[i] = __ldg(rot_g + i);
 	for (int ss = 0; ss < n_super; ss++) {
 		float2 rt[N96];
 #pragma unroll
-		for (int i = 0; i < N96; i++) rt[i] = __ldg(rot_g + ss * N96 + i);
+		for (int i = 0; i < N96; i++) rt[i] = rt_next[i];
+		if (ss + 1 < n_super) {
+#pragma unroll
+			for (int i = 0; i < N96; i++) rt_next[i] = __ldg(rot_g + (ss + 1) * N96 + i);
+		}
 		c64 pend[K + 1];  // pend[l]: even-indexed input waiting at level l+1 (l = 1..K-1), pend[K]: unused
 		c64 upE = 0ull, dnE = 0ull, waE = 0ull, wbE = 0ull;
 		c64 outA0 = 0ull, outA1 = 0ull, outB0 = 0ull, outB1 = 0ull;
@@ -1059,6 +1066,7 @@ __global__ void __launch_bounds__(CGF_THREADS) k_cgf_estimate(const float2 *__re
 		float *cs = cum + tid * CGF_ROWP;
 		float c = 0.0f;
 		cs[0] = 0.0f;
+#pragma unroll 16
 		for (int i = 1; i < CGF_N; i++) {
 			c = __fadd_rn(c, mg[i]);
 			cs[i] = c;
@@ -1118,6 +1126,7 @@ __global__ void k_cgf_rot(const int *__restrict__ stepidx, const float2 *__restr
 	float2 *o = rots + (long long)row * r_stride;
 	for (int b = 0; b < nblk; b++) {
 		const float2 st = steptab[stepidx[row * nblk + b]];
+#pragma unroll 16
 		for (int i = 0; i < CGF_N; i++) {
 			rot = cmul(rot, st);
 			o[b * CGF_N + i] = rot;
@@ -1559,13 +1568,9 @@ __global__ void __launch_bounds__(PS_THREADS) k_phase_search(const K3Params p) {
 		uint32_t word = 0;
 		for (int sl = 0; sl < s_end; sl++) {
 			const float2 x = my[sl * 5];
-			float re, im; // (1j)^rot pre-rotation (Demod.cpp:44-65)
-			switch (rot) {
-			case 0: re = x.x; im = x.y; break;
-			case 1: im = x.x; re = -x.y; break;
-			case 2: re = -x.x; im = -x.y; break;
-			default: im = -x.x; re = x.y; break;
-			}
+			// (1j)^rot pre-rotation (Demod.cpp:44-65), branch free: swap on odd rot, negate on rot >= 2 (sign flips are exact)
+			float re = (rot & 1) ? -x.y : x.x, im = (rot & 1) ? x.x : x.y;
+			if (rot & 2) { re = -re; im = -im; }
 			rot = (rot + 1) & 3;
 			const float tt = __fadd_rn(__fmul_rn(re, cj), __fmul_rn(im, sj));
 			hist = (hist << 1) | (tt > 0.0f ? 1u : 0u);

@@ -262,6 +262,7 @@ def main():
     e0.record(est)
     for i in range(args.steps):
         step(args.warmup + i)
+    eng.join()
     e1.record(est)
     e1.synchronize()
     barrier()
@@ -310,6 +311,7 @@ def main():
         a0.record(est2)
         for i in range(ks):
             eng2.submit_device(x[(3 + i) % R].data_ptr(), N, N)
+        eng2.join()
         a1.record(est2)
         a1.synchronize()
         ms2 = a0.elapsed_time(a1)

@@ -133,6 +133,11 @@ int aisgpu_counters(aisgpu_handle *h, uint64_t counters[8]);
 /* The CUDA stream the kernels are launched on (cudaStream_t as void*), for event timing by the caller. */
 void *aisgpu_cuda_stream(aisgpu_handle *h);
 
+/* The back end runs on more than one internal stream; this makes the stream returned by aisgpu_cuda_stream() wait
+ * (on the device, no host synchronisation) for everything submitted so far -- call it before recording an event that
+ * should mark the end of all submitted work. */
+int aisgpu_join(aisgpu_handle *h);
+
 /* Device time of the front-end kernel of the last submit in ms (CUDA events on the launch stream), <0 if n/a. */
 float aisgpu_last_frontend_ms(aisgpu_handle *h);
 

@@ -43,7 +43,7 @@ def run_case(built, model, fs, N, nchunks, B, ps_ema=True, afc_wide=True, droop=
         per = 1
     flags = (O.FLAG_PS_EMA if ps_ema else 0) | (O.FLAG_AFC_WIDE if afc_wide else 0) | (O.FLAG_DROOP if droop else 0)
     eng = aisgpu.Engine(model=model, sample_rate=fs, fmt=fmt, n_streams=B, max_chunk=N, ps_ema=ps_ema, afc_wide=afc_wide,
-                        droop=droop, taps=True)
+                        droop=droop, taps=check_taps)
     refs = [oracle_model(model=model, sample_rate=fs, fmt=fmt, flags=flags, taps=True) for _ in range(B)]
     problems = []
     got_msgs = [[] for _ in range(B)]
@@ -166,3 +166,16 @@ def test_resampled_rates(built, fs, N, model):
 def test_resampled_cu8(built):
     n = run_case(built, aisgpu.MODEL_DEFAULT, 6000000, 262144, 3, 2, fmt=aisgpu.FMT_CU8, check_taps=False, seed0=31)
     assert n >= 2
+
+
+@pytest.mark.parametrize("model", [aisgpu.MODEL_DEFAULT, aisgpu.MODEL_STANDARD])
+def test_pipelined_backend(built, model):
+    # without taps the back-end stages of consecutive submits overlap on two streams (per-stage events, double-buffered
+    # hand-off buffers): many short submits, frames only
+    n = run_case(built, model, 1536000, 32768, 16, 4, check_taps=False, seed0=41)
+    assert n >= 8
+
+
+def test_pipelined_backend_tiny_chunks(built):
+    # chunks below one CGF block: several submits share a 512-block, Ec / Cbuf leftovers hop between the streams
+    run_case(built, aisgpu.MODEL_DEFAULT, 1536000, 4096, 64, 2, check_taps=False, seed0=43)

@@ -51,6 +51,7 @@ for st in settings:
     e0.record(est)
     for i in range(K):
         eng.submit_device(x[i % R].data_ptr(), N, N)
+    eng.join()
     e1.record(est)
     e1.synchronize()
     step = e0.elapsed_time(e1) / K
