@@ -98,7 +98,7 @@ struct aisgpu_handle {
 	int max_n48 = 0;
 	int fe_warps = 4, fe_tile = 0, fe_ctas = 4096;
 	int fe_ws = 0;               // AISGPU_FE_WS=1: warp-specialised stage pipeline instead of the barrier-synchronised kernel
-	int fe_st = 1, st_S = 0;     // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane
+	int fe_st = 1, st_S = 0, st_nb = 8; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
 	bool fe_ws_laidout = false;
 	int dec_rpw = 6, decoder = 3; // rows per warp / which decoder kernel // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
@@ -334,13 +334,23 @@ int launch_fe_ws_k(aisgpu_handle *h, dim3 grid, size_t smem) {
 	}
 }
 
-template <int FMT, int K>
-int launch_fe_st(aisgpu_handle *h, int ctas) {
-	const size_t smem = (size_t)ST_WARPS * ST_NB * 32 * StFmt<FMT>::SLOT;
-	CU(cudaFuncSetAttribute(k_frontend_st<FMT, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	k_frontend_st<FMT, K><<<ctas, ST_WARPS * 32, smem, h->fe_stream>>>(h->fe);
+template <int FMT, int K, int NB>
+int launch_fe_st_nb(aisgpu_handle *h, int ctas) {
+	const size_t smem = (size_t)ST_WARPS * NB * 32 * StFmt<FMT>::SLOT;
+	CU(cudaFuncSetAttribute(k_frontend_st<FMT, K, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_frontend_st<FMT, K, NB><<<ctas, ST_WARPS * 32, smem, h->fe_stream>>>(h->fe);
 	CU(cudaGetLastError());
 	return 0;
+}
+// ring depth = bytes in flight per warp: HBM needs ~20 MB in flight chip-wide, i.e. most of the shared memory
+template <int FMT, int K>
+int launch_fe_st(aisgpu_handle *h, int ctas) {
+	if (FMT == 0) {
+		if (h->st_nb == 4) return launch_fe_st_nb<FMT, K, 4>(h, ctas);
+		if (h->st_nb == 6) return launch_fe_st_nb<FMT, K, 6>(h, ctas);
+		return launch_fe_st_nb<FMT, K, 8>(h, ctas);
+	}
+	return launch_fe_st_nb<FMT, K, 8>(h, ctas); // integer formats: 4x smaller chunks
 }
 template <int FMT>
 int launch_fe_st_k(aisgpu_handle *h, int ctas) {
@@ -1127,6 +1137,7 @@ static int create_impl(aisgpu_handle *h) {
 #else
 	h->fe_warps = 4;
 #endif
+	h->dec_rpw = c.model == AISGPU_MODEL_DEFAULT ? 1 : 6; // measured best per chain
 	if (const char *e = getenv("AISGPU_DEC_RPW")) {
 		h->dec_rpw = atoi(e);
 		if (h->dec_rpw != 1 && h->dec_rpw != 3) h->dec_rpw = 6;
@@ -1139,6 +1150,7 @@ static int create_impl(aisgpu_handle *h) {
 	if (const char *e = getenv("AISGPU_FE_WS")) h->fe_ws = atoi(e) ? 1 : 0;
 	if (const char *e = getenv("AISGPU_FE_ST")) h->fe_st = atoi(e) ? 1 : 0;
 	if (const char *e = getenv("AISGPU_ST_S")) h->st_S = atoi(e);
+	if (const char *e = getenv("AISGPU_ST_NB")) h->st_nb = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_CTAS")) h->fe_ctas = std::max(1, atoi(e));
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {

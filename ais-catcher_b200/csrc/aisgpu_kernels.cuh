@@ -737,7 +737,6 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 
 constexpr int ST_WARPS = 4;  // warps per CTA (independent of each other)
 constexpr int ST_G = 16;     // samples per lane per staged chunk
-constexpr int ST_NB = 4;     // chunks in the ring
 template <int FMT>
 struct StFmt {
 	static constexpr int BPS = FMT == 0 ? 8 : (FMT == 3 ? 4 : 2);
@@ -770,7 +769,7 @@ __device__ __forceinline__ void st_read_pair(const unsigned char *slot, int j, c
 	}
 }
 
-template <int FMT, int K>
+template <int FMT, int K, int ST_NB>
 __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p) {
 	static_assert(K >= 3 && K <= 5, "streaming front end: 768 kS/s .. 3072 kS/s");
 	typedef StFmt<FMT> F;
@@ -821,16 +820,24 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p)
 	const int warm_super = p.P / SS;
 #pragma unroll
 	for (int c = 0; c < ST_NB - 1; c++) prefetch(c);
-	float2 rt_next[N96]; // Rotate phasors of the next super-step: loaded one super-step ahead of their use
+	// Rotate phasors: loaded two super-steps ahead of their use (under load a global load can take longer than one
+	// super-step of arithmetic)
+	float2 rt_n1[N96], rt_n2[N96];
 #pragma unroll
-	for (int i = 0; i < N96; i++) rt_next[i] = __ldg(rot_g + i);
+	for (int i = 0; i < N96; i++) {
+		rt_n1[i] = __ldg(rot_g + i);
+		rt_n2[i] = __ldg(rot_g + (n_super > 1 ? N96 : 0) + i);
+	}
 	for (int ss = 0; ss < n_super; ss++) {
 		float2 rt[N96];
 #pragma unroll
-		for (int i = 0; i < N96; i++) rt[i] = rt_next[i];
-		if (ss + 1 < n_super) {
+		for (int i = 0; i < N96; i++) {
+			rt[i] = rt_n1[i];
+			rt_n1[i] = rt_n2[i];
+		}
+		if (ss + 2 < n_super) {
 #pragma unroll
-			for (int i = 0; i < N96; i++) rt_next[i] = __ldg(rot_g + (ss + 1) * N96 + i);
+			for (int i = 0; i < N96; i++) rt_n2[i] = __ldg(rot_g + (ss + 2) * N96 + i);
 		}
 		c64 pend[K + 1];  // pend[l]: even-indexed input waiting at level l+1 (l = 1..K-1), pend[K]: unused
 		c64 upE = 0ull, dnE = 0ull, waE = 0ull, wbE = 0ull;
@@ -1118,22 +1125,34 @@ __global__ void __launch_bounds__(CGF_THREADS) k_cgf_estimate(const float2 *__re
 // K2b: the CGF derotation phasor chain (DSP.cpp:457-465): rot *= rot_step per sample, rot /= |rot| per block.
 // Strictly sequential per (stream, channel); one thread per row, all rows in flight at once.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_cgf_rot(const int *__restrict__ stepidx, const float2 *__restrict__ steptab, float2 *__restrict__ rot_state,
-						  float2 *__restrict__ rots, long long r_stride, int nblk, int rows) {
-	const int row = blockIdx.x * blockDim.x + threadIdx.x;
-	if (row >= rows) return;
-	float2 rot = rot_state[row];
-	float2 *o = rots + (long long)row * r_stride;
+__global__ void __launch_bounds__(32) k_cgf_rot(const int *__restrict__ stepidx, const float2 *__restrict__ steptab, float2 *__restrict__ rot_state,
+												  float2 *__restrict__ rots, long long r_stride, int nblk, int rows) {
+	// lane = row.  The phasors of 32 consecutive steps are staged in shared memory and written out row by row, so that
+	// every store instruction covers 256 contiguous bytes (a store per step and lane would touch 32 separate sectors
+	// and make the store unit, not the multiply chain, the pace).
+	__shared__ float2 tile[32][33];
+	const int lane = threadIdx.x;
+	const int row0 = blockIdx.x * 32;
+	const int row = row0 + lane;
+	const bool act = row < rows;
+	float2 rot = act ? rot_state[row] : make_float2(1.0f, 0.0f);
 	for (int b = 0; b < nblk; b++) {
-		const float2 st = steptab[stepidx[row * nblk + b]];
-#pragma unroll 16
-		for (int i = 0; i < CGF_N; i++) {
-			rot = cmul(rot, st);
-			o[b * CGF_N + i] = rot;
+		const float2 st = act ? steptab[stepidx[row * nblk + b]] : make_float2(1.0f, 0.0f);
+		for (int i0 = 0; i0 < CGF_N; i0 += 32) {
+#pragma unroll
+			for (int i = 0; i < 32; i++) {
+				rot = cmul(rot, st);
+				tile[lane][i] = rot;
+			}
+			__syncwarp();
+#pragma unroll 8
+			for (int r = 0; r < 32; r++)
+				if (row0 + r < rows) rots[(long long)(row0 + r) * r_stride + b * CGF_N + i0 + lane] = tile[r][lane];
+			__syncwarp();
 		}
 		rot = cnormalize(rot);
 	}
-	rot_state[row] = rot;
+	if (act) rot_state[row] = rot;
 }
 
 // ---------------------------------------------------------------------------------------------
