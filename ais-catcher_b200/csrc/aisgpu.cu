@@ -98,7 +98,7 @@ struct aisgpu_handle {
 	int max_n48 = 0;
 	int fe_warps = 4, fe_tile = 0, fe_ctas = 4096;
 	int fe_ws = 0;               // AISGPU_FE_WS=1: warp-specialised stage pipeline instead of the barrier-synchronised kernel
-	int fe_st = 1, st_S = 0, st_nb = 8; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
+	int fe_st = 1, st_S = 0, st_nb = 8, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
 	bool fe_ws_laidout = false;
 	int dec_rpw = 6, decoder = 3; // rows per warp / which decoder kernel // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
@@ -357,7 +357,9 @@ int launch_fe_st_k(aisgpu_handle *h, int ctas) {
 	switch (h->k) {
 	case 3: return launch_fe_st<FMT, 3>(h, ctas);
 	case 4: return launch_fe_st<FMT, 4>(h, ctas);
-	default: return launch_fe_st<FMT, 5>(h, ctas);
+	case 5: return launch_fe_st<FMT, 5>(h, ctas);
+	case 6: return launch_fe_st<FMT, 6>(h, ctas);
+	default: return launch_fe_st<FMT, 7>(h, ctas);
 	}
 }
 
@@ -452,12 +454,13 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 	p.c_stride = h->c_stride;
 	p.c_off = HC;
 	// 768 kS/s .. 3072 kS/s: per-thread streaming pipeline (state in registers) when the rows are 16-byte aligned
-	if (h->fe_st && h->k >= 3 && h->k <= 5 && ((stride * h->bps) % 16) == 0 && (((size_t)dev_in) % 16) == 0) {
+	if (h->fe_st && h->k >= 3 && h->k <= h->st_kmax && ((stride * h->bps) % 16) == 0 && (((size_t)dev_in) % 16) == 0) {
 		// every lane of a warp gets S samples, S a multiple of a super-step; N must split into whole warps of lanes
 		const int SS = 1 << (h->k + 2);
 		int S = h->st_S > 0 ? h->st_S / SS * SS : 0;
 		if (S <= 0) {
-			S = 4096;
+			S = 2048; // about 10 x the warm-up history P (192 samples at K = 3, doubling per stage)
+			for (int i = 3; i < h->k; i++) S *= 2;
 			while (S >= 2 * SS && S / 2 >= 4 * h->P && N % (32 * S) != 0) S /= 2; // longer sub-segments = smaller warm-up share
 		}
 		if (S >= SS && N % (32 * S) == 0) {
@@ -1151,6 +1154,7 @@ static int create_impl(aisgpu_handle *h) {
 	if (const char *e = getenv("AISGPU_FE_ST")) h->fe_st = atoi(e) ? 1 : 0;
 	if (const char *e = getenv("AISGPU_ST_S")) h->st_S = atoi(e);
 	if (const char *e = getenv("AISGPU_ST_NB")) h->st_nb = atoi(e);
+	if (const char *e = getenv("AISGPU_ST_KMAX")) h->st_kmax = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_CTAS")) h->fe_ctas = std::max(1, atoi(e));
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {

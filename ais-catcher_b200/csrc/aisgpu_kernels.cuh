@@ -771,7 +771,7 @@ __device__ __forceinline__ void st_read_pair(const unsigned char *slot, int j, c
 
 template <int FMT, int K, int ST_NB>
 __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p) {
-	static_assert(K >= 3 && K <= 5, "streaming front end: 768 kS/s .. 3072 kS/s");
+	static_assert(K >= 3 && K <= 7, "streaming front end: 768 kS/s .. 12288 kS/s");
 	typedef StFmt<FMT> F;
 	constexpr int SS = 1 << (K + 2);     // inputs per super-step: two 48 kHz samples per channel
 	constexpr int NCH = SS / ST_G;       // chunks per super-step
