@@ -242,7 +242,7 @@ int plan_frontend(aisgpu_handle *h) {
 			h->in_fmt = AISGPU_FMT_CF32;
 			h->us_inc = (float)sr / (float)bucket; // Upsample::setParams (DSP.h:174-178)
 			int pa = 5 * ((1 << h->kA) - 1);       // history a kA-stage CIC cascade needs (input samples)
-			const int g = std::max(4, 2 << h->kA);    // every level of a tile must hold an even number of samples
+			const int g = std::max(4, 4 << h->kA);    // a whole number of super-steps of the streaming kernel (and even tiles at every level)
 			h->PA = std::max(g, (pa + g - 1) / g * g);
 		}
 		else h->k = k_total;
@@ -369,6 +369,25 @@ int launch_fe(aisgpu_handle *h, dim3 grid, size_t smem) {
 	k_frontend<FMT, NW, K><<<grid, NW * 32, smem, h->fe_stream>>>(h->fe);
 	CU(cudaGetLastError());
 	return 0;
+}
+
+// the same with the per-thread streaming kernel (kA = 3..5)
+template <int FMT, int K>
+int launch_pre_st(aisgpu_handle *h, int ctas) {
+	constexpr int NB = 8;
+	const size_t smem = (size_t)ST_WARPS * NB * 32 * StFmt<FMT>::SLOT;
+	CU(cudaFuncSetAttribute(k_frontend_st<FMT, K, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_frontend_st<FMT, K, NB, true><<<ctas, ST_WARPS * 32, smem, h->fe_stream>>>(h->fe_pre);
+	CU(cudaGetLastError());
+	return 0;
+}
+template <int FMT>
+int launch_pre_st_k(aisgpu_handle *h, int ctas) {
+	switch (h->kA) {
+	case 3: return launch_pre_st<FMT, 3>(h, ctas);
+	case 4: return launch_pre_st<FMT, 4>(h, ctas);
+	default: return launch_pre_st<FMT, 5>(h, ctas);
+	}
 }
 
 // decimation in front of DSP::Upsample: kA <= 5 CIC stages, level-kA samples to HBM
@@ -914,7 +933,27 @@ int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) 
 			pp.d0_off = 2;
 			const size_t smem = (size_t)pp.smem_f2 * sizeof(float2);
 			dim3 grid(n_seg, B);
-			switch (h->cfg.format) {
+			bool st_done = false;
+			if (h->fe_st && h->kA >= 3 && h->kA <= 5 && ((stride * h->obps) % 16) == 0 && (((size_t)dev_in) % 16) == 0) {
+				const int SS = 1 << (h->kA + 2);
+				int S = 2048;
+				for (int i = 3; i < h->kA; i++) S *= 2;
+				while (S >= 2 * SS && S / 2 >= 4 * h->PA && N % (32 * S) != 0) S /= 2;
+				if (N % (32 * S) == 0) {
+					pp.st_S = S;
+					pp.st_wps = N / (32 * S);
+					pp.st_B = B;
+					const int ctas = (int)(((long long)B * pp.st_wps + ST_WARPS - 1) / ST_WARPS);
+					switch (h->cfg.format) {
+					case AISGPU_FMT_CF32: rc = launch_pre_st_k<0>(h, ctas); break;
+					case AISGPU_FMT_CU8: rc = launch_pre_st_k<1>(h, ctas); break;
+					case AISGPU_FMT_CS8: rc = launch_pre_st_k<2>(h, ctas); break;
+					default: rc = launch_pre_st_k<3>(h, ctas); break;
+					}
+					st_done = true;
+				}
+			}
+			if (!st_done) switch (h->cfg.format) {
 			case AISGPU_FMT_CF32: rc = launch_pre_k<0>(h, grid, smem); break;
 			case AISGPU_FMT_CU8: rc = launch_pre_k<1>(h, grid, smem); break;
 			case AISGPU_FMT_CS8: rc = launch_pre_k<2>(h, grid, smem); break;

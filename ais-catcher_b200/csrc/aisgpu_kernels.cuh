@@ -769,7 +769,7 @@ __device__ __forceinline__ void st_read_pair(const unsigned char *slot, int j, c
 	}
 }
 
-template <int FMT, int K, int ST_NB>
+template <int FMT, int K, int ST_NB, bool PRE = false>
 __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p) {
 	static_assert(K >= 3 && K <= 7, "streaming front end: 768 kS/s .. 12288 kS/s");
 	typedef StFmt<FMT> F;
@@ -814,8 +814,10 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p)
 	for (int l = 0; l < K; l++) cic5_zero(lv[l]);
 	cic5_zero(chA); cic5_zero(chB); cic5_zero(fA); cic5_zero(fB);
 	c64 fd1 = 0ull, fd2 = 0ull; // FilterComplex3Tap h1, h2
-	const float2 *rot_g = p.rot + (p.P >> K) + ((a - p.P) >> K);
-	float2 *Cg = p.C + (long long)(stream * 2) * p.c_stride + p.c_off + ((a - p.P) >> (K + 1));
+	// PRE: decimation in front of DSP::Upsample -- the level-K samples go to D0 and nothing else is computed
+	const float2 *rot_g = PRE ? nullptr : p.rot + (p.P >> K) + ((a - p.P) >> K);
+	float2 *Cg = PRE ? p.D0 + (long long)stream * p.d0_stride + p.d0_off + ((a - p.P) >> K)
+					 : p.C + (long long)(stream * 2) * p.c_stride + p.c_off + ((a - p.P) >> (K + 1));
 	const int n_super = warp_chunks / NCH;
 	const int warm_super = p.P / SS;
 #pragma unroll
@@ -825,8 +827,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p)
 	float2 rt_n1[N96], rt_n2[N96];
 #pragma unroll
 	for (int i = 0; i < N96; i++) {
-		rt_n1[i] = __ldg(rot_g + i);
-		rt_n2[i] = __ldg(rot_g + (n_super > 1 ? N96 : 0) + i);
+		rt_n1[i] = PRE ? make_float2(0.f, 0.f) : __ldg(rot_g + i);
+		rt_n2[i] = PRE ? make_float2(0.f, 0.f) : __ldg(rot_g + (n_super > 1 ? N96 : 0) + i);
 	}
 	for (int ss = 0; ss < n_super; ss++) {
 		float2 rt[N96];
@@ -835,10 +837,11 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p)
 			rt[i] = rt_n1[i];
 			rt_n1[i] = rt_n2[i];
 		}
-		if (ss + 2 < n_super) {
+		if (!PRE && ss + 2 < n_super) {
 #pragma unroll
 			for (int i = 0; i < N96; i++) rt_n2[i] = __ldg(rot_g + (ss + 2) * N96 + i);
 		}
+		c64 lvK[N96]; // PRE: the super-step's level-K outputs
 		c64 pend[K + 1];  // pend[l]: even-indexed input waiting at level l+1 (l = 1..K-1), pend[K]: unused
 		c64 upE = 0ull, dnE = 0ull, waE = 0ull, wbE = 0ull;
 		c64 outA0 = 0ull, outA1 = 0ull, outB0 = 0ull, outB1 = 0ull;
@@ -866,7 +869,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p)
 							else { y = ds2_pair(lv[l], pend[l], y, sc); idx >>= 1; }
 						}
 					}
-					if (live) { // y is 96 kHz sample idx (0..N96-1) of the super-step
+					if (live && PRE) lvK[idx] = y;
+					if (live && !PRE) { // y is 96 kHz sample idx (0..N96-1) of the super-step
 						c64 x = y;
 						if (p.use_fdc) { // FilterComplex3Tap: alpha * (h1 + x) + h2 * beta (DSP.cpp:283-293)
 							// scalar intrinsics: ptxas would contract a packed mul + add pair into FFMA2 here, and these products are not exact
@@ -896,7 +900,14 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p)
 			}
 			__syncwarp(); // the ring slot may be refilled by a later prefetch
 		}
-		if (ss >= warm_super) { // two 48 kHz samples per channel
+		if (PRE) {
+			if (ss >= warm_super) {
+				float2 *o = Cg + ss * N96;
+#pragma unroll
+				for (int i = 0; i < N96; i += 2) *reinterpret_cast<ulonglong2 *>(o + i) = make_ulonglong2(lvK[i], lvK[i + 1]);
+			}
+		}
+		else if (ss >= warm_super) { // two 48 kHz samples per channel
 			float2 *o = Cg + ss * 2;
 			*reinterpret_cast<ulonglong2 *>(o) = make_ulonglong2(outA0, outA1);
 			*reinterpret_cast<ulonglong2 *>(o + p.c_stride) = make_ulonglong2(outB0, outB1);
