@@ -38,6 +38,16 @@ def run_case(built, model, fs, N, nchunks, B, ps_ema=True, afc_wide=True, droop=
     if fmt == aisgpu.FMT_CU8:
         raw = [S.to_cu8(x) for x in xs]
         per = 2
+    elif fmt == aisgpu.FMT_CS8:
+        raw = [(S.to_cu8(x).astype(np.int16) - 128).astype(np.int8) for x in xs]
+        per = 2
+    elif fmt == aisgpu.FMT_CS16:
+        raw = []
+        for x in xs:
+            v = np.empty(2 * len(x), dtype=np.float32)
+            v[0::2], v[1::2] = x.real, x.imag
+            raw.append(np.clip(np.round(v * 32767.0), -32768, 32767).astype(np.int16))
+        per = 2
     else:
         raw = xs
         per = 1
@@ -179,3 +189,12 @@ def test_pipelined_backend(built, model):
 def test_pipelined_backend_tiny_chunks(built):
     # chunks below one CGF block: several submits share a 512-block, Ec / Cbuf leftovers hop between the streams
     run_case(built, aisgpu.MODEL_DEFAULT, 1536000, 4096, 64, 2, check_taps=False, seed0=43)
+
+
+@pytest.mark.parametrize("fmt", [aisgpu.FMT_CS8, aisgpu.FMT_CS16])
+@pytest.mark.parametrize("fs,N", [(1536000, 65536), (384000, 16384)])
+def test_signed_integer_formats(built, fmt, fs, N):
+    # Convert::toFloat(CS8) / (CS16) (reference Utilities/Convert.cpp:266-286) through the streaming (1536k) and the tiled
+    # (384k) front end
+    n = run_case(built, aisgpu.MODEL_DEFAULT, fs, N, 3, 2, fmt=fmt, seed0=37)
+    assert n >= 2
