@@ -61,7 +61,7 @@ extern "C" {
 typedef struct aisgpu_config {
 	uint32_t struct_size;       /* = sizeof(aisgpu_config) */
 	int32_t model;              /* AISGPU_MODEL_*                                   (Receiver.cpp:155-195) */
-	int32_t sample_rate;        /* 96000..12288000; non-bucket rates are upsampled   (Model.cpp:109-149) */
+	int32_t sample_rate;        /* 96000..12288000; non-bucket rates are upsampled, 288000 is /3-filtered (Model.cpp:109-149, 308-313) */
 	int32_t format;             /* AISGPU_FMT_*                                      (Common.h:290-295 RAW.format) */
 	int32_t n_streams;          /* batch of independent IQ streams, >= 1 */
 	int32_t max_chunk_samples;  /* upper bound of n_samples per stream per submit */
@@ -107,9 +107,11 @@ int aisgpu_create(const aisgpu_config *cfg, aisgpu_handle **out);
 int aisgpu_chunk_granule(const aisgpu_config *cfg);
 
 /* == StreamIn<RAW>::Receive(const RAW*, 1, TAG&) for every stream of the batch (Stream.h:41; Model.cpp:33).
- * host_samples: n_streams contiguous runs of n_samples samples (stream-major), borrowed for the call only
- * (copied to a pinned staging buffer before returning).  n_samples must be a multiple of 2*fs/48000
- * rounded up to a power of two (DSP.cpp:94,135 assert(len%2==0) at every CIC stage).  Asynchronous. */
+ * host_samples: n_streams contiguous runs of n_samples samples (stream-major), borrowed for the call only (the call
+ * returns when the host-to-device copy into the engine's staging buffer has completed; the kernels run
+ * asynchronously).  n_samples must be a multiple of aisgpu_chunk_granule() -- every CIC stage needs an even block
+ * (DSP.cpp:94,135 assert(len%2==0)) -- and, at rates the reference serves through DSP::Upsample, the same for every
+ * call (Upsample re-blocks by the length of its input block, DSP.cpp:203).  Pinned host memory gives full PCIe speed. */
 int aisgpu_submit(aisgpu_handle *h, const void *host_samples, int n_samples);
 
 /* Same, with the batch already resident in device memory ([n_streams][stride_samples], first n_samples used). */
