@@ -17,7 +17,7 @@
 #include <vector>
 
 #include "../../include/aisgpu.h"
-#include "aisgpu_kernels.cuh"
+#include "params.h"
 
 using namespace aisgpu;
 
@@ -97,9 +97,7 @@ struct aisgpu_handle {
 	int rows = 0;
 	int max_n48 = 0;
 	int fe_warps = 4, fe_tile = 0, fe_ctas = 4096;
-	int fe_ws = 0;               // AISGPU_FE_WS=1: warp-specialised stage pipeline instead of the barrier-synchronised kernel
-	int fe_st = 1, st_S = 0, st_nb = 8, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
-	bool fe_ws_laidout = false;
+	int fe_st = 1, st_S = 0, st_nb = 6, st_wpc = 1, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
 	int dec_rpw = 6, decoder = 3; // rows per warp / which decoder kernel // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
 	// for timing).  The front end of submit c+1 overlaps the back end of submit c; Cbuf is double buffered for that.
@@ -193,7 +191,7 @@ namespace {
 		cudaError_t e_ = (call);                                                                   \
 		if (e_ != cudaSuccess) {                                                                   \
 			char b_[256];                                                                          \
-			snprintf(b_, sizeof(b_), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+			snprintf(b_, sizeof(b_), "%s:%d %.120s: %s", "aisgpu.cu", __LINE__, #call, cudaGetErrorString(e_)); \
 			h->err = b_;                                                                           \
 			return AISGPU_ECUDA;                                                                   \
 		}                                                                                          \
@@ -293,149 +291,6 @@ void layout_frontend(FeParams &p, int k, int tile) {
 	p.tile = tile;
 }
 
-// shared-memory layout of the warp-specialised kernel: level 1 and level 3 are double buffered (hand-offs between warps)
-void layout_frontend_ws(FeParams &p, int k, int tile) {
-	int off = 0;
-	auto take = [&](int n) {
-		int o = off;
-		off += (FE_HIST + n + FE_SLACK + 1) & ~1;
-		return o;
-	};
-	p.off_in[0] = take(tile);
-	p.off_in[1] = take(tile);
-	p.off_rot[0] = p.off_rot[1] = 0;
-	p.off_lv[0] = 0;
-	for (int l = 1; l <= k; l++) p.off_lv[l] = take(tile >> l);
-	p.off_l1b = take(tile >> 1);
-	p.off_l3b = take(tile >> 3);
-	p.off_up = take(tile >> k);
-	p.off_dn = take(tile >> k);
-	p.off_wa = take(tile >> (k + 1));
-	p.off_wb = take(tile >> (k + 1));
-	p.smem_f2 = off;
-	p.tile = tile;
-}
-
-template <int FMT, int K>
-int launch_fe_ws(aisgpu_handle *h, dim3 grid, size_t smem) {
-	CU(cudaFuncSetAttribute(k_frontend_ws<FMT, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	k_frontend_ws<FMT, K><<<grid, WS_THREADS, smem, h->fe_stream>>>(h->fe);
-	CU(cudaGetLastError());
-	return 0;
-}
-template <int FMT>
-int launch_fe_ws_k(aisgpu_handle *h, dim3 grid, size_t smem) {
-	switch (h->k) {
-	case 3: return launch_fe_ws<FMT, 3>(h, grid, smem);
-	case 4: return launch_fe_ws<FMT, 4>(h, grid, smem);
-	case 5: return launch_fe_ws<FMT, 5>(h, grid, smem);
-	case 6: return launch_fe_ws<FMT, 6>(h, grid, smem);
-	default: return launch_fe_ws<FMT, 7>(h, grid, smem);
-	}
-}
-
-template <int FMT, int K, int NB>
-int launch_fe_st_nb(aisgpu_handle *h, int ctas) {
-	const size_t smem = (size_t)ST_WARPS * NB * 32 * StFmt<FMT>::SLOT;
-	CU(cudaFuncSetAttribute(k_frontend_st<FMT, K, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	k_frontend_st<FMT, K, NB><<<ctas, ST_WARPS * 32, smem, h->fe_stream>>>(h->fe);
-	CU(cudaGetLastError());
-	return 0;
-}
-// ring depth = bytes in flight per warp: HBM needs ~20 MB in flight chip-wide, i.e. most of the shared memory
-template <int FMT, int K>
-int launch_fe_st(aisgpu_handle *h, int ctas) {
-	if (FMT == 0) {
-		if (h->st_nb == 4) return launch_fe_st_nb<FMT, K, 4>(h, ctas);
-		if (h->st_nb == 6) return launch_fe_st_nb<FMT, K, 6>(h, ctas);
-		return launch_fe_st_nb<FMT, K, 8>(h, ctas);
-	}
-	return launch_fe_st_nb<FMT, K, 8>(h, ctas); // integer formats: 4x smaller chunks
-}
-template <int FMT>
-int launch_fe_st_k(aisgpu_handle *h, int ctas) {
-	switch (h->k) {
-	case 3: return launch_fe_st<FMT, 3>(h, ctas);
-	case 4: return launch_fe_st<FMT, 4>(h, ctas);
-	case 5: return launch_fe_st<FMT, 5>(h, ctas);
-	case 6: return launch_fe_st<FMT, 6>(h, ctas);
-	default: return launch_fe_st<FMT, 7>(h, ctas);
-	}
-}
-
-template <int FMT, int NW, int K>
-int launch_fe(aisgpu_handle *h, dim3 grid, size_t smem) {
-	CU(cudaFuncSetAttribute(k_frontend<FMT, NW, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	k_frontend<FMT, NW, K><<<grid, NW * 32, smem, h->fe_stream>>>(h->fe);
-	CU(cudaGetLastError());
-	return 0;
-}
-
-// the same with the per-thread streaming kernel (kA = 3..5)
-template <int FMT, int K>
-int launch_pre_st(aisgpu_handle *h, int ctas) {
-	constexpr int NB = 8;
-	const size_t smem = (size_t)ST_WARPS * NB * 32 * StFmt<FMT>::SLOT;
-	CU(cudaFuncSetAttribute(k_frontend_st<FMT, K, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	k_frontend_st<FMT, K, NB, true><<<ctas, ST_WARPS * 32, smem, h->fe_stream>>>(h->fe_pre);
-	CU(cudaGetLastError());
-	return 0;
-}
-template <int FMT>
-int launch_pre_st_k(aisgpu_handle *h, int ctas) {
-	switch (h->kA) {
-	case 3: return launch_pre_st<FMT, 3>(h, ctas);
-	case 4: return launch_pre_st<FMT, 4>(h, ctas);
-	default: return launch_pre_st<FMT, 5>(h, ctas);
-	}
-}
-
-// decimation in front of DSP::Upsample: kA <= 5 CIC stages, level-kA samples to HBM
-template <int FMT, int K>
-int launch_pre(aisgpu_handle *h, dim3 grid, size_t smem) {
-	CU(cudaFuncSetAttribute(k_frontend<FMT, 4, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	k_frontend<FMT, 4, K, true><<<grid, 128, smem, h->fe_stream>>>(h->fe_pre);
-	CU(cudaGetLastError());
-	return 0;
-}
-template <int FMT>
-int launch_pre_k(aisgpu_handle *h, dim3 grid, size_t smem) {
-	switch (h->kA) {
-	case 0: return launch_pre<FMT, 0>(h, grid, smem);
-	case 1: return launch_pre<FMT, 1>(h, grid, smem);
-	case 2: return launch_pre<FMT, 2>(h, grid, smem);
-	case 3: return launch_pre<FMT, 3>(h, grid, smem);
-	case 4: return launch_pre<FMT, 4>(h, grid, smem);
-	default: return launch_pre<FMT, 5>(h, grid, smem);
-	}
-}
-
-template <int FMT, int NW>
-int launch_fe_k(aisgpu_handle *h, dim3 grid, size_t smem) {
-	switch (h->k) {
-	case 0: return launch_fe<FMT, NW, 0>(h, grid, smem);
-	case 1: return launch_fe<FMT, NW, 1>(h, grid, smem);
-	case 2: return launch_fe<FMT, NW, 2>(h, grid, smem);
-	case 3: return launch_fe<FMT, NW, 3>(h, grid, smem);
-	case 4: return launch_fe<FMT, NW, 4>(h, grid, smem);
-	case 5: return launch_fe<FMT, NW, 5>(h, grid, smem);
-	case 6: return launch_fe<FMT, NW, 6>(h, grid, smem);
-	default: return launch_fe<FMT, NW, 7>(h, grid, smem);
-	}
-}
-
-template <int FMT>
-int launch_fe_nw(aisgpu_handle *h, dim3 grid, size_t smem) {
-#ifdef AISGPU_FE_ALL_WARP_COUNTS
-	switch (h->fe_warps) {
-	case 2: return launch_fe_k<FMT, 2>(h, grid, smem);
-	case 8: return launch_fe_k<FMT, 8>(h, grid, smem);
-	default: break;
-	}
-#endif
-	return launch_fe_k<FMT, 4>(h, grid, smem);
-}
-
 int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int N) {
 	FeParams &p = h->fe;
 	const int q = 1 << (h->k + 2);
@@ -443,12 +298,7 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 	int tile = h->fe_tile > 0 ? h->fe_tile : 320 * h->fe_warps;
 	if (tile % q) tile = (tile / q + 1) * q;
 	if (tile > N) tile = N;
-	const bool ws = h->fe_ws && h->k >= 3; // warp-specialised stage pipeline for the high-rate front ends
-	if (tile != p.tile || ws != h->fe_ws_laidout) {
-		if (ws) layout_frontend_ws(p, h->k, tile);
-		else layout_frontend(p, h->k, tile);
-		h->fe_ws_laidout = ws;
-	}
+	if (tile != p.tile) layout_frontend(p, h->k, tile);
 	h->tile = tile;
 	const int B = h->cfg.n_streams;
 	int n_seg = (h->fe_ctas + B - 1) / B; // enough CTAs for several waves over 148 SMs
@@ -487,32 +337,13 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 			p.st_S = S;
 			p.st_wps = N / (32 * S);
 			p.st_B = B;
-			const long long warps = (long long)B * p.st_wps;
-			const int ctas = (int)((warps + ST_WARPS - 1) / ST_WARPS);
-			switch (h->in_fmt) {
-			case AISGPU_FMT_CF32: return launch_fe_st_k<0>(h, ctas);
-			case AISGPU_FMT_CU8: return launch_fe_st_k<1>(h, ctas);
-			case AISGPU_FMT_CS8: return launch_fe_st_k<2>(h, ctas);
-			default: return launch_fe_st_k<3>(h, ctas);
-			}
+			CU(launch_frontend_stream(p, h->in_fmt, h->k, h->st_nb, h->st_wpc, false, (long long)B * p.st_wps, h->fe_stream));
+			return 0;
 		}
 	}
 	const size_t smem = (size_t)p.smem_f2 * sizeof(float2);
-	dim3 grid(n_seg, B);
-	if (ws) {
-		switch (h->in_fmt) {
-		case AISGPU_FMT_CF32: return launch_fe_ws_k<0>(h, grid, smem);
-		case AISGPU_FMT_CU8: return launch_fe_ws_k<1>(h, grid, smem);
-		case AISGPU_FMT_CS8: return launch_fe_ws_k<2>(h, grid, smem);
-		default: return launch_fe_ws_k<3>(h, grid, smem);
-		}
-	}
-	switch (h->in_fmt) {
-	case AISGPU_FMT_CF32: return launch_fe_nw<0>(h, grid, smem);
-	case AISGPU_FMT_CU8: return launch_fe_nw<1>(h, grid, smem);
-	case AISGPU_FMT_CS8: return launch_fe_nw<2>(h, grid, smem);
-	default: return launch_fe_nw<3>(h, grid, smem);
-	}
+	CU(launch_frontend_tiled(p, h->in_fmt, h->k, false, dim3(n_seg, B), smem, h->fe_stream));
+	return 0;
 }
 
 // stage s of this submit may start when stage s of the previous submit (other stream) has finished
@@ -529,47 +360,17 @@ int stage_end(aisgpu_handle *h, int s) {
 	return 0;
 }
 
-template <typename T>
-int carry(aisgpu_handle *h, T *buf, long long stride, int src_begin, int dst_begin, int cnt) {
+int carry(aisgpu_handle *h, float2 *buf, long long stride, int src_begin, int dst_begin, int cnt) {
 	if (cnt <= 0 || src_begin == dst_begin) return 0;
-	k_carry<T><<<h->rows, 128, cnt * sizeof(T), h->bs>>>(buf, stride, src_begin, dst_begin, cnt);
-	CU(cudaGetLastError());
+	CU(launch_carry_f2(buf, stride, src_begin, dst_begin, cnt, h->rows, h->bs));
 	h->last_launches++;
 	return 0;
 }
 
-template <typename T>
-int carry2(aisgpu_handle *h, const T *src, T *dst, long long stride, int src_begin, int dst_begin, int cnt) {
+int carry2(aisgpu_handle *h, const float2 *src, float2 *dst, long long stride, int src_begin, int dst_begin, int cnt) {
 	if (cnt <= 0) return 0;
-	k_carry2<T><<<h->rows, 128, 0, h->bs>>>(src, dst, stride, src_begin, dst_begin, cnt);
-	CU(cudaGetLastError());
+	CU(launch_carry2_f2(src, dst, stride, src_begin, dst_begin, cnt, h->rows, h->bs));
 	h->last_launches++;
-	return 0;
-}
-
-// Five AIS::Decoder instances per row.  decoder = 3: word-parallel kernel (default), 2: event-driven kernel with the
-// bit-serial machine inside frames, 1: plain bit-serial kernel (one row per warp) -- the older ones stay in the tree as
-// cross-checks (AISGPU_DECODER).  dec_rpw rows share a warp (AISGPU_DEC_RPW = 1, 3, 6).
-template <int MODEL>
-int launch_decode(aisgpu_handle *h, const K3Params &p) {
-	const int rpw = h->dec_rpw;
-	if (h->decoder == 1) {
-		const int grid = (h->rows + DK_THREADS / 32 - 1) / (DK_THREADS / 32);
-		k_decode<MODEL, false><<<grid, DK_THREADS, 0, h->bs>>>(p);
-	}
-	else if (h->decoder == 2) {
-		const int grid = (h->rows + rpw * DK2_WARPS - 1) / (rpw * DK2_WARPS);
-		if (rpw == 1) k_decode2<MODEL, false, 1><<<grid, DK2_WARPS * 32, 0, h->bs>>>(p);
-		else if (rpw == 3) k_decode2<MODEL, false, 3><<<grid, DK2_WARPS * 32, 0, h->bs>>>(p);
-		else k_decode2<MODEL, false, 6><<<grid, DK2_WARPS * 32, 0, h->bs>>>(p);
-	}
-	else {
-		const int grid = (h->rows + rpw * DK3_WARPS - 1) / (rpw * DK3_WARPS);
-		if (rpw == 1) k_decode3<MODEL, 1><<<grid, DK3_WARPS * 32, 0, h->bs>>>(p);
-		else if (rpw == 3) k_decode3<MODEL, 3><<<grid, DK3_WARPS * 32, 0, h->bs>>>(p);
-		else k_decode3<MODEL, 6><<<grid, DK3_WARPS * 32, 0, h->bs>>>(p);
-	}
-	CU(cudaGetLastError());
 	return 0;
 }
 
@@ -606,7 +407,7 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.dbits = h->d_dbits2[h->pb];
 		p.dwords = h->dwords;
 		if (int rc = stage_begin(h, 4)) return rc;
-		if (int rc = launch_decode<0>(h, p)) return rc;
+		CU(launch_decode(0, h->decoder, h->dec_rpw, p, h->bs));
 		if (int rc = stage_end(h, 4)) return rc;
 		h->last_launches++;
 		h->e_abs = a1;
@@ -652,17 +453,15 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.dwords = h->dwords;
 		p.lvl = h->d_lvl2[h->pb];
 		p.lvl_stride = h->dwords * K3_TS;
-		const long long ps_warps = ((long long)h->rows * 5 + 1) / 2;
 		if (int rc = stage_begin(h, 3)) return rc;
-		k_phase_search<<<(unsigned)((ps_warps + PS_THREADS / 32 - 1) / (PS_THREADS / 32)), PS_THREADS, 0, h->bs>>>(p);
-		CU(cudaGetLastError());
+		CU(launch_phase_search(p, h->bs));
 		// the incomplete group of 5 at the end moves to the front for the next submit (Ec is single buffered: the next
 		// submit's derotation waits for this stage)
 		const int nl = total - nsym * 5;
 		if (carry(h, h->d_Ec2[0], h->e_stride, e_begin + nsym * 5, HE - nl, nl)) return AISGPU_ECUDA;
 		if (int rc = stage_end(h, 3)) return rc;
 		if (int rc = stage_begin(h, 4)) return rc;
-		if (int rc = launch_decode<2>(h, p)) return rc;
+		CU(launch_decode(2, h->decoder, h->dec_rpw, p, h->bs));
 		if (int rc = stage_end(h, 4)) return rc;
 		h->last_launches += 2;
 	}
@@ -684,8 +483,7 @@ int enqueue_rot_table(aisgpu_handle *h, long long c, int n96) {
 	if (h->k1_recorded[slot]) CU(cudaStreamWaitEvent(h->side_stream, h->ev_k1[slot], 0));
 	const float2 *prev_tail = c > 0 ? h->d_rot[prev] + h->rot_n96[prev] : nullptr;
 	const float2 *state_in = c > 0 ? h->d_rot_state + 1 + prev : h->d_rot_state;
-	k_rot_table<<<1, 32, 0, h->side_stream>>>(h->d_rot[slot], prev_tail, state_in, h->d_rot_state + 1 + slot, h->mult, h->P96, n96);
-	CU(cudaGetLastError());
+	CU(launch_rot_table(h->d_rot[slot], prev_tail, state_in, h->d_rot_state + 1 + slot, h->mult, h->P96, n96, h->side_stream));
 	CU(cudaEventRecord(h->ev_rot[slot], h->side_stream));
 	h->rot_n96[slot] = n96;
 	h->rot_ready_chunk = c;
@@ -732,10 +530,7 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 	{
 		const int nxt = h->tail_cur ^ 1;
 		const int p_w = h->P * h->bps / 8;
-		dim3 grid((p_w + 127) / 128, B);
-		k_tail_update<<<grid, 128, 0, h->fe_stream>>>((uint2 *)h->d_tail[nxt], (const uint2 *)h->d_tail[h->tail_cur], (const uint2 *)dev_in,
-													stride * h->bps / 8, (long long)N * h->bps / 8, p_w);
-		CU(cudaGetLastError());
+		CU(launch_tail_update(h->d_tail[nxt], h->d_tail[h->tail_cur], dev_in, stride * h->bps / 8, (long long)N * h->bps / 8, p_w, B, h->fe_stream));
 		h->tail_cur = nxt;
 		h->last_launches++;
 	}
@@ -762,25 +557,18 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 		h->c_hist = newcnt;
 		if (nblk > 0) {
 			const int total_blocks = h->rows * nblk;
-			const int ctas = (total_blocks + CGF_BLK_PER_CTA - 1) / CGF_BLK_PER_CTA;
-			const size_t smem = 4096 + 2 * (size_t)CGF_BLK_PER_CTA * CGF_ROWP * 4;
 			int *stepidx = h->d_stepidx2[h->pb];
 			float2 *rots = h->d_rots2[h->pb];
 			// stepidx / rots / dbits / lvl are double buffered by submit parity == stream, so stream order protects them
-			k_cgf_estimate<<<ctas, CGF_THREADS, smem, h->bs>>>(Ccur, h->c_stride, c_begin, nblk, total_blocks, h->d_omega, h->cfg.afc_wide, stepidx);
-			CU(cudaGetLastError());
+			CU(launch_cgf_estimate(Ccur, h->c_stride, c_begin, nblk, total_blocks, h->d_omega, h->cfg.afc_wide, stepidx, h->bs));
 			if (int rc = stage_begin(h, 1)) return rc;
-			k_cgf_rot<<<(h->rows + 31) / 32, 32, 0, h->bs>>>(stepidx, h->d_steptab, h->d_cgf_rot, rots, h->r_stride, nblk, h->rows);
-			CU(cudaGetLastError());
+			CU(launch_cgf_rot(stepidx, h->d_steptab, h->d_cgf_rot, rots, h->r_stride, nblk, h->rows, h->bs));
 			if (int rc = stage_end(h, 1)) return rc;
 			const int nE = nblk * CGF_N;
-			dim3 grid((nE + FIRC_TILE - 1) / FIRC_TILE, h->rows);
 			if (int rc = stage_begin(h, 2)) return rc;
 			if (int rc = stage_begin(h, 3)) return rc; // Ec is free once the previous submit's phase search has read it
-			k_cgf_derot_fir<<<grid, FIRC_TILE, 0, h->bs>>>(Ccur, h->c_stride, c_begin, rots, h->r_stride, nE, h->d_fir_hist[h->fir_cur],
-															 h->d_fir_hist[h->fir_cur ^ 1], h->d_Ec2[0], h->e_stride, HE,
-															 h->cfg.enable_taps ? h->d_tap_cgf : nullptr, h->r_stride);
-			CU(cudaGetLastError());
+			CU(launch_cgf_derot_fir(Ccur, h->c_stride, c_begin, rots, h->r_stride, nE, h->d_fir_hist[h->fir_cur], h->d_fir_hist[h->fir_cur ^ 1], h->d_Ec2[0],
+									h->e_stride, HE, h->cfg.enable_taps ? h->d_tap_cgf : nullptr, h->r_stride, h->rows, h->bs));
 			if (int rc = stage_end(h, 2)) return rc;
 			h->fir_cur ^= 1;
 			h->last_launches += 3;
@@ -818,10 +606,8 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 			f.tap_fm = h->cfg.enable_taps ? h->d_tap_fm : nullptr;
 			f.tap_stride = h->r_stride;
 			f.tap_dec = (h->cfg.enable_taps && h->cfg.model == AISGPU_MODEL_STANDARD) ? h->d_tap_dec : nullptr;
-			dim3 grid((nslots + FM5_THREADS - 1) / FM5_THREADS, h->rows);
 			if (int rc = stage_begin(h, 0)) return rc; // Ef (single buffered) is only read by taps / k_base, which do not pipeline
-			k_fm_fir5<<<grid, FM5_THREADS, 0, h->bs>>>(f);
-			CU(cudaGetLastError());
+			CU(launch_fm_fir5(f, h->rows, h->bs));
 			if (int rc = stage_end(h, 0)) return rc;
 		}
 		CU(cudaEventRecord(h->ev_be_done[cb], h->bs));
@@ -832,20 +618,13 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 			if (int rc = run_symbols(h, n48)) return rc;
 		}
 		else {
-			k_base<<<(h->rows + K3_THREADS - 1) / K3_THREADS, K3_THREADS, 0, h->bs>>>(
-				h->d_Ef2[0], h->e_stride, HE, n48, h->rows, h->d_pll, h->d_dec, h->d_dec_data, h->d_ring, h->d_ring_count, h->ring_cap, (int)h->msg_chunk, (int)h->chunk,
-				h->cfg.enable_taps ? h->d_tap_dec : nullptr, h->cfg.enable_taps ? h->d_tap_cnt : nullptr);
-			CU(cudaGetLastError());
+			CU(launch_base(h->d_Ef2[0], h->e_stride, HE, n48, h->rows, h->d_pll, h->d_dec, h->d_dec_data, h->d_ring, h->d_ring_count, h->ring_cap, (int)h->msg_chunk,
+						   (int)h->chunk, h->cfg.enable_taps ? h->d_tap_dec : nullptr, h->cfg.enable_taps ? h->d_tap_cnt : nullptr, h->bs));
 			h->last_launches++;
 		}
 	}
 	h->chunk++;
 	return 0;
-}
-
-__global__ void k_d0_carry(float2 *__restrict__ D0, long long d0_stride, int d0_off, int L, int rows) {
-	const int r = blockIdx.x * blockDim.x + threadIdx.x;
-	if (r < rows) D0[(long long)r * d0_stride + d0_off - 1] = D0[(long long)r * d0_stride + d0_off + L - 1]; // Upsample::a = b
 }
 
 // DownsampleKFilter over N input samples per stream (any format) -> ring of 96 kS/s samples
@@ -854,14 +633,7 @@ int run_dsk(aisgpu_handle *h, const void *in, long long stride, int fmt, int N, 
 	const int first = h->dsk_first;
 	const int n_out = first < N ? (N - first + 2) / 3 : 0;
 	if (n_out > 0) {
-		dim3 grid((n_out + DSK_THREADS - 1) / DSK_THREADS, B);
-		switch (fmt) {
-		case AISGPU_FMT_CF32: k_dsk<0><<<grid, DSK_THREADS, 0, h->fe_stream>>>(in, stride, tail, 32, first, n_out, S, s_stride, produced, cap); break;
-		case AISGPU_FMT_CU8: k_dsk<1><<<grid, DSK_THREADS, 0, h->fe_stream>>>(in, stride, tail, 32, first, n_out, S, s_stride, produced, cap); break;
-		case AISGPU_FMT_CS8: k_dsk<2><<<grid, DSK_THREADS, 0, h->fe_stream>>>(in, stride, tail, 32, first, n_out, S, s_stride, produced, cap); break;
-		default: k_dsk<3><<<grid, DSK_THREADS, 0, h->fe_stream>>>(in, stride, tail, 32, first, n_out, S, s_stride, produced, cap); break;
-		}
-		CU(cudaGetLastError());
+		CU(launch_dsk(fmt, in, stride, tail, 32, first, n_out, B, S, s_stride, produced, cap, h->fe_stream));
 		h->last_launches++;
 	}
 	h->dsk_first = first + 3 * n_out - N;
@@ -943,22 +715,11 @@ int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) 
 					pp.st_S = S;
 					pp.st_wps = N / (32 * S);
 					pp.st_B = B;
-					const int ctas = (int)(((long long)B * pp.st_wps + ST_WARPS - 1) / ST_WARPS);
-					switch (h->cfg.format) {
-					case AISGPU_FMT_CF32: rc = launch_pre_st_k<0>(h, ctas); break;
-					case AISGPU_FMT_CU8: rc = launch_pre_st_k<1>(h, ctas); break;
-					case AISGPU_FMT_CS8: rc = launch_pre_st_k<2>(h, ctas); break;
-					default: rc = launch_pre_st_k<3>(h, ctas); break;
-					}
+					CU(launch_frontend_stream(pp, h->cfg.format, h->kA, 6, 1, true, (long long)B * pp.st_wps, h->fe_stream));
 					st_done = true;
 				}
 			}
-			if (!st_done) switch (h->cfg.format) {
-			case AISGPU_FMT_CF32: rc = launch_pre_k<0>(h, grid, smem); break;
-			case AISGPU_FMT_CU8: rc = launch_pre_k<1>(h, grid, smem); break;
-			case AISGPU_FMT_CS8: rc = launch_pre_k<2>(h, grid, smem); break;
-			default: rc = launch_pre_k<3>(h, grid, smem); break;
-			}
+			if (!st_done) CU(launch_frontend_tiled(pp, h->cfg.format, h->kA, true, grid, smem, h->fe_stream));
 			if (rc) return rc;
 			tail_len = h->PA;
 			// replay Upsample's float accumulator: one (input index, alpha) pair per output (DSP.cpp:196-209)
@@ -978,11 +739,8 @@ int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) 
 			const int M = (int)h->h_us_src.size();
 			CU(cudaMemcpyAsync(h->d_us_src, h->h_us_src.data(), (size_t)M * sizeof(int), cudaMemcpyHostToDevice, h->fe_stream));
 			CU(cudaMemcpyAsync(h->d_us_alpha, h->h_us_alpha.data(), (size_t)M * sizeof(float), cudaMemcpyHostToDevice, h->fe_stream));
-			k_upsample<<<dim3((M + 255) / 256, B), 256, 0, h->fe_stream>>>(h->d_D0, h->d0_stride, 2, h->d_us_src, h->d_us_alpha, M, h->d_S, h->s_stride,
-																			  h->s_produced, h->s_cap);
-			CU(cudaGetLastError());
-			k_d0_carry<<<(B + 127) / 128, 128, 0, h->fe_stream>>>(h->d_D0, h->d0_stride, 2, L, B);
-			CU(cudaGetLastError());
+			CU(launch_upsample(h->d_D0, h->d0_stride, 2, h->d_us_src, h->d_us_alpha, M, B, h->d_S, h->s_stride, h->s_produced, h->s_cap, h->fe_stream));
+			CU(launch_d0_carry(h->d_D0, h->d0_stride, 2, L, B, h->fe_stream));
 			h->s_produced += M;
 			h->last_launches += 3;
 		}
@@ -992,10 +750,7 @@ int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) 
 		}
 		{ // raw-format history of the pre-stage for the next submit
 			const int p_w = tail_len * h->obps / 8;
-			dim3 grid((p_w + 127) / 128, B);
-			k_tail_update<<<grid, 128, 0, h->fe_stream>>>((uint2 *)h->d_ptail[nxt], (const uint2 *)h->d_ptail[cur], (const uint2 *)dev_in,
-														stride * h->obps / 8, (long long)N * h->obps / 8, p_w);
-			CU(cudaGetLastError());
+			CU(launch_tail_update(h->d_ptail[nxt], h->d_ptail[cur], dev_in, stride * h->obps / 8, (long long)N * h->obps / 8, p_w, B, h->fe_stream));
 			h->ptail_cur = nxt;
 			h->last_launches++;
 		}
@@ -1004,9 +759,7 @@ int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) 
 				const int slot = (int)(h->s_consumed % h->s_cap);
 				const int c2 = h->ptail2_cur;
 				if ((rc = run_dsk(h, h->d_S + slot, h->s_stride, AISGPU_FMT_CF32, h->us_blk, h->d_ptail2[c2], h->d_S2, h->s2_stride, h->s2_produced, h->s2_cap))) return rc;
-				k_tail_update<<<dim3(1, B), 128, 0, h->fe_stream>>>((uint2 *)h->d_ptail2[c2 ^ 1], (const uint2 *)h->d_ptail2[c2], (const uint2 *)(h->d_S + slot),
-																	 h->s_stride, (long long)h->us_blk, 32);
-				CU(cudaGetLastError());
+				CU(launch_tail_update(h->d_ptail2[c2 ^ 1], h->d_ptail2[c2], h->d_S + slot, h->s_stride, (long long)h->us_blk, 32, B, h->fe_stream));
 				h->ptail2_cur = c2 ^ 1;
 				h->s_consumed += h->us_blk;
 			}
@@ -1189,10 +942,10 @@ static int create_impl(aisgpu_handle *h) {
 		if (h->decoder != 1 && h->decoder != 2) h->decoder = 3;
 	}
 	if (const char *e = getenv("AISGPU_FE_TILE")) h->fe_tile = atoi(e);
-	if (const char *e = getenv("AISGPU_FE_WS")) h->fe_ws = atoi(e) ? 1 : 0;
 	if (const char *e = getenv("AISGPU_FE_ST")) h->fe_st = atoi(e) ? 1 : 0;
 	if (const char *e = getenv("AISGPU_ST_S")) h->st_S = atoi(e);
 	if (const char *e = getenv("AISGPU_ST_NB")) h->st_nb = atoi(e);
+	if (const char *e = getenv("AISGPU_ST_WPC")) h->st_wpc = atoi(e) == 4 ? 4 : 1;
 	if (const char *e = getenv("AISGPU_ST_KMAX")) h->st_kmax = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_CTAS")) h->fe_ctas = std::max(1, atoi(e));
 	int ndev = 0;
@@ -1267,7 +1020,7 @@ static int create_impl(aisgpu_handle *h) {
 		}
 		if (h->pre >= 2) {
 			const int cap96 = ((2 * maxN / 3 + 1 + h->blk + h->blk - 1) / h->blk + 1) * h->blk; // behind Upsample up to 2x the samples
-			CU(cudaMemcpyToSymbol(c_taps_bh28_3, H_TAPS_BH28_3, sizeof(H_TAPS_BH28_3)));
+			CU(set_taps_bh28_3(H_TAPS_BH28_3));
 			if (h->pre == 2) {
 				h->s_cap = cap96;
 				h->s_stride = cap96;
@@ -1343,7 +1096,6 @@ static int create_impl(aisgpu_handle *h) {
 		CU(cudaMemcpyAsync(h->d_steptab, st.data(), st.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
 		CU(cudaMemcpyAsync(h->d_ppmtab, pp.data(), pp.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
 		CU(cudaStreamSynchronize(h->stream)); // host vectors go out of scope
-		CU(cudaFuncSetAttribute(k_cgf_estimate, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 + 2 * CGF_BLK_PER_CTA * CGF_ROWP * 4));
 		if (c.enable_taps)
 			if (int rc = dalloc(h, &h->d_tap_cgf, (size_t)h->rows * h->r_stride)) return rc;
 	}
@@ -1369,15 +1121,13 @@ static int create_impl(aisgpu_handle *h) {
 		if (int rc = dalloc(h, &h->d_tap_dec, (size_t)h->rows * 5 * (nEmax / 5 + 2))) return rc;
 	if (getenv("AISGPU_DEBUG"))
 		if (int rc = dalloc(h, &h->d_dbg, (size_t)h->rows * 4)) return rc;
-	CU(cudaMemcpyToSymbol(c_taps_coherent, H_TAPS_COHERENT, sizeof(H_TAPS_COHERENT)));
-	CU(cudaMemcpyToSymbol(c_taps_receiver, H_TAPS_RECEIVER, sizeof(H_TAPS_RECEIVER)));
-	CU(cudaMemcpyToSymbol(c_ps_cos, H_PS_COS, sizeof(H_PS_COS)));
-	CU(cudaMemcpyToSymbol(c_ps_sin, H_PS_SIN, sizeof(H_PS_SIN)));
+	CU(cgf_init(H_TAPS_COHERENT));
+	CU(fm_init(H_TAPS_RECEIVER));
 	{
 		uint32_t ab[35] = { 0 };
 		const int pos[] = { 30, 62, 96, 168, 184, 192, 336, 385, 448, MAX_FRAME_BITS }; // AIS.cpp:111-142, AIS.h:172
 		for (int q : pos) ab[q >> 5] |= 1u << (q & 31);
-		CU(cudaMemcpyToSymbol(c_abort_bits, ab, sizeof(ab)));
+		CU(sym_init(H_PS_COS, H_PS_SIN, ab));
 	}
 	h->ring_cap = c.max_frames > 0 ? c.max_frames : std::max(4096, B * 64);
 	if (int rc = dalloc(h, &h->d_ring, (size_t)h->ring_cap)) return rc;

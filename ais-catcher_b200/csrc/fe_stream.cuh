@@ -1,0 +1,268 @@
+#pragma once
+#include "exact.cuh"
+#include "params.h"
+
+namespace aisgpu {
+
+// ---------------------------------------------------------------------------------------------
+// K1'': the front end as the reference writes it -- a per-sample streaming pipeline with its state in registers --
+// run by every THREAD on its own sub-segment of a stream.  A lane walks [a - P, a + S): the first P samples only warm
+// the state up from zero (each CIC stage is a pure function of its last six inputs, see k_frontend), after that every
+// 2^(K+1) inputs yield one 48 kHz sample per channel.  Per input pair a Downsample2CIC5 stage costs 9 packed adds and
+// one packed multiply (DSP.cpp:93-117, literally: r_k = z; z += h_k / h_k = z; z += r_k) and nothing goes through shared
+// memory between stages (ptxas fuses the exact 1/32 scaling of a stage with the first add of the next one into FFMA2;
+// a power-of-two factor makes that bit-identical to the separate multiply unless a value is subnormal); shared memory only stages the input: the warp fetches the next 16 samples of all 32 lanes with
+// coalesced 16-byte cp.async copies (raw format, converted when read) into a ring, four chunks ahead.
+// ---------------------------------------------------------------------------------------------
+struct Cic5 { c64 h0, h1, h2, h3, h4; };
+__device__ __forceinline__ void cic5_zero(Cic5 &s) { s.h0 = s.h1 = s.h2 = s.h3 = s.h4 = 0ull; }
+// one even/odd input pair of Downsample2CIC5 -> one output
+__device__ __forceinline__ c64 ds2_pair(Cic5 &s, c64 xe, c64 xo, c64 sc) {
+	c64 z = xe;
+	const c64 r0 = z; z = padd(z, s.h0);
+	const c64 r1 = z; z = padd(z, s.h1);
+	const c64 r2 = z; z = padd(z, s.h2);
+	const c64 r3 = z; z = padd(z, s.h3);
+	const c64 r4 = z; z = padd(z, s.h4);
+	const c64 out = pmul(z, sc);
+	z = xo;
+	s.h0 = z; z = padd(z, r0);
+	s.h1 = z; z = padd(z, r1);
+	s.h2 = z; z = padd(z, r2);
+	s.h3 = z; z = padd(z, r3);
+	s.h4 = z;
+	(void)r4;
+	return out;
+}
+// one even/odd input pair of FilterCIC5 -> two outputs (DSP.cpp:132-157)
+__device__ __forceinline__ void fcic_pair(Cic5 &s, c64 xe, c64 xo, c64 sc, c64 &oe, c64 &oo) {
+	c64 z = xe;
+	const c64 r0 = z; z = padd(z, s.h0);
+	const c64 r1 = z; z = padd(z, s.h1);
+	const c64 r2 = z; z = padd(z, s.h2);
+	const c64 r3 = z; z = padd(z, s.h3);
+	const c64 r4 = z; z = padd(z, s.h4);
+	oe = pmul(z, sc);
+	z = xo;
+	s.h0 = z; z = padd(z, r0);
+	s.h1 = z; z = padd(z, r1);
+	s.h2 = z; z = padd(z, r2);
+	s.h3 = z; z = padd(z, r3);
+	s.h4 = z; z = padd(z, r4);
+	oo = pmul(z, sc);
+}
+template <int FMT>
+struct StFmt {
+	static constexpr int BPS = FMT == 0 ? 8 : (FMT == 3 ? 4 : 2);
+	static constexpr int CHUNK = ST_G * BPS;      // bytes of one lane's chunk: 128 / 32 / 32 / 64
+	static constexpr int PIECES = CHUNK / 16;     // 16-byte pieces per lane chunk = cp.async instructions per warp chunk
+	static constexpr int SLOT = CHUNK + 16;       // lane stride in the ring (odd multiple of 16 bytes: conflict-free 16-byte reads)
+};
+// sample pair j (samples 2j, 2j+1) of a staged chunk
+template <int FMT>
+__device__ __forceinline__ void st_read_pair(const unsigned char *slot, int j, c64 &xe, c64 &xo) {
+	if (FMT == 0) {
+		const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(slot + j * 16);
+		xe = v.x;
+		xo = v.y;
+	}
+	else if (FMT == 1) {
+		const uchar4 v = *reinterpret_cast<const uchar4 *>(slot + j * 4);
+		xe = pack2(__fmul_rn((float)((int)v.x - 128), 0.0078125f), __fmul_rn((float)((int)v.y - 128), 0.0078125f));
+		xo = pack2(__fmul_rn((float)((int)v.z - 128), 0.0078125f), __fmul_rn((float)((int)v.w - 128), 0.0078125f));
+	}
+	else if (FMT == 2) {
+		const char4 v = *reinterpret_cast<const char4 *>(slot + j * 4);
+		xe = pack2(__fmul_rn((float)v.x, 0.0078125f), __fmul_rn((float)v.y, 0.0078125f));
+		xo = pack2(__fmul_rn((float)v.z, 0.0078125f), __fmul_rn((float)v.w, 0.0078125f));
+	}
+	else {
+		const short4 v = *reinterpret_cast<const short4 *>(slot + j * 8);
+		xe = pack2(__fmul_rn((float)v.x, 3.0517578125e-05f), __fmul_rn((float)v.y, 3.0517578125e-05f));
+		xo = pack2(__fmul_rn((float)v.z, 3.0517578125e-05f), __fmul_rn((float)v.w, 3.0517578125e-05f));
+	}
+}
+
+// ST_WARPS: warps per CTA (independent of each other).  One-warp CTAs with a ring of 6 chunks (27.6 KB for CF32) let eight
+// CTAs share an SM and let the block scheduler spread B x st_wps warps evenly over the 148 SMs (1024 warps: 7 + 6.9 avg);
+// the 4-warp / ring-of-8 shape (147 KB per CTA, one CTA per SM, 1.73 waves at 1024 warps) is the round-1 shape, kept for A/B.
+template <int FMT, int K, int ST_NB, int ST_WARPS, bool PRE = false>
+__global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p) {
+	static_assert(K >= 3 && K <= 7, "streaming front end: 768 kS/s .. 12288 kS/s");
+	typedef StFmt<FMT> F;
+	constexpr int SS = 1 << (K + 2);     // inputs per super-step: two 48 kHz samples per channel
+	constexpr int NCH = SS / ST_G;       // chunks per super-step
+	constexpr int N96 = SS >> K;         // 96 kHz samples per super-step (4)
+	extern __shared__ __align__(16) unsigned char st_ring[]; // [ST_WARPS][ST_NB][32 * SLOT]
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const long long wg = (long long)blockIdx.x * ST_WARPS + wib;
+	const int stream = (int)(wg / p.st_wps);
+	if (stream >= p.st_B) return; // whole warp
+	const int sub0 = (int)(wg - (long long)stream * p.st_wps) * 32;
+	const int S = p.st_S;
+	unsigned char(*ring)[32 * F::SLOT] = reinterpret_cast<unsigned char(*)[32 * F::SLOT]>(st_ring + (size_t)wib * ST_NB * 32 * F::SLOT);
+	// every lane owns S samples [a, a + S) (the host only picks this kernel when N is a multiple of 32 * S * st_wps)
+	const long long a = (long long)(sub0 + lane) * S;
+	const int warp_chunks = (S + p.P) / ST_G; // warm-up included
+	const unsigned char *in_b = reinterpret_cast<const unsigned char *>(p.in) + (long long)stream * p.in_stride * F::BPS;
+	const unsigned char *tl_b = reinterpret_cast<const unsigned char *>(p.tail) + ((long long)stream * p.P + p.P) * F::BPS;
+	// staging: in instruction `it` lane j fetches 16-byte piece (j % PIECES) of the chunk of owner it*(32/PIECES) + j / PIECES
+	constexpr int OWN_PER_IT = 32 / F::PIECES;
+	const int o0 = lane / F::PIECES, q0 = lane % F::PIECES;
+	const long long lane_off = ((long long)(sub0 + o0) * S - p.P) * F::BPS + q0 * 16; // byte offset of chunk 0, piece q0, owner o0
+	const long long it_step = (long long)OWN_PER_IT * S * F::BPS;                        // next instruction: next group of owners
+	const int dst_off = o0 * F::SLOT + q0 * 16;
+	const bool from_tail = sub0 == 0 && o0 == 0; // only the first sub-segment of a stream starts in the previous submit
+	auto prefetch = [&](int c) {
+		if (c < warp_chunks) {
+			const long long coff = lane_off + (long long)c * (ST_G * F::BPS);
+			unsigned char *dst = &ring[c % ST_NB][dst_off];
+#pragma unroll
+			for (int it = 0; it < F::PIECES; it++) {
+				const unsigned char *src = ((it == 0 && from_tail && c * ST_G < p.P) ? tl_b : in_b) + coff + it * it_step;
+				cp_async16(dst + it * OWN_PER_IT * F::SLOT, src);
+			}
+		}
+		cp_async_commit();
+	};
+	const c64 sc = pack2(0.03125f, 0.03125f);
+	Cic5 lv[K], chA, chB, fA, fB;
+#pragma unroll
+	for (int l = 0; l < K; l++) cic5_zero(lv[l]);
+	cic5_zero(chA); cic5_zero(chB); cic5_zero(fA); cic5_zero(fB);
+	c64 fd1 = 0ull, fd2 = 0ull; // FilterComplex3Tap h1, h2
+	// PRE: decimation in front of DSP::Upsample -- the level-K samples go to D0 and nothing else is computed
+	const float2 *rot_g = PRE ? nullptr : p.rot + (p.P >> K) + ((a - p.P) >> K);
+	float2 *Cg = PRE ? p.D0 + (long long)stream * p.d0_stride + p.d0_off + ((a - p.P) >> K)
+					 : p.C + (long long)(stream * 2) * p.c_stride + p.c_off + ((a - p.P) >> (K + 1));
+	const int n_super = warp_chunks / NCH;
+	const int warm_super = p.P / SS;
+#pragma unroll
+	for (int c = 0; c < ST_NB - 1; c++) prefetch(c);
+	// Rotate phasors: loaded two super-steps ahead of their use (under load a global load can take longer than one
+	// super-step of arithmetic)
+	float2 rt_n1[N96], rt_n2[N96];
+#pragma unroll
+	for (int i = 0; i < N96; i++) {
+		rt_n1[i] = PRE ? make_float2(0.f, 0.f) : __ldg(rot_g + i);
+		rt_n2[i] = PRE ? make_float2(0.f, 0.f) : __ldg(rot_g + (n_super > 1 ? N96 : 0) + i);
+	}
+	for (int ss = 0; ss < n_super; ss++) {
+		float2 rt[N96];
+#pragma unroll
+		for (int i = 0; i < N96; i++) {
+			rt[i] = rt_n1[i];
+			rt_n1[i] = rt_n2[i];
+		}
+		if (!PRE && ss + 2 < n_super) {
+#pragma unroll
+			for (int i = 0; i < N96; i++) rt_n2[i] = __ldg(rot_g + (ss + 2) * N96 + i);
+		}
+		c64 lvK[N96]; // PRE: the super-step's level-K outputs
+		c64 pend[K + 1];  // pend[l]: even-indexed input waiting at level l+1 (l = 1..K-1), pend[K]: unused
+		c64 upE = 0ull, dnE = 0ull, waE = 0ull, wbE = 0ull;
+		c64 outA0 = 0ull, outA1 = 0ull, outB0 = 0ull, outB1 = 0ull;
+#pragma unroll
+		for (int cc = 0; cc < NCH; cc++) {
+			const int c = ss * NCH + cc;
+			prefetch(c + ST_NB - 1);
+			cp_async_wait<ST_NB - 1>(); // chunk c has landed
+			__syncwarp();
+			{
+				const unsigned char *slot = &ring[c % ST_NB][lane * F::SLOT];
+#pragma unroll
+				for (int j = 0; j < ST_G / 2; j++) {
+					const int n1 = cc * (ST_G / 2) + j; // index of this pair's output at level 1 within the super-step
+					c64 xe, xo;
+					st_read_pair<FMT>(slot, j, xe, xo);
+					c64 y = ds2_pair(lv[0], xe, xo, sc);
+					// ripple through the deeper levels: an output with an odd index completes a pair one level down
+					int idx = n1;
+					bool live = true;
+#pragma unroll
+					for (int l = 1; l < K; l++) {
+						if (live) {
+							if ((idx & 1) == 0) { pend[l] = y; live = false; }
+							else { y = ds2_pair(lv[l], pend[l], y, sc); idx >>= 1; }
+						}
+					}
+					if (live && PRE) lvK[idx] = y;
+					if (live && !PRE) { // y is 96 kHz sample idx (0..N96-1) of the super-step
+						c64 x = y;
+						if (p.use_fdc) { // FilterComplex3Tap: alpha * (h1 + x) + h2 * beta (DSP.cpp:283-293)
+							// scalar intrinsics: ptxas would contract a packed mul + add pair into FFMA2 here, and these products are not exact
+							const float2 h1 = unpack2(fd1), h2 = unpack2(fd2), yv = unpack2(y);
+							const float tx = __fadd_rn(h1.x, yv.x), ty = __fadd_rn(h1.y, yv.y);
+							x = pack2(__fadd_rn(__fmul_rn(p.fdc_alpha, tx), __fmul_rn(h2.x, p.fdc_beta)),
+									  __fadd_rn(__fmul_rn(p.fdc_alpha, ty), __fmul_rn(h2.y, p.fdc_beta)));
+							fd1 = fd2;
+							fd2 = y;
+						}
+						const float2 xv = unpack2(x);
+						const float2 r = rt[idx];
+						const float RR = __fmul_rn(xv.x, r.x), II = __fmul_rn(xv.y, r.y), RI = __fmul_rn(xv.x, r.y), IR = __fmul_rn(xv.y, r.x);
+						const c64 up = pack2(__fsub_rn(RR, II), __fadd_rn(IR, RI));
+						const c64 dn = pack2(__fadd_rn(RR, II), __fsub_rn(IR, RI));
+						if ((idx & 1) == 0) { upE = up; dnE = dn; }
+						else {
+							const c64 wa = ds2_pair(chA, upE, up, sc), wb = ds2_pair(chB, dnE, dn, sc);
+							if ((idx & 2) == 0) { waE = wa; wbE = wb; }
+							else {
+								fcic_pair(fA, waE, wa, sc, outA0, outA1);
+								fcic_pair(fB, wbE, wb, sc, outB0, outB1);
+							}
+						}
+					}
+				}
+			}
+			__syncwarp(); // the ring slot may be refilled by a later prefetch
+		}
+		if (PRE) {
+			if (ss >= warm_super) {
+				float2 *o = Cg + ss * N96;
+#pragma unroll
+				for (int i = 0; i < N96; i += 2) *reinterpret_cast<ulonglong2 *>(o + i) = make_ulonglong2(lvK[i], lvK[i + 1]);
+			}
+		}
+		else if (ss >= warm_super) { // two 48 kHz samples per channel
+			float2 *o = Cg + ss * 2;
+			*reinterpret_cast<ulonglong2 *>(o) = make_ulonglong2(outA0, outA1);
+			*reinterpret_cast<ulonglong2 *>(o + p.c_stride) = make_ulonglong2(outB0, outB1);
+		}
+	}
+	cp_async_wait<0>();
+}
+
+// ---- launch entry point of one sample format (instantiated by fe_stream_f<FMT>.cu) ----
+template <int FMT, int K, int NB, int WPC, bool PRE>
+static cudaError_t launch_st_one(const FeParams &p, long long n_warps, cudaStream_t s) {
+	const size_t smem = (size_t)WPC * NB * 32 * StFmt<FMT>::SLOT;
+	cudaError_t e = cudaFuncSetAttribute(k_frontend_st<FMT, K, NB, WPC, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return e;
+	const unsigned ctas = (unsigned)((n_warps + WPC - 1) / WPC);
+	k_frontend_st<FMT, K, NB, WPC, PRE><<<ctas, WPC * 32, smem, s>>>(p);
+	return cudaGetLastError();
+}
+// ring depth x warps per CTA: CF32 (128-byte lane chunks) has the shapes {4 or 6 chunks, 1 warp} and {8 chunks, 4 warps}, one
+// translation unit each; the integer formats (32/64-byte lane chunks) always run one-warp CTAs with 8 chunks
+template <int FMT, int NB, int WPC>
+cudaError_t launch_frontend_stream_shape(const FeParams &p, int k, bool pre, long long n_warps, cudaStream_t s) {
+	if (pre) {
+		switch (k) { // CIC stages in front of DSP::Upsample
+		case 3: return launch_st_one<FMT, 3, NB, WPC, true>(p, n_warps, s);
+		case 4: return launch_st_one<FMT, 4, NB, WPC, true>(p, n_warps, s);
+		case 5: return launch_st_one<FMT, 5, NB, WPC, true>(p, n_warps, s);
+		default: return cudaErrorInvalidValue;
+		}
+	}
+	switch (k) {
+	case 3: return launch_st_one<FMT, 3, NB, WPC, false>(p, n_warps, s);
+	case 4: return launch_st_one<FMT, 4, NB, WPC, false>(p, n_warps, s);
+	case 5: return launch_st_one<FMT, 5, NB, WPC, false>(p, n_warps, s);
+	case 6: return launch_st_one<FMT, 6, NB, WPC, false>(p, n_warps, s);
+	case 7: return launch_st_one<FMT, 7, NB, WPC, false>(p, n_warps, s);
+	default: return cudaErrorInvalidValue;
+	}
+}
+
+} // namespace aisgpu

@@ -22,6 +22,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "ais-catcher_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # aissynth: the seeded stimulus generator shared with the parity tests
 
 FS = 1536000
 N_CHUNK = 131072

@@ -17,7 +17,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-for p in (os.path.join(ROOT, "ais-catcher_b200"), os.path.join(ROOT, "oracle")):
+for p in (os.path.join(ROOT, "ais-catcher_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import aissynth as S  # noqa: E402
 import oracle as O  # noqa: E402

@@ -52,7 +52,7 @@ def _decode_slice(lo, hi, fs, N, nchunks):
 
 
 def _worker(rank, world, port, B, fs, N, nchunks, q):
-    for p in (ROOT, os.path.join(ROOT, "ais-catcher_b200"), os.path.join(ROOT, "oracle")):
+    for p in (ROOT, os.path.join(ROOT, "ais-catcher_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
     import torch.distributed as dist
     import shard as sh

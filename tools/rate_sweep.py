@@ -7,6 +7,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "ais-catcher_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import torch
 import aisgpu
