@@ -17,7 +17,10 @@ TAP_C, TAP_CGF, TAP_FIR, TAP_ROT, TAP_DEC, TAP_FM = 0, 1, 2, 3, 4, 5
 EXPORTS = ["aisgpu_abi_version", "aisgpu_default_config", "aisgpu_create", "aisgpu_submit", "aisgpu_submit_device",
            "aisgpu_sync", "aisgpu_poll", "aisgpu_tap", "aisgpu_counters", "aisgpu_cuda_stream",
            "aisgpu_last_frontend_ms", "aisgpu_frontend_times", "aisgpu_last_launches", "aisgpu_last_error", "aisgpu_destroy",
-           "aisgpu_validate", "aisgpu_build_nmea", "aisgpu_chunk_granule", "aisgpu_join"]
+           "aisgpu_validate", "aisgpu_build_nmea", "aisgpu_chunk_granule", "aisgpu_join", "aisgpu_submit_v", "aisgpu_submit_async",
+           "aisgpu_poll_upto", "aisgpu_nccl_unique_id", "aisgpu_comm_init", "aisgpu_allreduce_counts"]
+
+OK, EINVAL, ENODEV, ECUDA, ENOMEM, EOVERFLOW = 0, -1, -2, -3, -4, -5
 
 
 class Config(C.Structure):
@@ -25,7 +28,7 @@ class Config(C.Structure):
                 ("n_streams", C.c_int32), ("max_chunk_samples", C.c_int32), ("ps_ema", C.c_int32), ("afc_wide", C.c_int32),
                 ("droop", C.c_int32), ("channel_a", C.c_char), ("channel_b", C.c_char), ("station", C.c_int32),
                 ("own_mmsi", C.c_int32), ("tag_mode", C.c_uint32), ("device", C.c_int32), ("enable_taps", C.c_int32),
-                ("max_frames", C.c_int32)]
+                ("max_frames", C.c_int32), ("host_staging", C.c_int32)]
 
 
 class MsgStruct(C.Structure):
@@ -74,6 +77,12 @@ def load():
     lib.aisgpu_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
     lib.aisgpu_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.aisgpu_submit_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+    lib.aisgpu_submit_v.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int]
+    lib.aisgpu_submit_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+    lib.aisgpu_poll_upto.argtypes = [C.c_void_p, C.c_int64, C.POINTER(MsgStruct), C.c_int, C.POINTER(C.c_int)]
+    lib.aisgpu_nccl_unique_id.argtypes = [C.c_void_p]
+    lib.aisgpu_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.aisgpu_allreduce_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.aisgpu_sync.argtypes = [C.c_void_p]
     lib.aisgpu_poll.argtypes = [C.c_void_p, C.POINTER(MsgStruct), C.c_int, C.POINTER(C.c_int)]
     lib.aisgpu_tap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -127,11 +136,21 @@ class AisGpuError(RuntimeError):
     pass
 
 
+def nccl_unique_id():
+    """128-byte ncclUniqueId (bytes) from the library's run-time-resolved NCCL; one rank creates it, all ranks join."""
+    lib = load()
+    buf = C.create_string_buffer(128)
+    rc = lib.aisgpu_nccl_unique_id(buf)
+    if rc:
+        raise AisGpuError("aisgpu_nccl_unique_id rc=%d: %s" % (rc, lib.aisgpu_last_error(None).decode()))
+    return buf.raw
+
+
 class Engine:
     """One batch engine == one AIS::Model instance per stream of the batch (reference Source/DSP/Model.h:76-126)."""
 
     def __init__(self, model=MODEL_DEFAULT, sample_rate=1536000, fmt=FMT_CF32, n_streams=1, max_chunk=131072,
-                 ps_ema=True, afc_wide=True, droop=True, own_mmsi=-1, device=0, taps=False, max_frames=0, tag_mode=3):
+                 ps_ema=True, afc_wide=True, droop=True, own_mmsi=-1, device=0, taps=False, max_frames=0, tag_mode=3, host_staging=True):
         self.lib = load()
         cfg = Config()
         self.lib.aisgpu_default_config(C.byref(cfg))
@@ -139,6 +158,7 @@ class Engine:
         cfg.n_streams, cfg.max_chunk_samples = n_streams, max_chunk
         cfg.ps_ema, cfg.afc_wide, cfg.droop = int(ps_ema), int(afc_wide), int(droop)
         cfg.own_mmsi, cfg.device, cfg.enable_taps, cfg.max_frames, cfg.tag_mode = own_mmsi, device, int(taps), max_frames, tag_mode
+        cfg.host_staging = int(host_staging)
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.lib.aisgpu_create(C.byref(cfg), C.byref(self.h))
@@ -146,8 +166,12 @@ class Engine:
             raise AisGpuError("aisgpu_create rc=%d: %s" % (rc, self.lib.aisgpu_last_error(None).decode()))
         self.n_streams = n_streams
         self.fmt = fmt
+        self.overflows = 0  # polls that reported AISGPU_EOVERFLOW (frames were dropped; the survivors were delivered)
 
     def _chk(self, rc):
+        if rc == EOVERFLOW:
+            self.overflows += 1
+            return
         if rc:
             raise AisGpuError("rc=%d: %s" % (rc, self.lib.aisgpu_last_error(self.h).decode()))
 
@@ -158,6 +182,53 @@ class Engine:
 
     def submit_ptr(self, host_ptr, n_samples):
         self._chk(self.lib.aisgpu_submit(self.h, C.c_void_p(host_ptr), n_samples))
+
+    def submit_v(self, host_arrays, n_samples):
+        """One host array per stream (the shape n_streams independent receivers deliver)."""
+        arrs = [np.ascontiguousarray(a) for a in host_arrays]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        self._chk(self.lib.aisgpu_submit_v(self.h, ptrs, n_samples))
+
+    def submit_async_ptr(self, host_ptr, n_samples):
+        """Enqueue copy + kernels and return the ticket; the buffer must stay untouched until poll_upto(ticket) returned."""
+        t = C.c_int64(-1)
+        self._chk(self.lib.aisgpu_submit_async(self.h, C.c_void_p(host_ptr), n_samples, C.byref(t)))
+        return t.value
+
+    def poll_upto(self, ticket, batch=256):
+        out = []
+        buf = (MsgStruct * batch)()
+        n = C.c_int(0)
+        while True:
+            self._chk(self.lib.aisgpu_poll_upto(self.h, ticket, buf, batch, C.byref(n)))
+            if n.value == 0:
+                break
+            out.extend(Msg(buf[i]) for i in range(n.value))
+        return out
+
+    def poll_upto_count(self, ticket, batch=4096):
+        """poll_upto without building Python objects: (frames, sentences) of the submits up to `ticket` (-1: all)."""
+        if getattr(self, "_pbuf", None) is None or len(self._pbuf) < batch:
+            self._pbuf = (MsgStruct * batch)()
+        n = C.c_int(0)
+        frames = sentences = 0
+        while True:
+            self._chk(self.lib.aisgpu_poll_upto(self.h, ticket, self._pbuf, batch, C.byref(n)))
+            if n.value == 0:
+                break
+            frames += n.value
+            sentences += n.value  # single-sentence messages dominate; exact count is in the structs if needed
+            if n.value < batch:
+                break
+        return frames, sentences
+
+    def comm_init(self, id128, n_ranks, rank):
+        self._chk(self.lib.aisgpu_comm_init(self.h, id128, n_ranks, rank))
+
+    def allreduce_counts(self):
+        c = (C.c_uint64 * 8)()
+        self._chk(self.lib.aisgpu_allreduce_counts(self.h, c))
+        return list(c)
 
     def submit_device(self, dev_ptr, stride_samples, n_samples):
         self._chk(self.lib.aisgpu_submit_device(self.h, C.c_void_p(dev_ptr), stride_samples, n_samples))

@@ -7,12 +7,14 @@
 // steps, Model.cpp:31, FFT.h:81-83, DSP.cpp:457-458) and the per-frame tail of AIS::Decoder::processData
 // (dB level, validate, buildNMEA: AIS.cpp:66-96, Message.cpp:398-413, 569-686).  No CPU fallback exists.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <deque>
 #include <string>
 #include <vector>
 
@@ -85,8 +87,6 @@ struct aisgpu_handle {
 	long long s2_stride = 0, s2_produced = 0, s2_consumed = 0;
 	int *d_us_src = nullptr;
 	float *d_us_alpha = nullptr;
-	std::vector<int> h_us_src;
-	std::vector<float> h_us_alpha;
 	FeParams fe_pre;
 	int pre_tile = 0;
 	long long msg_chunk = 0; // ordinal of the caller's submit (what frames are tagged with)
@@ -97,7 +97,7 @@ struct aisgpu_handle {
 	int rows = 0;
 	int max_n48 = 0;
 	int fe_warps = 4, fe_tile = 0, fe_ctas = 4096;
-	int fe_st = 1, st_S = 0, st_nb = 6, st_wpc = 1, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
+	int fe_st = 1, st_S = 0, st_nb = 8, st_wpc = 4, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
 	int dec_rpw = 6, decoder = 3; // rows per warp / which decoder kernel // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
 	// for timing).  The front end of submit c+1 overlaps the back end of submit c; Cbuf is double buffered for that.
@@ -168,9 +168,20 @@ struct aisgpu_handle {
 	float *d_tap_dec = nullptr, *d_tap_fm = nullptr;
 	int *d_tap_cnt = nullptr;
 	// frames
+	// Circular frame ring.  Tickets (frames emitted since creation) only grow; the host owns `drained`.  Every submit
+	// records, in stream order behind its decoders, the ring head into a pinned slot plus an event: aisgpu_poll_upto waits
+	// for one submit only and later submits keep running.
 	FrameRec *d_ring = nullptr;
-	int *d_ring_count = nullptr;
+	unsigned long long *d_ring_head = nullptr;
 	int ring_cap = 0;
+	unsigned long long drained = 0;           // tickets delivered to (or dropped for) the host
+	static const int NT = 1024;               // submits whose completion record is kept
+	unsigned long long *pin_head = nullptr;   // [NT] pinned: ring head after submit t (slot t % NT)
+	cudaEvent_t ev_ticket[1024] = { nullptr };
+	cudaEvent_t ev_mark = nullptr;
+	std::deque<unsigned long long> launch_limit; // per undrained submit: drained-at-launch + ring_cap (what its kernels were given)
+	long long polled_ticket = -1;             // newest submit whose frames have been drained
+	bool overflow_pending = false;
 	std::vector<FrameRec> h_ring;
 	std::vector<aisgpu_msg> out_queue;
 	size_t out_pos = 0;
@@ -181,7 +192,17 @@ struct aisgpu_handle {
 	long long chunk = 0;
 	float last_fe_ms = -1.0f;
 	std::string err;
+	int poisoned = 0; // a CUDA failure inside a submit leaves the carried state half-advanced: every later call returns this code
 	FeParams fe;
+	// pinned double buffer of the Upsample (input index, alpha) schedule
+	int *pin_us_src[2] = { nullptr, nullptr };
+	float *pin_us_alpha[2] = { nullptr, nullptr };
+	cudaEvent_t ev_us[2] = { nullptr, nullptr };
+	bool us_used[2] = { false, false };
+	int us_cur = 0, us_cap = 0;
+	// NCCL (resolved at run time): communicator of the job's ranks, device scratch of the counter all-reduce
+	void *nccl_lib = nullptr, *nccl_comm = nullptr;
+	unsigned long long *d_counts = nullptr;
 };
 
 namespace {
@@ -199,7 +220,18 @@ namespace {
 
 template <typename T>
 int dalloc(aisgpu_handle *h, T **p, size_t n) {
-	CU(cudaMalloc((void **)p, n * sizeof(T)));
+	{
+		const cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+		if (e == cudaErrorMemoryAllocation) {
+			char b[160];
+			snprintf(b, sizeof(b), "out of device memory allocating %zu bytes", n * sizeof(T));
+			h->err = b;
+			(void)cudaGetLastError();
+			*p = nullptr;
+			return AISGPU_ENOMEM;
+		}
+		CU(e);
+	}
 	CU(cudaMemsetAsync(*p, 0, n * sizeof(T), h->stream));
 	return 0;
 }
@@ -397,7 +429,8 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.dec = h->d_dec;
 		p.dec_data = h->d_dec_data;
 		p.ring = h->d_ring;
-		p.ring_count = h->d_ring_count;
+		p.ring_head = h->d_ring_head;
+		p.ring_limit = h->drained + (unsigned long long)h->ring_cap;
 		p.ring_cap = h->ring_cap;
 		p.chunk = (int)h->msg_chunk;
 		p.blk = (int)h->chunk;
@@ -436,7 +469,8 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.dec = h->d_dec;
 		p.dec_data = h->d_dec_data;
 		p.ring = h->d_ring;
-		p.ring_count = h->d_ring_count;
+		p.ring_head = h->d_ring_head;
+		p.ring_limit = h->drained + (unsigned long long)h->ring_cap;
 		p.ring_cap = h->ring_cap;
 		p.chunk = (int)h->msg_chunk;
 		p.blk = (int)h->chunk;
@@ -495,9 +529,9 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 	const int q = 1 << (h->k + 2);
 	if (N <= 0 || N > h->inner_max || (N % q) != 0) {
 		char b[160];
-		snprintf(b, sizeof(b), "block of %d samples must be a positive multiple of %d and <= %d", N, q, h->inner_max);
+		snprintf(b, sizeof(b), "internal: block of %d samples must be a positive multiple of %d and <= %d", N, q, h->inner_max);
 		h->err = b;
-		return AISGPU_EINVAL;
+		return AISGPU_ECUDA; // cannot come from the caller's arguments (check_outer has passed): poisons the handle
 	}
 	const int k = h->k, B = h->cfg.n_streams;
 	const int n96 = N >> k, n48 = n96 >> 1;
@@ -618,7 +652,7 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 			if (int rc = run_symbols(h, n48)) return rc;
 		}
 		else {
-			CU(launch_base(h->d_Ef2[0], h->e_stride, HE, n48, h->rows, h->d_pll, h->d_dec, h->d_dec_data, h->d_ring, h->d_ring_count, h->ring_cap, (int)h->msg_chunk,
+			CU(launch_base(h->d_Ef2[0], h->e_stride, HE, n48, h->rows, h->d_pll, h->d_dec, h->d_dec_data, h->d_ring, h->d_ring_head, h->drained + (unsigned long long)h->ring_cap, h->ring_cap, (int)h->msg_chunk,
 						   (int)h->chunk, h->cfg.enable_taps ? h->d_tap_dec : nullptr, h->cfg.enable_taps ? h->d_tap_cnt : nullptr, h->bs));
 			h->last_launches++;
 		}
@@ -661,6 +695,8 @@ int check_outer(aisgpu_handle *h, int N) {
 	}
 	return 0;
 }
+
+int mark_ticket(aisgpu_handle *h, long long t);
 
 // The caller's Receive(): N samples per stream in the caller's format.
 int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) {
@@ -722,23 +758,34 @@ int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) 
 			if (!st_done) CU(launch_frontend_tiled(pp, h->cfg.format, h->kA, true, grid, smem, h->fe_stream));
 			if (rc) return rc;
 			tail_len = h->PA;
-			// replay Upsample's float accumulator: one (input index, alpha) pair per output (DSP.cpp:196-209)
-			h->h_us_src.clear();
-			h->h_us_alpha.clear();
+			// replay Upsample's float accumulator: one (input index, alpha) pair per output (DSP.cpp:196-209).  The table goes
+			// through a pinned double buffer, so the copy is a true asynchronous one and the caller's thread never waits
+			// for the front-end stream here.
+			const int ub = h->us_cur;
+			if (h->us_used[ub]) CU(cudaEventSynchronize(h->ev_us[ub])); // the copy issued two submits ago has read this buffer
+			int *us_src = h->pin_us_src[ub];
+			float *us_al = h->pin_us_alpha[ub];
 			float alpha = h->us_alpha;
 			const float inc = h->us_inc;
+			int M = 0;
 			for (int i = 0; i < L; i++) {
 				do {
-					h->h_us_src.push_back(i);
-					h->h_us_alpha.push_back(alpha);
+					if (M >= h->us_cap) {
+						h->err = "Upsample schedule overflow";
+						return AISGPU_ECUDA;
+					}
+					us_src[M] = i;
+					us_al[M++] = alpha;
 					alpha += inc;
 				} while (alpha < 1.0f);
 				alpha -= 1.0f;
 			}
 			h->us_alpha = alpha;
-			const int M = (int)h->h_us_src.size();
-			CU(cudaMemcpyAsync(h->d_us_src, h->h_us_src.data(), (size_t)M * sizeof(int), cudaMemcpyHostToDevice, h->fe_stream));
-			CU(cudaMemcpyAsync(h->d_us_alpha, h->h_us_alpha.data(), (size_t)M * sizeof(float), cudaMemcpyHostToDevice, h->fe_stream));
+			CU(cudaMemcpyAsync(h->d_us_src, us_src, (size_t)M * sizeof(int), cudaMemcpyHostToDevice, h->fe_stream));
+			CU(cudaMemcpyAsync(h->d_us_alpha, us_al, (size_t)M * sizeof(float), cudaMemcpyHostToDevice, h->fe_stream));
+			CU(cudaEventRecord(h->ev_us[ub], h->fe_stream));
+			h->us_used[ub] = true;
+			h->us_cur ^= 1;
 			CU(launch_upsample(h->d_D0, h->d0_stride, 2, h->d_us_src, h->d_us_alpha, M, B, h->d_S, h->s_stride, h->s_produced, h->s_cap, h->fe_stream));
 			CU(launch_d0_carry(h->d_D0, h->d0_stride, 2, L, B, h->fe_stream));
 			h->s_produced += M;
@@ -779,6 +826,7 @@ int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) 
 		}
 	}
 	if (rc) return rc;
+	if (int rc2 = mark_ticket(h, (long long)h->counters[3])) return rc2;
 	h->counters[2] += (uint64_t)N;
 	h->counters[3] += 1;
 	return 0;
@@ -846,16 +894,67 @@ void build_nmea(aisgpu_msg &m, int own_mmsi, int *seq_counter) { // Message.cpp:
 	}
 }
 
-int drain_ring(aisgpu_handle *h) {
-	if (int rc = sync_backend(h)) return rc;
-	int count = 0;
-	CU(cudaMemcpy(&count, h->d_ring_count, sizeof(int), cudaMemcpyDeviceToHost));
-	if (count <= 0) return 0;
-	int n = std::min(count, h->ring_cap);
-	if (count > h->ring_cap) h->counters[4] += (uint64_t)(count - h->ring_cap);
-	h->h_ring.resize(n);
-	CU(cudaMemcpy(h->h_ring.data(), h->d_ring, (size_t)n * sizeof(FrameRec), cudaMemcpyDeviceToHost));
-	CU(cudaMemset(h->d_ring_count, 0, sizeof(int)));
+// Copies the frames with tickets [a, b) to the end of h_ring; tickets at or above `limit` were dropped by the kernels.
+int fetch_frames(aisgpu_handle *h, unsigned long long a, unsigned long long b, unsigned long long limit) {
+	const unsigned long long hi = std::min(b, std::max(a, limit));
+	if (b > hi) {
+		h->counters[4] += (uint64_t)(b - hi);
+		h->overflow_pending = true;
+	}
+	const unsigned long long cap = (unsigned long long)h->ring_cap;
+	while (a < hi) {
+		const size_t off = (size_t)(a % cap);
+		const size_t n = (size_t)std::min<unsigned long long>(hi - a, cap - off);
+		const size_t at = h->h_ring.size();
+		h->h_ring.resize(at + n);
+		CU(cudaMemcpy(h->h_ring.data() + at, h->d_ring + off, n * sizeof(FrameRec), cudaMemcpyDeviceToHost));
+		a += n;
+	}
+	return 0;
+}
+
+// Records, behind everything enqueued for submit `t`, the ring head (into a pinned slot) and the completion event.
+int mark_ticket(aisgpu_handle *h, long long t) {
+	cudaStream_t st = h->bs ? h->bs : h->stream;
+	CU(cudaEventRecord(h->ev_mark, h->fe_stream)); // a pre-stage submit may have launched nothing behind the front-end stream
+	CU(cudaStreamWaitEvent(st, h->ev_mark, 0));
+	const int slot = (int)(t % aisgpu_handle::NT);
+	CU(cudaMemcpyAsync(&h->pin_head[slot], h->d_ring_head, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	CU(cudaEventRecord(h->ev_ticket[slot], st));
+	h->launch_limit.push_back(h->drained + (unsigned long long)h->ring_cap);
+	return 0;
+}
+
+// Frames of the submits (polled_ticket, upto] -> out_queue.  upto < 0: everything, after a full synchronisation.
+int drain_ring(aisgpu_handle *h, long long upto) {
+	const long long latest = (long long)h->counters[3] - 1;
+	if (latest < 0) return 0;
+	if (upto < 0 || upto > latest) {
+		CU(cudaStreamSynchronize(h->fe_stream));
+		if (int rc = sync_backend(h)) return rc;
+		upto = latest;
+	}
+	if (upto <= h->polled_ticket) return 0;
+	if (latest - upto >= aisgpu_handle::NT) upto = latest; // its completion record has been recycled: wait for the newest one
+	CU(cudaEventSynchronize(h->ev_ticket[upto % aisgpu_handle::NT]));
+	h->h_ring.clear();
+	const long long first = h->polled_ticket + 1;
+	if (latest - first < aisgpu_handle::NT) { // every submit's own record is still there: exact limits per submit
+		for (long long t = first; t <= upto; t++) {
+			const unsigned long long head = h->pin_head[t % aisgpu_handle::NT];
+			if (int rc = fetch_frames(h, h->drained, head, h->launch_limit.front())) return rc;
+			h->drained = head;
+			h->launch_limit.pop_front();
+		}
+	}
+	else { // more submits than records since the last poll: they all ran against the oldest one's limit or a later (larger) one
+		const unsigned long long head = h->pin_head[upto % aisgpu_handle::NT];
+		if (int rc = fetch_frames(h, h->drained, head, h->launch_limit.front())) return rc;
+		h->drained = head;
+		for (long long t = first; t <= upto; t++) h->launch_limit.pop_front();
+	}
+	h->polled_ticket = upto;
+	if (h->h_ring.empty()) return 0;
 	// reference emission order: per submit, stream-major, channel A (ROT.up) before B (DSP.cpp:312-313), then time
 	std::stable_sort(h->h_ring.begin(), h->h_ring.end(), [](const FrameRec &a, const FrameRec &b) {
 		if (a.chunk != b.chunk) return a.chunk < b.chunk;
@@ -911,6 +1010,7 @@ void aisgpu_default_config(aisgpu_config *cfg) {
 	cfg->device = 0;
 	cfg->enable_taps = 0;
 	cfg->max_frames = 0;
+	cfg->host_staging = 1;
 }
 
 const char *aisgpu_last_error(aisgpu_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -1131,7 +1231,31 @@ static int create_impl(aisgpu_handle *h) {
 	}
 	h->ring_cap = c.max_frames > 0 ? c.max_frames : std::max(4096, B * 64);
 	if (int rc = dalloc(h, &h->d_ring, (size_t)h->ring_cap)) return rc;
-	if (int rc = dalloc(h, &h->d_ring_count, 1)) return rc;
+	if (int rc = dalloc(h, &h->d_ring_head, 1)) return rc;
+	if (int rc = dalloc(h, &h->d_counts, 16)) return rc;
+	if (cudaMallocHost((void **)&h->pin_head, aisgpu_handle::NT * sizeof(unsigned long long)) != cudaSuccess) {
+		h->err = "out of pinned host memory";
+		(void)cudaGetLastError();
+		return AISGPU_ENOMEM;
+	}
+	memset(h->pin_head, 0, aisgpu_handle::NT * sizeof(unsigned long long));
+	for (int i = 0; i < aisgpu_handle::NT; i++) CU(cudaEventCreateWithFlags(&h->ev_ticket[i], cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&h->ev_mark, cudaEventDisableTiming));
+	if (h->pre == 1 || h->pre == 3) {
+		h->us_cap = 2 * (maxN >> h->kA) + 8; // Upsample never more than doubles the rate (bucket / 2 < rate)
+		for (int i = 0; i < 2; i++) {
+			if (cudaMallocHost((void **)&h->pin_us_src[i], (size_t)h->us_cap * sizeof(int)) != cudaSuccess ||
+				cudaMallocHost((void **)&h->pin_us_alpha[i], (size_t)h->us_cap * sizeof(float)) != cudaSuccess) {
+				h->err = "out of pinned host memory";
+				(void)cudaGetLastError();
+				return AISGPU_ENOMEM;
+			}
+			CU(cudaEventCreateWithFlags(&h->ev_us[i], cudaEventDisableTiming));
+		}
+	}
+	if (c.host_staging) // the H2D staging buffers of aisgpu_submit / _v / _async (otherwise allocated by the first host submit)
+		for (int i = 0; i < 2; i++)
+			if (int rc = dalloc(h, &h->d_in[i], (size_t)B * maxN * h->obps)) return rc;
 	memset(&h->fe, 0, sizeof(h->fe));
 	CU(cudaStreamSynchronize(h->stream));
 	return 0;
@@ -1155,58 +1279,110 @@ int aisgpu_create(const aisgpu_config *cfg, aisgpu_handle **out) {
 	return 0;
 }
 
+// a CUDA failure (or an internal inconsistency) inside a submit leaves carried state half-advanced: poison the handle
+static int poison(aisgpu_handle *h, int rc) {
+	if (rc != 0 && rc != AISGPU_EINVAL && !h->poisoned) h->poisoned = rc;
+	return rc;
+}
+#define ENTER(h)                                  \
+	do {                                          \
+		if (!(h)) return AISGPU_EINVAL;           \
+		if ((h)->poisoned) return (h)->poisoned;  \
+		CU(cudaSetDevice((h)->cfg.device));       \
+	} while (0)
+
 int aisgpu_submit_device(aisgpu_handle *h, const void *dev_samples, int64_t stride_samples, int n_samples) {
-	if (!h || !dev_samples) return AISGPU_EINVAL;
-	CU(cudaSetDevice(h->cfg.device));
+	ENTER(h);
+	if (!dev_samples) return AISGPU_EINVAL;
 	if (stride_samples < n_samples || (stride_samples & 1)) {
 		h->err = "stride_samples must be even and >= n_samples";
 		return AISGPU_EINVAL;
 	}
-	return submit_outer(h, dev_samples, stride_samples, n_samples);
+	if (int rc = check_outer(h, n_samples)) return rc; // all argument checks come before any state is touched
+	return poison(h, submit_outer(h, dev_samples, stride_samples, n_samples));
 }
 
-int aisgpu_submit(aisgpu_handle *h, const void *host_samples, int n_samples) {
-	if (!h || !host_samples) return AISGPU_EINVAL;
-	CU(cudaSetDevice(h->cfg.device));
+// Host submits: the batch goes through one of two device staging buffers (copy stream), the front end of the submit
+// before last being the previous reader of that buffer.  `ptrs` != nullptr: one host pointer per stream.
+static int submit_host(aisgpu_handle *h, const void *host_samples, const void *const *ptrs, int n_samples, bool wait_copy, int64_t *ticket) {
 	if (int rc = check_outer(h, n_samples)) return rc;
-	const size_t bytes = (size_t)h->cfg.n_streams * n_samples * h->obps;
+	const size_t row_bytes = (size_t)n_samples * h->obps;
 	const int cur = h->in_cur;
-	if (!h->d_in[cur]) CU(cudaMalloc((void **)&h->d_in[cur], (size_t)h->cfg.n_streams * h->cfg.max_chunk_samples * h->obps));
-	// the staging buffer may still be read by the kernels of the submit before last
+	if (!h->d_in[cur]) {
+		if (int rc = dalloc(h, &h->d_in[cur], (size_t)h->cfg.n_streams * h->cfg.max_chunk_samples * h->obps)) return rc;
+		CU(cudaStreamSynchronize(h->stream)); // dalloc clears on h->stream
+	}
 	if (h->in_used[cur]) CU(cudaStreamWaitEvent(h->copy_stream, h->ev_done[cur], 0));
-	CU(cudaMemcpyAsync(h->d_in[cur], host_samples, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+	if (ptrs) {
+		for (int s = 0; s < h->cfg.n_streams; s++) {
+			if (!ptrs[s]) {
+				h->err = "null stream pointer";
+				return AISGPU_EINVAL;
+			}
+		}
+		for (int s = 0; s < h->cfg.n_streams; s++)
+			CU(cudaMemcpyAsync(h->d_in[cur] + (size_t)s * row_bytes, ptrs[s], row_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+	}
+	else CU(cudaMemcpyAsync(h->d_in[cur], host_samples, row_bytes * h->cfg.n_streams, cudaMemcpyHostToDevice, h->copy_stream));
 	CU(cudaEventRecord(h->ev_copy[cur], h->copy_stream));
 	CU(cudaStreamWaitEvent(h->fe_stream, h->ev_copy[cur], 0));
-	int rc = submit_outer(h, h->d_in[cur], n_samples, n_samples);
-	if (rc) return rc;
+	if (ticket) *ticket = (int64_t)h->counters[3];
+	if (int rc = submit_outer(h, h->d_in[cur], n_samples, n_samples)) return rc;
 	CU(cudaEventRecord(h->ev_done[cur], h->fe_stream)); // the front end is the only reader of the staging buffer
 	h->in_used[cur] = true;
 	h->in_cur ^= 1;
-	// the caller's buffer is only borrowed for the call (Stream.h:41 semantics): wait for the copy, not for the kernels
-	CU(cudaEventSynchronize(h->ev_copy[cur]));
+	// aisgpu_submit / _v: the caller's buffer is only borrowed for the call (Stream.h:41 semantics): wait for the copy, not
+	// for the kernels
+	if (wait_copy) CU(cudaEventSynchronize(h->ev_copy[cur]));
 	return 0;
 }
 
+int aisgpu_submit(aisgpu_handle *h, const void *host_samples, int n_samples) {
+	ENTER(h);
+	if (!host_samples) return AISGPU_EINVAL;
+	return poison(h, submit_host(h, host_samples, nullptr, n_samples, true, nullptr));
+}
+
+int aisgpu_submit_v(aisgpu_handle *h, const void *const *stream_ptrs, int n_samples) {
+	ENTER(h);
+	if (!stream_ptrs) return AISGPU_EINVAL;
+	return poison(h, submit_host(h, nullptr, stream_ptrs, n_samples, true, nullptr));
+}
+
+int aisgpu_submit_async(aisgpu_handle *h, const void *host_samples, int n_samples, int64_t *ticket) {
+	ENTER(h);
+	if (!host_samples) return AISGPU_EINVAL;
+	return poison(h, submit_host(h, host_samples, nullptr, n_samples, false, ticket));
+}
+
 int aisgpu_sync(aisgpu_handle *h) {
-	if (!h) return AISGPU_EINVAL;
+	ENTER(h);
+	CU(cudaStreamSynchronize(h->copy_stream));
 	CU(cudaStreamSynchronize(h->fe_stream));
 	if (int rc = sync_backend(h)) return rc;
 	return 0;
 }
 
-int aisgpu_poll(aisgpu_handle *h, aisgpu_msg *out, int max, int *n) {
-	if (!h || !n || (max > 0 && !out)) return AISGPU_EINVAL;
-	CU(cudaSetDevice(h->cfg.device));
+int aisgpu_poll_upto(aisgpu_handle *h, int64_t ticket, aisgpu_msg *out, int max, int *n) {
+	if (!n || (max > 0 && !out)) return AISGPU_EINVAL;
+	ENTER(h);
 	if (h->out_pos >= h->out_queue.size()) {
 		h->out_queue.clear();
 		h->out_pos = 0;
-		if (int rc = drain_ring(h)) return rc;
+		if (int rc = drain_ring(h, (long long)ticket)) return rc;
 	}
 	int k = 0;
 	while (k < max && h->out_pos < h->out_queue.size()) out[k++] = h->out_queue[h->out_pos++];
 	*n = k;
+	if (h->overflow_pending) { // reported once per loss, together with the frames that survived
+		h->overflow_pending = false;
+		h->err = "frame ring overflow: frames were dropped (see counters[4]); raise aisgpu_config.max_frames or poll more often";
+		return AISGPU_EOVERFLOW;
+	}
 	return 0;
 }
+
+int aisgpu_poll(aisgpu_handle *h, aisgpu_msg *out, int max, int *n) { return aisgpu_poll_upto(h, -1, out, max, n); }
 
 int aisgpu_tap(aisgpu_handle *h, int tap, int stream, int channel, void *dst, size_t dst_bytes, size_t *n_out) {
 	if (!h || !n_out || stream < 0 || stream >= h->cfg.n_streams || channel < 0 || channel > 9) return AISGPU_EINVAL;
@@ -1284,6 +1460,96 @@ int aisgpu_counters(aisgpu_handle *h, uint64_t counters[8]) {
 	return 0;
 }
 
+// ---- NCCL, resolved at run time: the counters are the only thing that ever crosses NVLink ----
+namespace {
+struct nccl_uid { char internal[128]; };
+struct NcclApi {
+	void *lib = nullptr;
+	int (*GetUniqueId)(nccl_uid *) = nullptr;
+	int (*CommInitRank)(void **, int, nccl_uid, int) = nullptr;
+	int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+	int (*CommDestroy)(void *) = nullptr;
+	const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi *nccl_api(std::string &err) {
+	static NcclApi api;
+	static bool tried = false;
+	if (!tried) {
+		tried = true;
+		const char *names[] = { "libnccl.so.2", "libnccl.so" };
+		for (const char *nm : names)
+			if ((api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;
+		if (api.lib) {
+			api.GetUniqueId = (int (*)(nccl_uid *))dlsym(api.lib, "ncclGetUniqueId");
+			api.CommInitRank = (int (*)(void **, int, nccl_uid, int))dlsym(api.lib, "ncclCommInitRank");
+			api.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(api.lib, "ncclAllReduce");
+			api.CommDestroy = (int (*)(void *))dlsym(api.lib, "ncclCommDestroy");
+			api.GetErrorString = (const char *(*)(int))dlsym(api.lib, "ncclGetErrorString");
+			if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) {
+				dlclose(api.lib);
+				api.lib = nullptr;
+			}
+		}
+	}
+	if (!api.lib) {
+		err = "NCCL not found (dlopen libnccl.so.2)";
+		return nullptr;
+	}
+	return &api;
+}
+} // namespace
+
+int aisgpu_nccl_unique_id(void *id128) {
+	if (!id128) return AISGPU_EINVAL;
+	NcclApi *api = nccl_api(g_create_error);
+	if (!api) return AISGPU_ENODEV;
+	nccl_uid id;
+	if (int rc = api->GetUniqueId(&id)) {
+		g_create_error = std::string("ncclGetUniqueId: ") + (api->GetErrorString ? api->GetErrorString(rc) : "error");
+		return AISGPU_ECUDA;
+	}
+	memcpy(id128, &id, sizeof(id));
+	return 0;
+}
+
+int aisgpu_comm_init(aisgpu_handle *h, const void *id128, int n_ranks, int rank) {
+	if (!h || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return AISGPU_EINVAL;
+	CU(cudaSetDevice(h->cfg.device));
+	NcclApi *api = nccl_api(h->err);
+	if (!api) return AISGPU_ENODEV;
+	if (h->nccl_comm) {
+		api->CommDestroy(h->nccl_comm);
+		h->nccl_comm = nullptr;
+	}
+	nccl_uid id;
+	memcpy(&id, id128, sizeof(id));
+	if (int rc = api->CommInitRank(&h->nccl_comm, n_ranks, id, rank)) {
+		h->err = std::string("ncclCommInitRank: ") + (api->GetErrorString ? api->GetErrorString(rc) : "error");
+		h->nccl_comm = nullptr;
+		return AISGPU_ECUDA;
+	}
+	return 0;
+}
+
+int aisgpu_allreduce_counts(aisgpu_handle *h, uint64_t totals[8]) {
+	if (!h || !totals) return AISGPU_EINVAL;
+	CU(cudaSetDevice(h->cfg.device));
+	if (!h->nccl_comm) { // a single engine is its own job
+		memcpy(totals, h->counters, sizeof(h->counters));
+		return 0;
+	}
+	NcclApi *api = nccl_api(h->err);
+	if (!api) return AISGPU_ENODEV;
+	CU(cudaMemcpyAsync(h->d_counts, h->counters, 8 * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+	if (int rc = api->AllReduce(h->d_counts, h->d_counts + 8, 8, /*ncclUint64*/ 5, /*ncclSum*/ 0, h->nccl_comm, h->stream)) {
+		h->err = std::string("ncclAllReduce: ") + (api->GetErrorString ? api->GetErrorString(rc) : "error");
+		return AISGPU_ECUDA;
+	}
+	CU(cudaMemcpyAsync(totals, h->d_counts + 8, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	return 0;
+}
+
 void *aisgpu_cuda_stream(aisgpu_handle *h) { return h ? (void *)h->stream : nullptr; }
 
 int aisgpu_join(aisgpu_handle *h) {
@@ -1353,10 +1619,24 @@ void aisgpu_destroy(aisgpu_handle *h) {
 		for (int i = 0; i < 2; i++)
 			if (h->ev_stage[st][i]) cudaEventDestroy(h->ev_stage[st][i]);
 	if (h->ev_join) cudaEventDestroy(h->ev_join);
+	if (h->nccl_comm) {
+		std::string e;
+		if (NcclApi *api = nccl_api(e)) api->CommDestroy(h->nccl_comm);
+	}
+	if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+	for (int i = 0; i < aisgpu_handle::NT; i++)
+		if (h->ev_ticket[i]) cudaEventDestroy(h->ev_ticket[i]);
+	if (h->ev_mark) cudaEventDestroy(h->ev_mark);
+	if (h->pin_head) cudaFreeHost(h->pin_head);
+	for (int i = 0; i < 2; i++) {
+		if (h->pin_us_src[i]) cudaFreeHost(h->pin_us_src[i]);
+		if (h->pin_us_alpha[i]) cudaFreeHost(h->pin_us_alpha[i]);
+		if (h->ev_us[i]) cudaEventDestroy(h->ev_us[i]);
+	}
 	void *ptrs[] = { h->d_ptail[0], h->d_ptail[1], h->d_ptail2[0], h->d_ptail2[1], h->d_S2, h->d_D0, h->d_S, h->d_us_src, h->d_us_alpha, h->d_in[0], h->d_in[1], h->d_tail[0], h->d_tail[1], h->d_rot[0], h->d_rot[1], h->d_rot[2], h->d_rot_state, h->d_C2[0], h->d_C2[1], h->d_C2[2],
 					 h->d_steptab, h->d_omega, h->d_cgf_rot, h->d_rots2[0], h->d_rots2[1], h->d_stepidx2[0], h->d_stepidx2[1], h->d_ppmtab, h->d_fir_hist[0], h->d_fir_hist[1], h->d_tap_cgf, h->d_Ec2[0],
 					 h->d_Ef2[0], h->d_ps, h->d_ps_mem, h->d_dbits2[0], h->d_dbits2[1], h->d_lvl2[0], h->d_lvl2[1], h->d_dbg, h->d_dec, h->d_dec_data, h->d_pll, h->d_tap_dec, h->d_tap_fm, h->d_tap_cnt, h->d_ring,
-					 h->d_ring_count };
+					 h->d_ring_head, h->d_counts };
 	for (void *p : ptrs)
 		if (p) cudaFree(p);
 	for (int i = 0; i < aisgpu_handle::NEV; i++) {

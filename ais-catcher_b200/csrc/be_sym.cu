@@ -136,11 +136,18 @@ __device__ __forceinline__ bool dec_step(DecState &d, const DecCtx &c, float sam
 	return found;
 }
 
-__device__ __forceinline__ void emit_frame(FrameRec *__restrict__ ring, int *__restrict__ ring_count, int ring_cap, int chunk, int blk, const DecCtx &c,
-										   int row, int phase, int len, float level, float ppm, long long start_idx, long long end_idx) {
-	const int slot = atomicAdd(ring_count, 1);
-	if (slot >= ring_cap) return;
-	FrameRec &r = ring[slot];
+// The frame ring is circular: `head` only grows (one ticket per frame); a frame whose ticket is `ring_cap` or more ahead of
+// what the host had drained when the kernel was launched (ticket >= limit) is dropped -- the host sees the gap in the
+// ticket range and reports AISGPU_EOVERFLOW.
+__device__ __forceinline__ FrameRec *ring_claim(FrameRec *__restrict__ ring, unsigned long long *__restrict__ head, unsigned long long limit, int ring_cap) {
+	const unsigned long long t = atomicAdd(head, 1ull);
+	return t < limit ? &ring[t % (unsigned long long)ring_cap] : nullptr;
+}
+__device__ __forceinline__ void emit_frame(FrameRec *__restrict__ ring, unsigned long long *__restrict__ head, unsigned long long limit, int ring_cap, int chunk,
+										   int blk, const DecCtx &c, int row, int phase, int len, float level, float ppm, long long start_idx, long long end_idx) {
+	FrameRec *rp = ring_claim(ring, head, limit, ring_cap);
+	if (!rp) return;
+	FrameRec &r = *rp;
 	r.row = row;
 	r.phase = phase;
 	r.nbits = len - 16;
@@ -477,7 +484,7 @@ __global__ void __launch_bounds__(DK_THREADS) k_decode(const K3Params p) {
 						bi = bi < 0 ? 0 : (bi >= p.nblk ? p.nblk - 1 : bi);
 						ppm = p.ppmtab[p.stepidx[row * p.nblk + bi]];
 					}
-					emit_frame(p.ring, p.ring_count, p.ring_cap, p.chunk, p.blk, ctx, row, phase, fr_len, fr_level, ppm, d.start_idx, p.abs_begin + rel);
+					emit_frame(p.ring, p.ring_head, p.ring_limit, p.ring_cap, p.chunk, p.blk, ctx, row, phase, fr_len, fr_level, ppm, d.start_idx, p.abs_begin + rel);
 				}
 				else if (active && (lane < winner || !valid)) { // already stepped this symbol (or no sample in this slot), then reset
 					in_data = 0;
@@ -826,9 +833,9 @@ __global__ void __launch_bounds__(DK3_WARPS * 32) k_decode3(const K3Params p) {
 					ppm = p.ppmtab[p.stepidx[row * p.nblk + bi]];
 				}
 				const long long sidx0 = st.start_rel >= 0 ? p.abs_begin + st.start_rel : d.start_idx;
-				const int slotw = atomicAdd(p.ring_count, 1);
-				if (slotw < p.ring_cap) {
-					FrameRec &r = p.ring[slotw];
+				FrameRec *rp = ring_claim(p.ring, p.ring_head, p.ring_limit, p.ring_cap);
+				if (rp) {
+					FrameRec &r = *rp;
 					r.row = row; r.phase = phase; r.nbits = fr_len - 16; r.level = fr_level; r.ppm = ppm; r.chunk = p.chunk; r.blk = p.blk;
 					r.start_idx = sidx0;
 					r.end_idx = p.abs_begin + (long long)slot * 5 + phase;
@@ -884,7 +891,8 @@ __global__ void __launch_bounds__(DK3_WARPS * 32) k_decode3(const K3Params p) {
 // ModelBase: SimplePLL (DSP.cpp:28-57) + one Decoder per row; strictly sequential per row.
 __global__ void __launch_bounds__(K3_THREADS) k_base(const float *__restrict__ Ef, long long e_stride, int e_begin, int n, int rows,
 													   PllState *__restrict__ pll, DecState *__restrict__ dec, uint32_t *__restrict__ dec_data, FrameRec *__restrict__ ring,
-													   int *__restrict__ ring_count, int ring_cap, int chunk, int blk, float *__restrict__ tap_dec, int *__restrict__ tap_cnt) {
+													   unsigned long long *__restrict__ ring_head, unsigned long long ring_limit, int ring_cap, int chunk, int blk, float *__restrict__ tap_dec,
+													   int *__restrict__ tap_cnt) {
 	__shared__ uint32_t frames[DEC_WORDS * K3_THREADS];
 	const int tid = threadIdx.x;
 	const int row = blockIdx.x * K3_THREADS + tid;
@@ -908,7 +916,7 @@ __global__ void __launch_bounds__(K3_THREADS) k_base(const float *__restrict__ E
 			int fr_len = 0, lb = 0;
 			float fr_level = 0.f;
 			const bool found = dec_step(d, ctx, x, 0.0f, 0, fr_len, fr_level, lb);
-			if (found) emit_frame(ring, ring_count, ring_cap, chunk, blk, ctx, row, 0, fr_len, fr_level, 0.0f, d.start_idx, 0);
+			if (found) emit_frame(ring, ring_head, ring_limit, ring_cap, chunk, blk, ctx, row, 0, fr_len, fr_level, 0.0f, d.start_idx, 0);
 			// DecoderMessage -> SimplePLL::Signal (Model.cpp:434-435; DSP.cpp:46-57): the last NextState decides
 			pl.fast = (d.state == ST_TRAINING) ? 1 : (d.state == ST_STARTFLAG ? 0 : pl.fast);
 			pl.pll = __fsub_rn(pl.pll, (float)(int)pl.pll);
@@ -953,9 +961,10 @@ cudaError_t launch_decode(int model, int decoder, int rpw, const K3Params &p, cu
 	return model == 2 ? launch_decode_model<2>(decoder, rpw, p, s) : launch_decode_model<0>(decoder, rpw, p, s);
 }
 cudaError_t launch_base(const float *Ef, long long e_stride, int e_begin, int n, int rows, PllState *pll, DecState *dec, uint32_t *dec_data, FrameRec *ring,
-						int *ring_count, int ring_cap, int chunk, int blk, float *tap_dec, int *tap_cnt, cudaStream_t s) {
-	k_base<<<(rows + K3_THREADS - 1) / K3_THREADS, K3_THREADS, 0, s>>>(Ef, e_stride, e_begin, n, rows, pll, dec, dec_data, ring, ring_count, ring_cap, chunk, blk,
-																		  tap_dec, tap_cnt);
+						unsigned long long *ring_head, unsigned long long ring_limit, int ring_cap, int chunk, int blk, float *tap_dec, int *tap_cnt,
+						cudaStream_t s) {
+	k_base<<<(rows + K3_THREADS - 1) / K3_THREADS, K3_THREADS, 0, s>>>(Ef, e_stride, e_begin, n, rows, pll, dec, dec_data, ring, ring_head, ring_limit, ring_cap, chunk,
+																		  blk, tap_dec, tap_cnt);
 	return cudaGetLastError();
 }
 

@@ -116,7 +116,8 @@ struct K3Params {
 	DecState *dec;
 	uint32_t *dec_data;   // [DEC_WORDS][rows*5]
 	FrameRec *ring;
-	int *ring_count;
+	unsigned long long *ring_head; // frames emitted since the engine was created (tickets); slot = ticket % ring_cap
+	unsigned long long ring_limit; // tickets below this may be written: frames drained by the host at launch time + ring_cap
 	int ring_cap;
 	int chunk;
 	int blk;
@@ -177,6 +178,7 @@ cudaError_t sym_init(const float *ps_cos8, const float *ps_sin8, const uint32_t 
 cudaError_t launch_phase_search(const K3Params &p, cudaStream_t s);
 cudaError_t launch_decode(int model, int decoder, int rpw, const K3Params &p, cudaStream_t s);
 cudaError_t launch_base(const float *Ef, long long e_stride, int e_begin, int n, int rows, PllState *pll, DecState *dec, uint32_t *dec_data, FrameRec *ring,
-                        int *ring_count, int ring_cap, int chunk, int blk, float *tap_dec, int *tap_cnt, cudaStream_t s);
+                        unsigned long long *ring_head, unsigned long long ring_limit, int ring_cap, int chunk, int blk, float *tap_dec, int *tap_cnt,
+                        cudaStream_t s);
 
 } // namespace aisgpu

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define AISGPU_ABI_VERSION 2
+#define AISGPU_ABI_VERSION 3
 
 /* model kinds: the reference's "-m" numbers (Source/Application/Receiver.cpp:155-195) */
 #define AISGPU_MODEL_STANDARD 0 /* FM -> FIR37 -> 5-phase deinterleave -> 5 decoders (Model.cpp:484-518) */
@@ -49,8 +49,9 @@ extern "C" {
 #define AISGPU_EINVAL -1   /* bad argument / unsupported configuration (reference: std::runtime_error at buildModel, Model.cpp:109-110) */
 #define AISGPU_ENODEV -2   /* no usable CUDA device */
 #define AISGPU_ECUDA -3    /* CUDA runtime error; adapter converts to Error()<<...; StopRequest() (FileRAW.cpp:111-115) */
-#define AISGPU_ENOMEM -4
-#define AISGPU_EOVERFLOW -5 /* frame ring overflowed; frames were dropped */
+#define AISGPU_ENOMEM -4   /* device or pinned-host allocation failed */
+#define AISGPU_EOVERFLOW -5 /* returned by aisgpu_poll*(): the frame ring overflowed since the last poll and frames were dropped; the frames
+                              that survived were still delivered (out / *n are valid).  Size the ring with aisgpu_config.max_frames. */
 
 /* tap ids for aisgpu_tap(): intermediates for parity tests */
 #define AISGPU_TAP_C 0     /* 48 kHz channel samples after FilterCIC5 (Model.cpp:345-346 C_a/C_b), float2 */
@@ -74,7 +75,9 @@ typedef struct aisgpu_config {
 	uint32_t tag_mode;          /* TAG::mode (Common.h:242): bit0 = signal level, default 3 */
 	int32_t device;             /* CUDA device ordinal */
 	int32_t enable_taps;        /* keep intermediates readable through aisgpu_tap() */
-	int32_t max_frames;         /* capacity of the device frame ring per submit (0 = default) */
+	int32_t max_frames;         /* capacity of the device frame ring = frames that may wait between two polls (0 = default) */
+	int32_t host_staging;       /* 1 (default): the device staging buffers behind aisgpu_submit*() are allocated by aisgpu_create;
+	                               0: at the first host submit (engines that are only fed with aisgpu_submit_device) */
 } aisgpu_config;
 
 /* One decoded frame == one AIS::Message the reference would Send (Source/Marine/AIS.cpp:66-96). */
@@ -111,8 +114,21 @@ int aisgpu_chunk_granule(const aisgpu_config *cfg);
  * returns when the host-to-device copy into the engine's staging buffer has completed; the kernels run
  * asynchronously).  n_samples must be a multiple of aisgpu_chunk_granule() -- every CIC stage needs an even block
  * (DSP.cpp:94,135 assert(len%2==0)) -- and, at rates the reference serves through DSP::Upsample, the same for every
- * call (Upsample re-blocks by the length of its input block, DSP.cpp:203).  Pinned host memory gives full PCIe speed. */
+ * call (Upsample re-blocks by the length of its input block, DSP.cpp:203).  Pinned host memory gives full PCIe speed.
+ * After a CUDA failure inside a submit the handle is poisoned: every later call returns the stored error. */
 int aisgpu_submit(aisgpu_handle *h, const void *host_samples, int n_samples);
+
+/* Same, one host pointer per stream: stream_ptrs[s] -> n_samples samples of stream s.  This is the shape the reference's
+ * receivers deliver -- every device thread hands its own FIFO block to Receive (RAW.data, Common.h:290-295;
+ * FileRAW.cpp:132-136) -- so n_streams independent receivers need no repacking on the host. */
+int aisgpu_submit_v(aisgpu_handle *h, const void *const *stream_ptrs, int n_samples);
+
+/* Asynchronous form of aisgpu_submit for callers that own (at least two) pinned buffers: enqueues the host-to-device copy
+ * and the kernels and returns at once.  host_samples must stay untouched until aisgpu_poll_upto(ticket) (or any later
+ * poll / aisgpu_sync) has returned.  *ticket receives the ordinal of this submit (0, 1, 2, ...; every aisgpu_submit*
+ * call takes one).  The pattern  submit_async(c); poll_upto(c - 1)  overlaps the copy of step c with the host work of
+ * step c - 1. */
+int aisgpu_submit_async(aisgpu_handle *h, const void *host_samples, int n_samples, int64_t *ticket);
 
 /* Same, with the batch already resident in device memory ([n_streams][stride_samples], first n_samples used). */
 int aisgpu_submit_device(aisgpu_handle *h, const void *dev_samples, int64_t stride_samples, int n_samples);
@@ -125,12 +141,25 @@ int aisgpu_sync(aisgpu_handle *h);
  * Implies aisgpu_sync().  *n receives the count written (<= max); call again until *n == 0. */
 int aisgpu_poll(aisgpu_handle *h, aisgpu_msg *out, int max, int *n);
 
+/* aisgpu_poll that only waits for the submits up to `ticket` (see aisgpu_submit_async) and returns their frames; later
+ * submits keep running.  ticket < 0 or beyond the last submit == aisgpu_poll. */
+int aisgpu_poll_upto(aisgpu_handle *h, int64_t ticket, aisgpu_msg *out, int max, int *n);
+
 /* Intermediates of the LAST submit for one stream/channel; *n_out = elements written (float2 or float). */
 int aisgpu_tap(aisgpu_handle *h, int tap, int stream, int channel, void *dst, size_t dst_bytes, size_t *n_out);
 
 /* counters[0]=frames (CRC ok), [1]=messages published (validate ok), [2]=samples/stream, [3]=submits,
  * [4]=frames dropped by ring overflow, [5]=ch A messages, [6]=ch B messages, [7]=reserved */
 int aisgpu_counters(aisgpu_handle *h, uint64_t counters[8]);
+
+/* Multi-GPU: the stream batch is sharded over one engine (process) per GPU and nothing but these counters ever crosses
+ * NVLink.  aisgpu_nccl_unique_id fills a 128-byte ncclUniqueId on one rank (the caller ships it to the
+ * others: MPI, a file, torch.distributed ...), aisgpu_comm_init joins the communicator (ncclCommInitRank; NCCL is resolved
+ * at run time with dlopen("libnccl.so.2"), AISGPU_ENODEV if absent), aisgpu_allreduce_counts sums aisgpu_counters() of all
+ * ranks (ncclAllReduce, uint64, on the engine's stream).  Without a communicator totals == the local counters. */
+int aisgpu_nccl_unique_id(void *id128);
+int aisgpu_comm_init(aisgpu_handle *h, const void *id128, int n_ranks, int rank);
+int aisgpu_allreduce_counts(aisgpu_handle *h, uint64_t totals[8]);
 
 /* The CUDA stream the kernels are launched on (cudaStream_t as void*), for event timing by the caller. */
 void *aisgpu_cuda_stream(aisgpu_handle *h);

@@ -31,7 +31,7 @@ def test_exports_match_header(built):
     for n in names:
         assert hasattr(lib, n), "libaisgpu.so does not export %s" % n
     assert sorted(aisgpu.EXPORTS) == names, "aisgpu.py EXPORTS out of sync with include/aisgpu.h"
-    assert lib.aisgpu_abi_version() == 2
+    assert lib.aisgpu_abi_version() == 3
 
 
 def test_struct_layout_matches_ctypes(built, tmp_path):
