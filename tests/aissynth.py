@@ -225,3 +225,51 @@ def to_cu8(x):
     v[0::2] = x.real
     v[1::2] = x.imag
     return np.clip(np.round(127.0 * v + 128.0), 0, 255).astype(np.uint8)
+
+
+def fuzz_stream(fs, n_samples, seed, noise_sigma=0.02):
+    """Decoder stress stimulus: densely packed bursts of random length (40..1064 bits) whose payloads are biased towards long
+    runs of ones (heavy bit stuffing), with random -- also invalid -- type fields, amplitudes from below the noise to strong
+    (some frames fail their CRC, noise-only stretches raise false start flags), short gaps, occasional collisions on a
+    channel and truncated preambles.  Returns (complex64 samples, number of bursts).  Truth is whatever the oracle decodes."""
+    rng = np.random.default_rng(0xF0221 + seed)
+    bursts = []
+    for ch in "AB":
+        t = int(rng.integers(0, fs // 50))
+        while True:
+            nbits = 8 * int(rng.integers(5, 134))  # 40 .. 1064
+            r = rng.random()
+            ty = -1
+            if r < 0.6:  # a (type, length) pair Decoder::cannotBeValid / Message::validate let through (AIS.cpp:111-142, Message.cpp:398-413)
+                fixed = [(1, 168), (2, 168), (3, 168), (4, 168), (18, 168), (5, 424), (19, 312), (21, 360), (24, 160), (27, 96), (9, 168), (11, 168)]
+                if rng.random() < 0.5:
+                    ty, nbits = fixed[int(rng.integers(0, len(fixed)))]
+                else:
+                    ty = int(rng.choice([6, 8, 12, 14, 17, 26]))
+                    nbits = 8 * int(rng.integers(12, 134))
+            elif r < 0.7:  # type 0 or > 28: cannotBeValid fires at bit 30
+                ty = int(rng.choice([0, 29, 40, 63]))
+            p1 = float(rng.choice([0.5, 0.5, 0.7, 0.85, 0.95]))
+            bits = (rng.random(nbits) < p1).astype(np.uint8)
+            if ty >= 0:
+                for k in range(6):
+                    bits[k] = (ty >> (5 - k)) & 1
+                if nbits >= 38 and rng.random() < 0.9:
+                    mm = int(rng.integers(1, 999999999))
+                    for k in range(30):
+                        bits[8 + k] = (mm >> (29 - k)) & 1
+            ln = burst_len_samples(nbits, fs)
+            if t + ln >= n_samples:
+                break
+            amp = float(rng.choice([0.012, 0.02, 0.03, 0.05, 0.1, 0.2, 0.3, 0.4]))
+            b = Burst(t, ch, bits, amp=amp, foffs=rng.uniform(-600, 600), timing=rng.uniform(0, 1))
+            bursts.append(b)
+            g = rng.random()
+            if g < 0.15:
+                t += int(ln * rng.uniform(0.3, 0.9))  # the next burst collides with the tail of this one
+            elif g < 0.6:
+                t += ln - int(rng.integers(0, 24) * fs / 9600.0)  # back to back, tails may touch the next preamble
+            else:
+                t += ln + int(rng.integers(0, fs // 10))  # a stretch of noise
+    x = render_stream(fs, n_samples, bursts, noise_sigma=noise_sigma, seed=0xF0221 * 3 + seed)
+    return x, len(bursts)
