@@ -98,6 +98,7 @@ struct aisgpu_handle {
 	int max_n48 = 0;
 	int fe_warps = 4, fe_tile = 0, fe_ctas = 4096;
 	int fe_st = 1, st_S = 0, st_nb = 8, st_wpc = 4, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
+	int be_v1 = 0; // AISGPU_BE_V1=1: round-1 back-end kernels (k_cgf_rot + k_cgf_derot_fir, one hypothesis per lane) for A/B runs
 	int dec_rpw = 6, decoder = 3; // rows per warp / which decoder kernel // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
 	// for timing).  The front end of submit c+1 overlaps the back end of submit c; Cbuf is double buffered for that.
@@ -488,7 +489,7 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.lvl = h->d_lvl2[h->pb];
 		p.lvl_stride = h->dwords * K3_TS;
 		if (int rc = stage_begin(h, 3)) return rc;
-		CU(launch_phase_search(p, h->bs));
+		CU(launch_phase_search(p, h->be_v1, h->bs));
 		// the incomplete group of 5 at the end moves to the front for the next submit (Ec is single buffered: the next
 		// submit's derotation waits for this stage)
 		const int nl = total - nsym * 5;
@@ -592,20 +593,32 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 		if (nblk > 0) {
 			const int total_blocks = h->rows * nblk;
 			int *stepidx = h->d_stepidx2[h->pb];
-			float2 *rots = h->d_rots2[h->pb];
+			float2 *rots = h->d_rots2[h->pb]; // round-1 kernels only
 			// stepidx / rots / dbits / lvl are double buffered by submit parity == stream, so stream order protects them
 			CU(launch_cgf_estimate(Ccur, h->c_stride, c_begin, nblk, total_blocks, h->d_omega, h->cfg.afc_wide, stepidx, h->bs));
-			if (int rc = stage_begin(h, 1)) return rc;
-			CU(launch_cgf_rot(stepidx, h->d_steptab, h->d_cgf_rot, rots, h->r_stride, nblk, h->rows, h->bs));
-			if (int rc = stage_end(h, 1)) return rc;
 			const int nE = nblk * CGF_N;
-			if (int rc = stage_begin(h, 2)) return rc;
-			if (int rc = stage_begin(h, 3)) return rc; // Ec is free once the previous submit's phase search has read it
-			CU(launch_cgf_derot_fir(Ccur, h->c_stride, c_begin, rots, h->r_stride, nE, h->d_fir_hist[h->fir_cur], h->d_fir_hist[h->fir_cur ^ 1], h->d_Ec2[0],
-									h->e_stride, HE, h->cfg.enable_taps ? h->d_tap_cgf : nullptr, h->r_stride, h->rows, h->bs));
-			if (int rc = stage_end(h, 2)) return rc;
+			if (h->be_v1) {
+				if (int rc = stage_begin(h, 1)) return rc;
+				CU(launch_cgf_rot(stepidx, h->d_steptab, h->d_cgf_rot, rots, h->r_stride, nblk, h->rows, h->bs));
+				if (int rc = stage_end(h, 1)) return rc;
+				if (int rc = stage_begin(h, 2)) return rc;
+				if (int rc = stage_begin(h, 3)) return rc; // Ec is free once the previous submit's phase search has read it
+				CU(launch_cgf_derot_fir(Ccur, h->c_stride, c_begin, rots, h->r_stride, nE, h->d_fir_hist[h->fir_cur], h->d_fir_hist[h->fir_cur ^ 1], h->d_Ec2[0],
+										h->e_stride, HE, h->cfg.enable_taps ? h->d_tap_cgf : nullptr, h->r_stride, h->rows, h->bs));
+				if (int rc = stage_end(h, 2)) return rc;
+				h->last_launches++;
+			}
+			else { // phasor chain + derotation + FIR17 in one kernel: waits for what carries its state (stages 1, 2) and for Ec (stage 3)
+				if (int rc = stage_begin(h, 1)) return rc;
+				if (int rc = stage_begin(h, 2)) return rc;
+				if (int rc = stage_begin(h, 3)) return rc;
+				CU(launch_cgf_fused(Ccur, h->c_stride, c_begin, stepidx, h->d_steptab, h->d_cgf_rot, nblk, h->rows, h->d_fir_hist[h->fir_cur],
+									h->d_fir_hist[h->fir_cur ^ 1], h->d_Ec2[0], h->e_stride, HE, h->cfg.enable_taps ? h->d_tap_cgf : nullptr, h->r_stride, h->bs));
+				if (int rc = stage_end(h, 1)) return rc;
+				if (int rc = stage_end(h, 2)) return rc;
+			}
 			h->fir_cur ^= 1;
-			h->last_launches += 3;
+			h->last_launches += 2;
 			h->last_nE = nE;
 		}
 		CU(cudaEventRecord(h->ev_be_done[cb], h->bs)); // last reader of Cbuf[cb]
@@ -1041,6 +1054,7 @@ static int create_impl(aisgpu_handle *h) {
 		h->decoder = atoi(e);
 		if (h->decoder != 1 && h->decoder != 2) h->decoder = 3;
 	}
+	if (const char *e = getenv("AISGPU_BE_V1")) h->be_v1 = atoi(e) ? 1 : 0;
 	if (const char *e = getenv("AISGPU_FE_TILE")) h->fe_tile = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_ST")) h->fe_st = atoi(e) ? 1 : 0;
 	if (const char *e = getenv("AISGPU_ST_S")) h->st_S = atoi(e);
@@ -1162,7 +1176,8 @@ static int create_impl(aisgpu_handle *h) {
 		h->c_hist = 0;
 		for (int i = 0; i < 2; i++) {
 			if (int rc = dalloc(h, &h->d_stepidx2[i], (size_t)h->rows * (nEmax / CGF_N + 1))) return rc;
-			if (int rc = dalloc(h, &h->d_rots2[i], (size_t)h->rows * h->r_stride)) return rc;
+			if (h->be_v1)
+				if (int rc = dalloc(h, &h->d_rots2[i], (size_t)h->rows * h->r_stride)) return rc;
 		}
 		if (int rc = dalloc(h, &h->d_cgf_rot, (size_t)h->rows)) return rc;
 		if (int rc = dalloc(h, &h->d_Ec2[0], (size_t)h->rows * h->e_stride)) return rc;
@@ -1221,7 +1236,11 @@ static int create_impl(aisgpu_handle *h) {
 		if (int rc = dalloc(h, &h->d_tap_dec, (size_t)h->rows * 5 * (nEmax / 5 + 2))) return rc;
 	if (getenv("AISGPU_DEBUG"))
 		if (int rc = dalloc(h, &h->d_dbg, (size_t)h->rows * 4)) return rc;
-	CU(cgf_init(H_TAPS_COHERENT));
+	{
+		std::vector<float2> om(CGF_N / 2);
+		for (int s = 0; s < CGF_N / 2; s++) om[s] = polar1((float)(-2.0 * PI_F) * (float)s / (float)CGF_N); // FFT.h:81-83
+		CU(cgf_init(H_TAPS_COHERENT, om.data()));
+	}
 	CU(fm_init(H_TAPS_RECEIVER));
 	{
 		uint32_t ab[35] = { 0 };

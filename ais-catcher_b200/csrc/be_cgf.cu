@@ -6,52 +6,108 @@ namespace aisgpu {
 
 // ---------------------------------------------------------------------------------------------
 // K2a: SquareFreqOffsetCorrection, estimation half (DSP.cpp:417-455, FFT.h:93-130).
-// One warp per 512-sample block: x^2 in bit-reversed order, the reference's radix-2 DIT butterflies stage by
-// stage, |F| in fftshift order; then (one lane per block) the sequential float cumsum, then the parallel
+// One warp per 512-sample block.  The reference's radix-2 DIT butterflies (t = Omega[j * N / 2m] * x[hi]; x[hi] = x[lo] - t;
+// x[lo] += t, FFT.h:104-129) are evaluated with the block held in REGISTERS, 16 complex values per lane -- every butterfly
+// is the reference's own arithmetic on the reference's own operands, only who computes it changes, so the spectrum is
+// bit-identical whatever the schedule:
+//   layout A  lane = p[8:4], register = p[3:0]  (p = position in the bit-reversed array): stages 0..3 are lane-local,
+//             stage 4 pairs lane l with l ^ 1 (one shuffle per value; both lanes form t, a - t is evaluated as a + (-t));
+//   layout C  lane = p[4:0], register = p[8:5]  after one transpose through a padded shared tile: stages 5..8 lane-local.
+// Twiddles of stages 0..4 are warp-uniform (constant memory), those of stages 5..8 are 15 per-lane registers loaded once.
+// |F| in fftshift order goes to shared memory; then (one lane per block) the sequential float cumsum, then the parallel
 // first-maximum searches.  Result: an index into the host-built phasor-step table.
 // ---------------------------------------------------------------------------------------------
+__constant__ float2 c_cgf_omega[CGF_N / 2]; // Omega[s] = polar(1, -2 pi s / N), host-computed (FFT.h:81-83)
+constexpr int CGF_TB = CGF_N + CGF_N / 16;  // transpose tile: one pad slot per 16 values
+
+__device__ __forceinline__ constexpr int cgf_rev4(int m) { return ((m & 1) << 3) | ((m & 2) << 1) | ((m & 4) >> 1) | ((m & 8) >> 3); }
+
+// FFT of x^2 for one block; leaves |F[(i + 256) & 511]| in mg[i]
+__device__ __forceinline__ void cgf_fft_block(const float2 *__restrict__ src, float2 *__restrict__ tb, float *__restrict__ mg, int lane, const float2 (&tw)[15]) {
+	float2 x[16];
+	const int rl = (int)(__brev((unsigned)lane) >> 27);
+#pragma unroll
+	for (int m = 0; m < 16; m++) { // position p = 16 lane + e holds sample rev9(p) = rev5(lane) + 32 rev4(e)
+		const float2 v = src[rl + 32 * m];
+		x[cgf_rev4(m)] = cmul(v, v);
+	}
+#pragma unroll
+	for (int s = 0; s < 4; s++) {
+		const int m2 = 1 << s;
+#pragma unroll
+		for (int q = 0; q < 8; q++) {
+			const int j = q & (m2 - 1);
+			const int lo = ((q >> s) << (s + 1)) + j, hi = lo + m2;
+			const float2 t = cmul(c_cgf_omega[j << (8 - s)], x[hi]);
+			const float2 a = x[lo];
+			x[hi] = csub(a, t);
+			x[lo] = cadd(a, t);
+		}
+	}
+	{ // stage 4: positions p and p + 16 live in lanes l and l ^ 1, j = p & 15 = register index
+		const bool odd = lane & 1;
+#pragma unroll
+		for (int e = 0; e < 16; e++) {
+			const float2 mine = x[e];
+			float2 other;
+			other.x = __shfl_xor_sync(0xffffffffu, mine.x, 1);
+			other.y = __shfl_xor_sync(0xffffffffu, mine.y, 1);
+			const float2 hi = odd ? mine : other, lo = odd ? other : mine;
+			float2 t = cmul(c_cgf_omega[e << 4], hi);
+			if (odd) { t.x = -t.x; t.y = -t.y; } // x[hi] = a - t == a + (-t), exactly
+			x[e] = cadd(lo, t);
+		}
+	}
+	__syncwarp();
+#pragma unroll
+	for (int e = 0; e < 16; e++) tb[17 * lane + e] = x[e]; // slot p + (p >> 4), p = 16 lane + e
+	__syncwarp();
+#pragma unroll
+	for (int r = 0; r < 16; r++) {
+		const int p = lane + 32 * r;
+		x[r] = tb[p + (p >> 4)];
+	}
+#pragma unroll
+	for (int s = 5; s < 9; s++) { // positions p = lane + 32 r: bit s of p is bit s - 5 of r; j = p & (2^s - 1) = lane + 32 (r & (2^(s-5) - 1))
+		const int sb = s - 5, m2r = 1 << sb;
+#pragma unroll
+		for (int q = 0; q < 8; q++) {
+			const int jr = q & (m2r - 1);
+			const int lo = ((q >> sb) << (sb + 1)) + jr, hi = lo + m2r;
+			const float2 t = cmul(tw[m2r - 1 + jr], x[hi]);
+			const float2 a = x[lo];
+			x[hi] = csub(a, t);
+			x[lo] = cadd(a, t);
+		}
+	}
+#pragma unroll
+	for (int r = 0; r < 16; r++) mg[(lane + 32 * r) ^ 256] = habs(x[r]);
+}
+
 __global__ void __launch_bounds__(CGF_THREADS) k_cgf_estimate(const float2 *__restrict__ Cbuf, long long c_stride, int c_begin, int nblk,
 																 int total_blocks, const float2 *__restrict__ omega_g, int wide,
 																 int *__restrict__ stepidx) {
 	extern __shared__ __align__(16) unsigned char cgf_sm[];
-	float2 *omega = reinterpret_cast<float2 *>(cgf_sm);                      // 512 float2
-	float *mag = reinterpret_cast<float *>(cgf_sm + 4096);                   // [16][513]
-	unsigned char *scratch = cgf_sm + 4096 + CGF_BLK_PER_CTA * CGF_ROWP * 4; // fft buffers, later cumsum [16][513]
-	float2 *fftbuf = reinterpret_cast<float2 *>(scratch);
+	float *mag = reinterpret_cast<float *>(cgf_sm);                       // [16][513]
+	unsigned char *scratch = cgf_sm + CGF_BLK_PER_CTA * CGF_ROWP * 4;     // transpose tiles (8 x 544 float2), later cumsum [16][513]
 	float *cum = reinterpret_cast<float *>(scratch);
 
 	const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-	for (int i = tid; i < CGF_N; i += CGF_THREADS) omega[i] = omega_g[i];
-	__syncthreads();
+	float2 tw[15]; // Omega[(lane + 32 jr) << (3 - sb)] for stage 5 + sb, jr < 2^sb
+#pragma unroll
+	for (int sb = 0; sb < 4; sb++)
+#pragma unroll
+		for (int jr = 0; jr < (1 << sb); jr++) tw[(1 << sb) - 1 + jr] = omega_g[(lane + 32 * jr) << (3 - sb)];
 
 	const int blk0 = blockIdx.x * CGF_BLK_PER_CTA;
-	float2 *x = fftbuf + w * CGF_N;
+	float2 *tb = reinterpret_cast<float2 *>(scratch) + w * CGF_TB;
 	for (int rep = 0; rep < 2; rep++) {
 		const int lb = w + rep * 8;
 		const int id = blk0 + lb;
 		if (id < total_blocks) {
 			const int row = id / nblk, b = id - row * nblk;
 			const float2 *src = Cbuf + (long long)row * c_stride + c_begin + (long long)b * CGF_N;
-			for (int i = lane; i < CGF_N; i += 32) {
-				float2 v = src[i];
-				x[__brev((unsigned)i) >> 23] = cmul(v, v);
-			}
-			__syncwarp();
-			for (int s = 0; s < 9; s++) {
-				const int m2 = 1 << s;
-				for (int q = lane; q < 256; q += 32) {
-					const int j = q & (m2 - 1);
-					const int lo = ((q >> s) << (s + 1)) + j, hi = lo + m2;
-					const float2 o = omega[j << (8 - s)];
-					const float2 t = cmul(o, x[hi]);
-					const float2 a = x[lo];
-					x[hi] = csub(a, t);
-					x[lo] = cadd(a, t);
-				}
-				__syncwarp();
-			}
-			float *mg = mag + lb * CGF_ROWP;
-			for (int i = lane; i < CGF_N; i += 32) mg[i] = habs(x[(i + 256) & 511]);
+			cgf_fft_block(src, tb, mag + lb * CGF_ROWP, lane, tw);
 		}
 		__syncwarp();
 	}
@@ -185,17 +241,146 @@ __global__ void __launch_bounds__(FIRC_TILE) k_cgf_derot_fir(const float2 *__res
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// K2bc: the derotation phasor chain, output[i] *= rot and FilterComplex 17 taps in ONE kernel (DSP.cpp:457-465, 215-246).
+// The chain rot *= rot_step is strictly sequential per row (4096 dependent complex products per submit at the bench
+// shape: ~17 us is the floor for the whole stage), everything else is parallel.  A CTA owns CF_ROWS rows: warp 0 runs
+// the chains, one lane per row, CF_T steps ahead into a double-buffered shared tile; meanwhile the four consumer warps
+// derotate the previous tile (coalesced loads of the 48 kHz samples), and run the FIR out of a shared ring that keeps
+// the 16-sample history.  The phasors never travel through HBM (the old k_cgf_rot wrote 67 MB per submit and
+// k_cgf_derot_fir read them back).  FIR: products by scalar FMUL, the (re, im) accumulation by one packed FADD2 --
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, a scalar product feeding a packed add stays two roundings.
+// ---------------------------------------------------------------------------------------------
+constexpr int CF_ROWS = 8;
+constexpr int CF_T = 64;               // samples per tile and row (a 512-block = 8 tiles)
+constexpr int CF_CONS = 4;             // consumer warps: CF_ROWS * CF_T / 4 outputs per thread and tile
+constexpr int CF_THREADS = 32 * (1 + CF_CONS);
+constexpr int CF_DERP = 2 * CF_T + 2 * CF_T / 4; // ring row: two tiles, one pad slot after every four samples
+// ring position n (0 .. 2 CF_T - 1) -> slot: threads that own four consecutive outputs read n = 4c + i; 5c + i hits 16 different
+// 8-byte banks over a half warp
+__device__ __forceinline__ int cf_slot(int n) { return n + (n >> 2); }
+
+struct CfParams {
+	const float2 *Cbuf;
+	long long c_stride;
+	int c_begin;
+	const int *stepidx;     // [rows][nblk]
+	const float2 *steptab;
+	float2 *rot_state;      // [rows]
+	int nblk, rows;
+	const float2 *hist_old; // [rows][16]
+	float2 *hist_new;
+	float2 *Ebuf;
+	long long e_stride;
+	int e_off;
+	float2 *tap_cgf;        // optional
+	long long tap_stride;
+};
+
+__device__ __forceinline__ void cf_consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * CF_CONS)); }
+
+__global__ void __launch_bounds__(CF_THREADS) k_cgf_fused(const CfParams p) {
+	__shared__ __align__(16) float2 rotb[2][CF_ROWS][CF_T + 2]; // +2: the chain lanes (one row each) store to different banks
+	__shared__ __align__(16) float2 der[CF_ROWS][CF_DERP]; // der[r][cf_slot((t & 1) * CF_T + j)] = derotated sample j of tile t
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int row0 = blockIdx.x * CF_ROWS;
+	const int ntiles = p.nblk * (CGF_N / CF_T);
+	const int ct = tid - 32; // consumer thread index 0..127 (negative in the chain warp)
+	if (warp != 0) { // FIR history of the previous submit sits where "tile -1" would have left it
+		for (int i = ct; i < CF_ROWS * (FIRC_T - 1); i += 32 * CF_CONS) {
+			const int r = i / (FIRC_T - 1), k = i - r * (FIRC_T - 1);
+			const int row = row0 + r;
+			der[r][cf_slot(CF_T + CF_T - (FIRC_T - 1) + k)] = row < p.rows ? p.hist_old[row * (FIRC_T - 1) + k] : make_float2(0.f, 0.f);
+		}
+	}
+	// chain state (warp 0, lanes < CF_ROWS)
+	const int crow = row0 + lane;
+	const bool chain = warp == 0 && lane < CF_ROWS && crow < p.rows;
+	float2 rot = chain ? p.rot_state[crow] : make_float2(1.0f, 0.0f);
+	float2 st = make_float2(1.0f, 0.0f);
+	__syncthreads();
+	for (int it = 0; it <= ntiles; it++) {
+		if (warp == 0) {
+			if (it < ntiles && lane < CF_ROWS) {
+				const int b = it / (CGF_N / CF_T);
+				if ((it % (CGF_N / CF_T)) == 0 && chain) st = p.steptab[p.stepidx[crow * p.nblk + b]];
+				float2 *o = rotb[it & 1][lane];
+#pragma unroll 16
+				for (int i = 0; i < CF_T; i++) {
+					rot = cmul(rot, st);
+					o[i] = rot;
+				}
+				if ((it % (CGF_N / CF_T)) == (CGF_N / CF_T) - 1) rot = cnormalize(rot); // once per 512-block (DSP.cpp:465)
+			}
+		}
+		else if (it >= 1) {
+			const int t = it - 1;
+			const int half = (t & 1) * CF_T;
+			// derotate: thread -> (row r, sample j), a warp covers 32 consecutive samples of one row
+#pragma unroll
+			for (int u = 0; u < CF_ROWS * CF_T / (32 * CF_CONS); u++) {
+				const int q = ct + u * 32 * CF_CONS;
+				const int r = q / CF_T, j = q - r * CF_T;
+				const int row = row0 + r;
+				float2 v = make_float2(0.f, 0.f);
+				if (row < p.rows) {
+					const int n = t * CF_T + j;
+					v = cmul(p.Cbuf[(long long)row * p.c_stride + p.c_begin + n], rotb[t & 1][r][j]);
+					if (p.tap_cgf) p.tap_cgf[(long long)row * p.tap_stride + n] = v;
+				}
+				der[r][cf_slot(half + j)] = v;
+			}
+			cf_consumer_barrier();
+			// FIR: thread -> (row r, four consecutive outputs j0..j0+3): 20 ring samples in registers
+			{
+				const int r = ct >> 4, j0 = (ct & 15) * 4;
+				const int row = row0 + r;
+				float2 x[FIRC_T + 3];
+#pragma unroll
+				for (int i = 0; i < FIRC_T + 3; i++) x[i] = der[r][cf_slot((half + j0 - (FIRC_T - 1) + i) & (2 * CF_T - 1))];
+				if (row < p.rows) {
+					float2 y[4];
+#pragma unroll
+					for (int o = 0; o < 4; o++) {
+						c64 acc = pack2(0.0f, 0.0f);
+#pragma unroll
+						for (int k = 0; k < FIRC_T; k++)
+							acc = padd(acc, pack2(__fmul_rn(c_taps_coherent[k], x[o + k].x), __fmul_rn(c_taps_coherent[k], x[o + k].y)));
+						y[o] = unpack2(acc);
+					}
+					// Ebuf rows start at an even float2 index (e_stride and e_off are even), j0 is a multiple of 4: 16-byte stores
+					float4 *e = reinterpret_cast<float4 *>(p.Ebuf + (long long)row * p.e_stride + p.e_off + t * CF_T + j0);
+					e[0] = make_float4(y[0].x, y[0].y, y[1].x, y[1].y);
+					e[1] = make_float4(y[2].x, y[2].y, y[3].x, y[3].y);
+				}
+			}
+		}
+		__syncthreads();
+	}
+	if (chain) p.rot_state[crow] = rot;
+	if (warp != 0) { // history for the next submit: the last 16 derotated samples
+		const int half = ((ntiles - 1) & 1) * CF_T;
+		for (int i = ct; i < CF_ROWS * (FIRC_T - 1); i += 32 * CF_CONS) {
+			const int r = i / (FIRC_T - 1), k = i - r * (FIRC_T - 1);
+			const int row = row0 + r;
+			if (row < p.rows) p.hist_new[row * (FIRC_T - 1) + k] = der[r][cf_slot(half + CF_T - (FIRC_T - 1) + k)];
+		}
+	}
+}
+
 // ---- launch entry points ----
-cudaError_t cgf_init(const float *taps17) {
+constexpr int CGF_EST_SMEM = CGF_BLK_PER_CTA * CGF_ROWP * 4 + (8 * CGF_TB * 8 > CGF_BLK_PER_CTA * CGF_ROWP * 4 ? 8 * CGF_TB * 8 : CGF_BLK_PER_CTA * CGF_ROWP * 4);
+cudaError_t cgf_init(const float *taps17, const float2 *omega256) {
 	cudaError_t e = cudaMemcpyToSymbol(c_taps_coherent, taps17, FIRC_T * sizeof(float));
 	if (e != cudaSuccess) return e;
-	return cudaFuncSetAttribute(k_cgf_estimate, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 + 2 * CGF_BLK_PER_CTA * CGF_ROWP * 4);
+	e = cudaMemcpyToSymbol(c_cgf_omega, omega256, (CGF_N / 2) * sizeof(float2));
+	if (e != cudaSuccess) return e;
+	return cudaFuncSetAttribute(k_cgf_estimate, cudaFuncAttributeMaxDynamicSharedMemorySize, CGF_EST_SMEM);
 }
 cudaError_t launch_cgf_estimate(const float2 *Cbuf, long long c_stride, int c_begin, int nblk, int total_blocks, const float2 *omega, int wide, int *stepidx,
 								cudaStream_t s) {
 	const int ctas = (total_blocks + CGF_BLK_PER_CTA - 1) / CGF_BLK_PER_CTA;
-	const size_t smem = 4096 + 2 * (size_t)CGF_BLK_PER_CTA * CGF_ROWP * 4;
-	k_cgf_estimate<<<ctas, CGF_THREADS, smem, s>>>(Cbuf, c_stride, c_begin, nblk, total_blocks, omega, wide, stepidx);
+	k_cgf_estimate<<<ctas, CGF_THREADS, CGF_EST_SMEM, s>>>(Cbuf, c_stride, c_begin, nblk, total_blocks, omega, wide, stepidx);
 	return cudaGetLastError();
 }
 cudaError_t launch_cgf_rot(const int *stepidx, const float2 *steptab, float2 *rot_state, float2 *rots, long long r_stride, int nblk, int rows, cudaStream_t s) {
@@ -206,6 +391,16 @@ cudaError_t launch_cgf_derot_fir(const float2 *Cbuf, long long c_stride, int c_b
 								 float2 *hist_new, float2 *Ebuf, long long e_stride, int e_off, float2 *tap_cgf, long long tap_stride, int rows, cudaStream_t s) {
 	dim3 grid((nE + FIRC_TILE - 1) / FIRC_TILE, rows);
 	k_cgf_derot_fir<<<grid, FIRC_TILE, 0, s>>>(Cbuf, c_stride, c_begin, rots, r_stride, nE, hist_old, hist_new, Ebuf, e_stride, e_off, tap_cgf, tap_stride);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_cgf_fused(const float2 *Cbuf, long long c_stride, int c_begin, const int *stepidx, const float2 *steptab, float2 *rot_state, int nblk, int rows,
+							 const float2 *hist_old, float2 *hist_new, float2 *Ebuf, long long e_stride, int e_off, float2 *tap_cgf, long long tap_stride, cudaStream_t s) {
+	CfParams p;
+	p.Cbuf = Cbuf; p.c_stride = c_stride; p.c_begin = c_begin; p.stepidx = stepidx; p.steptab = steptab; p.rot_state = rot_state;
+	p.nblk = nblk; p.rows = rows; p.hist_old = hist_old; p.hist_new = hist_new; p.Ebuf = Ebuf; p.e_stride = e_stride; p.e_off = e_off;
+	p.tap_cgf = tap_cgf; p.tap_stride = tap_stride;
+	k_cgf_fused<<<(rows + CF_ROWS - 1) / CF_ROWS, CF_THREADS, 0, s>>>(p);
 	return cudaGetLastError();
 }
 

@@ -300,6 +300,152 @@ __global__ void __launch_bounds__(PS_THREADS) k_phase_search(const K3Params p) {
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// K3a': PhaseSearchEMA (Demod.cpp:39-101) with four hypotheses per lane.  A CTA owns PS2_ROWS rows = 40 (row, sampling
+// phase) instances, four lanes each (lane q holds hypotheses 4q .. 4q+3: its EMAs, its sign histories).  Per symbol:
+//   * t, |t| and the EMA update of the lane's four hypotheses -- plain per-lane arithmetic in the reference's order;
+//   * the decision "best of (i0, i0+1, i0+2)" (strict >, first wins, Demod.cpp:80-91) does not depend on which i0 the
+//     search is at, so every lane evaluates it for ITS four values of i0 (two EMAs of the next lane come by shuffle) and
+//     the 16 two-bit results are OR-combined over the four lanes into one 32-bit table (redux.sync);
+//   * the only sequential part left is  i0 = (max_idx - 1) & 15; max_idx = (i0 + table[i0]) & 15  -- integer work that no
+//     longer waits for floating-point results of the same symbol;
+//   * the lane that holds hypothesis max_idx contributes the demodulated bit (its decisions 3 and 4 symbols ago, XORed).
+// 2.7x fewer warp instructions per (instance, symbol) than one hypothesis per lane, and one redux + two shuffles instead
+// of four dependent shuffles.  Demod::PhaseSearch (PS_EMA off) keeps the one-hypothesis-per-lane kernel above.
+// ---------------------------------------------------------------------------------------------
+constexpr int PS2_ROWS = 8;
+constexpr int PS2_THREADS = PS2_ROWS * 5 * 4; // 160
+constexpr int PS2_ROWP = K3_ROWLEN + 5;       // padded tile row: the instances of a warp read different banks
+__global__ void __launch_bounds__(PS2_THREADS) k_phase_search_ema4(const K3Params p) {
+	__shared__ float2 tile[2][PS2_ROWS][PS2_ROWP];
+	const int tid = threadIdx.x, lane = tid & 31;
+	const int ii = tid >> 2, q = tid & 3;                 // instance within the CTA, hypothesis group
+	const int rin = ii / 5, phase = ii - 5 * rin;
+	const int row0 = blockIdx.x * PS2_ROWS;
+	const int row = row0 + rin;
+	const bool active = row < p.rows;
+	const long long inst = (long long)row * 5 + phase;
+	const unsigned gmask = 0xfu << (lane & ~3);
+	const int nxt = (lane & ~3) | ((q + 1) & 3);          // the lane holding hypotheses 4(q+1) .. of the same instance
+	const float weight = 0.85f, omw = __fsub_rn(1.0f, 0.85f);
+	float cj[4], sj[4];
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const int h = 4 * q + k, j = h < 8 ? h : 15 - h;
+		cj[k] = c_ps_cos[j];
+		sj[k] = h < 8 ? c_ps_sin[j] : -c_ps_sin[j]; // a - b == a + (-b) and im * (-s) == -(im * s), exactly
+	}
+	float ma[4] = { 0.f, 0.f, 0.f, 0.f };
+	uint32_t hist[4] = { 0u, 0u, 0u, 0u }; // bit d = sign decision d symbols ago
+	int max_idx = 0, rot = 0;
+	if (active) {
+		const PsState &st = p.ps[inst];
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			ma[k] = st.ma[4 * q + k];
+#pragma unroll
+			for (int dd = 0; dd < 5; dd++) hist[k] |= ((st.plane[dd] >> (4 * q + k)) & 1u) << dd;
+		}
+		max_idx = st.max_idx;
+		rot = st.rot;
+	}
+	const int nsamp = p.nsym * 5;
+	auto prefetch = [&](int buf, int s0) {
+		const int base = s0 * 5;
+		for (int e = tid; e < PS2_ROWS * K3_ROWLEN; e += PS2_THREADS) {
+			const int r = e / K3_ROWLEN, c = e - r * K3_ROWLEN;
+			if (row0 + r < p.rows && base + c < nsamp) cp_async_f(&tile[buf][r][c], p.Ec + (long long)(row0 + r) * p.e_stride + p.e_begin + base + c);
+		}
+		cp_async_commit();
+	};
+	const int ntiles = (p.nsym + K3_TS - 1) / K3_TS;
+	if (ntiles > 0) prefetch(0, 0);
+	for (int t = 0; t < ntiles; t++) {
+		if (t + 1 < ntiles) {
+			prefetch((t + 1) & 1, (t + 1) * K3_TS);
+			cp_async_wait<1>();
+		}
+		else cp_async_wait<0>();
+		__syncthreads();
+		const float2 *my = &tile[t & 1][rin][phase];
+		const int s_end = min(K3_TS, p.nsym - t * K3_TS);
+		uint32_t word = 0;
+		for (int sl = 0; sl < s_end; sl++) {
+			const float2 x = my[sl * 5];
+			// (1j)^rot pre-rotation (Demod.cpp:44-65), branch free: swap on odd rot, negate on rot >= 2 (sign flips are exact)
+			float re = (rot & 1) ? -x.y : x.x, im = (rot & 1) ? x.x : x.y;
+			if (rot & 2) { re = -re; im = -im; }
+			rot = (rot + 1) & 3;
+			uint32_t xm = 0; // bit k: demodulated bit hypothesis 4q + k would deliver (nDelay = 3, Model.h:219)
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				const float tt = __fadd_rn(__fmul_rn(re, cj[k]), __fmul_rn(im, sj[k]));
+				hist[k] = (hist[k] << 1) | (tt > 0.0f ? 1u : 0u);
+				ma[k] = __fadd_rn(__fmul_rn(weight, ma[k]), __fmul_rn(omw, fabsf(tt))); // Demod.cpp:67-78
+				xm |= (((hist[k] >> 3) ^ (hist[k] >> 4)) & 1u) << k;
+			}
+			const float v4 = __shfl_sync(0xffffffffu, ma[0], nxt), v5 = __shfl_sync(0xffffffffu, ma[1], nxt);
+			const float v[6] = { ma[0], ma[1], ma[2], ma[3], v4, v5 };
+			uint32_t tab = 0;
+#pragma unroll
+			for (int k = 0; k < 4; k++) { // search started at i0 = 4q + k: strict >, the first maximum wins (Demod.cpp:80-91)
+				float mv = v[k];
+				uint32_t best = 0;
+				if (v[k + 1] > mv) { mv = v[k + 1]; best = 1; }
+				if (v[k + 2] > mv) best = 2;
+				tab |= best << (2 * k);
+			}
+			tab = __reduce_or_sync(gmask, tab << (8 * q));
+			const int i0 = (max_idx - 1) & 15;
+			max_idx = (i0 + ((tab >> (2 * i0)) & 3u)) & 15;
+			const uint32_t bit = ((max_idx >> 2) == q) ? ((xm >> (max_idx & 3)) & 1u) : 0u;
+			word |= bit << sl;
+			if (p.tap_dec) {
+				const uint32_t b = __reduce_or_sync(gmask, bit);
+				if (active && q == 0) p.tap_dec[inst * p.nsym + t * K3_TS + sl] = b ? 1.0f : -1.0f;
+			}
+		}
+		word = __reduce_or_sync(gmask, word);
+		if (active && q == 0) p.dbits[inst * p.dwords + t] = word;
+		if (p.mode_level) { // ScatterPLL level: ((((0+n0)+n1)+n2)+n3)+n4, then / 5 (DSP.h:100-106)
+			for (int e = tid; e < PS2_ROWS * K3_TS; e += PS2_THREADS) {
+				const int r = e / K3_TS, sl = e - r * K3_TS;
+				if (row0 + r < p.rows && sl < s_end) {
+					const float2 *rowt = &tile[t & 1][r][sl * 5];
+					float acc = 0.0f;
+#pragma unroll
+					for (int jx = 0; jx < 5; jx++) {
+						const float2 xx = rowt[jx];
+						acc = __fadd_rn(acc, __fadd_rn(__fmul_rn(xx.x, xx.x), __fmul_rn(xx.y, xx.y)));
+					}
+					p.lvl[(long long)(row0 + r) * p.lvl_stride + t * K3_TS + sl] = __fdiv_rn(acc, 5.0f);
+				}
+			}
+		}
+		__syncthreads();
+	}
+	// state back: the bit planes are OR-combined over the four lanes of the instance
+	uint32_t planes[5];
+#pragma unroll
+	for (int dd = 0; dd < 5; dd++) {
+		uint32_t pl = 0;
+#pragma unroll
+		for (int k = 0; k < 4; k++) pl |= ((hist[k] >> dd) & 1u) << (4 * q + k);
+		planes[dd] = __reduce_or_sync(gmask, pl);
+	}
+	if (active) {
+		PsState &st = p.ps[inst];
+#pragma unroll
+		for (int k = 0; k < 4; k++) st.ma[4 * q + k] = ma[k];
+		if (q == 0) {
+#pragma unroll
+			for (int dd = 0; dd < 5; dd++) st.plane[dd] = planes[dd];
+			st.max_idx = max_idx;
+			st.rot = rot;
+		}
+	}
+}
+
 // positions at which Decoder::cannotBeValid (AIS.cpp:111-142) can fire: 30 62 96 168 184 192 336 385 448,
 // plus MAX_FRAME_BITS (AIS.h:172) -- one bit per frame position
 __constant__ uint32_t c_abort_bits[35];
@@ -936,7 +1082,11 @@ cudaError_t sym_init(const float *ps_cos8, const float *ps_sin8, const uint32_t 
 	if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_abort_bits, abort_bits35, 35 * sizeof(uint32_t));
 	return e;
 }
-cudaError_t launch_phase_search(const K3Params &p, cudaStream_t s) {
+cudaError_t launch_phase_search(const K3Params &p, int v1, cudaStream_t s) {
+	if (p.ps_ema && !v1) { // four hypotheses per lane (PhaseSearchEMA only)
+		k_phase_search_ema4<<<(p.rows + PS2_ROWS - 1) / PS2_ROWS, PS2_THREADS, 0, s>>>(p);
+		return cudaGetLastError();
+	}
 	const long long ps_warps = ((long long)p.rows * 5 + 1) / 2;
 	k_phase_search<<<(unsigned)((ps_warps + PS_THREADS / 32 - 1) / (PS_THREADS / 32)), PS_THREADS, 0, s>>>(p);
 	return cudaGetLastError();

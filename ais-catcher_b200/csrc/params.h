@@ -165,17 +165,19 @@ cudaError_t launch_frontend_stream(const FeParams &p, int fmt, int k, int nb, in
 template <int FMT, int NB, int WPC>
 cudaError_t launch_frontend_stream_shape(const FeParams &p, int k, bool pre, long long n_warps, cudaStream_t s);
 // be_cgf.cu
-cudaError_t cgf_init(const float *taps17);
+cudaError_t cgf_init(const float *taps17, const float2 *omega256);
 cudaError_t launch_cgf_estimate(const float2 *Cbuf, long long c_stride, int c_begin, int nblk, int total_blocks, const float2 *omega, int wide, int *stepidx, cudaStream_t s);
 cudaError_t launch_cgf_rot(const int *stepidx, const float2 *steptab, float2 *rot_state, float2 *rots, long long r_stride, int nblk, int rows, cudaStream_t s);
 cudaError_t launch_cgf_derot_fir(const float2 *Cbuf, long long c_stride, int c_begin, const float2 *rots, long long r_stride, int nE, const float2 *hist_old,
                                  float2 *hist_new, float2 *Ebuf, long long e_stride, int e_off, float2 *tap_cgf, long long tap_stride, int rows, cudaStream_t s);
+cudaError_t launch_cgf_fused(const float2 *Cbuf, long long c_stride, int c_begin, const int *stepidx, const float2 *steptab, float2 *rot_state, int nblk, int rows,
+                             const float2 *hist_old, float2 *hist_new, float2 *Ebuf, long long e_stride, int e_off, float2 *tap_cgf, long long tap_stride, cudaStream_t s);
 // be_fm.cu
 cudaError_t fm_init(const float *taps37);
 cudaError_t launch_fm_fir5(const Fm5Params &p, int rows, cudaStream_t s);
 // be_sym.cu
 cudaError_t sym_init(const float *ps_cos8, const float *ps_sin8, const uint32_t *abort_bits35);
-cudaError_t launch_phase_search(const K3Params &p, cudaStream_t s);
+cudaError_t launch_phase_search(const K3Params &p, int v1, cudaStream_t s);
 cudaError_t launch_decode(int model, int decoder, int rpw, const K3Params &p, cudaStream_t s);
 cudaError_t launch_base(const float *Ef, long long e_stride, int e_begin, int n, int rows, PllState *pll, DecState *dec, uint32_t *dec_data, FrameRec *ring,
                         unsigned long long *ring_head, unsigned long long ring_limit, int ring_cap, int chunk, int blk, float *tap_dec, int *tap_cnt,
