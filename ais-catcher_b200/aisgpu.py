@@ -28,7 +28,7 @@ class Config(C.Structure):
                 ("n_streams", C.c_int32), ("max_chunk_samples", C.c_int32), ("ps_ema", C.c_int32), ("afc_wide", C.c_int32),
                 ("droop", C.c_int32), ("channel_a", C.c_char), ("channel_b", C.c_char), ("station", C.c_int32),
                 ("own_mmsi", C.c_int32), ("tag_mode", C.c_uint32), ("device", C.c_int32), ("enable_taps", C.c_int32),
-                ("max_frames", C.c_int32), ("host_staging", C.c_int32)]
+                ("max_frames", C.c_int32), ("host_staging", C.c_int32), ("dsk", C.c_int32), ("fp_ds", C.c_int32)]
 
 
 class MsgStruct(C.Structure):
@@ -105,12 +105,12 @@ def load():
     return lib
 
 
-def chunk_granule(sample_rate, model=MODEL_DEFAULT):
+def chunk_granule(sample_rate, model=MODEL_DEFAULT, dsk=False, fp_ds=False, fmt=FMT_CF32):
     """Granule (samples) every submit length must be a multiple of; raises with the reference's wording if unsupported."""
     lib = load()
     cfg = Config()
     lib.aisgpu_default_config(C.byref(cfg))
-    cfg.sample_rate, cfg.model = sample_rate, model
+    cfg.sample_rate, cfg.model, cfg.dsk, cfg.fp_ds, cfg.format = sample_rate, model, int(dsk), int(fp_ds), fmt
     g = lib.aisgpu_chunk_granule(C.byref(cfg))
     if g <= 0:
         raise AisGpuError("rc=%d: %s" % (g, lib.aisgpu_last_error(None).decode()))
@@ -150,7 +150,8 @@ class Engine:
     """One batch engine == one AIS::Model instance per stream of the batch (reference Source/DSP/Model.h:76-126)."""
 
     def __init__(self, model=MODEL_DEFAULT, sample_rate=1536000, fmt=FMT_CF32, n_streams=1, max_chunk=131072,
-                 ps_ema=True, afc_wide=True, droop=True, own_mmsi=-1, device=0, taps=False, max_frames=0, tag_mode=3, host_staging=True):
+                 ps_ema=True, afc_wide=True, droop=True, own_mmsi=-1, device=0, taps=False, max_frames=0, tag_mode=3, host_staging=True,
+                 dsk=False, fp_ds=False):
         self.lib = load()
         cfg = Config()
         self.lib.aisgpu_default_config(C.byref(cfg))
@@ -158,7 +159,7 @@ class Engine:
         cfg.n_streams, cfg.max_chunk_samples = n_streams, max_chunk
         cfg.ps_ema, cfg.afc_wide, cfg.droop = int(ps_ema), int(afc_wide), int(droop)
         cfg.own_mmsi, cfg.device, cfg.enable_taps, cfg.max_frames, cfg.tag_mode = own_mmsi, device, int(taps), max_frames, tag_mode
-        cfg.host_staging = int(host_staging)
+        cfg.host_staging, cfg.dsk, cfg.fp_ds = int(host_staging), int(dsk), int(fp_ds)
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.lib.aisgpu_create(C.byref(cfg), C.byref(self.h))

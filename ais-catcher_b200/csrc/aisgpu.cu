@@ -93,6 +93,7 @@ struct aisgpu_handle {
 	int obps = 8;            // bytes per sample of the caller's format (bps: of what the front end proper reads)
 	int inner_max = 0;       // longest block the front end proper can be handed
 	int use_fdc = 0;
+	int fp_ds = 0; // integer CIC front end (DS_UINT16 x 4, DSP.cpp:499-665): CU8 @1536K with -go FP_DS on
 	float fdc_alpha = 0, fdc_beta = 1;
 	int rows = 0;
 	int max_n48 = 0;
@@ -244,20 +245,35 @@ int plan_frontend(aisgpu_handle *h) {
 		h->err = "Model: sample rate must be between 96K and 12288K (inclusive).";
 		return AISGPU_EINVAL;
 	}
-	static const int buckets[9] = { 96000, 192000, 288000, 384000, 768000, 1536000, 3072000, 6144000, 12288000 }; // Model.cpp:129
+	static const int rates_nodsk[] = { 96000, 192000, 288000, 384000, 768000, 1536000, 3072000, 6144000, 12288000 };                           // Model.cpp:129
+	static const int rates_dsk[] = { 96000, 192000, 288000, 384000, 576000, 768000, 1152000, 1536000, 2304000, 3072000, 6144000, 12288000 }; // Model.cpp:130 (-go DSK on)
 	int bucket = 0;
-	for (int b : buckets)
-		if (b >= sr) { bucket = b; break; }
+	if (h->cfg.dsk) {
+		for (int b : rates_dsk)
+			if (b >= sr) { bucket = b; break; }
+	}
+	else {
+		for (int b : rates_nodsk)
+			if (b >= sr) { bucket = b; break; }
+	}
 	const bool interp = bucket != sr; // "sample rate ...K upsampled to ...K." (Model.cpp:146-147)
 	h->pre = 0;
 	h->kA = 0;
+	h->fp_ds = 0;
 	h->in_fmt = h->cfg.format;
 	int k_total = 0;
-	if (bucket == 288000) { // [US ->] DSK(BlackmanHarris_28_3, 3) -> ROT, no droop filter (Model.cpp:308-313)
-		h->pre = interp ? 3 : 2; // 3: Upsample to 288K first (Model.cpp:308-313 with `interpolated`)
-		if (interp) {
-			h->us_inc = (float)sr / (float)bucket;
-			h->PA = 4;
+	bool dsk_family = false;
+	if (bucket == 288000 || bucket == 576000 || bucket == 1152000 || bucket == 2304000) {
+		// kA x Downsample2CIC5 -> [Upsample ->] DownsampleKFilter(BlackmanHarris_28_3, 3) -> ROT, no droop filter
+		// (Model.cpp:208-218, 248-258, 278-288, 308-313)
+		dsk_family = true;
+		for (int b = bucket; b > 288000; b >>= 1) h->kA++;
+		h->pre = interp ? 3 : (h->kA ? 4 : 2); // 2: DSK on the raw input, 3: [CIC ->] Upsample -> DSK, 4: CIC -> DSK
+		if (interp) h->us_inc = (float)sr / (float)bucket;
+		if (h->pre != 2) {
+			const int pa = 5 * ((1 << h->kA) - 1);
+			const int g = std::max(4, 4 << h->kA);
+			h->PA = std::max(g, (pa + g - 1) / g * g);
 		}
 		h->k = 0;
 		h->blk = 8192; // DownsampleKFilter::outputSize (DSP.h:193)
@@ -278,6 +294,14 @@ int plan_frontend(aisgpu_handle *h) {
 		}
 		else h->k = k_total;
 	}
+	if (h->cfg.fp_ds) { // -go FP_DS on: only the exact 1536K bucket has an integer front end, and it is fed by convert.outCU8 (Model.cpp:222-236)
+		if (sr == 1536000 && h->cfg.format == AISGPU_FMT_CU8) h->fp_ds = 1;
+		else if (sr == 1536000) {
+			h->err = "FP_DS on: the integer front end (Downsample16_CU8, Model.cpp:233-236) needs CU8 input";
+			return AISGPU_EINVAL;
+		}
+	}
+	(void)dsk_family;
 	h->use_fdc = (h->cfg.droop && k_total > 0) ? 1 : 0;
 	float a = 0.0f;
 	switch (bucket) {
@@ -301,7 +325,10 @@ int plan_frontend(aisgpu_handle *h) {
 }
 
 // granule of the caller's submit length: every CIC stage needs an even block (DSP.cpp:94,135)
-int outer_granule(const aisgpu_handle *h) { return h->pre >= 2 ? 64 : (1 << (h->k + h->kA + 2)); }
+int outer_granule(const aisgpu_handle *h) {
+	if (h->fp_ds) return 2048; // 32 lane sub-segments of at least one super-step (64 samples) of the streaming kernel
+	return h->pre >= 2 ? std::max(64, 1 << (h->kA + 2)) : (1 << (h->k + h->kA + 2));
+}
 
 void layout_frontend(FeParams &p, int k, int tile) {
 	int off = 0;
@@ -363,16 +390,21 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 		if (S <= 0) {
 			S = 2048; // about 10 x the warm-up history P (192 samples at K = 3, doubling per stage)
 			for (int i = 3; i < h->k; i++) S *= 2;
-			while (S >= 2 * SS && S / 2 >= 4 * h->P && N % (32 * S) != 0) S /= 2; // longer sub-segments = smaller warm-up share
+			while (S >= 2 * SS && (S / 2 >= 4 * h->P || h->fp_ds) && N % (32 * S) != 0) S /= 2; // longer sub-segments = smaller warm-up share
 		}
 		if (S >= SS && N % (32 * S) == 0) {
 			p.in = dev_in;
 			p.st_S = S;
 			p.st_wps = N / (32 * S);
 			p.st_B = B;
-			CU(launch_frontend_stream(p, h->in_fmt, h->k, h->st_nb, h->st_wpc, false, (long long)B * p.st_wps, h->fe_stream));
+			if (h->fp_ds) CU(launch_frontend_stream_fpds(p, (long long)B * p.st_wps, h->fe_stream));
+			else CU(launch_frontend_stream(p, h->in_fmt, h->k, h->st_nb, h->st_wpc, false, (long long)B * p.st_wps, h->fe_stream));
 			return 0;
 		}
+	}
+	if (h->fp_ds) { // the integer CIC stages only exist in the streaming kernel
+		h->err = "FP_DS on: n_samples must be a multiple of 2048 and the batch 16-byte aligned";
+		return AISGPU_EINVAL;
 	}
 	const size_t smem = (size_t)p.smem_f2 * sizeof(float2);
 	CU(launch_frontend_tiled(p, h->in_fmt, h->k, false, dim3(n_seg, B), smem, h->fe_stream));
@@ -722,9 +754,9 @@ int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) 
 	else {
 		const int cur = h->ptail_cur, nxt = cur ^ 1;
 		int tail_len = 0;
-		if (h->pre == 1 || h->pre == 3) { // [kA x Downsample2CIC5 ->] Upsample (Model.cpp:183-189; DSP.cpp:192-212)
+		if (h->pre == 1 || h->pre == 3 || h->pre == 4) { // kA x Downsample2CIC5 -> Upsample | DownsampleKFilter (Model.cpp:183-189, 208-218; DSP.cpp:192-212)
 			const int L = N >> h->kA;
-			if (!h->outer_N) {
+			if (!h->outer_N && h->pre != 4) {
 				h->outer_N = N;
 				h->us_blk = L;
 				if (h->pre == 1) h->blk = L;
@@ -771,6 +803,14 @@ int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) 
 			if (!st_done) CU(launch_frontend_tiled(pp, h->cfg.format, h->kA, true, grid, smem, h->fe_stream));
 			if (rc) return rc;
 			tail_len = h->PA;
+			if (h->pre == 4) { // the level-kA stream goes straight through DownsampleKFilter into the 96 kS/s ring
+				const int c2 = h->ptail2_cur;
+				if ((rc = run_dsk(h, h->d_D0 + 2, h->d0_stride, AISGPU_FMT_CF32, L, h->d_ptail2[c2], h->d_S, h->s_stride, h->s_produced, h->s_cap))) return rc;
+				CU(launch_tail_update(h->d_ptail2[c2 ^ 1], h->d_ptail2[c2], h->d_D0 + 2, h->d0_stride, (long long)L, 32, B, h->fe_stream));
+				h->ptail2_cur = c2 ^ 1;
+				h->last_launches += 2;
+			}
+			else {
 			// replay Upsample's float accumulator: one (input index, alpha) pair per output (DSP.cpp:196-209).  The table goes
 			// through a pinned double buffer, so the copy is a true asynchronous one and the caller's thread never waits
 			// for the front-end stream here.
@@ -803,6 +843,7 @@ int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) 
 			CU(launch_d0_carry(h->d_D0, h->d0_stride, 2, L, B, h->fe_stream));
 			h->s_produced += M;
 			h->last_launches += 3;
+			}
 		}
 		else { // DownsampleKFilter(BlackmanHarris_28_3, 3) (Model.cpp:308-313; DSP.cpp:160-189)
 			tail_len = 32;
@@ -1024,6 +1065,8 @@ void aisgpu_default_config(aisgpu_config *cfg) {
 	cfg->enable_taps = 0;
 	cfg->max_frames = 0;
 	cfg->host_staging = 1;
+	cfg->dsk = 0;
+	cfg->fp_ds = 0;
 }
 
 const char *aisgpu_last_error(aisgpu_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -1123,19 +1166,21 @@ static int create_impl(aisgpu_handle *h) {
 			if (int rc = dalloc(h, &h->d_ptail[i], (size_t)B * tl * h->obps)) return rc;
 			if (c.format == AISGPU_FMT_CU8) CU(cudaMemsetAsync(h->d_ptail[i], 0x80, (size_t)B * tl * h->obps, h->stream));
 		}
-		if (h->pre == 1 || h->pre == 3) {
+		if (h->pre == 1 || h->pre == 3 || h->pre == 4) {
 			const int Lmax = maxN >> h->kA;
 			h->d0_stride = (Lmax + 4 + 1) & ~1LL;
 			if (int rc = dalloc(h, &h->d_D0, (size_t)B * h->d0_stride)) return rc;
-			if (int rc = dalloc(h, &h->d_us_src, (size_t)2 * Lmax + 8)) return rc;
-			if (int rc = dalloc(h, &h->d_us_alpha, (size_t)2 * Lmax + 8)) return rc;
-			h->s_stride = 4LL * Lmax;
 			memset(&h->fe_pre, 0, sizeof(h->fe_pre));
+			if (h->pre != 4) {
+				if (int rc = dalloc(h, &h->d_us_src, (size_t)2 * Lmax + 8)) return rc;
+				if (int rc = dalloc(h, &h->d_us_alpha, (size_t)2 * Lmax + 8)) return rc;
+				h->s_stride = 4LL * Lmax;
+			}
 		}
 		if (h->pre >= 2) {
 			const int cap96 = ((2 * maxN / 3 + 1 + h->blk + h->blk - 1) / h->blk + 1) * h->blk; // behind Upsample up to 2x the samples
 			CU(set_taps_bh28_3(H_TAPS_BH28_3));
-			if (h->pre == 2) {
+			if (h->pre == 2 || h->pre == 4) { // DownsampleKFilter writes the 96 kS/s ring directly
 				h->s_cap = cap96;
 				h->s_stride = cap96;
 			}
@@ -1143,15 +1188,16 @@ static int create_impl(aisgpu_handle *h) {
 				h->s2_cap = cap96;
 				h->s2_stride = cap96;
 				if (int rc = dalloc(h, &h->d_S2, (size_t)B * h->s2_stride)) return rc;
+			}
+			if (h->pre != 2)
 				for (int i = 0; i < 2; i++)
 					if (int rc = dalloc(h, &h->d_ptail2[i], (size_t)B * 32)) return rc;
-			}
 		}
 		if (int rc = dalloc(h, &h->d_S, (size_t)B * h->s_stride)) return rc;
 	}
 	for (int i = 0; i < 2; i++) {
 		if (int rc = dalloc(h, &h->d_tail[i], (size_t)B * h->P * h->bps)) return rc;
-		if (h->in_fmt == AISGPU_FMT_CU8) // the reference's zero initial filter state is byte value 128 in CU8
+		if (h->in_fmt == AISGPU_FMT_CU8 && !h->fp_ds) // the reference's zero initial filter state is byte value 128 in CU8 (0 for the unbiased integer pipeline)
 			CU(cudaMemsetAsync(h->d_tail[i], 0x80, (size_t)B * h->P * h->bps, h->stream));
 		if (int rc = dalloc(h, &h->d_fir_hist[i], (size_t)h->rows * 16)) return rc;
 	}

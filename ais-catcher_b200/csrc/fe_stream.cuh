@@ -51,9 +51,38 @@ __device__ __forceinline__ void fcic_pair(Cic5 &s, c64 xe, c64 xo, c64 sc, c64 &
 	s.h4 = z; z = padd(z, r4);
 	oo = pmul(z, sc);
 }
+// ---- -go FP_DS on (Model.cpp:233-236): DSP::Downsample16_CU8 = four DS_UINT16 stages on I/Q packed as two uint16 in one
+// ---- uint32 (DSP.cpp:499-665, shifts 3, 4, 5, then 0 with the conversion to float).  Plain integer adds: bit-exact by
+// ---- construction, including the carry of I into Q that the reference's masks "clean up" after the shift.
+struct Cic5u { uint32_t h0, h1, h2, h3, h4; };
+__device__ __forceinline__ void cic5u_zero(Cic5u &s) { s.h0 = s.h1 = s.h2 = s.h3 = s.h4 = 0u; }
+template <int SHIFT>
+__device__ __forceinline__ uint32_t ds2u_pair(Cic5u &s, uint32_t xe, uint32_t xo) { // MA1 x 5, emit, MA2 x 5 (DSP.cpp:85-90, 508-527)
+	constexpr uint32_t m16 = 0xFFFFu >> SHIFT, mask = m16 | (m16 << 16);
+	uint32_t z = xe;
+	const uint32_t r0 = z; z += s.h0;
+	const uint32_t r1 = z; z += s.h1;
+	const uint32_t r2 = z; z += s.h2;
+	const uint32_t r3 = z; z += s.h3;
+	z += s.h4;
+	const uint32_t out = (z >> SHIFT) & mask;
+	z = xo;
+	s.h0 = z; z += r0;
+	s.h1 = z; z += r1;
+	s.h2 = z; z += r2;
+	s.h3 = z; z += r3;
+	s.h4 = z;
+	return out;
+}
+// last stage: uint16 pair -> int16 pair (sign bits flipped) -> float / 32768 (DSP.cpp:610-617)
+__device__ __forceinline__ c64 u16pair_to_c64(uint32_t z) {
+	z ^= 0x80008000u;
+	return pack2(__fmul_rn((float)(short)(z & 0xFFFFu), 3.0517578125e-05f), __fmul_rn((float)(short)(z >> 16), 3.0517578125e-05f));
+}
+
 template <int FMT>
 struct StFmt {
-	static constexpr int BPS = FMT == 0 ? 8 : (FMT == 3 ? 4 : 2);
+	static constexpr int BPS = FMT == 0 ? 8 : (FMT == 3 ? 4 : 2); // FMT 4: CU8 through the integer CIC stages (-go FP_DS on)
 	static constexpr int CHUNK = ST_G * BPS;      // bytes of one lane's chunk: 128 / 32 / 32 / 64
 	static constexpr int PIECES = CHUNK / 16;     // 16-byte pieces per lane chunk = cp.async instructions per warp chunk
 	static constexpr int SLOT = CHUNK + 16;       // lane stride in the ring (odd multiple of 16 bytes: conflict-free 16-byte reads)
@@ -126,7 +155,12 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p)
 		cp_async_commit();
 	};
 	const c64 sc = pack2(0.03125f, 0.03125f);
+	static_assert(FMT != 4 || (K == 4 && !PRE), "the integer front end exists for the exact 1536K bucket only (Model.cpp:222-236)");
 	Cic5 lv[K], chA, chB, fA, fB;
+	Cic5u lu[4];
+	uint32_t pendu[4];
+#pragma unroll
+	for (int l = 0; l < 4; l++) { cic5u_zero(lu[l]); pendu[l] = 0u; }
 #pragma unroll
 	for (int l = 0; l < K; l++) cic5_zero(lv[l]);
 	cic5_zero(chA); cic5_zero(chB); cic5_zero(fA); cic5_zero(fB);
@@ -173,17 +207,34 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p)
 #pragma unroll
 				for (int j = 0; j < ST_G / 2; j++) {
 					const int n1 = cc * (ST_G / 2) + j; // index of this pair's output at level 1 within the super-step
-					c64 xe, xo;
-					st_read_pair<FMT>(slot, j, xe, xo);
-					c64 y = ds2_pair(lv[0], xe, xo, sc);
-					// ripple through the deeper levels: an output with an odd index completes a pair one level down
+					c64 y = 0ull;
 					int idx = n1;
 					bool live = true;
-#pragma unroll
-					for (int l = 1; l < K; l++) {
+					if (FMT == 4) { // integer stages 1..4; the fourth one delivers the 96 kHz float sample
+						const uchar4 v = *reinterpret_cast<const uchar4 *>(slot + j * 4);
+						uint32_t yu = ds2u_pair<3>(lu[0], (uint32_t)v.x | ((uint32_t)v.y << 16), (uint32_t)v.z | ((uint32_t)v.w << 16));
+						if ((idx & 1) == 0) { pendu[1] = yu; live = false; }
+						else { yu = ds2u_pair<4>(lu[1], pendu[1], yu); idx >>= 1; }
 						if (live) {
-							if ((idx & 1) == 0) { pend[l] = y; live = false; }
-							else { y = ds2_pair(lv[l], pend[l], y, sc); idx >>= 1; }
+							if ((idx & 1) == 0) { pendu[2] = yu; live = false; }
+							else { yu = ds2u_pair<5>(lu[2], pendu[2], yu); idx >>= 1; }
+						}
+						if (live) {
+							if ((idx & 1) == 0) { pendu[3] = yu; live = false; }
+							else { y = u16pair_to_c64(ds2u_pair<0>(lu[3], pendu[3], yu)); idx >>= 1; }
+						}
+					}
+					else {
+						c64 xe, xo;
+						st_read_pair<FMT == 4 ? 1 : FMT>(slot, j, xe, xo);
+						y = ds2_pair(lv[0], xe, xo, sc);
+						// ripple through the deeper levels: an output with an odd index completes a pair one level down
+#pragma unroll
+						for (int l = 1; l < K; l++) {
+							if (live) {
+								if ((idx & 1) == 0) { pend[l] = y; live = false; }
+								else { y = ds2_pair(lv[l], pend[l], y, sc); idx >>= 1; }
+							}
 						}
 					}
 					if (live && PRE) lvK[idx] = y;

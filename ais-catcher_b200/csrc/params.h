@@ -162,6 +162,7 @@ cudaError_t set_taps_bh28_3(const float *taps26);
 cudaError_t launch_frontend_tiled(const FeParams &p, int fmt, int k, bool pre, dim3 grid, size_t smem, cudaStream_t s);
 // fe_stream_f{0,1,2,3}.cu: n_warps warps (one per 32 lane sub-segments), wpc warps per CTA (1 or 4), ring of nb chunks
 cudaError_t launch_frontend_stream(const FeParams &p, int fmt, int k, int nb, int wpc, bool pre, long long n_warps, cudaStream_t s);
+cudaError_t launch_frontend_stream_fpds(const FeParams &p, long long n_warps, cudaStream_t s); // fe_stream_fp.cu: CU8, integer CIC stages, 1536K
 template <int FMT, int NB, int WPC>
 cudaError_t launch_frontend_stream_shape(const FeParams &p, int k, bool pre, long long n_warps, cudaStream_t s);
 // be_cgf.cu

@@ -33,8 +33,9 @@ class ModelGPU : public Model, public StreamIn<RAW> {
 	aisgpu_config cfg;
 	Message msg;
 	std::vector<aisgpu_msg> frames;
-	std::vector<unsigned char> carry; // input bytes that did not fill a whole granule yet
+	std::vector<unsigned char> fifo;  // input bytes that have not filled a whole block yet
 	int granule = 64;                 // samples: every CIC stage needs an even block (DSP.cpp:94,135)
+	size_t blockBytes = 0;            // every submit has this length (fixed by the first Receive, see there)
 	bool failed = false;
 
 	static int formatOf(Format f) {
@@ -71,7 +72,9 @@ class ModelGPU : public Model, public StreamIn<RAW> {
 	void publish(TAG &tag) {
 		int n = 0;
 		do {
-			if (aisgpu_poll(engine, frames.data(), (int)frames.size(), &n) != AISGPU_OK) {
+			const int rc = aisgpu_poll(engine, frames.data(), (int)frames.size(), &n);
+			if (rc == AISGPU_EOVERFLOW) Warning() << "ModelGPU: " << aisgpu_last_error(engine); // the surviving frames are still delivered
+			else if (rc != AISGPU_OK) {
 				fail(aisgpu_last_error(engine));
 				return;
 			}
@@ -128,28 +131,36 @@ public:
 			if (!failed) fail("unsupported or changing sample format");
 			return;
 		}
+		// The engine is handed blocks of ONE length: that of the device's first buffer, rounded down to the granule (the
+		// reference's results depend on the block length -- Rotate renormalises and Upsample re-blocks per Receive,
+		// DSP.cpp:203,309-315 -- and at interpolated rates the engine insists on a constant one).  A device that always
+		// delivers that length (every file / SDR device does) is passed through without a copy; odd, short or varying
+		// buffers (network sources, the last block of a file) go through a byte FIFO.
 		const int bps = bytesPerSample(cfg.format);
-		const size_t gran = (size_t)granule * bps;
 		const unsigned char *p = (const unsigned char *)raw->data;
 		size_t n = (size_t)raw->size;
-		if (!carry.empty()) { // complete the granule left over from the previous block
-			const size_t need = gran - carry.size(), take = n < need ? n : need;
-			carry.insert(carry.end(), p, p + take);
-			p += take;
-			n -= take;
-			if (carry.size() < gran) return;
-			if (aisgpu_submit(engine, carry.data(), granule) != AISGPU_OK) return fail(aisgpu_last_error(engine));
-			carry.clear();
+		if (!blockBytes) {
+			size_t samples = n / bps / granule * granule;
+			if (samples < (size_t)granule) samples = (size_t)granule;
+			if (samples > (size_t)cfg.max_chunk_samples / granule * granule) samples = (size_t)cfg.max_chunk_samples / granule * granule;
+			blockBytes = samples * bps;
 		}
-		const size_t whole = n / gran * gran;
-		for (size_t off = 0; off < whole;) {
-			size_t part = whole - off;
-			const size_t maxb = (size_t)cfg.max_chunk_samples / granule * gran;
-			if (part > maxb) part = maxb;
-			if (aisgpu_submit(engine, p + off, (int)(part / bps)) != AISGPU_OK) return fail(aisgpu_last_error(engine));
-			off += part;
+		if (fifo.empty()) { // whole blocks straight from the device buffer
+			while (n >= blockBytes) {
+				if (aisgpu_submit(engine, p, (int)(blockBytes / bps)) != AISGPU_OK) return fail(aisgpu_last_error(engine));
+				p += blockBytes;
+				n -= blockBytes;
+			}
 		}
-		carry.assign(p + whole, p + n);
+		if (n) {
+			fifo.insert(fifo.end(), p, p + n);
+			size_t off = 0;
+			while (fifo.size() - off >= blockBytes) {
+				if (aisgpu_submit(engine, fifo.data() + off, (int)(blockBytes / bps)) != AISGPU_OK) return fail(aisgpu_last_error(engine));
+				off += blockBytes;
+			}
+			if (off) fifo.erase(fifo.begin(), fifo.begin() + off);
+		}
 		publish(tag);
 	}
 
@@ -158,11 +169,11 @@ public:
 		case AIS::KEY_SETTING_PS_EMA: cfg.ps_ema = Util::Parse::Switch(arg); break;     // ModelDefault::SetKey, Model.cpp:583-585
 		case AIS::KEY_SETTING_AFC_WIDE: cfg.afc_wide = Util::Parse::Switch(arg); break; // Model.cpp:586-588
 		case AIS::KEY_SETTING_DROOP: cfg.droop = Util::Parse::Switch(arg); break;       // ModelFrontend::SetKey, Model.cpp:384-386
-		case AIS::KEY_SETTING_FP_DS:
+		case AIS::KEY_SETTING_FP_DS: cfg.fp_ds = Util::Parse::Switch(arg); break;       // Model.cpp:362-365 (CU8 @1536K only, as in the reference)
+		case AIS::KEY_SETTING_DSK: cfg.dsk = Util::Parse::Switch(arg); break;           // Model.cpp:377-379
 		case AIS::KEY_SETTING_SOXR:
 		case AIS::KEY_SETTING_SRC:
 		case AIS::KEY_SETTING_MA:
-		case AIS::KEY_SETTING_DSK:
 		case AIS::KEY_SETTING_DUMP:
 			if (key != AIS::KEY_SETTING_DUMP && !Util::Parse::Switch(arg)) break; // "off" is what the engine does anyway
 			throw std::runtime_error(getName() + ": setting \"" + AIS::KeyMap[key][JSON_DICT_SETTING] + "\" is not available on the GPU engine");
@@ -173,7 +184,7 @@ public:
 
 	std::string Get() override {
 		return "gpu on ps_ema " + Util::Convert::toString((bool)cfg.ps_ema) + " afc_wide " + Util::Convert::toString((bool)cfg.afc_wide) + " droop " +
-			   Util::Convert::toString((bool)cfg.droop);
+			   Util::Convert::toString((bool)cfg.droop) + " fp_ds " + Util::Convert::toString((bool)cfg.fp_ds) + " dsk " + Util::Convert::toString((bool)cfg.dsk);
 	}
 
 	void setDeviceOrdinal(int d) { cfg.device = d; }

@@ -78,6 +78,8 @@ typedef struct aisgpu_config {
 	int32_t max_frames;         /* capacity of the device frame ring = frames that may wait between two polls (0 = default) */
 	int32_t host_staging;       /* 1 (default): the device staging buffers behind aisgpu_submit*() are allocated by aisgpu_create;
 	                               0: at the first host submit (engines that are only fed with aisgpu_submit_device) */
+	int32_t dsk;                /* -go DSK   (Model.cpp:377-379): adds the 576K / 1152K / 2304K buckets (CIC stages -> /3 filter), default 0 */
+	int32_t fp_ds;              /* -go FP_DS (Model.cpp:362-365): integer CIC stages for CU8 input at exactly 1536000 (DSP.cpp:499-665), default 0 */
 } aisgpu_config;
 
 /* One decoded frame == one AIS::Message the reference would Send (Source/Marine/AIS.cpp:66-96). */

@@ -910,6 +910,7 @@ static int build_frontend(Handle *h) {
 /* ================= C entry points ================= */
 void *aisorc_create(int model, int sample_rate, int format, unsigned flags, int own_mmsi) {
 	if (model < 0 || model > 2 || format < 0 || format > 3) return NULL;
+	if (flags & (16u | 32u)) return NULL; /* -go FP_DS / DSK: checked against the compiled reference (ref_harness.cpp) only */
 	Handle *h = (Handle *)calloc(1, sizeof(Handle));
 	h->model = model;
 	h->sample_rate = sample_rate;

@@ -81,7 +81,7 @@ struct MsgSink : public StreamIn<AIS::Message> {
 };
 
 enum { MODEL_STANDARD = 0, MODEL_BASE = 1, MODEL_DEFAULT = 2 };
-enum { FLAG_PS_EMA = 1, FLAG_AFC_WIDE = 2, FLAG_DROOP = 4, FLAG_TAPS = 8 };
+enum { FLAG_PS_EMA = 1, FLAG_AFC_WIDE = 2, FLAG_DROOP = 4, FLAG_TAPS = 8, FLAG_FP_DS = 16, FLAG_DSK = 32 };
 static const int NTAPS_C = 9;  // 0: ROT in, 1/2: ROT up/down, 3/4: C_a/C_b, 5/6: CGF or (unused), 7/8: FC
 static const int NTAPS_F = 14; // 0..4 / 5..9: per-phase decoder inputs ch A / B; 10/11: FM out; 12/13: FR out
 
@@ -144,6 +144,8 @@ void *aisref_create(int model, int sample_rate, int format, unsigned flags, int 
 			return nullptr;
 		}
 		h->fe->SetKey(AIS::KEY_SETTING_DROOP, droop);
+		if (flags & FLAG_FP_DS) h->fe->SetKey(AIS::KEY_SETTING_FP_DS, "on"); // -go FP_DS on (Source/DSP/Model.cpp:362-365)
+		if (flags & FLAG_DSK) h->fe->SetKey(AIS::KEY_SETTING_DSK, "on");     // -go DSK on   (Source/DSP/Model.cpp:377-379)
 		h->fe->setOwnMMSI(own_mmsi);
 		h->dev.setFormat(h->fmt);
 		h->dev.setSampleRate(sample_rate);
@@ -153,7 +155,7 @@ void *aisref_create(int model, int sample_rate, int format, unsigned flags, int 
 		if (flags & FLAG_TAPS) {
 			AIS::ModelFrontend *fe = h->fe;
 			// whichever Connection feeds ROT (depends on the rate, Source/DSP/Model.cpp:157-338)
-			Connection<CFLOAT32> *cands[] = {&fe->FDC.out, &fe->DS2_1.out, &fe->DSK.out, &fe->US.out, &fe->convert.out};
+			Connection<CFLOAT32> *cands[] = {&fe->FDC.out, &fe->DS2_1.out, &fe->DSK.out, &fe->US.out, &fe->DS16_CU8.out, &fe->convert.out};
 			for (auto c : cands)
 				if (feeds<CFLOAT32>(*c, &fe->ROT)) {
 					c->Connect(&h->tc[0]);

@@ -79,6 +79,8 @@ int main(int argc, char **argv) {
 			else if (!strcmp(argv[i], "AFC_WIDE")) key = AIS::KEY_SETTING_AFC_WIDE;
 			else if (!strcmp(argv[i], "DROOP")) key = AIS::KEY_SETTING_DROOP;
 			else if (!strcmp(argv[i], "FP_DS")) key = AIS::KEY_SETTING_FP_DS;
+			else if (!strcmp(argv[i], "DSK")) key = AIS::KEY_SETTING_DSK;
+			else if (!strcmp(argv[i], "SOXR")) key = AIS::KEY_SETTING_SOXR;
 			model->SetKey(key, argv[i + 1]);
 		}
 		model->buildModel('A', 'B', rate, false, &dev);
@@ -89,7 +91,21 @@ int main(int argc, char **argv) {
 	}
 	model->Output().out.Connect(&sink);
 	const size_t step = (size_t)block * bps;
-	for (size_t off = 0; off + step <= data.size() && !g_stop_requests; off += step) dev.push(data.data() + off, (int)step, fmt);
+	if (getenv("ADAPTER_VARY")) { // odd, short and varying device buffers after a first one of the nominal length (network sources)
+		const size_t total = data.size() / step * step; // the same samples a fixed-length run consumes
+		size_t off = 0;
+		int k = 0;
+		while (off < total && !g_stop_requests) {
+			static const int num[] = { 8, 3, 13, 1, 8, 5, 16, 2 };
+			size_t n = k == 0 ? step : step * num[k & 7] / 8 + (size_t)bps * (k % 3);
+			if (n > total - off) n = total - off;
+			dev.push(data.data() + off, (int)n, fmt);
+			off += n;
+			k++;
+		}
+	}
+	else
+		for (size_t off = 0; off + step <= data.size() && !g_stop_requests; off += step) dev.push(data.data() + off, (int)step, fmt);
 	fprintf(stderr, "%ld messages, %d stop requests, settings: %s\n", sink.count, g_stop_requests, model->Get().c_str());
 	delete model;
 	return g_stop_requests ? 3 : 0;

@@ -33,7 +33,8 @@ def first_diff(a, b):
     return (int(d[0]), int(len(d))) if len(d) else (-1, 0)
 
 
-def run_case(built, model, fs, N, nchunks, B, ps_ema=True, afc_wide=True, droop=True, fmt=aisgpu.FMT_CF32, check_taps=True, seed0=0):
+def run_case(built, model, fs, N, nchunks, B, ps_ema=True, afc_wide=True, droop=True, fmt=aisgpu.FMT_CF32, check_taps=True, seed0=0, dsk=False,
+             fp_ds=False):
     xs = [S.random_stream(fs, N * nchunks, seed0 + s)[0] for s in range(B)]
     if fmt == aisgpu.FMT_CU8:
         raw = [S.to_cu8(x) for x in xs]
@@ -52,8 +53,11 @@ def run_case(built, model, fs, N, nchunks, B, ps_ema=True, afc_wide=True, droop=
         raw = xs
         per = 1
     flags = (O.FLAG_PS_EMA if ps_ema else 0) | (O.FLAG_AFC_WIDE if afc_wide else 0) | (O.FLAG_DROOP if droop else 0)
+    flags |= (O.FLAG_DSK if dsk else 0) | (O.FLAG_FP_DS if fp_ds else 0)
+    if (dsk or fp_ds) and not O.have_ref():
+        pytest.skip("-go DSK / FP_DS are checked against the compiled reference only")
     eng = aisgpu.Engine(model=model, sample_rate=fs, fmt=fmt, n_streams=B, max_chunk=N, ps_ema=ps_ema, afc_wide=afc_wide,
-                        droop=droop, taps=check_taps)
+                        droop=droop, taps=check_taps, dsk=dsk, fp_ds=fp_ds)
     refs = [oracle_model(model=model, sample_rate=fs, fmt=fmt, flags=flags, taps=True) for _ in range(B)]
     problems = []
     got_msgs = [[] for _ in range(B)]
@@ -198,3 +202,35 @@ def test_signed_integer_formats(built, fmt, fs, N):
     # (384k) front end
     n = run_case(built, aisgpu.MODEL_DEFAULT, fs, N, 3, 2, fmt=fmt, seed0=37)
     assert n >= 2
+
+
+@pytest.mark.parametrize("fs,N,model", [(576000, 24576, aisgpu.MODEL_DEFAULT), (1152000, 49152, aisgpu.MODEL_STANDARD), (2304000, 98304, aisgpu.MODEL_DEFAULT),
+                                        (500000, 16384, aisgpu.MODEL_DEFAULT), (1000000, 32768, aisgpu.MODEL_DEFAULT), (2000000, 65536, aisgpu.MODEL_STANDARD),
+                                        (288000, 12288, aisgpu.MODEL_DEFAULT), (1536000, 65536, aisgpu.MODEL_DEFAULT)])
+def test_dsk_buckets(built, fs, N, model):
+    # -go DSK on (reference Model.cpp:130, 208-218, 248-258, 278-288): the 576K / 1152K / 2304K buckets = CIC stages ->
+    # DownsampleKFilter /3, exact and interpolated (CIC -> Upsample -> /3); rates outside those buckets keep their chain
+    n = run_case(built, model, fs, N, 6, 2, check_taps=False, seed0=51, dsk=True)
+    assert n >= 2
+
+
+def test_dsk_cu8(built):
+    n = run_case(built, aisgpu.MODEL_DEFAULT, 1152000, 49152, 4, 2, fmt=aisgpu.FMT_CU8, check_taps=False, seed0=53, dsk=True)
+    assert n >= 2
+
+
+@pytest.mark.parametrize("model", [aisgpu.MODEL_DEFAULT, aisgpu.MODEL_STANDARD])
+def test_fp_ds_integer_frontend(built, model):
+    # -go FP_DS on (Model.cpp:233-236; DSP.cpp:499-665): CU8 @1536K through four packed-uint16 CIC stages; the 48 kHz taps and
+    # everything behind them are compared bit for bit
+    n = run_case(built, model, 1536000, 65536, 4, 3, fmt=aisgpu.FMT_CU8, seed0=57, fp_ds=True)
+    assert n >= 4
+
+
+def test_fp_ds_small_blocks(built):
+    run_case(built, aisgpu.MODEL_DEFAULT, 1536000, 2048, 64, 2, fmt=aisgpu.FMT_CU8, seed0=59, fp_ds=True)
+
+
+def test_fp_ds_needs_cu8(built):
+    with pytest.raises(aisgpu.AisGpuError, match="needs CU8"):
+        aisgpu.Engine(sample_rate=1536000, fmt=aisgpu.FMT_CF32, fp_ds=True)
