@@ -98,7 +98,7 @@ struct aisgpu_handle {
 	int rows = 0;
 	int max_n48 = 0;
 	int fe_warps = 4, fe_tile = 0, fe_ctas = 4096;
-	int fe_st = 1, st_S = 0, st_nb = 8, st_wpc = 4, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
+	int fe_st = 1, st_S = 0, st_g = 16, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
 	int be_v1 = 0; // AISGPU_BE_V1=1: round-1 back-end kernels (k_cgf_rot + k_cgf_derot_fir, one hypothesis per lane) for A/B runs
 	int dec_rpw = 6, decoder = 3; // rows per warp / which decoder kernel // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
@@ -398,7 +398,7 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 			p.st_wps = N / (32 * S);
 			p.st_B = B;
 			if (h->fp_ds) CU(launch_frontend_stream_fpds(p, (long long)B * p.st_wps, h->fe_stream));
-			else CU(launch_frontend_stream(p, h->in_fmt, h->k, h->st_nb, h->st_wpc, false, (long long)B * p.st_wps, h->fe_stream));
+			else CU(launch_frontend_stream(p, h->in_fmt, h->k, h->st_g, false, (long long)B * p.st_wps, h->fe_stream));
 			return 0;
 		}
 	}
@@ -796,7 +796,7 @@ int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) 
 					pp.st_S = S;
 					pp.st_wps = N / (32 * S);
 					pp.st_B = B;
-					CU(launch_frontend_stream(pp, h->cfg.format, h->kA, 6, 1, true, (long long)B * pp.st_wps, h->fe_stream));
+					CU(launch_frontend_stream(pp, h->cfg.format, h->kA, 16, true, (long long)B * pp.st_wps, h->fe_stream));
 					st_done = true;
 				}
 			}
@@ -1101,8 +1101,7 @@ static int create_impl(aisgpu_handle *h) {
 	if (const char *e = getenv("AISGPU_FE_TILE")) h->fe_tile = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_ST")) h->fe_st = atoi(e) ? 1 : 0;
 	if (const char *e = getenv("AISGPU_ST_S")) h->st_S = atoi(e);
-	if (const char *e = getenv("AISGPU_ST_NB")) h->st_nb = atoi(e);
-	if (const char *e = getenv("AISGPU_ST_WPC")) h->st_wpc = atoi(e) == 4 ? 4 : 1;
+	if (const char *e = getenv("AISGPU_ST_G")) h->st_g = atoi(e) == 64 ? 64 : (atoi(e) == 32 ? 32 : 16);
 	if (const char *e = getenv("AISGPU_ST_KMAX")) h->st_kmax = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_CTAS")) h->fe_ctas = std::max(1, atoi(e));
 	int ndev = 0;

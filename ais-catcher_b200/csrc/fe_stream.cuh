@@ -80,10 +80,10 @@ __device__ __forceinline__ c64 u16pair_to_c64(uint32_t z) {
 	return pack2(__fmul_rn((float)(short)(z & 0xFFFFu), 3.0517578125e-05f), __fmul_rn((float)(short)(z >> 16), 3.0517578125e-05f));
 }
 
-template <int FMT>
+template <int FMT, int G>
 struct StFmt {
 	static constexpr int BPS = FMT == 0 ? 8 : (FMT == 3 ? 4 : 2); // FMT 4: CU8 through the integer CIC stages (-go FP_DS on)
-	static constexpr int CHUNK = ST_G * BPS;      // bytes of one lane's chunk: 128 / 32 / 32 / 64
+	static constexpr int CHUNK = G * BPS;         // bytes of one lane's chunk (G = 16: 128 / 32 / 32 / 64)
 	static constexpr int PIECES = CHUNK / 16;     // 16-byte pieces per lane chunk = cp.async instructions per warp chunk
 	static constexpr int SLOT = CHUNK + 16;       // lane stride in the ring (odd multiple of 16 bytes: conflict-free 16-byte reads)
 };
@@ -115,10 +115,14 @@ __device__ __forceinline__ void st_read_pair(const unsigned char *slot, int j, c
 // ST_WARPS: warps per CTA (independent of each other).  One-warp CTAs with a ring of 6 chunks (27.6 KB for CF32) let eight
 // CTAs share an SM and let the block scheduler spread B x st_wps warps evenly over the 148 SMs (1024 warps: 7 + 6.9 avg);
 // the 4-warp / ring-of-8 shape (147 KB per CTA, one CTA per SM, 1.73 waves at 1024 warps) is the round-1 shape, kept for A/B.
-template <int FMT, int K, int ST_NB, int ST_WARPS, bool PRE = false>
+// ST_G: samples a lane fetches per visit of its sub-segment.  Every lane is an independent sequential stream for DRAM (1024 warps
+// = 32768 streams, far more than there are banks), so the bytes per visit decide the row-buffer locality: 16 samples = one
+// 128-byte line per visit, 64 samples = four consecutive lines.
+template <int FMT, int K, int ST_G, int ST_NB, int ST_WARPS, bool PRE = false>
 __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p) {
 	static_assert(K >= 3 && K <= 7, "streaming front end: 768 kS/s .. 12288 kS/s");
-	typedef StFmt<FMT> F;
+	static_assert(ST_G <= (1 << (K + 2)) && (ST_G % 16) == 0, "a chunk must not be longer than a super-step");
+	typedef StFmt<FMT, ST_G> F;
 	constexpr int SS = 1 << (K + 2);     // inputs per super-step: two 48 kHz samples per channel
 	constexpr int NCH = SS / ST_G;       // chunks per super-step
 	constexpr int N96 = SS >> K;         // 96 kHz samples per super-step (4)
@@ -285,33 +289,34 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p)
 }
 
 // ---- launch entry point of one sample format (instantiated by fe_stream_f<FMT>.cu) ----
-template <int FMT, int K, int NB, int WPC, bool PRE>
+template <int FMT, int K, int G, int NB, int WPC, bool PRE>
 static cudaError_t launch_st_one(const FeParams &p, long long n_warps, cudaStream_t s) {
-	const size_t smem = (size_t)WPC * NB * 32 * StFmt<FMT>::SLOT;
-	cudaError_t e = cudaFuncSetAttribute(k_frontend_st<FMT, K, NB, WPC, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	constexpr int GG = G <= (1 << (K + 2)) ? G : (1 << (K + 2)); // K = 3: a super-step is 32 samples
+	const size_t smem = (size_t)WPC * NB * 32 * StFmt<FMT, GG>::SLOT;
+	cudaError_t e = cudaFuncSetAttribute(k_frontend_st<FMT, K, GG, NB, WPC, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	const unsigned ctas = (unsigned)((n_warps + WPC - 1) / WPC);
-	k_frontend_st<FMT, K, NB, WPC, PRE><<<ctas, WPC * 32, smem, s>>>(p);
+	k_frontend_st<FMT, K, GG, NB, WPC, PRE><<<ctas, WPC * 32, smem, s>>>(p);
 	return cudaGetLastError();
 }
 // ring depth x warps per CTA: CF32 (128-byte lane chunks) has the shapes {4 or 6 chunks, 1 warp} and {8 chunks, 4 warps}, one
 // translation unit each; the integer formats (32/64-byte lane chunks) always run one-warp CTAs with 8 chunks
-template <int FMT, int NB, int WPC>
+template <int FMT, int G, int NB, int WPC>
 cudaError_t launch_frontend_stream_shape(const FeParams &p, int k, bool pre, long long n_warps, cudaStream_t s) {
 	if (pre) {
 		switch (k) { // CIC stages in front of DSP::Upsample
-		case 3: return launch_st_one<FMT, 3, NB, WPC, true>(p, n_warps, s);
-		case 4: return launch_st_one<FMT, 4, NB, WPC, true>(p, n_warps, s);
-		case 5: return launch_st_one<FMT, 5, NB, WPC, true>(p, n_warps, s);
+		case 3: return launch_st_one<FMT, 3, G, NB, WPC, true>(p, n_warps, s);
+		case 4: return launch_st_one<FMT, 4, G, NB, WPC, true>(p, n_warps, s);
+		case 5: return launch_st_one<FMT, 5, G, NB, WPC, true>(p, n_warps, s);
 		default: return cudaErrorInvalidValue;
 		}
 	}
 	switch (k) {
-	case 3: return launch_st_one<FMT, 3, NB, WPC, false>(p, n_warps, s);
-	case 4: return launch_st_one<FMT, 4, NB, WPC, false>(p, n_warps, s);
-	case 5: return launch_st_one<FMT, 5, NB, WPC, false>(p, n_warps, s);
-	case 6: return launch_st_one<FMT, 6, NB, WPC, false>(p, n_warps, s);
-	case 7: return launch_st_one<FMT, 7, NB, WPC, false>(p, n_warps, s);
+	case 3: return launch_st_one<FMT, 3, G, NB, WPC, false>(p, n_warps, s);
+	case 4: return launch_st_one<FMT, 4, G, NB, WPC, false>(p, n_warps, s);
+	case 5: return launch_st_one<FMT, 5, G, NB, WPC, false>(p, n_warps, s);
+	case 6: return launch_st_one<FMT, 6, G, NB, WPC, false>(p, n_warps, s);
+	case 7: return launch_st_one<FMT, 7, G, NB, WPC, false>(p, n_warps, s);
 	default: return cudaErrorInvalidValue;
 	}
 }

@@ -1,20 +1,20 @@
-// fe_stream_f0.cu -- streaming front end: CF32, ring of 6 chunks, one-warp CTAs (the default shape); one translation unit per shape keeps the build parallel.
+// fe_stream_f0.cu -- streaming front end: CF32 in front of DSP::Upsample (one-warp CTAs, 16-sample chunks, ring of 6); one translation unit per shape keeps the build parallel.
 #include "fe_stream.cuh"
 
 namespace aisgpu {
 
-template cudaError_t launch_frontend_stream_shape<0, 6, 1>(const FeParams &, int, bool, long long, cudaStream_t);
+template cudaError_t launch_frontend_stream_shape<0, 16, 6, 1>(const FeParams &, int, bool, long long, cudaStream_t);
 
-cudaError_t launch_frontend_stream(const FeParams &p, int fmt, int k, int nb, int wpc, bool pre, long long n_warps, cudaStream_t s) {
+cudaError_t launch_frontend_stream(const FeParams &p, int fmt, int k, int g, bool pre, long long n_warps, cudaStream_t s) {
 	switch (fmt) {
 	case 0:
-		if (pre) return launch_frontend_stream_shape<0, 6, 1>(p, k, true, n_warps, s);
-		if (wpc == 4) return launch_frontend_stream_shape<0, 8, 4>(p, k, false, n_warps, s);
-		if (nb == 4) return launch_frontend_stream_shape<0, 4, 1>(p, k, false, n_warps, s);
-		return launch_frontend_stream_shape<0, 6, 1>(p, k, false, n_warps, s);
-	case 1: return launch_frontend_stream_shape<1, 8, 1>(p, k, pre, n_warps, s);
-	case 2: return launch_frontend_stream_shape<2, 8, 1>(p, k, pre, n_warps, s);
-	default: return launch_frontend_stream_shape<3, 8, 1>(p, k, pre, n_warps, s);
+		if (pre) return launch_frontend_stream_shape<0, 16, 6, 1>(p, k, true, n_warps, s);
+		if (g == 64) return launch_frontend_stream_shape<0, 64, 3, 4>(p, k, false, n_warps, s);
+		if (g == 32) return launch_frontend_stream_shape<0, 32, 5, 4>(p, k, false, n_warps, s);
+		return launch_frontend_stream_shape<0, 16, 8, 4>(p, k, false, n_warps, s);
+	case 1: return launch_frontend_stream_shape<1, 16, 8, 1>(p, k, pre, n_warps, s);
+	case 2: return launch_frontend_stream_shape<2, 16, 8, 1>(p, k, pre, n_warps, s);
+	default: return launch_frontend_stream_shape<3, 16, 8, 1>(p, k, pre, n_warps, s);
 	}
 }
 

@@ -141,10 +141,7 @@ constexpr int DK_THREADS = 128;
 constexpr int DK3_WARPS = 2;
 constexpr int DSK_T = 26;
 constexpr int DSK_THREADS = 256;
-constexpr int ST_G = 16; // streaming front end: samples per lane per staged chunk
 
-// bytes of one lane's slot in the streaming front end's staging ring (see fe_stream.cuh StFmt)
-inline int st_slot_bytes(int fmt) { return ST_G * (fmt == 0 ? 8 : (fmt == 3 ? 4 : 2)) + 16; }
 
 // ---- launch entry points (one translation unit per kernel family; every function returns cudaGetLastError()) ----
 // fe_misc.cu
@@ -160,10 +157,10 @@ cudaError_t launch_carry2_f2(const float2 *src, float2 *dst, long long stride, i
 cudaError_t set_taps_bh28_3(const float *taps26);
 // fe_tiled.cu
 cudaError_t launch_frontend_tiled(const FeParams &p, int fmt, int k, bool pre, dim3 grid, size_t smem, cudaStream_t s);
-// fe_stream_f{0,1,2,3}.cu: n_warps warps (one per 32 lane sub-segments), wpc warps per CTA (1 or 4), ring of nb chunks
-cudaError_t launch_frontend_stream(const FeParams &p, int fmt, int k, int nb, int wpc, bool pre, long long n_warps, cudaStream_t s);
+// fe_stream_f*.cu: n_warps warps (one per 32 lane sub-segments); g = samples per lane per staged chunk (CF32: 16, 32 or 64)
+cudaError_t launch_frontend_stream(const FeParams &p, int fmt, int k, int g, bool pre, long long n_warps, cudaStream_t s);
 cudaError_t launch_frontend_stream_fpds(const FeParams &p, long long n_warps, cudaStream_t s); // fe_stream_fp.cu: CU8, integer CIC stages, 1536K
-template <int FMT, int NB, int WPC>
+template <int FMT, int G, int NB, int WPC>
 cudaError_t launch_frontend_stream_shape(const FeParams &p, int k, bool pre, long long n_warps, cudaStream_t s);
 // be_cgf.cu
 cudaError_t cgf_init(const float *taps17, const float2 *omega256);

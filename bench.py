@@ -418,6 +418,18 @@ def main():
     delta = [a - b for a, b in zip(c1, c0)]
     delta[2] = B * N * args.steps * args.blocks  # samples of this rank's slice (the engine counts samples per stream)
     tot = shard.gather_counts(delta, device=dev)
+    # the same reduction inside the C library (aisgpu_comm_init / aisgpu_allreduce_counts: NCCL resolved with dlopen, no
+    # torch on that path): the counters since engine creation, summed over the ranks -- what a C++ host would call
+    c_totals = None
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(aisgpu.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        eng.comm_init(bytes(uid.cpu().numpy().tobytes()), world, rank)
+        c_totals = eng.allreduce_counts()
+        local_all = shard.gather_counts(c1, device=dev)
+        assert c_totals[0] == local_all[0] and c_totals[1] == local_all[1], "C-side NCCL all-reduce disagrees with torch.distributed"
     value = world * B * N * args.steps / (ms_max * 1e-3) / 1e6
     region_ms = shard.max_over_ranks(sum(blk_ms), device=dev)
     msgs_per_s = float(tot[1]) / (region_ms * 1e-3)
@@ -576,6 +588,7 @@ def main():
                        "note": "median of %d blocks of %d steps (this rank); value uses the max over ranks of the per-rank medians" % (args.blocks, args.steps)},
             "per_rank_ms": [v / args.steps for v in per_rank],
             "msgs_per_s": msgs_per_s,
+            "counters_allreduce_c": c_totals,
             "parity": parity,
             "e2e": {"value": e2e_value, "unit": "MSamples/s", "h2d_bytes_per_step": B * N * 8,
                     "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
