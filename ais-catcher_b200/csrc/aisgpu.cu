@@ -397,6 +397,7 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 			p.st_S = S;
 			p.st_wps = N / (32 * S);
 			p.st_B = B;
+			p.st_first = h->chunk == 0 ? 1 : 0;
 			if (h->fp_ds) CU(launch_frontend_stream_fpds(p, (long long)B * p.st_wps, h->fe_stream));
 			else CU(launch_frontend_stream(p, h->in_fmt, h->k, h->st_g, false, (long long)B * p.st_wps, h->fe_stream));
 			return 0;

@@ -245,15 +245,15 @@ __global__ void __launch_bounds__(FIRC_TILE) k_cgf_derot_fir(const float2 *__res
 // K2bc: the derotation phasor chain, output[i] *= rot and FilterComplex 17 taps in ONE kernel (DSP.cpp:457-465, 215-246).
 // The chain rot *= rot_step is strictly sequential per row (4096 dependent complex products per submit at the bench
 // shape: ~17 us is the floor for the whole stage), everything else is parallel.  A CTA owns CF_ROWS rows: warp 0 runs
-// the chains, one lane per row, CF_T steps ahead into a double-buffered shared tile; meanwhile the four consumer warps
-// derotate the previous tile (coalesced loads of the 48 kHz samples), and run the FIR out of a shared ring that keeps
-// the 16-sample history.  The phasors never travel through HBM (the old k_cgf_rot wrote 67 MB per submit and
+// the chains, one lane per row, CF_T steps ahead into a double-buffered shared tile; meanwhile the two consumer warps
+// derotate the previous tile (coalesced loads of the 48 kHz samples, requested one tile ahead), and run the FIR out of a
+// shared ring that keeps the 16-sample history.  The phasors never travel through HBM (the old k_cgf_rot wrote 67 MB per submit and
 // k_cgf_derot_fir read them back).  FIR: products by scalar FMUL, the (re, im) accumulation by one packed FADD2 --
 // ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, a scalar product feeding a packed add stays two roundings.
 // ---------------------------------------------------------------------------------------------
-constexpr int CF_ROWS = 8;
+constexpr int CF_ROWS = 4;             // 512 CTAs at 2048 rows: 3-4 per SM, so one CTA's barrier waits overlap another's arithmetic
 constexpr int CF_T = 64;               // samples per tile and row (a 512-block = 8 tiles)
-constexpr int CF_CONS = 4;             // consumer warps: CF_ROWS * CF_T / 4 outputs per thread and tile
+constexpr int CF_CONS = 2;             // consumer warps: CF_ROWS * CF_T / (32 CF_CONS) = 4 outputs per thread and tile
 constexpr int CF_THREADS = 32 * (1 + CF_CONS);
 constexpr int CF_DERP = 2 * CF_T + 2 * CF_T / 4; // ring row: two tiles, one pad slot after every four samples
 // ring position n (0 .. 2 CF_T - 1) -> slot: threads that own four consecutive outputs read n = 4c + i; 5c + i hits 16 different
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(CF_THREADS) k_cgf_fused(const CfParams p) {
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int row0 = blockIdx.x * CF_ROWS;
 	const int ntiles = p.nblk * (CGF_N / CF_T);
-	const int ct = tid - 32; // consumer thread index 0..127 (negative in the chain warp)
+	const int ct = tid - 32; // consumer thread index 0..63 (negative in the chain warp)
 	if (warp != 0) { // FIR history of the previous submit sits where "tile -1" would have left it
 		for (int i = ct; i < CF_ROWS * (FIRC_T - 1); i += 32 * CF_CONS) {
 			const int r = i / (FIRC_T - 1), k = i - r * (FIRC_T - 1);
@@ -298,6 +298,14 @@ __global__ void __launch_bounds__(CF_THREADS) k_cgf_fused(const CfParams p) {
 	const bool chain = warp == 0 && lane < CF_ROWS && crow < p.rows;
 	float2 rot = chain ? p.rot_state[crow] : make_float2(1.0f, 0.0f);
 	float2 st = make_float2(1.0f, 0.0f);
+	constexpr int CF_PER = CF_ROWS * CF_T / (32 * CF_CONS);
+	float2 cpre[CF_PER]; // the consumer threads' 48 kHz samples of the tile about to be derotated
+#pragma unroll
+	for (int u = 0; u < CF_PER; u++) {
+		const int q = ct + u * 32 * CF_CONS;
+		const int r = q / CF_T, j = q - r * CF_T;
+		cpre[u] = (warp != 0 && row0 + r < p.rows) ? p.Cbuf[(long long)(row0 + r) * p.c_stride + p.c_begin + j] : make_float2(0.f, 0.f);
+	}
 	__syncthreads();
 	for (int it = 0; it <= ntiles; it++) {
 		if (warp == 0) {
@@ -316,20 +324,30 @@ __global__ void __launch_bounds__(CF_THREADS) k_cgf_fused(const CfParams p) {
 		else if (it >= 1) {
 			const int t = it - 1;
 			const int half = (t & 1) * CF_T;
-			// derotate: thread -> (row r, sample j), a warp covers 32 consecutive samples of one row
+			// derotate: thread -> (row r, sample j), a warp covers 32 consecutive samples of one row.  The 48 kHz samples of the
+			// NEXT tile are requested before this tile is touched, so their HBM/L2 latency hides behind the FIR below.
+			float2 cnext[CF_PER];
 #pragma unroll
-			for (int u = 0; u < CF_ROWS * CF_T / (32 * CF_CONS); u++) {
+			for (int u = 0; u < CF_PER; u++) {
+				const int q = ct + u * 32 * CF_CONS;
+				const int r = q / CF_T, j = q - r * CF_T;
+				cnext[u] = (row0 + r < p.rows && t + 1 < ntiles) ? p.Cbuf[(long long)(row0 + r) * p.c_stride + p.c_begin + (t + 1) * CF_T + j] : make_float2(0.f, 0.f);
+			}
+#pragma unroll
+			for (int u = 0; u < CF_PER; u++) {
 				const int q = ct + u * 32 * CF_CONS;
 				const int r = q / CF_T, j = q - r * CF_T;
 				const int row = row0 + r;
 				float2 v = make_float2(0.f, 0.f);
 				if (row < p.rows) {
 					const int n = t * CF_T + j;
-					v = cmul(p.Cbuf[(long long)row * p.c_stride + p.c_begin + n], rotb[t & 1][r][j]);
+					v = cmul(cpre[u], rotb[t & 1][r][j]);
 					if (p.tap_cgf) p.tap_cgf[(long long)row * p.tap_stride + n] = v;
 				}
 				der[r][cf_slot(half + j)] = v;
 			}
+#pragma unroll
+			for (int u = 0; u < CF_PER; u++) cpre[u] = cnext[u];
 			cf_consumer_barrier();
 			// FIR: thread -> (row r, four consecutive outputs j0..j0+3): 20 ring samples in registers
 			{

@@ -306,12 +306,12 @@ __global__ void __launch_bounds__(PS_THREADS) k_phase_search(const K3Params p) {
 //   * t, |t| and the EMA update of the lane's four hypotheses -- plain per-lane arithmetic in the reference's order;
 //   * the decision "best of (i0, i0+1, i0+2)" (strict >, first wins, Demod.cpp:80-91) does not depend on which i0 the
 //     search is at, so every lane evaluates it for ITS four values of i0 (two EMAs of the next lane come by shuffle) and
-//     the 16 two-bit results are OR-combined over the four lanes into one 32-bit table (redux.sync);
-//   * the only sequential part left is  i0 = (max_idx - 1) & 15; max_idx = (i0 + table[i0]) & 15  -- integer work that no
-//     longer waits for floating-point results of the same symbol;
+//     the 16 two-bit results form a table spread over the four lanes;
+//   * the only sequential part left is  i0 = (max_idx - 1) & 15; max_idx = (i0 + table[i0]) & 15  -- one shuffle (from the
+//     lane holding entry i0) and integer work that no longer waits for floating-point results of the same symbol;
 //   * the lane that holds hypothesis max_idx contributes the demodulated bit (its decisions 3 and 4 symbols ago, XORed).
-// 2.7x fewer warp instructions per (instance, symbol) than one hypothesis per lane, and one redux + two shuffles instead
-// of four dependent shuffles.  Demod::PhaseSearch (PS_EMA off) keeps the one-hypothesis-per-lane kernel above.
+// 2.7x fewer warp instructions per (instance, symbol) than one hypothesis per lane, three shuffles (one of them on the
+// sequential chain) instead of four dependent ones.  Demod::PhaseSearch (PS_EMA off) keeps the one-hypothesis-per-lane kernel above.
 // ---------------------------------------------------------------------------------------------
 constexpr int PS2_ROWS = 8;
 constexpr int PS2_THREADS = PS2_ROWS * 5 * 4; // 160
@@ -325,8 +325,15 @@ __global__ void __launch_bounds__(PS2_THREADS) k_phase_search_ema4(const K3Param
 	const int row = row0 + rin;
 	const bool active = row < p.rows;
 	const long long inst = (long long)row * 5 + phase;
-	const unsigned gmask = 0xfu << (lane & ~3);
-	const int nxt = (lane & ~3) | ((q + 1) & 3);          // the lane holding hypotheses 4(q+1) .. of the same instance
+	const int gbase = lane & ~3;                          // first lane of this instance's group of four
+	const int nxt = gbase | ((q + 1) & 3);                // the lane holding hypotheses 4(q+1) .. of the same instance
+	// OR over the four lanes of an instance: two xor-shuffles with the full mask (redux.sync with a different member
+	// mask per group is executed once per distinct mask -- eight times per warp -- and was 9x slower)
+	auto or4 = [](uint32_t v) {
+		v |= __shfl_xor_sync(0xffffffffu, v, 1);
+		v |= __shfl_xor_sync(0xffffffffu, v, 2);
+		return v;
+	};
 	const float weight = 0.85f, omw = __fsub_rn(1.0f, 0.85f);
 	float cj[4], sj[4];
 #pragma unroll
@@ -395,17 +402,18 @@ __global__ void __launch_bounds__(PS2_THREADS) k_phase_search_ema4(const K3Param
 				if (v[k + 2] > mv) best = 2;
 				tab |= best << (2 * k);
 			}
-			tab = __reduce_or_sync(gmask, tab << (8 * q));
+			// only entry i0 of the 16-entry table is needed: it sits in lane i0 / 4 of the group (i0 is the same in all four lanes)
 			const int i0 = (max_idx - 1) & 15;
-			max_idx = (i0 + ((tab >> (2 * i0)) & 3u)) & 15;
+			const uint32_t tsel = __shfl_sync(0xffffffffu, tab, gbase | (i0 >> 2));
+			max_idx = (i0 + ((tsel >> (2 * (i0 & 3))) & 3u)) & 15;
 			const uint32_t bit = ((max_idx >> 2) == q) ? ((xm >> (max_idx & 3)) & 1u) : 0u;
 			word |= bit << sl;
 			if (p.tap_dec) {
-				const uint32_t b = __reduce_or_sync(gmask, bit);
+				const uint32_t b = or4(bit);
 				if (active && q == 0) p.tap_dec[inst * p.nsym + t * K3_TS + sl] = b ? 1.0f : -1.0f;
 			}
 		}
-		word = __reduce_or_sync(gmask, word);
+		word = or4(word);
 		if (active && q == 0) p.dbits[inst * p.dwords + t] = word;
 		if (p.mode_level) { // ScatterPLL level: ((((0+n0)+n1)+n2)+n3)+n4, then / 5 (DSP.h:100-106)
 			for (int e = tid; e < PS2_ROWS * K3_TS; e += PS2_THREADS) {
@@ -431,7 +439,7 @@ __global__ void __launch_bounds__(PS2_THREADS) k_phase_search_ema4(const K3Param
 		uint32_t pl = 0;
 #pragma unroll
 		for (int k = 0; k < 4; k++) pl |= ((hist[k] >> dd) & 1u) << (4 * q + k);
-		planes[dd] = __reduce_or_sync(gmask, pl);
+		planes[dd] = or4(pl);
 	}
 	if (active) {
 		PsState &st = p.ps[inst];

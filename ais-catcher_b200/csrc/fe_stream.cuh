@@ -225,7 +225,13 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p)
 						}
 						if (live) {
 							if ((idx & 1) == 0) { pendu[3] = yu; live = false; }
-							else { y = u16pair_to_c64(ds2u_pair<0>(lu[3], pendu[3], yu)); idx >>= 1; }
+							else {
+								y = u16pair_to_c64(ds2u_pair<0>(lu[3], pendu[3], yu));
+								// before the first sample of a stream the reference's float stages hold 0.0f, while the all-zero bytes
+								// of the (virtual) history convert to -1.0f: silence the warm-up outputs of the stream's first lane
+								if (p.st_first && sub0 + lane == 0 && ss < warm_super) y = 0ull;
+								idx >>= 1;
+							}
 						}
 					}
 					else {

@@ -34,6 +34,7 @@ struct FeParams {
 	int off_lv[FE_MAXK + 1]; // level arrays 1..k (off_lv[0] unused)
 	int off_up, off_dn, off_wa, off_wb;
 	int st_S, st_wps, st_B; // streaming kernel: samples per lane sub-segment, warps per stream, streams
+	int st_first;           // 1 in the first block of a stream (the integer front end's virtual history, see fe_stream.cuh)
 	int smem_f2;          // total float2
 	float2 *D0;           // PRE mode (decimation in front of DSP::Upsample): level-K samples, [B][d0_stride], sample i at d0_off + i
 	long long d0_stride;
