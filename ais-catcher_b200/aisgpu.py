@@ -10,7 +10,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libaisgpu.so")
 
-MODEL_STANDARD, MODEL_BASE, MODEL_DEFAULT = 0, 1, 2
+MODEL_STANDARD, MODEL_BASE, MODEL_DEFAULT, MODEL_V2 = 0, 1, 2, 11
 FMT_CF32, FMT_CU8, FMT_CS8, FMT_CS16 = 0, 1, 2, 3
 TAP_C, TAP_CGF, TAP_FIR, TAP_ROT, TAP_DEC, TAP_FM = 0, 1, 2, 3, 4, 5
 
@@ -28,7 +28,7 @@ class Config(C.Structure):
                 ("n_streams", C.c_int32), ("max_chunk_samples", C.c_int32), ("ps_ema", C.c_int32), ("afc_wide", C.c_int32),
                 ("droop", C.c_int32), ("channel_a", C.c_char), ("channel_b", C.c_char), ("station", C.c_int32),
                 ("own_mmsi", C.c_int32), ("tag_mode", C.c_uint32), ("device", C.c_int32), ("enable_taps", C.c_int32),
-                ("max_frames", C.c_int32), ("host_staging", C.c_int32), ("dsk", C.c_int32), ("fp_ds", C.c_int32)]
+                ("max_frames", C.c_int32), ("host_staging", C.c_int32), ("dsk", C.c_int32), ("fp_ds", C.c_int32), ("dd_train", C.c_float), ("dd_weight", C.c_float)]
 
 
 class MsgStruct(C.Structure):

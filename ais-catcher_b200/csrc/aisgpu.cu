@@ -56,7 +56,9 @@ const float H_PS_COS[8] = { 9.9518472640441780e-01f, 9.5694033335306883e-01f, 8.
 const float H_PS_SIN[8] = { 9.8017143048367339e-02f, 2.9028468509743588e-01f, 4.7139674887287397e-01f, 6.3439329894649099e-01f,
 							7.7301046896098113e-01f, 8.8192127851457169e-01f, 9.5694034604181499e-01f, 9.9518473068888236e-01f };
 
-constexpr int HC = 512; // room in front of new 48 kHz samples: unconsumed CGF samples (<512) or FM/FIR history (37)
+constexpr int HC = 1024; // room in front of new 48 kHz samples: unconsumed CGF samples (<512), FM/FIR history (37), or the V2 engine's
+                         // block awaiting its lookahead plus a partial block (<1024)
+constexpr int V2_BLK = 512; // V2::BLOCK_SIZE (V2Engine.h:30)
 constexpr int HE = 8;   // room in front of new symbol-stage samples: an incomplete group of 5 (<=4)
 
 int bytes_per_sample(int fmt) { return fmt == AISGPU_FMT_CF32 ? 8 : (fmt == AISGPU_FMT_CS16 ? 4 : 2); }
@@ -98,7 +100,7 @@ struct aisgpu_handle {
 	int rows = 0;
 	int max_n48 = 0;
 	int fe_warps = 4, fe_tile = 0, fe_ctas = 4096;
-	int fe_st = 1, st_S = 0, st_g = 16, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
+	int fe_st = 1, st_S = 0, st_g = 32, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
 	int be_v1 = 0; // AISGPU_BE_V1=1: round-1 back-end kernels (k_cgf_rot + k_cgf_derot_fir, one hypothesis per lane) for A/B runs
 	int dec_rpw = 6, decoder = 3; // rows per warp / which decoder kernel // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
@@ -167,6 +169,8 @@ struct aisgpu_handle {
 	DecState *d_dec = nullptr;
 	uint32_t *d_dec_data = nullptr;
 	PllState *d_pll = nullptr;
+	V2State *d_v2 = nullptr;     // V2 engine: per-row state
+	float2 *d_tap_coh = nullptr;
 	float *d_tap_dec = nullptr, *d_tap_fm = nullptr;
 	int *d_tap_cnt = nullptr;
 	// frames
@@ -326,7 +330,7 @@ int plan_frontend(aisgpu_handle *h) {
 
 // granule of the caller's submit length: every CIC stage needs an even block (DSP.cpp:94,135)
 int outer_granule(const aisgpu_handle *h) {
-	if (h->fp_ds) return 2048; // 32 lane sub-segments of at least one super-step (64 samples) of the streaming kernel
+	if (h->fp_ds) return 16384; // 32 lane sub-segments of 512 samples: the shortest the streaming kernel takes (sub-segment >= warm-up history, 384)
 	return h->pre >= 2 ? std::max(64, 1 << (h->kA + 2)) : (1 << (h->k + h->kA + 2));
 }
 
@@ -390,7 +394,9 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 		if (S <= 0) {
 			S = 2048; // about 10 x the warm-up history P (192 samples at K = 3, doubling per stage)
 			for (int i = 3; i < h->k; i++) S *= 2;
-			while (S >= 2 * SS && (S / 2 >= 4 * h->P || h->fp_ds) && N % (32 * S) != 0) S /= 2; // longer sub-segments = smaller warm-up share
+			// longer sub-segments = smaller warm-up share; a lane's warm-up must not reach beyond its left neighbour's segment start
+			// (only the stream's first lane reads the previous submit's tail), so S >= P always
+			while (S >= 2 * SS && S / 2 >= (h->fp_ds ? 1 : 4) * h->P && N % (32 * S) != 0) S /= 2;
 		}
 		if (S >= SS && N % (32 * S) == 0) {
 			p.in = dev_in;
@@ -404,7 +410,7 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 		}
 	}
 	if (h->fp_ds) { // the integer CIC stages only exist in the streaming kernel
-		h->err = "FP_DS on: n_samples must be a multiple of 2048 and the batch 16-byte aligned";
+		h->err = "FP_DS on: n_samples must be a multiple of 16384 and the batch 16-byte aligned";
 		return AISGPU_EINVAL;
 	}
 	const size_t smem = (size_t)p.smem_f2 * sizeof(float2);
@@ -611,7 +617,28 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 	h->last_nE = 0;
 	h->last_nsym = 0;
 	// ---- back end (stage-pipelined over consecutive submits, see aisgpu_handle::be_streams) ----
-	if (h->cfg.model == AISGPU_MODEL_DEFAULT) {
+	if (h->cfg.model == AISGPU_MODEL_V2) {
+		// Engine::Receive (V2Engine.cpp:379-395): a block is decoded once the NEXT block is complete (it is the estimator's
+		// lookahead), so one whole block plus the partial one wait in front of the new samples
+		const int cnt = h->c_hist;
+		const int total = cnt + n48;
+		const int nproc = std::max(0, total / V2_BLK - 1);
+		const int c_begin = HC - cnt;
+		const int newcnt = total - nproc * V2_BLK;
+		if (int rc = carry2(h, Ccur, Cnext, h->c_stride, c_begin + nproc * V2_BLK, HC - newcnt, newcnt)) return rc;
+		h->c_hist = newcnt;
+		if (nproc > 0) {
+			CU(launch_v2_engine(Ccur, h->c_stride, c_begin, nproc, h->rows, h->d_v2, h->d_dec, h->d_dec_data, h->d_ring, h->d_ring_head,
+								h->drained + (unsigned long long)h->ring_cap, h->ring_cap, (int)h->msg_chunk, (int)h->chunk, (h->cfg.tag_mode & 1) ? 1 : 0, h->d_omega,
+								h->cfg.dd_train, h->cfg.dd_weight, h->cfg.enable_taps ? h->d_tap_cgf : nullptr, h->cfg.enable_taps ? h->d_tap_coh : nullptr,
+								h->cfg.enable_taps ? h->d_tap_fm : nullptr, h->r_stride, h->bs));
+			h->last_launches++;
+		}
+		h->last_nE = nproc * V2_BLK;
+		CU(cudaEventRecord(h->ev_be_done[cb], h->bs));
+		h->be_recorded[cb] = true;
+	}
+	else if (h->cfg.model == AISGPU_MODEL_DEFAULT) {
 		const int cnt = h->c_hist; // unconsumed samples in front of HC
 		const int total = cnt + n48;
 		const int nblk = total / CGF_N;
@@ -1068,13 +1095,15 @@ void aisgpu_default_config(aisgpu_config *cfg) {
 	cfg->host_staging = 1;
 	cfg->dsk = 0;
 	cfg->fp_ds = 0;
+	cfg->dd_train = 0.75f;
+	cfg->dd_weight = 0.86f;
 }
 
 const char *aisgpu_last_error(aisgpu_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 static int create_impl(aisgpu_handle *h) {
 	const aisgpu_config &c = h->cfg;
-	if (c.model != AISGPU_MODEL_DEFAULT && c.model != AISGPU_MODEL_STANDARD && c.model != AISGPU_MODEL_BASE) {
+	if (c.model != AISGPU_MODEL_DEFAULT && c.model != AISGPU_MODEL_STANDARD && c.model != AISGPU_MODEL_BASE && c.model != AISGPU_MODEL_V2) {
 		h->err = "unknown model kind";
 		return AISGPU_EINVAL;
 	}
@@ -1124,7 +1153,7 @@ static int create_impl(aisgpu_handle *h) {
 	{
 		const char *e = getenv("AISGPU_BE_PIPE");
 		// measured: overlapping the stages of consecutive submits pays for the FM chain (+6 %), not for the coherent one
-		const bool pipe = (e ? atoi(e) != 0 : c.model == AISGPU_MODEL_STANDARD) && !c.enable_taps && c.model != AISGPU_MODEL_BASE;
+		const bool pipe = (e ? atoi(e) != 0 : c.model == AISGPU_MODEL_STANDARD) && !c.enable_taps && c.model != AISGPU_MODEL_BASE && c.model != AISGPU_MODEL_V2;
 		if (pipe) CU(cudaStreamCreateWithPriority(&h->be_streams[1], cudaStreamNonBlocking, prio_hi));
 	}
 	h->bs = h->stream;
@@ -1216,9 +1245,34 @@ static int create_impl(aisgpu_handle *h) {
 	const int nEmax = HC + h->max_n48;
 	h->e_stride = (HE + nEmax + 8 + 1) & ~1LL;
 	h->r_stride = nEmax;
-	if (int rc = dalloc(h, &h->d_dec, (size_t)h->rows * 5)) return rc;
-	if (int rc = dalloc(h, &h->d_dec_data, (size_t)h->rows * 5 * DEC_WORDS)) return rc;
-	if (c.model == AISGPU_MODEL_DEFAULT) {
+	const int ndec = c.model == AISGPU_MODEL_V2 ? 6 : 5; // decoders per row
+	if (int rc = dalloc(h, &h->d_dec, (size_t)h->rows * ndec)) return rc;
+	if (int rc = dalloc(h, &h->d_dec_data, (size_t)h->rows * ndec * DEC_WORDS)) return rc;
+	if (c.model == AISGPU_MODEL_V2) {
+		h->c_hist = V2_BLK; // Engine::raw starts as a block of zeros that is decoded when the first real block has arrived (V2Engine.cpp:274-277, 379-395)
+		if (int rc = dalloc(h, &h->d_v2, (size_t)h->rows)) return rc;
+		if (int rc = dalloc(h, &h->d_omega, CGF_N)) return rc;
+		{
+			std::vector<V2State> init(h->rows);
+			memset(init.data(), 0, init.size() * sizeof(V2State));
+			for (auto &v : init) {
+				v.fo_rot = make_float2(1.0f, 0.0f);
+				v.fm_prev = make_float2(1.0f, 0.0f);
+			}
+			std::vector<float2> om(CGF_N);
+			for (int s = 0; s < CGF_N; s++) om[s] = polar1((float)(-2.0 * PI_F) * (float)s / (float)CGF_N);
+			CU(cudaMemcpyAsync(h->d_v2, init.data(), init.size() * sizeof(V2State), cudaMemcpyHostToDevice, h->stream));
+			CU(cudaMemcpyAsync(h->d_omega, om.data(), om.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+			CU(cudaStreamSynchronize(h->stream));
+			CU(v2_init(H_TAPS_COHERENT, H_TAPS_RECEIVER, om.data()));
+		}
+		if (c.enable_taps) {
+			if (int rc = dalloc(h, &h->d_tap_cgf, (size_t)h->rows * h->r_stride)) return rc;
+			if (int rc = dalloc(h, &h->d_tap_coh, (size_t)h->rows * h->r_stride)) return rc;
+			if (int rc = dalloc(h, &h->d_tap_fm, (size_t)h->rows * h->r_stride)) return rc;
+		}
+	}
+	else if (c.model == AISGPU_MODEL_DEFAULT) {
 		h->c_hist = 0;
 		for (int i = 0; i < 2; i++) {
 			if (int rc = dalloc(h, &h->d_stepidx2[i], (size_t)h->rows * (nEmax / CGF_N + 1))) return rc;
@@ -1468,7 +1522,11 @@ int aisgpu_tap(aisgpu_handle *h, int tap, int stream, int channel, void *dst, si
 		n = h->last_nE;
 		break;
 	case AISGPU_TAP_FIR:
-		if (h->cfg.model == AISGPU_MODEL_DEFAULT) src = h->d_Ec2[0] + (long long)row * h->e_stride + HE;
+		if (h->cfg.model == AISGPU_MODEL_V2) {
+			if (!h->d_tap_coh) { h->err = "taps not enabled"; return AISGPU_EINVAL; }
+			src = h->d_tap_coh + (long long)row * h->r_stride;
+		}
+		else if (h->cfg.model == AISGPU_MODEL_DEFAULT) src = h->d_Ec2[0] + (long long)row * h->e_stride + HE;
 		else { src = h->d_Ef2[0] + (long long)row * h->e_stride + HE; esz = 4; }
 		n = h->last_nE;
 		break;
@@ -1700,7 +1758,7 @@ void aisgpu_destroy(aisgpu_handle *h) {
 	}
 	void *ptrs[] = { h->d_ptail[0], h->d_ptail[1], h->d_ptail2[0], h->d_ptail2[1], h->d_S2, h->d_D0, h->d_S, h->d_us_src, h->d_us_alpha, h->d_in[0], h->d_in[1], h->d_tail[0], h->d_tail[1], h->d_rot[0], h->d_rot[1], h->d_rot[2], h->d_rot_state, h->d_C2[0], h->d_C2[1], h->d_C2[2],
 					 h->d_steptab, h->d_omega, h->d_cgf_rot, h->d_rots2[0], h->d_rots2[1], h->d_stepidx2[0], h->d_stepidx2[1], h->d_ppmtab, h->d_fir_hist[0], h->d_fir_hist[1], h->d_tap_cgf, h->d_Ec2[0],
-					 h->d_Ef2[0], h->d_ps, h->d_ps_mem, h->d_dbits2[0], h->d_dbits2[1], h->d_lvl2[0], h->d_lvl2[1], h->d_dbg, h->d_dec, h->d_dec_data, h->d_pll, h->d_tap_dec, h->d_tap_fm, h->d_tap_cnt, h->d_ring,
+					 h->d_Ef2[0], h->d_ps, h->d_ps_mem, h->d_dbits2[0], h->d_dbits2[1], h->d_lvl2[0], h->d_lvl2[1], h->d_dbg, h->d_dec, h->d_dec_data, h->d_pll, h->d_tap_dec, h->d_tap_fm, h->d_tap_cnt, h->d_v2, h->d_tap_coh, h->d_ring,
 					 h->d_ring_head, h->d_counts };
 	for (void *p : ptrs)
 		if (p) cudaFree(p);

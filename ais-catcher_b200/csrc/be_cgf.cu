@@ -1,6 +1,7 @@
 // be_cgf.cu -- ModelDefault back end, first half: SquareFreqOffsetCorrection + FilterComplex (DSP.cpp:215-246, 417-489).
 #include "exact.cuh"
 #include "params.h"
+#include "fft512.cuh"
 
 namespace aisgpu {
 
@@ -17,73 +18,6 @@ namespace aisgpu {
 // |F| in fftshift order goes to shared memory; then (one lane per block) the sequential float cumsum, then the parallel
 // first-maximum searches.  Result: an index into the host-built phasor-step table.
 // ---------------------------------------------------------------------------------------------
-__constant__ float2 c_cgf_omega[CGF_N / 2]; // Omega[s] = polar(1, -2 pi s / N), host-computed (FFT.h:81-83)
-constexpr int CGF_TB = CGF_N + CGF_N / 16;  // transpose tile: one pad slot per 16 values
-
-__device__ __forceinline__ constexpr int cgf_rev4(int m) { return ((m & 1) << 3) | ((m & 2) << 1) | ((m & 4) >> 1) | ((m & 8) >> 3); }
-
-// FFT of x^2 for one block; leaves |F[(i + 256) & 511]| in mg[i]
-__device__ __forceinline__ void cgf_fft_block(const float2 *__restrict__ src, float2 *__restrict__ tb, float *__restrict__ mg, int lane, const float2 (&tw)[15]) {
-	float2 x[16];
-	const int rl = (int)(__brev((unsigned)lane) >> 27);
-#pragma unroll
-	for (int m = 0; m < 16; m++) { // position p = 16 lane + e holds sample rev9(p) = rev5(lane) + 32 rev4(e)
-		const float2 v = src[rl + 32 * m];
-		x[cgf_rev4(m)] = cmul(v, v);
-	}
-#pragma unroll
-	for (int s = 0; s < 4; s++) {
-		const int m2 = 1 << s;
-#pragma unroll
-		for (int q = 0; q < 8; q++) {
-			const int j = q & (m2 - 1);
-			const int lo = ((q >> s) << (s + 1)) + j, hi = lo + m2;
-			const float2 t = cmul(c_cgf_omega[j << (8 - s)], x[hi]);
-			const float2 a = x[lo];
-			x[hi] = csub(a, t);
-			x[lo] = cadd(a, t);
-		}
-	}
-	{ // stage 4: positions p and p + 16 live in lanes l and l ^ 1, j = p & 15 = register index
-		const bool odd = lane & 1;
-#pragma unroll
-		for (int e = 0; e < 16; e++) {
-			const float2 mine = x[e];
-			float2 other;
-			other.x = __shfl_xor_sync(0xffffffffu, mine.x, 1);
-			other.y = __shfl_xor_sync(0xffffffffu, mine.y, 1);
-			const float2 hi = odd ? mine : other, lo = odd ? other : mine;
-			float2 t = cmul(c_cgf_omega[e << 4], hi);
-			if (odd) { t.x = -t.x; t.y = -t.y; } // x[hi] = a - t == a + (-t), exactly
-			x[e] = cadd(lo, t);
-		}
-	}
-	__syncwarp();
-#pragma unroll
-	for (int e = 0; e < 16; e++) tb[17 * lane + e] = x[e]; // slot p + (p >> 4), p = 16 lane + e
-	__syncwarp();
-#pragma unroll
-	for (int r = 0; r < 16; r++) {
-		const int p = lane + 32 * r;
-		x[r] = tb[p + (p >> 4)];
-	}
-#pragma unroll
-	for (int s = 5; s < 9; s++) { // positions p = lane + 32 r: bit s of p is bit s - 5 of r; j = p & (2^s - 1) = lane + 32 (r & (2^(s-5) - 1))
-		const int sb = s - 5, m2r = 1 << sb;
-#pragma unroll
-		for (int q = 0; q < 8; q++) {
-			const int jr = q & (m2r - 1);
-			const int lo = ((q >> sb) << (sb + 1)) + jr, hi = lo + m2r;
-			const float2 t = cmul(tw[m2r - 1 + jr], x[hi]);
-			const float2 a = x[lo];
-			x[hi] = csub(a, t);
-			x[lo] = cadd(a, t);
-		}
-	}
-#pragma unroll
-	for (int r = 0; r < 16; r++) mg[(lane + 32 * r) ^ 256] = habs(x[r]);
-}
-
 __global__ void __launch_bounds__(CGF_THREADS) k_cgf_estimate(const float2 *__restrict__ Cbuf, long long c_stride, int c_begin, int nblk,
 																 int total_blocks, const float2 *__restrict__ omega_g, int wide,
 																 int *__restrict__ stepidx) {
@@ -93,11 +27,8 @@ __global__ void __launch_bounds__(CGF_THREADS) k_cgf_estimate(const float2 *__re
 	float *cum = reinterpret_cast<float *>(scratch);
 
 	const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-	float2 tw[15]; // Omega[(lane + 32 jr) << (3 - sb)] for stage 5 + sb, jr < 2^sb
-#pragma unroll
-	for (int sb = 0; sb < 4; sb++)
-#pragma unroll
-		for (int jr = 0; jr < (1 << sb); jr++) tw[(1 << sb) - 1 + jr] = omega_g[(lane + 32 * jr) << (3 - sb)];
+	float2 tw[15];
+	fft512_lane_twiddles(omega_g, lane, tw);
 
 	const int blk0 = blockIdx.x * CGF_BLK_PER_CTA;
 	float2 *tb = reinterpret_cast<float2 *>(scratch) + w * CGF_TB;
@@ -107,7 +38,7 @@ __global__ void __launch_bounds__(CGF_THREADS) k_cgf_estimate(const float2 *__re
 		if (id < total_blocks) {
 			const int row = id / nblk, b = id - row * nblk;
 			const float2 *src = Cbuf + (long long)row * c_stride + c_begin + (long long)b * CGF_N;
-			cgf_fft_block(src, tb, mag + lb * CGF_ROWP, lane, tw);
+			cgf_fft_block<true>(src, tb, mag + lb * CGF_ROWP, lane, tw);
 		}
 		__syncwarp();
 	}
@@ -391,7 +322,7 @@ constexpr int CGF_EST_SMEM = CGF_BLK_PER_CTA * CGF_ROWP * 4 + (8 * CGF_TB * 8 > 
 cudaError_t cgf_init(const float *taps17, const float2 *omega256) {
 	cudaError_t e = cudaMemcpyToSymbol(c_taps_coherent, taps17, FIRC_T * sizeof(float));
 	if (e != cudaSuccess) return e;
-	e = cudaMemcpyToSymbol(c_cgf_omega, omega256, (CGF_N / 2) * sizeof(float2));
+	e = fft512_set_omega(omega256);
 	if (e != cudaSuccess) return e;
 	return cudaFuncSetAttribute(k_cgf_estimate, cudaFuncAttributeMaxDynamicSharedMemorySize, CGF_EST_SMEM);
 }

@@ -1,6 +1,7 @@
 // be_sym.cu -- symbol timing + bit decoders: PhaseSearch[EMA], AIS::Decoder x 5 with the Reset cross-connect, SimplePLL.
 #include "exact.cuh"
 #include "params.h"
+#include "dec_core.cuh"
 
 namespace aisgpu {
 
@@ -12,154 +13,6 @@ namespace aisgpu {
 // One thread per (row, sampling phase); the five phases of a row sit in five adjacent lanes of one warp so the
 // decoder's Reset broadcast (AIS.cpp:47-49, Model.cpp:566-573) is a warp vote.  Frame bits live in shared memory.
 // ---------------------------------------------------------------------------------------------
-struct DecCtx {
-	uint32_t *frame; // shared memory, word w of this thread at frame[w * K3_THREADS]
-	int mode_level;
-};
-
-__device__ __forceinline__ uint32_t frame_word(const DecCtx &c, int w) { return c.frame[w * K3_THREADS]; }
-__device__ __forceinline__ int dec_type(const DecCtx &c) { return (frame_word(c, 0) & 0xff) >> 2; }
-__device__ __forceinline__ unsigned dec_mmsi(const DecCtx &c) {
-	const uint32_t w0 = frame_word(c, 0), w1 = frame_word(c, 1);
-	const unsigned d1 = (w0 >> 8) & 0xff, d2 = (w0 >> 16) & 0xff, d3 = (w0 >> 24) & 0xff, d4 = w1 & 0xff;
-	return (d1 << 22) | (d2 << 14) | (d3 << 6) | (d4 >> 2);
-}
-__device__ __forceinline__ bool dec_cannot_be_valid(const DecCtx &c, int len) { // AIS.cpp:111-142
-	if (len < 30) return false;
-	const int t = dec_type(c);
-	switch (len) {
-	case 30: return t > 28 || t == 0;
-	case 62: return dec_mmsi(c) > 999999999u;
-	case 96: return t == 10;
-	case 168: return t == 16;
-	case 184: return t == 15 || t == 20 || t == 23;
-	case 192: return t == 1 || t == 2 || t == 3 || t == 4 || t == 7 || t == 9 || t == 11 || t == 18 || t == 22 || t == 24 || t == 25 || t == 27 || t == 28;
-	case 336: return t == 19;
-	case 385: return t == 21;
-	case 448: return t == 5;
-	}
-	return false;
-}
-// Same CRC (AIS.cpp:55-64: reflected 0x8408, init 0xFFFF, good residue 0xF0B8), eight bits per step: the frame words
-// hold the bits LSB first, which is the order the reflected CRC consumes them.
-__device__ __forceinline__ bool dec_crc16_bytes(const DecCtx &c, int len) {
-	unsigned crc = 0xFFFF;
-	const int nbytes = len >> 3;
-	uint32_t w = 0;
-	for (int k = 0; k < nbytes; k++) {
-		if ((k & 3) == 0) w = frame_word(c, k >> 2);
-		unsigned dta = ((w >> ((k & 3) * 8)) ^ crc) & 0xffu;
-		dta ^= (dta << 4) & 0xffu;
-		crc = (((dta << 8) | (crc >> 8)) ^ (dta >> 4) ^ (dta << 3)) & 0xffffu;
-	}
-	for (int i = nbytes * 8; i < len; i++) {
-		const unsigned bit = (frame_word(c, i >> 5) >> (i & 31)) & 1u;
-		crc = ((bit ^ crc) & 1u) ? ((crc >> 1) ^ 0x8408u) : (crc >> 1);
-	}
-	return crc == 0xF0B8u;
-}
-__device__ __forceinline__ bool dec_crc16(const DecCtx &c, int len) { // AIS.cpp:55-64
-	unsigned crc = 0xFFFF;
-	for (int i = 0; i < len; i++) {
-		const unsigned bit = (frame_word(c, i >> 5) >> (i & 31)) & 1u;
-		crc = ((bit ^ crc) & 1u) ? ((crc >> 1) ^ 0x8408u) : (crc >> 1);
-	}
-	return crc == 0xF0B8u;
-}
-
-// One Decoder::Run (AIS.h:91-181).  Returns true when a frame with a good CRC just completed (processData true);
-// in that case fr_len = payload bits + 16 and the caller emits and performs the FOUNDMESSAGE/Reset protocol.
-__device__ __forceinline__ bool dec_step(DecState &d, const DecCtx &c, float sample, float sample_lvl, long long sample_idx, int &fr_len,
-										 float &fr_level, int &lastBit_before) {
-	const int dd = sample > 0.0f;
-	const int Bit = !(dd ^ d.prev);
-	d.prev = dd;
-	lastBit_before = d.lastBit;
-	bool found = false;
-	switch (d.state) {
-	case ST_TRAINING:
-		if (Bit != d.lastBit) d.position++;
-		else {
-			if (d.position > 4) {
-				d.start_idx = sample_idx;
-				d.state = ST_STARTFLAG;
-				d.position = Bit ? 3 : 1;
-				d.one_seq = 0;
-			}
-			else { d.state = ST_TRAINING; d.position = 0; d.one_seq = 0; }
-		}
-		break;
-	case ST_STARTFLAG:
-		if (d.position == 7) {
-			if (Bit == 0) {
-				d.state = ST_DATAFCS; d.position = 0; d.one_seq = 0;
-				d.level = 0.0f;
-				for (int w = 0; w < DEC_WORDS; w++) c.frame[w * K3_THREADS] = 0u; // msg.clear()
-			}
-			else { d.state = ST_TRAINING; d.position = 0; d.one_seq = 0; }
-		}
-		else {
-			if (Bit == 1) d.position++;
-			else { d.state = ST_TRAINING; d.position = 0; d.one_seq = 0; }
-		}
-		break;
-	case ST_DATAFCS: {
-		const int pos = d.position++;
-		if (pos < MAX_FRAME_BITS) { // Message::setBit (Message.h:264-273)
-			uint32_t *wp = &c.frame[(pos >> 5) * K3_THREADS];
-			const uint32_t m = 1u << (pos & 31);
-			*wp = Bit ? (*wp | m) : (*wp & ~m);
-		}
-		if (c.mode_level) d.level = __fadd_rn(d.level, sample_lvl);
-		if (Bit == 1) {
-			if (d.one_seq == 5) {
-				fr_level = c.mode_level ? __fdiv_rn(d.level, (float)d.position) : 0.0f;
-				const int len = d.position - 7;
-				if (len >= 16 && dec_crc16(c, len)) {
-					found = true;
-					fr_len = len;
-				}
-				d.state = ST_TRAINING; d.position = 0; d.one_seq = 0;
-			}
-			else d.one_seq++;
-		}
-		else {
-			if (d.one_seq == 5) d.position--;
-			d.one_seq = 0;
-		}
-		if (d.position == MAX_FRAME_BITS || dec_cannot_be_valid(c, d.position)) { d.state = ST_TRAINING; d.position = 0; d.one_seq = 0; }
-		break;
-	}
-	default: break;
-	}
-	d.lastBit = Bit;
-	return found;
-}
-
-// The frame ring is circular: `head` only grows (one ticket per frame); a frame whose ticket is `ring_cap` or more ahead of
-// what the host had drained when the kernel was launched (ticket >= limit) is dropped -- the host sees the gap in the
-// ticket range and reports AISGPU_EOVERFLOW.
-__device__ __forceinline__ FrameRec *ring_claim(FrameRec *__restrict__ ring, unsigned long long *__restrict__ head, unsigned long long limit, int ring_cap) {
-	const unsigned long long t = atomicAdd(head, 1ull);
-	return t < limit ? &ring[t % (unsigned long long)ring_cap] : nullptr;
-}
-__device__ __forceinline__ void emit_frame(FrameRec *__restrict__ ring, unsigned long long *__restrict__ head, unsigned long long limit, int ring_cap, int chunk,
-										   int blk, const DecCtx &c, int row, int phase, int len, float level, float ppm, long long start_idx, long long end_idx) {
-	FrameRec *rp = ring_claim(ring, head, limit, ring_cap);
-	if (!rp) return;
-	FrameRec &r = *rp;
-	r.row = row;
-	r.phase = phase;
-	r.nbits = len - 16;
-	r.level = level;
-	r.ppm = ppm;
-	r.chunk = chunk;
-	r.blk = blk;
-	r.start_idx = start_idx;
-	r.end_idx = end_idx;
-	for (int w = 0; w < DEC_WORDS; w++) r.data[w] = frame_word(c, w);
-}
-
 __constant__ float c_ps_cos[8];
 __constant__ float c_ps_sin[8];
 
@@ -343,16 +196,14 @@ __global__ void __launch_bounds__(PS2_THREADS) k_phase_search_ema4(const K3Param
 		sj[k] = h < 8 ? c_ps_sin[j] : -c_ps_sin[j]; // a - b == a + (-b) and im * (-s) == -(im * s), exactly
 	}
 	float ma[4] = { 0.f, 0.f, 0.f, 0.f };
-	uint32_t hist[4] = { 0u, 0u, 0u, 0u }; // bit d = sign decision d symbols ago
+	uint32_t hist = 0u; // nibble d (bits 4d .. 4d+3) = the sign decisions of the lane's four hypotheses d symbols ago
 	int max_idx = 0, rot = 0;
 	if (active) {
 		const PsState &st = p.ps[inst];
 #pragma unroll
-		for (int k = 0; k < 4; k++) {
-			ma[k] = st.ma[4 * q + k];
+		for (int k = 0; k < 4; k++) ma[k] = st.ma[4 * q + k];
 #pragma unroll
-			for (int dd = 0; dd < 5; dd++) hist[k] |= ((st.plane[dd] >> (4 * q + k)) & 1u) << dd;
-		}
+		for (int dd = 0; dd < 5; dd++) hist |= ((st.plane[dd] >> (4 * q)) & 0xfu) << (4 * dd);
 		max_idx = st.max_idx;
 		rot = st.rot;
 	}
@@ -377,20 +228,25 @@ __global__ void __launch_bounds__(PS2_THREADS) k_phase_search_ema4(const K3Param
 		const float2 *my = &tile[t & 1][rin][phase];
 		const int s_end = min(K3_TS, p.nsym - t * K3_TS);
 		uint32_t word = 0;
+		// two symbols per trip: the second one's arithmetic (independent of the first's decision chain) fills the issue slots
+		// the first one leaves while its shuffles are in flight
+#pragma unroll 2
 		for (int sl = 0; sl < s_end; sl++) {
 			const float2 x = my[sl * 5];
 			// (1j)^rot pre-rotation (Demod.cpp:44-65), branch free: swap on odd rot, negate on rot >= 2 (sign flips are exact)
 			float re = (rot & 1) ? -x.y : x.x, im = (rot & 1) ? x.x : x.y;
 			if (rot & 2) { re = -re; im = -im; }
 			rot = (rot + 1) & 3;
-			uint32_t xm = 0; // bit k: demodulated bit hypothesis 4q + k would deliver (nDelay = 3, Model.h:219)
+			uint32_t dnow = 0;
 #pragma unroll
 			for (int k = 0; k < 4; k++) {
 				const float tt = __fadd_rn(__fmul_rn(re, cj[k]), __fmul_rn(im, sj[k]));
-				hist[k] = (hist[k] << 1) | (tt > 0.0f ? 1u : 0u);
+				dnow |= (tt > 0.0f ? 1u : 0u) << k;
 				ma[k] = __fadd_rn(__fmul_rn(weight, ma[k]), __fmul_rn(omw, fabsf(tt))); // Demod.cpp:67-78
-				xm |= (((hist[k] >> 3) ^ (hist[k] >> 4)) & 1u) << k;
 			}
+			hist = (hist << 4) | dnow;
+			// bit k: demodulated bit hypothesis 4q + k would deliver = its decisions 3 and 4 symbols ago, XORed (nDelay = 3, Model.h:219)
+			const uint32_t xm = ((hist >> 12) ^ (hist >> 16)) & 0xfu;
 			const float v4 = __shfl_sync(0xffffffffu, ma[0], nxt), v5 = __shfl_sync(0xffffffffu, ma[1], nxt);
 			const float v[6] = { ma[0], ma[1], ma[2], ma[3], v4, v5 };
 			uint32_t tab = 0;
@@ -435,12 +291,7 @@ __global__ void __launch_bounds__(PS2_THREADS) k_phase_search_ema4(const K3Param
 	// state back: the bit planes are OR-combined over the four lanes of the instance
 	uint32_t planes[5];
 #pragma unroll
-	for (int dd = 0; dd < 5; dd++) {
-		uint32_t pl = 0;
-#pragma unroll
-		for (int k = 0; k < 4; k++) pl |= ((hist[k] >> dd) & 1u) << (4 * q + k);
-		planes[dd] = or4(pl);
-	}
+	for (int dd = 0; dd < 5; dd++) planes[dd] = or4(((hist >> (4 * dd)) & 0xfu) << (4 * q));
 	if (active) {
 		PsState &st = p.ps[inst];
 #pragma unroll
@@ -498,6 +349,7 @@ __global__ void __launch_bounds__(DK_THREADS) k_decode(const K3Params p) {
 	DecCtx ctx;
 	ctx.frame = frames_all[wib] + lane;
 	ctx.mode_level = p.mode_level;
+	ctx.stride = K3_THREADS;
 	DecState d;
 	const int sidx = row * 5 + (active ? phase : 0);
 	const long long nthr_total = (long long)p.rows * 5;
@@ -885,6 +737,7 @@ __global__ void __launch_bounds__(DK3_WARPS * 32) k_decode3(const K3Params p) {
 	DecCtx ctx;
 	ctx.frame = frames_all[wib] + lane;
 	ctx.mode_level = p.mode_level;
+	ctx.stride = K3_THREADS;
 	DecState d;
 	const int sidx = active ? row * 5 + phase : 0;
 	const long long nthr_total = (long long)p.rows * 5;
@@ -1054,6 +907,7 @@ __global__ void __launch_bounds__(K3_THREADS) k_base(const float *__restrict__ E
 	DecCtx ctx;
 	ctx.frame = frames + tid;
 	ctx.mode_level = 1;
+	ctx.stride = K3_THREADS;
 	DecState d = dec[row * 5];
 	const long long nthr_total = (long long)rows * 5;
 	for (int w = 0; w < DEC_WORDS; w++) frames[w * K3_THREADS + tid] = dec_data[(long long)w * nthr_total + row * 5];

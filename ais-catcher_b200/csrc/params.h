@@ -144,6 +144,21 @@ constexpr int DSK_T = 26;
 constexpr int DSK_THREADS = 256;
 
 
+// V2::Engine (Decoder/V2/V2Engine.h:95-155) per (stream, channel): everything the engine carries from block to block
+struct V2State {
+	float2 fo_rot;        // FreqOffset::rot
+	float2 slot_ema;      // slot-phase EMA
+	float2 fm_prev;       // FMDemod::prev
+	float last_f, ppm, pll_phase;
+	int slot_phase, di, pll_last;
+	long long sample_idx;
+	float2 f17_hist[16];  // FilterFL17::buffer
+	float f37_hist[36];   // FilterFL37::buffer
+	unsigned trk_rot[5];  // PhaseTracker x 5
+	float2 trk_s[5];
+	int trk_prev[5];
+};
+
 // ---- launch entry points (one translation unit per kernel family; every function returns cudaGetLastError()) ----
 // fe_misc.cu
 cudaError_t launch_rot_table(float2 *tab, const float2 *prev_tail, const float2 *state_in, float2 *state_out, float2 mult, int P96, int n96, cudaStream_t s);
@@ -171,6 +186,11 @@ cudaError_t launch_cgf_derot_fir(const float2 *Cbuf, long long c_stride, int c_b
                                  float2 *hist_new, float2 *Ebuf, long long e_stride, int e_off, float2 *tap_cgf, long long tap_stride, int rows, cudaStream_t s);
 cudaError_t launch_cgf_fused(const float2 *Cbuf, long long c_stride, int c_begin, const int *stepidx, const float2 *steptab, float2 *rot_state, int nblk, int rows,
                              const float2 *hist_old, float2 *hist_new, float2 *Ebuf, long long e_stride, int e_off, float2 *tap_cgf, long long tap_stride, cudaStream_t s);
+// be_v2.cu
+cudaError_t v2_init(const float *taps17, const float *taps37, const float2 *omega256);
+cudaError_t launch_v2_engine(const float2 *Cbuf, long long c_stride, int c_begin, int nproc, int rows, V2State *st, DecState *dec, uint32_t *dec_data, FrameRec *ring,
+                             unsigned long long *ring_head, unsigned long long ring_limit, int ring_cap, int chunk, int blk, int mode_level, const float2 *omega_g,
+                             float w_train, float w_track, float2 *tap_fc, float2 *tap_coh, float *tap_fmf, long long tap_stride, cudaStream_t s);
 // be_fm.cu
 cudaError_t fm_init(const float *taps37);
 cudaError_t launch_fm_fir5(const Fm5Params &p, int rows, cudaStream_t s);

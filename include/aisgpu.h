@@ -38,6 +38,8 @@ extern "C" {
 #define AISGPU_MODEL_STANDARD 0 /* FM -> FIR37 -> 5-phase deinterleave -> 5 decoders (Model.cpp:484-518) */
 #define AISGPU_MODEL_BASE 1     /* FM -> FIR37 -> SimplePLL -> 1 decoder            (Model.cpp:419-438) */
 #define AISGPU_MODEL_DEFAULT 2  /* CGF -> FIR17 -> 5 x PhaseSearch[EMA] -> 5 decoders (Model.cpp:520-577) */
+#define AISGPU_MODEL_V2 11      /* V2::Engine per channel: slot-predicted CGF, 5 PhaseTrackers + FM/BitPLL, 6 decoders (Model.cpp:440-460,
+                                   DSP/Decoder/V2/V2Engine.cpp) */
 
 /* input sample formats: subset of enum class Format (Source/Library/Common.h:89-104) */
 #define AISGPU_FMT_CF32 0
@@ -80,6 +82,7 @@ typedef struct aisgpu_config {
 	                               0: at the first host submit (engines that are only fed with aisgpu_submit_device) */
 	int32_t dsk;                /* -go DSK   (Model.cpp:377-379): adds the 576K / 1152K / 2304K buckets (CIC stages -> /3 filter), default 0 */
 	int32_t fp_ds;              /* -go FP_DS (Model.cpp:362-365): integer CIC stages for CU8 input at exactly 1536000 (DSP.cpp:499-665), default 0 */
+	float dd_train, dd_weight;  /* -go DD_TRAIN / DD_WEIGHT of the V2 engine (Model.cpp:462-474; Model.h:272), defaults 0.75 / 0.86 */
 } aisgpu_config;
 
 /* One decoded frame == one AIS::Message the reference would Send (Source/Marine/AIS.cpp:66-96). */

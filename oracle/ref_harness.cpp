@@ -80,7 +80,7 @@ struct MsgSink : public StreamIn<AIS::Message> {
 	}
 };
 
-enum { MODEL_STANDARD = 0, MODEL_BASE = 1, MODEL_DEFAULT = 2 };
+enum { MODEL_STANDARD = 0, MODEL_BASE = 1, MODEL_DEFAULT = 2, MODEL_V2 = 11 };
 enum { FLAG_PS_EMA = 1, FLAG_AFC_WIDE = 2, FLAG_DROOP = 4, FLAG_TAPS = 8, FLAG_FP_DS = 16, FLAG_DSK = 32 };
 static const int NTAPS_C = 9;  // 0: ROT in, 1/2: ROT up/down, 3/4: C_a/C_b, 5/6: CGF or (unused), 7/8: FC
 static const int NTAPS_F = 14; // 0..4 / 5..9: per-phase decoder inputs ch A / B; 10/11: FM out; 12/13: FR out
@@ -90,6 +90,8 @@ struct Handle {
 	AIS::ModelDefault *md = nullptr;
 	AIS::ModelStandard *ms = nullptr;
 	AIS::ModelBase *mb = nullptr;
+	AIS::ModelEngineV2 *mv = nullptr;
+	bool taps = false;
 	AIS::ModelFrontend *fe = nullptr;
 	MsgSink sink;
 	RecC tc[NTAPS_C];
@@ -100,6 +102,7 @@ struct Handle {
 		delete md;
 		delete ms;
 		delete mb;
+		delete mv;
 	}
 };
 
@@ -139,6 +142,10 @@ void *aisref_create(int model, int sample_rate, int format, unsigned flags, int 
 			h->mb = new AIS::ModelBase();
 			h->fe = h->mb;
 		}
+		else if (model == MODEL_V2) { // model 11 "v2_base" (Source/DSP/Model.cpp:440-460)
+			h->mv = new AIS::ModelEngineV2();
+			h->fe = h->mv;
+		}
 		else {
 			delete h;
 			return nullptr;
@@ -152,6 +159,7 @@ void *aisref_create(int model, int sample_rate, int format, unsigned flags, int 
 		h->fe->buildModel('A', 'B', sample_rate, false, &h->dev);
 		h->fe->Output() >> h->sink;
 
+		h->taps = (flags & FLAG_TAPS) != 0;
 		if (flags & FLAG_TAPS) {
 			AIS::ModelFrontend *fe = h->fe;
 			// whichever Connection feeds ROT (depends on the rate, Source/DSP/Model.cpp:157-338)
@@ -213,8 +221,24 @@ void *aisref_create(int model, int sample_rate, int format, unsigned flags, int 
 int aisref_push(void *hv, const void *data, long nbytes) {
 	Handle *h = (Handle *)hv;
 	AIS::Message::ID.store(h->seq);
+	long long before[2] = {0, 0};
+	if (h->mv && h->taps) {
+		before[0] = h->mv->V2_a.sample_idx;
+		before[1] = h->mv->V2_b.sample_idx;
+	}
 	h->dev.push((void *)data, (int)nbytes, h->fmt);
 	h->seq = AIS::Message::ID.load();
+	if (h->mv && h->taps) { // the arrays of the LAST block each engine decoded in this push (taps 5/6 CGF out, 7/8 FIR17 out, 12/13 FIR37 out)
+		V2::Engine *e[2] = {&h->mv->V2_a, &h->mv->V2_b};
+		for (int c = 0; c < 2; c++) {
+			if (e[c]->sample_idx == before[c]) continue;
+			const float *fc = (const float *)e[c]->freq_corrected, *co = (const float *)e[c]->coh_filtered;
+			h->tc[5 + c].v.insert(h->tc[5 + c].v.end(), fc, fc + 2 * V2::BLOCK_SIZE);
+			h->tc[5 + c].ppm.push_back(e[c]->ppm);
+			h->tc[7 + c].v.insert(h->tc[7 + c].v.end(), co, co + 2 * V2::BLOCK_SIZE);
+			h->tf[12 + c].v.insert(h->tf[12 + c].v.end(), e[c]->fm_filtered, e[c]->fm_filtered + V2::BLOCK_SIZE);
+		}
+	}
 	return 0;
 }
 

@@ -228,9 +228,71 @@ def test_fp_ds_integer_frontend(built, model):
 
 
 def test_fp_ds_small_blocks(built):
-    run_case(built, aisgpu.MODEL_DEFAULT, 1536000, 2048, 64, 2, fmt=aisgpu.FMT_CU8, seed0=59, fp_ds=True)
+    # the shortest block the integer front end takes (32 lane sub-segments of 512 samples)
+    run_case(built, aisgpu.MODEL_DEFAULT, 1536000, 16384, 12, 2, fmt=aisgpu.FMT_CU8, seed0=59, fp_ds=True)
 
 
 def test_fp_ds_needs_cu8(built):
     with pytest.raises(aisgpu.AisGpuError, match="needs CU8"):
         aisgpu.Engine(sample_rate=1536000, fmt=aisgpu.FMT_CF32, fp_ds=True)
+
+
+def run_v2_case(fs, N, nchunks, B, check_taps, seed0, fmt=aisgpu.FMT_CF32):
+    """Model 11 "v2_base" (reference DSP/Decoder/V2/V2Engine.cpp, Model.cpp:440-460) against the compiled reference."""
+    if not O.have_ref():
+        pytest.skip("the V2 engine is checked against the compiled reference only")
+    xs = [S.random_stream(fs, N * nchunks, seed0 + s, bursts_per_sec=(6, 12))[0] for s in range(B)]
+    eng = aisgpu.Engine(model=aisgpu.MODEL_V2, sample_rate=fs, fmt=fmt, n_streams=B, max_chunk=N, taps=check_taps)
+    refs = [O.RefModel(model=O.MODEL_V2, sample_rate=fs, fmt=fmt, taps=check_taps) for _ in range(B)]
+    problems = []
+    got = [[] for _ in range(B)]
+    want = [[] for _ in range(B)]
+    for c in range(nchunks):
+        eng.submit(np.stack([x[c * N:(c + 1) * N] for x in xs]), N)
+        for s in range(B):
+            refs[s].push(xs[s][c * N:(c + 1) * N])
+        if check_taps:
+            for s in range(B):
+                for ch in range(2):
+                    for name, g, w in (("V2.CGF", eng.tap(aisgpu.TAP_CGF, s, ch), refs[s].tap_c(O.TAP_CGF_A + ch)),
+                                       ("V2.FIR17", eng.tap(aisgpu.TAP_FIR, s, ch), refs[s].tap_c(O.TAP_FC_A + ch)),
+                                       ("V2.FIR37", eng.tap(aisgpu.TAP_FM, s, ch, dtype=np.float32), refs[s].tap_f(O.TAP_FR_A + ch))):
+                        if not bits_equal(g, w):
+                            problems.append((name, c, s, ch, len(g), len(w)) + first_diff(g, w))
+        for m in eng.poll():
+            got[m.stream].append(m)
+        for s in range(B):
+            want[s] += refs[s].messages()
+    n = 0
+    for s in range(B):
+        g = [(m.key(), m.start_idx, m.end_idx) for m in got[s]]
+        w = [(m.key(), m.start_idx, m.end_idx) for m in want[s]]
+        n += len(w)
+        if g != w:
+            problems.append(("MSG", s, len(g), len(w), [x for x in g if x not in w][:2], [x for x in w if x not in g][:2]))
+        else:
+            for a, b in zip(got[s], want[s]):
+                if np.float32(a.level).view(np.uint32) != np.float32(b.level).view(np.uint32) or \
+                        np.float32(a.ppm).view(np.uint32) != np.float32(b.ppm).view(np.uint32):
+                    problems.append(("TAG", s, a.level, b.level, a.ppm, b.ppm))
+    eng.close()
+    assert not problems, "parity problems (first 12): %r" % (problems[:12],)
+    return n
+
+
+def test_v2_engine_blockwise_taps(built):
+    # one 512-sample block per submit: every block's derotated samples, FIR17 and FIR37 outputs are compared bit for bit
+    n = run_v2_case(1536000, 16384, 40, 2, True, 61)
+    assert n >= 4
+
+
+@pytest.mark.parametrize("fs,N", [(1536000, 65536), (1536000, 36864), (384000, 16384), (6144000, 262144)])
+def test_v2_engine_messages(built, fs, N):
+    # several blocks per submit (and submits that are not whole blocks: 36864 / 32 = 1152 samples at 48 kHz)
+    n = run_v2_case(fs, N, 8, 3, False, 67)
+    assert n >= 6
+
+
+def test_v2_engine_cu8(built):
+    n = run_v2_case(1536000, 65536, 6, 2, False, 71, fmt=aisgpu.FMT_CU8)
+    assert n >= 4

@@ -1,18 +1,13 @@
 #!/bin/bash
-# GPU call 2: full parity suite (new back-end kernels), A/B against the round-1 kernels, bench line, launch list
+# GPU call 3: failing cases verbose, fuzz debug, launch list of the reworked ModelDefault back end, chunk-length sweep
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
-echo "== pytest (new kernels)"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -25
-echo "== pytest subset with round-1 back end"; AISGPU_BE_V1=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "default" 2>&1 | tail -3
-for m in 2; do
-SWEEP_MODEL=$m timeout 600 python tools/fe_sweep.py \
-  4,0,4096,AISGPU_BE_V1=1 \
-  4,0,4096,AISGPU_BE_V1=0 \
-  4,0,4096,AISGPU_BE_V1=0,AISGPU_BE_PIPE=1 \
-  4,0,4096,AISGPU_BE_V1=0,AISGPU_BE_PIPE=1,AISGPU_DEC_RPW=3 \
-  2>&1 | grep -v "^$" | tee -a gpurun_out/sweep2.jsonl
-done
-echo "== bench"; timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench2.json 2> gpurun_out/bench2.err; echo "bench rc=$?"; tail -5 gpurun_out/bench2.err; cat gpurun_out/bench2.json
+echo "== fuzz debug"; timeout 300 python tools/fuzz_debug.py 0 8192 4 2>&1 | tail -40
+timeout 300 python tools/fuzz_debug.py 2 8192 4 2>&1 | tail -25
+echo "== pytest"; timeout 1500 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_scale.py::test_decoder_fuzz_chunks --deselect tests/test_gpu_scale.py::test_decoder_fuzz_kernels > gpurun_out/pytest3.log 2>&1; tail -15 gpurun_out/pytest3.log
+echo "== sweeps"
+SWEEP_MODEL=2 timeout 600 python tools/fe_sweep.py 4,0,4096,AISGPU_BE_V1=0 4,0,4096,AISGPU_BE_V1=0,AISGPU_BE_PIPE=1 4,0,4096,AISGPU_BE_V1=0,AISGPU_BE_PIPE=1,AISGPU_DEC_RPW=3 2>&1 | grep -v "^$" | tee -a gpurun_out/sweep3.jsonl
+SWEEP_MODEL=0 timeout 600 python tools/fe_sweep.py 4,0,4096,AISGPU_ST_G=16 4,0,4096,AISGPU_ST_G=32 4,0,4096,AISGPU_ST_G=64 4,0,4096,AISGPU_ST_G=64,AISGPU_DEC_RPW=3 2>&1 | grep -v "^$" | tee -a gpurun_out/sweep3.jsonl
 echo "== ncu launch list (ModelDefault)"
 cat > /tmp/one.py <<'PY'
 import os, sys
@@ -32,20 +27,16 @@ for i in range(4):
     eng.sync()
 print(len(eng.poll()))
 PY
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2a_launches_default.csv python /tmp/one.py 2 > /dev/null 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2a_launches_standard.csv python /tmp/one.py 0 > /dev/null 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2b_launches_default.csv python /tmp/one.py 2 > /dev/null 2>&1
 python - <<'PY'
 import csv, collections
-for f in ("gpurun_out/r2a_launches_default.csv", "gpurun_out/r2a_launches_standard.csv"):
-    try:
-        rows = [r for r in csv.reader(open(f)) if len(r) > 5]
-    except Exception as e:
-        print(f, e); continue
+for f in ("gpurun_out/r2b_launches_default.csv",):
+    rows = [r for r in csv.reader(open(f)) if len(r) > 5]
     hdr = rows[0]; ik = hdr.index("Kernel Name"); iv = hdr.index("Metric Value")
     d = collections.defaultdict(list)
     for r in rows[1:]:
         try: d[r[ik][:60]].append(float(r[iv].replace(",", "")))
         except: pass
-    print(f)
-    for k, v in d.items(): print("  %-60s n=%d last=%.1f us" % (k, len(v), v[-1] / 1000.0 if v[-1] > 5000 else v[-1]))
+    for k, v in d.items():
+        if "aisgpu" in k: print("  %-60s n=%d last=%.1f us" % (k, len(v), v[-1] / 1000.0))
 PY
