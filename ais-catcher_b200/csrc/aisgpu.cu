@@ -101,6 +101,7 @@ struct aisgpu_handle {
 	int max_n48 = 0;
 	int fe_warps = 4, fe_tile = 0, fe_ctas = 4096;
 	int fe_st = 1, st_S = 0, st_g = 32, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
+	int cf_rows = 4; // AISGPU_CF_ROWS: rows per CTA of the fused CGF kernel (4 or 8)
 	int be_v1 = 0; // AISGPU_BE_V1=1: round-1 back-end kernels (k_cgf_rot + k_cgf_derot_fir, one hypothesis per lane) for A/B runs
 	int dec_rpw = 6, decoder = 3; // rows per warp / which decoder kernel // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
@@ -673,7 +674,7 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 				if (int rc = stage_begin(h, 2)) return rc;
 				if (int rc = stage_begin(h, 3)) return rc;
 				CU(launch_cgf_fused(Ccur, h->c_stride, c_begin, stepidx, h->d_steptab, h->d_cgf_rot, nblk, h->rows, h->d_fir_hist[h->fir_cur],
-									h->d_fir_hist[h->fir_cur ^ 1], h->d_Ec2[0], h->e_stride, HE, h->cfg.enable_taps ? h->d_tap_cgf : nullptr, h->r_stride, h->bs));
+									h->d_fir_hist[h->fir_cur ^ 1], h->d_Ec2[0], h->e_stride, HE, h->cfg.enable_taps ? h->d_tap_cgf : nullptr, h->r_stride, h->cf_rows, h->bs));
 				if (int rc = stage_end(h, 1)) return rc;
 				if (int rc = stage_end(h, 2)) return rc;
 			}
@@ -1128,6 +1129,7 @@ static int create_impl(aisgpu_handle *h) {
 		if (h->decoder != 1 && h->decoder != 2) h->decoder = 3;
 	}
 	if (const char *e = getenv("AISGPU_BE_V1")) h->be_v1 = atoi(e) ? 1 : 0;
+	if (const char *e = getenv("AISGPU_CF_ROWS")) h->cf_rows = atoi(e) == 8 ? 8 : 4;
 	if (const char *e = getenv("AISGPU_FE_TILE")) h->fe_tile = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_ST")) h->fe_st = atoi(e) ? 1 : 0;
 	if (const char *e = getenv("AISGPU_ST_S")) h->st_S = atoi(e);

@@ -182,10 +182,9 @@ __global__ void __launch_bounds__(FIRC_TILE) k_cgf_derot_fir(const float2 *__res
 // k_cgf_derot_fir read them back).  FIR: products by scalar FMUL, the (re, im) accumulation by one packed FADD2 --
 // ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, a scalar product feeding a packed add stays two roundings.
 // ---------------------------------------------------------------------------------------------
-constexpr int CF_ROWS = 4;             // 512 CTAs at 2048 rows: 3-4 per SM, so one CTA's barrier waits overlap another's arithmetic
 constexpr int CF_T = 64;               // samples per tile and row (a 512-block = 8 tiles)
-constexpr int CF_CONS = 2;             // consumer warps: CF_ROWS * CF_T / (32 CF_CONS) = 4 outputs per thread and tile
-constexpr int CF_THREADS = 32 * (1 + CF_CONS);
+// CF_ROWS rows per CTA, CF_CONS = CF_ROWS / 2 consumer warps (four outputs per thread and tile): 4 rows -> 512 CTAs at 2048 rows
+// (3-4 per SM, one CTA's barrier waits overlap another's arithmetic); 8 rows halve the chain warp's share of the issue slots
 constexpr int CF_DERP = 2 * CF_T + 2 * CF_T / 4; // ring row: two tiles, one pad slot after every four samples
 // ring position n (0 .. 2 CF_T - 1) -> slot: threads that own four consecutive outputs read n = 4c + i; 5c + i hits 16 different
 // 8-byte banks over a half warp
@@ -208,9 +207,9 @@ struct CfParams {
 	long long tap_stride;
 };
 
-__device__ __forceinline__ void cf_consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * CF_CONS)); }
-
-__global__ void __launch_bounds__(CF_THREADS) k_cgf_fused(const CfParams p) {
+template <int CF_ROWS>
+__global__ void __launch_bounds__(32 + 16 * CF_ROWS) k_cgf_fused(const CfParams p) {
+	constexpr int CF_CONS = CF_ROWS / 2;
 	__shared__ __align__(16) float2 rotb[2][CF_ROWS][CF_T + 2]; // +2: the chain lanes (one row each) store to different banks
 	__shared__ __align__(16) float2 der[CF_ROWS][CF_DERP]; // der[r][cf_slot((t & 1) * CF_T + j)] = derotated sample j of tile t
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -279,7 +278,7 @@ __global__ void __launch_bounds__(CF_THREADS) k_cgf_fused(const CfParams p) {
 			}
 #pragma unroll
 			for (int u = 0; u < CF_PER; u++) cpre[u] = cnext[u];
-			cf_consumer_barrier();
+			asm volatile("bar.sync 1, %0;" ::"n"(32 * CF_CONS));
 			// FIR: thread -> (row r, four consecutive outputs j0..j0+3): 20 ring samples in registers
 			{
 				const int r = ct >> 4, j0 = (ct & 15) * 4;
@@ -344,12 +343,13 @@ cudaError_t launch_cgf_derot_fir(const float2 *Cbuf, long long c_stride, int c_b
 }
 
 cudaError_t launch_cgf_fused(const float2 *Cbuf, long long c_stride, int c_begin, const int *stepidx, const float2 *steptab, float2 *rot_state, int nblk, int rows,
-							 const float2 *hist_old, float2 *hist_new, float2 *Ebuf, long long e_stride, int e_off, float2 *tap_cgf, long long tap_stride, cudaStream_t s) {
+							 const float2 *hist_old, float2 *hist_new, float2 *Ebuf, long long e_stride, int e_off, float2 *tap_cgf, long long tap_stride, int rows_per_cta, cudaStream_t s) {
 	CfParams p;
 	p.Cbuf = Cbuf; p.c_stride = c_stride; p.c_begin = c_begin; p.stepidx = stepidx; p.steptab = steptab; p.rot_state = rot_state;
 	p.nblk = nblk; p.rows = rows; p.hist_old = hist_old; p.hist_new = hist_new; p.Ebuf = Ebuf; p.e_stride = e_stride; p.e_off = e_off;
 	p.tap_cgf = tap_cgf; p.tap_stride = tap_stride;
-	k_cgf_fused<<<(rows + CF_ROWS - 1) / CF_ROWS, CF_THREADS, 0, s>>>(p);
+	if (rows_per_cta == 8) k_cgf_fused<8><<<(rows + 7) / 8, 32 + 16 * 8, 0, s>>>(p);
+	else k_cgf_fused<4><<<(rows + 3) / 4, 32 + 16 * 4, 0, s>>>(p);
 	return cudaGetLastError();
 }
 

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(PS_THREADS) k_phase_search(const K3Params p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3a': PhaseSearchEMA (Demod.cpp:39-101) with four hypotheses per lane.  A CTA owns PS2_ROWS rows = 40 (row, sampling
+// K3a': PhaseSearchEMA (Demod.cpp:39-101) with four hypotheses per lane.  A one-warp CTA owns eight consecutive (row, sampling
 // phase) instances, four lanes each (lane q holds hypotheses 4q .. 4q+3: its EMAs, its sign histories).  Per symbol:
 //   * t, |t| and the EMA update of the lane's four hypotheses -- plain per-lane arithmetic in the reference's order;
 //   * the decision "best of (i0, i0+1, i0+2)" (strict >, first wins, Demod.cpp:80-91) does not depend on which i0 the
@@ -166,18 +166,21 @@ __global__ void __launch_bounds__(PS_THREADS) k_phase_search(const K3Params p) {
 // 2.7x fewer warp instructions per (instance, symbol) than one hypothesis per lane, three shuffles (one of them on the
 // sequential chain) instead of four dependent ones.  Demod::PhaseSearch (PS_EMA off) keeps the one-hypothesis-per-lane kernel above.
 // ---------------------------------------------------------------------------------------------
-constexpr int PS2_ROWS = 8;
-constexpr int PS2_THREADS = PS2_ROWS * 5 * 4; // 160
+constexpr int PS2_INST = 8;                   // (row, phase) instances per warp; a CTA is ONE warp -- no CTA barrier anywhere
+constexpr int PS2_TROWS = 3;                  // rows eight consecutive instances can touch
 constexpr int PS2_ROWP = K3_ROWLEN + 5;       // padded tile row: the instances of a warp read different banks
-__global__ void __launch_bounds__(PS2_THREADS) k_phase_search_ema4(const K3Params p) {
-	__shared__ float2 tile[2][PS2_ROWS][PS2_ROWP];
-	const int tid = threadIdx.x, lane = tid & 31;
-	const int ii = tid >> 2, q = tid & 3;                 // instance within the CTA, hypothesis group
-	const int rin = ii / 5, phase = ii - 5 * rin;
-	const int row0 = blockIdx.x * PS2_ROWS;
-	const int row = row0 + rin;
-	const bool active = row < p.rows;
-	const long long inst = (long long)row * 5 + phase;
+__global__ void __launch_bounds__(32) k_phase_search_ema4(const K3Params p) {
+	__shared__ float2 tile[2][PS2_TROWS][PS2_ROWP];
+	const int lane = threadIdx.x;
+	const long long ninst = (long long)p.rows * 5;
+	const long long inst0 = (long long)blockIdx.x * PS2_INST; // first instance of this warp
+	const long long gi = inst0 + (lane >> 2);
+	const int q = lane & 3;                               // hypothesis group
+	const bool active = gi < ninst;
+	const long long inst = active ? gi : ninst - 1;
+	const int row = (int)(inst / 5), phase = (int)(inst - (long long)row * 5);
+	const int r_lo = (int)(inst0 / 5);                    // first row the warp touches
+	const int rin = row - r_lo;
 	const int gbase = lane & ~3;                          // first lane of this instance's group of four
 	const int nxt = gbase | ((q + 1) & 3);                // the lane holding hypotheses 4(q+1) .. of the same instance
 	// OR over the four lanes of an instance: two xor-shuffles with the full mask (redux.sync with a different member
@@ -210,9 +213,9 @@ __global__ void __launch_bounds__(PS2_THREADS) k_phase_search_ema4(const K3Param
 	const int nsamp = p.nsym * 5;
 	auto prefetch = [&](int buf, int s0) {
 		const int base = s0 * 5;
-		for (int e = tid; e < PS2_ROWS * K3_ROWLEN; e += PS2_THREADS) {
+		for (int e = lane; e < PS2_TROWS * K3_ROWLEN; e += 32) {
 			const int r = e / K3_ROWLEN, c = e - r * K3_ROWLEN;
-			if (row0 + r < p.rows && base + c < nsamp) cp_async_f(&tile[buf][r][c], p.Ec + (long long)(row0 + r) * p.e_stride + p.e_begin + base + c);
+			if (r_lo + r < p.rows && base + c < nsamp) cp_async_f(&tile[buf][r][c], p.Ec + (long long)(r_lo + r) * p.e_stride + p.e_begin + base + c);
 		}
 		cp_async_commit();
 	};
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(PS2_THREADS) k_phase_search_ema4(const K3Param
 			cp_async_wait<1>();
 		}
 		else cp_async_wait<0>();
-		__syncthreads();
+		__syncwarp();
 		const float2 *my = &tile[t & 1][rin][phase];
 		const int s_end = min(K3_TS, p.nsym - t * K3_TS);
 		uint32_t word = 0;
@@ -271,22 +274,23 @@ __global__ void __launch_bounds__(PS2_THREADS) k_phase_search_ema4(const K3Param
 		}
 		word = or4(word);
 		if (active && q == 0) p.dbits[inst * p.dwords + t] = word;
-		if (p.mode_level) { // ScatterPLL level: ((((0+n0)+n1)+n2)+n3)+n4, then / 5 (DSP.h:100-106)
-			for (int e = tid; e < PS2_ROWS * K3_TS; e += PS2_THREADS) {
-				const int r = e / K3_TS, sl = e - r * K3_TS;
-				if (row0 + r < p.rows && sl < s_end) {
-					const float2 *rowt = &tile[t & 1][r][sl * 5];
+		if (p.mode_level) { // ScatterPLL level: ((((0+n0)+n1)+n2)+n3)+n4, then / 5 (DSP.h:100-106), by the warp that holds the row's phase 0
+#pragma unroll
+			for (int r = 0; r < PS2_TROWS; r++) {
+				const long long first = (long long)(r_lo + r) * 5; // the row's phase-0 instance
+				if (first >= inst0 && first < inst0 + PS2_INST && r_lo + r < p.rows && lane < s_end) {
+					const float2 *rowt = &tile[t & 1][r][lane * 5];
 					float acc = 0.0f;
 #pragma unroll
 					for (int jx = 0; jx < 5; jx++) {
 						const float2 xx = rowt[jx];
 						acc = __fadd_rn(acc, __fadd_rn(__fmul_rn(xx.x, xx.x), __fmul_rn(xx.y, xx.y)));
 					}
-					p.lvl[(long long)(row0 + r) * p.lvl_stride + t * K3_TS + sl] = __fdiv_rn(acc, 5.0f);
+					p.lvl[(long long)(r_lo + r) * p.lvl_stride + t * K3_TS + lane] = __fdiv_rn(acc, 5.0f);
 				}
 			}
 		}
-		__syncthreads();
+		__syncwarp();
 	}
 	// state back: the bit planes are OR-combined over the four lanes of the instance
 	uint32_t planes[5];
@@ -946,7 +950,7 @@ cudaError_t sym_init(const float *ps_cos8, const float *ps_sin8, const uint32_t 
 }
 cudaError_t launch_phase_search(const K3Params &p, int v1, cudaStream_t s) {
 	if (p.ps_ema && !v1) { // four hypotheses per lane (PhaseSearchEMA only)
-		k_phase_search_ema4<<<(p.rows + PS2_ROWS - 1) / PS2_ROWS, PS2_THREADS, 0, s>>>(p);
+		k_phase_search_ema4<<<(unsigned)(((long long)p.rows * 5 + PS2_INST - 1) / PS2_INST), 32, 0, s>>>(p);
 		return cudaGetLastError();
 	}
 	const long long ps_warps = ((long long)p.rows * 5 + 1) / 2;

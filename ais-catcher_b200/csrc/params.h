@@ -185,7 +185,8 @@ cudaError_t launch_cgf_rot(const int *stepidx, const float2 *steptab, float2 *ro
 cudaError_t launch_cgf_derot_fir(const float2 *Cbuf, long long c_stride, int c_begin, const float2 *rots, long long r_stride, int nE, const float2 *hist_old,
                                  float2 *hist_new, float2 *Ebuf, long long e_stride, int e_off, float2 *tap_cgf, long long tap_stride, int rows, cudaStream_t s);
 cudaError_t launch_cgf_fused(const float2 *Cbuf, long long c_stride, int c_begin, const int *stepidx, const float2 *steptab, float2 *rot_state, int nblk, int rows,
-                             const float2 *hist_old, float2 *hist_new, float2 *Ebuf, long long e_stride, int e_off, float2 *tap_cgf, long long tap_stride, cudaStream_t s);
+                             const float2 *hist_old, float2 *hist_new, float2 *Ebuf, long long e_stride, int e_off, float2 *tap_cgf, long long tap_stride, int rows_per_cta,
+                             cudaStream_t s);
 // be_v2.cu
 cudaError_t v2_init(const float *taps17, const float *taps37, const float2 *omega256);
 cudaError_t launch_v2_engine(const float2 *Cbuf, long long c_stride, int c_begin, int nproc, int rows, V2State *st, DecState *dec, uint32_t *dec_data, FrameRec *ring,

@@ -143,7 +143,7 @@ class CpuReference:
         fast = O.have_ref(fast=True)
         self.kind = "reference" if fast else "port"
         Model = (lambda **kw: O.RefModel(fast=True, **kw)) if fast else O.PortModel
-        omodel = {0: O.MODEL_STANDARD, 1: O.MODEL_BASE, 2: O.MODEL_DEFAULT}[model]
+        omodel = model
         self.cpus = host_cpus()
         self.T = min(len(self.cpus), n_streams)
         self.n_streams = n_streams
@@ -527,6 +527,18 @@ def main():
                          "whole_chain_frac": ALGO_BYTES_PER_SAMPLE * B * N / (m2 / args.steps * 1e-3) / 1e9 / peaks()[0],
                          "frontend_ms": sum(fe2) / len(fe2), "frames": nm2, "parity": par2})
             eng2.close()
+        # the V2 engine (model 11) on the same data
+        engv = aisgpu.Engine(model=aisgpu.MODEL_V2, sample_rate=FS, n_streams=B, max_chunk=N, device=local_rank, max_frames=1 << 20, host_staging=False)
+        gotv = {s: [] for s in sample_streams[:8]}
+        bv, nv = timed_blocks(engv, x, N, 2, 4, 3)
+        nmv = poll_streams(engv, set(sample_streams[:8]), gotv)
+        parv = None
+        if not args.no_parity:
+            parv = oracle_check(sample_streams[:8], lambda c: {s: x[c % R][s].cpu().numpy() for s in sample_streams[:8]}, nv, gotv, 11, FS)
+        mv = median(bv)
+        also.append({"workload": "same data and batch, V2::Engine (model 11)", "value": B * N * 4 / (mv * 1e-3) / 1e6, "unit": "MSamples/s (this rank)",
+                     "ms_per_step": mv / 4, "frames": nmv, "parity": parv})
+        engv.close()
         del x
         torch.cuda.empty_cache()
         # BASELINE.json configs[2]: batch 4096 CF32 @6 MSPS (AirSpy shape: 4 CIC stages -> Upsample 125/128 -> 2 CIC stages), coherent chain

@@ -55,6 +55,28 @@ struct RecF : public StreamIn<FLOAT32> {
 struct MsgSink : public StreamIn<AIS::Message> {
 	std::string text;
 	long count = 0;
+	// The multi-sentence sequence id is a PROCESS-global atomic in the reference (Source/Marine/Message.cpp:28-39), so the digit
+	// a message gets depends on what every other model instance of the process has published -- and on thread timing when
+	// several instances run in parallel threads (tests, bench.py).  The harness therefore renumbers: every handle counts its
+	// own multi-sentence messages exactly as Message::nextSeqId does (0..9, wrapping), writes that digit into the sentences
+	// and recomputes their checksums.  Nothing else of the sentence changes.
+	int seq = 0;
+	static std::string renumber(const std::string &s, char digit) {
+		std::string r = s; // "!AIVDM,n,k,<seq>,C,payload,fill*HH": the id is the 4th field
+		size_t p = 0;
+		for (int commas = 0; p < r.size() && commas < 3; p++)
+			if (r[p] == ',') commas++;
+		if (p >= r.size() || r[p] < '0' || r[p] > '9') return r;
+		r[p] = digit;
+		size_t star = r.rfind('*');
+		if (star == std::string::npos || star + 2 >= r.size()) return r;
+		unsigned c = 0;
+		for (size_t k = 1; k < star; k++) c ^= (unsigned char)r[k];
+		static const char hex[] = "0123456789ABCDEF";
+		r[star + 1] = hex[(c >> 4) & 15];
+		r[star + 2] = hex[c & 15];
+		return r;
+	}
 	void Receive(const AIS::Message *m, int len, TAG &tag) {
 		for (int i = 0; i < len; i++) {
 			char buf[128];
@@ -69,11 +91,13 @@ struct MsgSink : public StreamIn<AIS::Message> {
 			}
 			text += "|";
 			bool first = true;
+			const bool multi = x.sentences().size() > 1;
 			for (const auto &s : x.sentences()) {
 				if (!first) text += " ";
-				text += s;
+				text += multi ? renumber(std::string(s.data(), s.size()), (char)('0' + seq)) : std::string(s.data(), s.size());
 				first = false;
 			}
+			if (multi) seq = (seq + 1) % 10;
 			text += "\n";
 			count++;
 		}
@@ -97,7 +121,6 @@ struct Handle {
 	RecC tc[NTAPS_C];
 	RecF tf[NTAPS_F];
 	Format fmt = Format::CF32;
-	int seq = 0; // per-handle stand-in for the process-global Message::ID (Source/Marine/Message.cpp:28)
 	~Handle() {
 		delete md;
 		delete ms;
@@ -220,14 +243,12 @@ void *aisref_create(int model, int sample_rate, int format, unsigned flags, int 
 // one RAW block == one Device callback (chunk length is part of the parity contract)
 int aisref_push(void *hv, const void *data, long nbytes) {
 	Handle *h = (Handle *)hv;
-	AIS::Message::ID.store(h->seq);
 	long long before[2] = {0, 0};
 	if (h->mv && h->taps) {
 		before[0] = h->mv->V2_a.sample_idx;
 		before[1] = h->mv->V2_b.sample_idx;
 	}
 	h->dev.push((void *)data, (int)nbytes, h->fmt);
-	h->seq = AIS::Message::ID.load();
 	if (h->mv && h->taps) { // the arrays of the LAST block each engine decoded in this push (taps 5/6 CGF out, 7/8 FIR17 out, 12/13 FIR37 out)
 		V2::Engine *e[2] = {&h->mv->V2_a, &h->mv->V2_b};
 		for (int c = 0; c < 2; c++) {
