@@ -10,7 +10,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libaisgpu.so")
 
-MODEL_STANDARD, MODEL_BASE, MODEL_DEFAULT, MODEL_V2 = 0, 1, 2, 11
+MODEL_STANDARD, MODEL_BASE, MODEL_DEFAULT, MODEL_CHALLENGER, MODEL_V2 = 0, 1, 2, 4, 11
 FMT_CF32, FMT_CU8, FMT_CS8, FMT_CS16 = 0, 1, 2, 3
 TAP_C, TAP_CGF, TAP_FIR, TAP_ROT, TAP_DEC, TAP_FM = 0, 1, 2, 3, 4, 5
 

@@ -59,6 +59,7 @@ const float H_PS_SIN[8] = { 9.8017143048367339e-02f, 2.9028468509743588e-01f, 4.
 constexpr int HC = 1024; // room in front of new 48 kHz samples: unconsumed CGF samples (<512), FM/FIR history (37), or the V2 engine's
                          // block awaiting its lookahead plus a partial block (<1024)
 constexpr int V2_BLK = 512; // V2::BLOCK_SIZE (V2Engine.h:30)
+constexpr int HD = 48;  // ModelChallenger: derotated samples kept in front of the new ones (FM needs 1, FIR37 36, a partial group 4)
 constexpr int HE = 8;   // room in front of new symbol-stage samples: an incomplete group of 5 (<=4)
 
 int bytes_per_sample(int fmt) { return fmt == AISGPU_FMT_CF32 ? 8 : (fmt == AISGPU_FMT_CS16 ? 4 : 2); }
@@ -171,6 +172,10 @@ struct aisgpu_handle {
 	uint32_t *d_dec_data = nullptr;
 	PllState *d_pll = nullptr;
 	V2State *d_v2 = nullptr;     // V2 engine: per-row state
+	float2 *d_Ed = nullptr;      // ModelChallenger: derotated 48 kHz samples [rows][HD + nE]
+	long long ed_stride = 0;
+	uint32_t *d_dbitsF[2] = { nullptr, nullptr };
+	float *d_lvl_prev = nullptr;
 	float2 *d_tap_coh = nullptr;
 	float *d_tap_dec = nullptr, *d_tap_fm = nullptr;
 	int *d_tap_cnt = nullptr;
@@ -516,7 +521,7 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.chunk = (int)h->msg_chunk;
 		p.blk = (int)h->chunk;
 		p.mode_level = (h->cfg.tag_mode & 1) ? 1 : 0;
-		if (h->cfg.model == AISGPU_MODEL_DEFAULT) {
+		if (h->cfg.model == AISGPU_MODEL_DEFAULT || h->cfg.model == AISGPU_MODEL_CHALLENGER) {
 			p.stepidx = h->d_stepidx2[h->pb];
 			p.ppmtab = h->d_ppmtab;
 			p.blk_abs0 = h->cgf_abs;
@@ -535,10 +540,38 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		const int nl = total - nsym * 5;
 		if (carry(h, h->d_Ec2[0], h->e_stride, e_begin + nsym * 5, HE - nl, nl)) return AISGPU_ECUDA;
 		if (int rc = stage_end(h, 3)) return rc;
-		if (int rc = stage_begin(h, 4)) return rc;
-		CU(launch_decode(2, h->decoder, h->dec_rpw, p, h->bs));
-		if (int rc = stage_end(h, 4)) return rc;
-		h->last_launches += 2;
+		if (h->cfg.model == AISGPU_MODEL_CHALLENGER) {
+			// FM branch on the derotated samples: Demod::FM -> Filter 37 -> Deinterleave (Model.cpp:637-639), all new samples at once
+			const long long a0 = h->e_abs + h->e_left, a1 = a0 + n_new; // absolute indices of the new samples
+			Fm5Params f;
+			memset(&f, 0, sizeof(f));
+			f.Cbuf = h->d_Ed;
+			f.c_stride = h->ed_stride;
+			f.c_new = HD;
+			f.n = n_new;
+			f.r0 = h->e_left;
+			f.nslots = (int)((a1 - h->e_abs + 4) / 5);
+			f.Fbuf = h->d_Ef2[0];
+			f.f_stride = h->e_stride;
+			f.f_off = HE;
+			f.dbits = h->d_dbitsF[h->pb];
+			f.dwords = h->dwords;
+			CU(launch_fm_fir5(f, h->rows, h->bs));
+			if (int rc = carry(h, h->d_Ed, h->ed_stride, HD + n_new - HD, 0, HD)) return rc; // the last HD derotated samples stay in front
+			p.dbits2 = h->d_dbitsF[h->pb];
+			p.nslots_fm = f.nslots;
+			p.lvl_prev = h->d_lvl_prev;
+			p.abs_lo = a0;
+			p.abs_hi = a1;
+			CU(launch_decode10(h->dec_rpw == 1 ? 1 : 3, p, h->bs));
+			h->last_launches += 3;
+		}
+		else {
+			if (int rc = stage_begin(h, 4)) return rc;
+			CU(launch_decode(2, h->decoder, h->dec_rpw, p, h->bs));
+			if (int rc = stage_end(h, 4)) return rc;
+			h->last_launches += 2;
+		}
 	}
 	const int new_left = total - nsym * 5;
 	if (nsym == 0) {
@@ -639,7 +672,7 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 		CU(cudaEventRecord(h->ev_be_done[cb], h->bs));
 		h->be_recorded[cb] = true;
 	}
-	else if (h->cfg.model == AISGPU_MODEL_DEFAULT) {
+	else if (h->cfg.model == AISGPU_MODEL_DEFAULT || h->cfg.model == AISGPU_MODEL_CHALLENGER) {
 		const int cnt = h->c_hist; // unconsumed samples in front of HC
 		const int total = cnt + n48;
 		const int nblk = total / CGF_N;
@@ -674,7 +707,8 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 				if (int rc = stage_begin(h, 2)) return rc;
 				if (int rc = stage_begin(h, 3)) return rc;
 				CU(launch_cgf_fused(Ccur, h->c_stride, c_begin, stepidx, h->d_steptab, h->d_cgf_rot, nblk, h->rows, h->d_fir_hist[h->fir_cur],
-									h->d_fir_hist[h->fir_cur ^ 1], h->d_Ec2[0], h->e_stride, HE, h->cfg.enable_taps ? h->d_tap_cgf : nullptr, h->r_stride, h->cf_rows, h->bs));
+									h->d_fir_hist[h->fir_cur ^ 1], h->d_Ec2[0], h->e_stride, HE,
+									h->d_Ed ? h->d_Ed + HD : (h->cfg.enable_taps ? h->d_tap_cgf : nullptr), h->d_Ed ? h->ed_stride : h->r_stride, h->cf_rows, h->bs));
 				if (int rc = stage_end(h, 1)) return rc;
 				if (int rc = stage_end(h, 2)) return rc;
 			}
@@ -1104,7 +1138,8 @@ const char *aisgpu_last_error(aisgpu_handle *h) { return h ? h->err.c_str() : g_
 
 static int create_impl(aisgpu_handle *h) {
 	const aisgpu_config &c = h->cfg;
-	if (c.model != AISGPU_MODEL_DEFAULT && c.model != AISGPU_MODEL_STANDARD && c.model != AISGPU_MODEL_BASE && c.model != AISGPU_MODEL_V2) {
+	if (c.model != AISGPU_MODEL_DEFAULT && c.model != AISGPU_MODEL_STANDARD && c.model != AISGPU_MODEL_BASE && c.model != AISGPU_MODEL_V2 &&
+		c.model != AISGPU_MODEL_CHALLENGER) {
 		h->err = "unknown model kind";
 		return AISGPU_EINVAL;
 	}
@@ -1130,6 +1165,10 @@ static int create_impl(aisgpu_handle *h) {
 	}
 	if (const char *e = getenv("AISGPU_BE_V1")) h->be_v1 = atoi(e) ? 1 : 0;
 	if (const char *e = getenv("AISGPU_CF_ROWS")) h->cf_rows = atoi(e) == 8 ? 8 : 4;
+	if (c.model == AISGPU_MODEL_CHALLENGER) { // ModelChallenger always demodulates with PhaseSearchEMA (Model.cpp:646-652) and needs the fused kernel's derotated output
+		h->be_v1 = 0;
+		h->cfg.ps_ema = 1;
+	}
 	if (const char *e = getenv("AISGPU_FE_TILE")) h->fe_tile = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_ST")) h->fe_st = atoi(e) ? 1 : 0;
 	if (const char *e = getenv("AISGPU_ST_S")) h->st_S = atoi(e);
@@ -1155,7 +1194,8 @@ static int create_impl(aisgpu_handle *h) {
 	{
 		const char *e = getenv("AISGPU_BE_PIPE");
 		// measured: overlapping the stages of consecutive submits pays for the FM chain (+6 %), not for the coherent one
-		const bool pipe = (e ? atoi(e) != 0 : c.model == AISGPU_MODEL_STANDARD) && !c.enable_taps && c.model != AISGPU_MODEL_BASE && c.model != AISGPU_MODEL_V2;
+		const bool pipe = (e ? atoi(e) != 0 : c.model == AISGPU_MODEL_STANDARD) && !c.enable_taps && c.model != AISGPU_MODEL_BASE && c.model != AISGPU_MODEL_V2 &&
+						  c.model != AISGPU_MODEL_CHALLENGER;
 		if (pipe) CU(cudaStreamCreateWithPriority(&h->be_streams[1], cudaStreamNonBlocking, prio_hi));
 	}
 	h->bs = h->stream;
@@ -1247,7 +1287,8 @@ static int create_impl(aisgpu_handle *h) {
 	const int nEmax = HC + h->max_n48;
 	h->e_stride = (HE + nEmax + 8 + 1) & ~1LL;
 	h->r_stride = nEmax;
-	const int ndec = c.model == AISGPU_MODEL_V2 ? 6 : 5; // decoders per row
+	const bool coherent = c.model == AISGPU_MODEL_DEFAULT || c.model == AISGPU_MODEL_CHALLENGER; // the CGF / FIR17 / PhaseSearch chain
+	const int ndec = c.model == AISGPU_MODEL_V2 ? 6 : (c.model == AISGPU_MODEL_CHALLENGER ? 10 : 5); // decoders per row
 	if (int rc = dalloc(h, &h->d_dec, (size_t)h->rows * ndec)) return rc;
 	if (int rc = dalloc(h, &h->d_dec_data, (size_t)h->rows * ndec * DEC_WORDS)) return rc;
 	if (c.model == AISGPU_MODEL_V2) {
@@ -1274,7 +1315,7 @@ static int create_impl(aisgpu_handle *h) {
 			if (int rc = dalloc(h, &h->d_tap_fm, (size_t)h->rows * h->r_stride)) return rc;
 		}
 	}
-	else if (c.model == AISGPU_MODEL_DEFAULT) {
+	else if (coherent) {
 		h->c_hist = 0;
 		for (int i = 0; i < 2; i++) {
 			if (int rc = dalloc(h, &h->d_stepidx2[i], (size_t)h->rows * (nEmax / CGF_N + 1))) return rc;
@@ -1291,6 +1332,14 @@ static int create_impl(aisgpu_handle *h) {
 		}
 		if (!c.ps_ema)
 			if (int rc = dalloc(h, &h->d_ps_mem, (size_t)h->rows * 5 * 16 * 12)) return rc;
+		if (c.model == AISGPU_MODEL_CHALLENGER) { // FM branch on the derotated samples (Model.cpp:637-639)
+			h->ed_stride = (HD + nEmax + 8 + 1) & ~1LL;
+			if (int rc = dalloc(h, &h->d_Ed, (size_t)h->rows * h->ed_stride)) return rc;
+			if (int rc = dalloc(h, &h->d_Ef2[0], (size_t)h->rows * h->e_stride)) return rc;
+			for (int i = 0; i < 2; i++)
+				if (int rc = dalloc(h, &h->d_dbitsF[i], (size_t)h->rows * 5 * h->dwords)) return rc;
+			if (int rc = dalloc(h, &h->d_lvl_prev, (size_t)h->rows)) return rc;
+		}
 		if (int rc = dalloc(h, &h->d_steptab, CGF_NIDX)) return rc;
 		if (int rc = dalloc(h, &h->d_ppmtab, CGF_NIDX)) return rc;
 		if (int rc = dalloc(h, &h->d_omega, CGF_N)) return rc;
@@ -1760,7 +1809,7 @@ void aisgpu_destroy(aisgpu_handle *h) {
 	}
 	void *ptrs[] = { h->d_ptail[0], h->d_ptail[1], h->d_ptail2[0], h->d_ptail2[1], h->d_S2, h->d_D0, h->d_S, h->d_us_src, h->d_us_alpha, h->d_in[0], h->d_in[1], h->d_tail[0], h->d_tail[1], h->d_rot[0], h->d_rot[1], h->d_rot[2], h->d_rot_state, h->d_C2[0], h->d_C2[1], h->d_C2[2],
 					 h->d_steptab, h->d_omega, h->d_cgf_rot, h->d_rots2[0], h->d_rots2[1], h->d_stepidx2[0], h->d_stepidx2[1], h->d_ppmtab, h->d_fir_hist[0], h->d_fir_hist[1], h->d_tap_cgf, h->d_Ec2[0],
-					 h->d_Ef2[0], h->d_ps, h->d_ps_mem, h->d_dbits2[0], h->d_dbits2[1], h->d_lvl2[0], h->d_lvl2[1], h->d_dbg, h->d_dec, h->d_dec_data, h->d_pll, h->d_tap_dec, h->d_tap_fm, h->d_tap_cnt, h->d_v2, h->d_tap_coh, h->d_ring,
+					 h->d_Ef2[0], h->d_ps, h->d_ps_mem, h->d_dbits2[0], h->d_dbits2[1], h->d_lvl2[0], h->d_lvl2[1], h->d_dbg, h->d_dec, h->d_dec_data, h->d_pll, h->d_tap_dec, h->d_tap_fm, h->d_tap_cnt, h->d_v2, h->d_tap_coh, h->d_Ed, h->d_dbitsF[0], h->d_dbitsF[1], h->d_lvl_prev, h->d_ring,
 					 h->d_ring_head, h->d_counts };
 	for (void *p : ptrs)
 		if (p) cudaFree(p);

@@ -899,6 +899,200 @@ __global__ void __launch_bounds__(DK3_WARPS * 32) k_decode3(const K3Params p) {
 	}
 }
 
+// K3d: ModelChallenger (Model.cpp:601-678): per row FIVE decoders behind the coherent branch (ScatterPLL: a group of five symbols
+// is handed out when its fifth sample has arrived) and FIVE behind the FM branch (Deinterleave: every sample is handed out at
+// once), all ten cross-connected by the Reset signal.  Both branches hang off one sample-by-sample throttle, so within a
+// group of five samples the reference's order is  f0 f1 f2 f3 | a0 a1 a2 a3 a4 | f4  (FM decoder j at sample 5g + j, the
+// coherent ones when sample 5g + 4 has passed the FIR).  Same word-parallel machine as k_decode3 with ten lanes per row and
+// that rank deciding who has "already stepped" when a frame completes.  The FM decoders see the signal level ScatterPLL
+// left in the tag: the previous group's for f0..f3, the current one's for f4 (DSP.h:100-106, the TAG travels by reference).
+template <int RPW>
+__global__ void __launch_bounds__(DK3_WARPS * 32) k_decode10(const K3Params p) {
+	constexpr int MODEL = 2;
+	__shared__ uint32_t frames_all[DK3_WARPS][DEC_WORDS * 32];
+	__shared__ float tile_all[DK3_WARPS][RPW][3][K3_TS + 2]; // entry 0: the level of the slot in front of the word; +1 over-read slack
+	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+	const int g = lane / 10, ph10 = lane - 10 * g;
+	const bool fm = ph10 >= 5;
+	const int phase = fm ? ph10 - 5 : ph10;
+	const int rank = fm ? (phase < 4 ? phase : 9) : 4 + phase; // order of the ten decoders within a group of five samples
+	const int row0 = (blockIdx.x * DK3_WARPS + wib) * RPW;
+	if (row0 >= p.rows) return; // whole warp
+	const int row = row0 + g;
+	const bool active = g < RPW && row < p.rows;
+	const int gbase = 10 * (g < RPW ? g : 0);
+	float(*tile)[3][K3_TS + 2] = tile_all[wib];
+
+	DecCtx ctx;
+	ctx.frame = frames_all[wib] + lane;
+	ctx.mode_level = p.mode_level;
+	ctx.stride = K3_THREADS;
+	DecState d;
+	const int sidx = active ? row * 10 + ph10 : 0;
+	const long long nthr_total = (long long)p.rows * 10;
+	Dk3 st;
+	st.mode = 0; st.sfP = 0; st.pos = 0; st.ones = 0; st.level = 0.0f; st.cur = 0u; st.e = -1; st.start_rel = -1;
+	int prev = 0, lastBit = 0;
+	uint32_t altprev = 0u;
+	if (active) {
+		d = p.dec[sidx];
+		prev = d.prev;
+		lastBit = d.lastBit;
+		if (d.state == ST_DATAFCS) {
+			st.mode = 2;
+			st.pos = d.position;
+			st.ones = d.one_seq;
+			st.level = d.level;
+			const int nw = (d.position >> 5) + 1;
+			for (int w = 0; w < nw && w < DEC_WORDS; w++) ctx.frame[w * K3_THREADS] = p.dec_data[(long long)w * nthr_total + sidx];
+			st.cur = (d.position & 31) ? ctx.frame[(d.position >> 5) * K3_THREADS] : 0u;
+		}
+		else if (d.state == ST_STARTFLAG) {
+			st.mode = 1;
+			st.sfP = d.position;
+		}
+		else { // TRAINING with `position` alternations counted so far (only "> 4" is ever tested)
+			const int q = min(d.position, 5);
+			st.e = -1 - q;
+			altprev = q ? (0xffffffffu << (32 - q)) : 0u;
+		}
+	}
+	const int lo_rel = (int)(p.abs_lo - p.abs_begin), hi_rel = (int)(p.abs_hi - p.abs_begin);
+	// FM lanes: Deinterleave forwards partial groups at both ends of a submit; coherent lanes: complete groups only
+	const int slot_lo = fm ? (phase >= lo_rel ? 0 : 1) : 0;
+	const int slot_hi = fm ? (hi_rel - phase + 4) / 5 : p.nsym;
+	const int nslots = max(p.nsym, p.nslots_fm);
+	const int ntiles = (nslots + K3_TS - 1) / K3_TS;
+	auto prefetch = [&](int buf, int s0) {
+#pragma unroll
+		for (int g2 = 0; g2 < RPW; g2++) {
+			const int r2 = row0 + g2;
+			if (r2 >= p.rows) continue;
+			for (int e = lane; e < K3_TS + 1; e += 32) { // entry e = level of slot s0 + e - 1
+				const int sl = s0 + e - 1;
+				if (sl < 0) cp_async_f(&tile[g2][buf][e], p.lvl_prev + r2);
+				else if (sl < p.nsym) cp_async_f(&tile[g2][buf][e], p.lvl + (long long)r2 * p.lvl_stride + sl);
+			}
+		}
+		cp_async_commit();
+	};
+	const uint32_t *mybits = (fm ? p.dbits2 : p.dbits) + (long long)(row * 5 + phase) * p.dwords;
+	auto load_dbits = [&](int t) -> uint32_t { return (active && t < ntiles) ? mybits[t] : 0u; };
+	uint32_t pre0 = load_dbits(0), pre1 = load_dbits(1), pre2 = load_dbits(2);
+	if (ntiles > 0) {
+		prefetch(0, 0);
+		if (ntiles > 1) prefetch(1, K3_TS);
+		else cp_async_commit();
+	}
+	int nbits_total = 0; // valid bits seen by this lane in this submit
+	for (int t = 0; t < ntiles; t++) {
+		if (t + 2 < ntiles) prefetch((t + 2) % 3, (t + 2) * K3_TS);
+		else cp_async_commit();
+		cp_async_wait<2>(); // tile t has landed
+		__syncwarp();
+		uint32_t dword = pre0;
+		pre0 = pre1;
+		pre1 = pre2;
+		pre2 = load_dbits(t + 3);
+		// valid slots of this word for this lane: [lo, hi)
+		int lo = max(0, slot_lo - t * K3_TS), hi = min(K3_TS, min(nslots, slot_hi) - t * K3_TS);
+		if (!active) hi = 0;
+		const int nb = max(0, hi - lo);
+		const int slot0 = t * K3_TS + lo;
+		dword >>= lo;
+		const uint32_t Bitw = ~(dword ^ ((dword << 1) | (uint32_t)prev)); // NRZI (AIS.h:93-96)
+		const uint32_t alt = Bitw ^ ((Bitw << 1) | (uint32_t)lastBit);
+		uint32_t run5 = __funnelshift_l(altprev, alt, 1);
+		run5 &= __funnelshift_l(altprev, alt, 2);
+		run5 &= __funnelshift_l(altprev, alt, 3);
+		run5 &= __funnelshift_l(altprev, alt, 4);
+		run5 &= __funnelshift_l(altprev, alt, 5);
+		const uint32_t E = ~alt & run5 & lowmask(nb);
+		const float *lvl = &tile[g < RPW ? g : 0][t % 3][lo + ((fm && phase < 4) ? 0 : 1)];
+		int i = 0;
+		for (;;) {
+			const Dk3 saved = st;
+			const int i_saved = i;
+			int fr_len = 0;
+			float fr_level = 0.0f;
+			const int x = dk3_run<MODEL == 2>(st, ctx, Bitw, E, i, nb, lvl, slot0, phase, fr_len, fr_level);
+			i = x < 32 ? x + 1 : nb;
+			if (!__any_sync(0xffffffffu, x < 32)) break;
+			// a frame with a good CRC closed somewhere in the warp: per row, the first one in (bit, phase) order wins
+			const int key = x < 32 ? (x + lo) * 16 + rank : 0x7fffffff; // bit index in slot units (lanes of a row may differ in lo)
+			int rowmin = 0x7fffffff;
+#pragma unroll
+			for (int k2 = 0; k2 < 10; k2++) rowmin = min(rowmin, __shfl_sync(0xffffffffu, key, gbase + k2));
+			if (rowmin == 0x7fffffff || !active) continue; // nothing in this row: its lanes have finished the word already
+			const int xs = rowmin >> 4, pw = rowmin & 15; // slot (relative to the word) and rank of the winner
+			if (key == rowmin) { // FOUNDMESSAGE: publish, Reset goes to the four siblings (AIS.cpp:47-49,98-108)
+				float ppm = 0.0f;
+				const int slot = t * K3_TS + xs;
+				if (p.ppmtab) { // tag.ppm of the CGF block that delivered the group's 5th sample (coherent) / this sample (FM)
+					const long long last_of_group = p.abs_begin + (long long)slot * 5 + (fm ? phase : 4);
+					int bi = (int)((last_of_group - p.blk_abs0) >> 9);
+					bi = bi < 0 ? 0 : (bi >= p.nblk ? p.nblk - 1 : bi);
+					ppm = p.ppmtab[p.stepidx[row * p.nblk + bi]];
+				}
+				const long long sidx0 = st.start_rel >= 0 ? p.abs_begin + st.start_rel : d.start_idx;
+				FrameRec *rp = ring_claim(p.ring, p.ring_head, p.ring_limit, p.ring_cap);
+				if (rp) {
+					FrameRec &r = *rp;
+					r.row = row; r.phase = ph10; r.nbits = fr_len - 16; r.level = fr_level; r.ppm = ppm; r.chunk = p.chunk; r.blk = p.blk;
+					r.start_idx = sidx0;
+					r.end_idx = p.abs_begin + (long long)slot * 5 + phase;
+					const int nw = (st.pos + 31) >> 5;
+					for (int w = 0; w < DEC_WORDS; w++) r.data[w] = w < nw ? frame_word(ctx, w) : 0u; // msg.clear() left the rest zero
+				}
+			}
+			else { // sibling: replay up to the winner's bit, then Reset -> NextState(TRAINING, 0)
+				st = saved;
+				const int xl = xs - lo; // the winner's slot as a bit index of this lane's word (may be -1 when lo = 1)
+				const int stop = max(i_saved, min(nb, rank < pw ? xl + 1 : xl)); // decoders of lower rank have already stepped that group
+				int fl = 0;
+				float fv = 0.0f;
+				if (stop > i_saved) dk3_run<MODEL == 2>(st, ctx, Bitw, E, i_saved, stop, lvl, slot0, phase, fl, fv);
+				st.mode = 0;
+				st.e = stop - 1;
+				i = stop;
+			}
+		}
+		if (nb > 0) {
+			altprev = nb >= 32 ? alt : ((alt << (32 - nb)) | (altprev >> nb)); // keep "bit 31 = latest alternation flag"
+			lastBit = (int)((Bitw >> (nb - 1)) & 1u);
+			prev = (int)((dword >> (nb - 1)) & 1u);
+			st.e = max(st.e - nb, -64);
+			nbits_total += nb;
+		}
+		__syncwarp();
+	}
+	if (active) {
+		if (st.mode == 2) {
+			d.state = ST_DATAFCS;
+			d.position = st.pos;
+			d.one_seq = st.ones;
+			if (st.pos & 31) ctx.frame[(st.pos >> 5) * K3_THREADS] = st.cur;
+			const int nw = (st.pos >> 5) + 1;
+			for (int w = 0; w < nw && w < DEC_WORDS; w++) p.dec_data[(long long)w * nthr_total + sidx] = ctx.frame[w * K3_THREADS];
+		}
+		else if (st.mode == 1) { d.state = ST_STARTFLAG; d.position = st.sfP; d.one_seq = 0; }
+		else { // TRAINING: alternations counted = trailing alternation flags that come after the last reset
+			const int n_alt = __clz((int)~altprev);
+			d.state = ST_TRAINING;
+			d.position = max(0, min(min(5, n_alt), -1 - st.e));
+			d.one_seq = 0;
+		}
+		if (st.mode != 0 && st.start_rel >= 0) d.start_idx = p.abs_begin + st.start_rel;
+		d.level = st.level;
+		d.prev = prev;
+		d.lastBit = lastBit;
+		p.dec[sidx] = d;
+		// ScatterPLL's level stays in the tag for the FM decoders of the next group: keep the last one for the next submit
+		if (ph10 == 0 && p.nsym > 0) p.lvl_prev[row] = p.lvl[(long long)row * p.lvl_stride + p.nsym - 1];
+	}
+}
+
+
 // ModelBase: SimplePLL (DSP.cpp:28-57) + one Decoder per row; strictly sequential per row.
 __global__ void __launch_bounds__(K3_THREADS) k_base(const float *__restrict__ Ef, long long e_stride, int e_begin, int n, int rows,
 													   PllState *__restrict__ pll, DecState *__restrict__ dec, uint32_t *__restrict__ dec_data, FrameRec *__restrict__ ring,
@@ -971,6 +1165,11 @@ static cudaError_t launch_decode_model(int decoder, int rpw, const K3Params &p, 
 		else if (rpw == 3) k_decode3<MODEL, 3><<<grid, DK3_WARPS * 32, 0, s>>>(p);
 		else k_decode3<MODEL, 6><<<grid, DK3_WARPS * 32, 0, s>>>(p);
 	}
+	return cudaGetLastError();
+}
+cudaError_t launch_decode10(int rpw, const K3Params &p, cudaStream_t s) {
+	if (rpw == 1) k_decode10<1><<<(p.rows + DK3_WARPS - 1) / DK3_WARPS, DK3_WARPS * 32, 0, s>>>(p);
+	else k_decode10<3><<<(p.rows + 3 * DK3_WARPS - 1) / (3 * DK3_WARPS), DK3_WARPS * 32, 0, s>>>(p);
 	return cudaGetLastError();
 }
 cudaError_t launch_decode(int model, int decoder, int rpw, const K3Params &p, cudaStream_t s) {

@@ -111,6 +111,9 @@ struct K3Params {
 	PsState *ps;
 	float *ps_mem;        // PhaseSearch history |t| [16*12][rows*5] (only when !ps_ema)
 	uint32_t *dbits;      // ModelDefault: demodulated bits, [rows*5][dwords], bit (s & 31) of word (s >> 5) = symbol s
+	uint32_t *dbits2;     // ModelChallenger: the FM branch's decision bits, same layout
+	int nslots_fm;        // ModelChallenger: slots the FM branch covers this submit
+	float *lvl_prev;      // ModelChallenger: [rows] ScatterPLL level of the last group of the previous submit
 	int dwords;
 	float *lvl;           // ModelDefault: ScatterPLL level of symbol s (TAG::sample_lvl, DSP.h:100-106), [rows][lvl_stride]
 	int lvl_stride;
@@ -199,6 +202,7 @@ cudaError_t launch_fm_fir5(const Fm5Params &p, int rows, cudaStream_t s);
 cudaError_t sym_init(const float *ps_cos8, const float *ps_sin8, const uint32_t *abort_bits35);
 cudaError_t launch_phase_search(const K3Params &p, int v1, cudaStream_t s);
 cudaError_t launch_decode(int model, int decoder, int rpw, const K3Params &p, cudaStream_t s);
+cudaError_t launch_decode10(int rpw, const K3Params &p, cudaStream_t s);
 cudaError_t launch_base(const float *Ef, long long e_stride, int e_begin, int n, int rows, PllState *pll, DecState *dec, uint32_t *dec_data, FrameRec *ring,
                         unsigned long long *ring_head, unsigned long long ring_limit, int ring_cap, int chunk, int blk, float *tap_dec, int *tap_cnt,
                         cudaStream_t s);

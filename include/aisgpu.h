@@ -38,6 +38,7 @@ extern "C" {
 #define AISGPU_MODEL_STANDARD 0 /* FM -> FIR37 -> 5-phase deinterleave -> 5 decoders (Model.cpp:484-518) */
 #define AISGPU_MODEL_BASE 1     /* FM -> FIR37 -> SimplePLL -> 1 decoder            (Model.cpp:419-438) */
 #define AISGPU_MODEL_DEFAULT 2  /* CGF -> FIR17 -> 5 x PhaseSearch[EMA] -> 5 decoders (Model.cpp:520-577) */
+#define AISGPU_MODEL_CHALLENGER 4 /* CGF -> { FIR17 -> 5 x PhaseSearchEMA | FM -> FIR37 } -> 10 cross-reset decoders (Model.cpp:601-678) */
 #define AISGPU_MODEL_V2 11      /* V2::Engine per channel: slot-predicted CGF, 5 PhaseTrackers + FM/BitPLL, 6 decoders (Model.cpp:440-460,
                                    DSP/Decoder/V2/V2Engine.cpp) */
 

@@ -13,7 +13,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-MODEL_STANDARD, MODEL_BASE, MODEL_DEFAULT, MODEL_V2 = 0, 1, 2, 11  # MODEL_V2: reference harness only
+MODEL_STANDARD, MODEL_BASE, MODEL_DEFAULT, MODEL_CHALLENGER, MODEL_V2 = 0, 1, 2, 4, 11  # CHALLENGER / V2: reference harness only
 FMT_CF32, FMT_CU8, FMT_CS8, FMT_CS16 = 0, 1, 2, 3
 FLAG_PS_EMA, FLAG_AFC_WIDE, FLAG_DROOP, FLAG_TAPS, FLAG_FP_DS, FLAG_DSK = 1, 2, 4, 8, 16, 32  # FP_DS / DSK: reference harness only
 DEFAULT_FLAGS = FLAG_PS_EMA | FLAG_AFC_WIDE | FLAG_DROOP

@@ -104,7 +104,7 @@ struct MsgSink : public StreamIn<AIS::Message> {
 	}
 };
 
-enum { MODEL_STANDARD = 0, MODEL_BASE = 1, MODEL_DEFAULT = 2, MODEL_V2 = 11 };
+enum { MODEL_STANDARD = 0, MODEL_BASE = 1, MODEL_DEFAULT = 2, MODEL_CHALLENGER = 4, MODEL_V2 = 11 };
 enum { FLAG_PS_EMA = 1, FLAG_AFC_WIDE = 2, FLAG_DROOP = 4, FLAG_TAPS = 8, FLAG_FP_DS = 16, FLAG_DSK = 32 };
 static const int NTAPS_C = 9;  // 0: ROT in, 1/2: ROT up/down, 3/4: C_a/C_b, 5/6: CGF or (unused), 7/8: FC
 static const int NTAPS_F = 14; // 0..4 / 5..9: per-phase decoder inputs ch A / B; 10/11: FM out; 12/13: FR out
@@ -115,6 +115,7 @@ struct Handle {
 	AIS::ModelStandard *ms = nullptr;
 	AIS::ModelBase *mb = nullptr;
 	AIS::ModelEngineV2 *mv = nullptr;
+	AIS::ModelChallenger *mc = nullptr;
 	bool taps = false;
 	AIS::ModelFrontend *fe = nullptr;
 	MsgSink sink;
@@ -126,6 +127,7 @@ struct Handle {
 		delete ms;
 		delete mb;
 		delete mv;
+		delete mc;
 	}
 };
 
@@ -164,6 +166,11 @@ void *aisref_create(int model, int sample_rate, int format, unsigned flags, int 
 		else if (model == MODEL_BASE) {
 			h->mb = new AIS::ModelBase();
 			h->fe = h->mb;
+		}
+		else if (model == MODEL_CHALLENGER) { // model 4 "v1_high" (Source/DSP/Model.cpp:601-678)
+			h->mc = new AIS::ModelChallenger();
+			h->fe = h->mc;
+			h->mc->SetKey(AIS::KEY_SETTING_AFC_WIDE, (flags & FLAG_AFC_WIDE) ? "on" : "off");
 		}
 		else if (model == MODEL_V2) { // model 11 "v2_base" (Source/DSP/Model.cpp:440-460)
 			h->mv = new AIS::ModelEngineV2();

@@ -242,15 +242,20 @@ def run_v2_case(fs, N, nchunks, B, check_taps, seed0, fmt=aisgpu.FMT_CF32):
     if not O.have_ref():
         pytest.skip("the V2 engine is checked against the compiled reference only")
     xs = [S.random_stream(fs, N * nchunks, seed0 + s, bursts_per_sec=(6, 12))[0] for s in range(B)]
+    per = 1
+    if fmt == aisgpu.FMT_CU8:
+        xs = [S.to_cu8(x) for x in xs]
+        per = 2
+    N_el = N * per  # array elements per chunk
     eng = aisgpu.Engine(model=aisgpu.MODEL_V2, sample_rate=fs, fmt=fmt, n_streams=B, max_chunk=N, taps=check_taps)
     refs = [O.RefModel(model=O.MODEL_V2, sample_rate=fs, fmt=fmt, taps=check_taps) for _ in range(B)]
     problems = []
     got = [[] for _ in range(B)]
     want = [[] for _ in range(B)]
     for c in range(nchunks):
-        eng.submit(np.stack([x[c * N:(c + 1) * N] for x in xs]), N)
+        eng.submit(np.stack([x[c * N_el:(c + 1) * N_el] for x in xs]), N)
         for s in range(B):
-            refs[s].push(xs[s][c * N:(c + 1) * N])
+            refs[s].push(xs[s][c * N_el:(c + 1) * N_el])
         if check_taps:
             for s in range(B):
                 for ch in range(2):
@@ -295,4 +300,61 @@ def test_v2_engine_messages(built, fs, N):
 
 def test_v2_engine_cu8(built):
     n = run_v2_case(1536000, 65536, 16, 2, False, 71, fmt=aisgpu.FMT_CU8)
-    assert n >= 1
+    assert n >= 8
+
+
+def run_msg_case(model, fs, N, nchunks, B, seed0, fmt=aisgpu.FMT_CF32, bursts=(6, 12)):
+    """Frames + tags of a model the oracle has no taps for, against the compiled reference."""
+    if not O.have_ref():
+        pytest.skip("checked against the compiled reference only")
+    xs = [S.random_stream(fs, N * nchunks, seed0 + s, bursts_per_sec=bursts)[0] for s in range(B)]
+    eng = aisgpu.Engine(model=model, sample_rate=fs, fmt=fmt, n_streams=B, max_chunk=N)
+    refs = [O.RefModel(model=model, sample_rate=fs, fmt=fmt) for _ in range(B)]
+    got = [[] for _ in range(B)]
+    want = [[] for _ in range(B)]
+    for c in range(nchunks):
+        eng.submit(np.stack([x[c * N:(c + 1) * N] for x in xs]), N)
+        for s in range(B):
+            refs[s].push(xs[s][c * N:(c + 1) * N])
+        for m in eng.poll():
+            got[m.stream].append(m)
+        for s in range(B):
+            want[s] += refs[s].messages()
+    problems, n = [], 0
+    for s in range(B):
+        g = [(m.key(), m.start_idx, m.end_idx) for m in got[s]]
+        w = [(m.key(), m.start_idx, m.end_idx) for m in want[s]]
+        n += len(w)
+        if g != w:
+            problems.append(("MSG", s, len(g), len(w), [x for x in g if x not in w][:2], [x for x in w if x not in g][:2]))
+        else:
+            for a, b in zip(got[s], want[s]):
+                if np.float32(a.level).view(np.uint32) != np.float32(b.level).view(np.uint32) or \
+                        np.float32(a.ppm).view(np.uint32) != np.float32(b.ppm).view(np.uint32):
+                    problems.append(("TAG", s, a.level, b.level, a.ppm, b.ppm))
+    eng.close()
+    assert not problems, "parity problems (first 12): %r" % (problems[:12],)
+    return n
+
+
+@pytest.mark.parametrize("fs,N", [(1536000, 65536), (1536000, 16384), (1536000, 4096), (384000, 16384), (3072000, 131072)])
+def test_challenger(built, fs, N):
+    # model 4 "v1_high" (Model.cpp:601-678): coherent and FM decoders side by side behind one CGF, ten cross-reset decoders per channel
+    n = run_msg_case(aisgpu.MODEL_CHALLENGER, fs, N, 8 if N >= 16384 else 64, 3, 81)
+    assert n >= 4
+
+
+def test_challenger_dense(built):
+    # many overlapping / back-to-back bursts: frames complete in both branches close together, the Reset crosses branches
+    xs = [S.fuzz_stream(96000, 262144, 300 + s)[0] for s in range(6)]
+    eng = aisgpu.Engine(model=aisgpu.MODEL_CHALLENGER, sample_rate=96000, n_streams=6, max_chunk=8192)
+    got = [[] for _ in range(6)]
+    for c in range(32):
+        eng.submit(np.stack([x[c * 8192:(c + 1) * 8192] for x in xs]), 8192)
+    for m in eng.poll():
+        got[m.stream].append((m.key(), m.start_idx, m.end_idx))
+    for s in range(6):
+        r = O.RefModel(model=O.MODEL_CHALLENGER, sample_rate=96000)
+        r.run(xs[s], 8192)
+        assert got[s] == [(m.key(), m.start_idx, m.end_idx) for m in r.messages()], "stream %d" % s
+    eng.close()

@@ -1,9 +1,10 @@
 #!/bin/bash
+# GPU call 7: whole parity suite, sweeps, bench line
 mkdir -p gpurun_out
-echo "== failing fuzz test"; timeout 600 python -m pytest "tests/test_gpu_scale.py::test_decoder_fuzz_kernels" -m gpu -q -x 2>&1 | grep -E "AssertionError|passed|failed" | head -5 | cut -c1-700
-echo "== seeds 32..159"
-FUZZ_SEED0=32 FUZZ_MODES=back_to_back,sync_every_submit timeout 600 python tools/fuzz_debug2.py 0 8192 128 2>&1 | tail -30 | cut -c1-400
-echo "== ncu full captures"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
+echo "== pytest"; timeout 1700 python -m pytest tests -m gpu -q > gpurun_out/pytest7.log 2>&1; tail -12 gpurun_out/pytest7.log | cut -c1-600
+echo "== sweeps"
+SWEEP_MODEL=2 timeout 600 python tools/fe_sweep.py 4,0,4096,AISGPU_BE_PIPE=1,AISGPU_DEC_RPW=3,AISGPU_CF_ROWS=4 4,0,4096,AISGPU_BE_PIPE=1,AISGPU_DEC_RPW=3,AISGPU_CF_ROWS=8 4,0,4096,AISGPU_BE_PIPE=0,AISGPU_DEC_RPW=3 2>&1 | grep -v "^$" | tee -a gpurun_out/sweep7.jsonl
 cat > /tmp/one.py <<'PY'
 import os, sys
 sys.path.insert(0, "ais-catcher_b200"); sys.path.insert(0, "tests")
@@ -17,13 +18,24 @@ for b0 in range(0, B, 8):
     x[:, b0:b0 + 8] = ud.permute(1, 0, 2, 3)
 x += torch.randn_like(x) * 0.005
 eng = aisgpu.Engine(model=model, sample_rate=FS, n_streams=B, max_chunk=N, max_frames=1 << 20, host_staging=False)
-for i in range(3):
+for i in range(4):
     eng.submit_device(x[i % 2].data_ptr(), N, N)
     eng.sync()
 print(len(eng.poll()))
 PY
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_phase_search_ema4 -s 2 -c 1 -o gpurun_out/r2c_phase_search python /tmp/one.py 2 > /dev/null 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_cgf_fused -s 2 -c 1 -o gpurun_out/r2c_cgf_fused python /tmp/one.py 2 > /dev/null 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_v2_engine -s 2 -c 1 -o gpurun_out/r2c_v2_engine python /tmp/one.py 11 > /dev/null 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_frontend_st -s 2 -c 1 -o gpurun_out/r2c_frontend_st python /tmp/one.py 0 > /dev/null 2>&1
-ls -la gpurun_out/*.ncu-rep
+for cf in 4 8; do
+AISGPU_CF_ROWS=$cf timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2d_launches_default_cf$cf.csv python /tmp/one.py 2 > /dev/null 2>&1
+python - $cf <<'PY'
+import csv, collections, sys
+f = "gpurun_out/r2d_launches_default_cf%s.csv" % sys.argv[1]
+rows = [r for r in csv.reader(open(f)) if len(r) > 5]
+hdr = rows[0]; ik = hdr.index("Kernel Name"); iv = hdr.index("Metric Value")
+d = collections.defaultdict(list)
+for r in rows[1:]:
+    try: d[r[ik][:60]].append(float(r[iv].replace(",", "")))
+    except: pass
+for k, v in d.items():
+    if "aisgpu" in k: print("  %-60s n=%d last=%.1f us" % (k, len(v), v[-1] / 1000.0))
+PY
+done
+echo "== bench"; timeout 1200 python bench.py --steps 20 --warmup 3 > gpurun_out/bench7.json 2> gpurun_out/bench7.err; echo "bench rc=$?"; tail -4 gpurun_out/bench7.err | cut -c1-400; cat gpurun_out/bench7.json | cut -c1-6000
