@@ -175,7 +175,8 @@ struct aisgpu_handle {
 	float2 *d_Ed = nullptr;      // ModelChallenger: derotated 48 kHz samples [rows][HD + nE]
 	long long ed_stride = 0;
 	uint32_t *d_dbitsF[2] = { nullptr, nullptr };
-	float *d_lvl_prev = nullptr;
+	float *d_lvl_prev = nullptr; // [2][rows], double buffered by decode launch
+	int lvlp_cur = 0;
 	float2 *d_tap_coh = nullptr;
 	float *d_tap_dec = nullptr, *d_tap_fm = nullptr;
 	int *d_tap_cnt = nullptr;
@@ -560,7 +561,9 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 			if (int rc = carry(h, h->d_Ed, h->ed_stride, HD + n_new - HD, 0, HD)) return rc; // the last HD derotated samples stay in front
 			p.dbits2 = h->d_dbitsF[h->pb];
 			p.nslots_fm = f.nslots;
-			p.lvl_prev = h->d_lvl_prev;
+			p.lvl_prev = h->d_lvl_prev + (size_t)h->lvlp_cur * h->rows;
+			p.lvl_prev_out = h->d_lvl_prev + (size_t)(h->lvlp_cur ^ 1) * h->rows;
+			h->lvlp_cur ^= 1;
 			p.abs_lo = a0;
 			p.abs_hi = a1;
 			CU(launch_decode10(h->dec_rpw == 1 ? 1 : 3, p, h->bs));
@@ -1338,7 +1341,7 @@ static int create_impl(aisgpu_handle *h) {
 			if (int rc = dalloc(h, &h->d_Ef2[0], (size_t)h->rows * h->e_stride)) return rc;
 			for (int i = 0; i < 2; i++)
 				if (int rc = dalloc(h, &h->d_dbitsF[i], (size_t)h->rows * 5 * h->dwords)) return rc;
-			if (int rc = dalloc(h, &h->d_lvl_prev, (size_t)h->rows)) return rc;
+			if (int rc = dalloc(h, &h->d_lvl_prev, (size_t)2 * h->rows)) return rc;
 		}
 		if (int rc = dalloc(h, &h->d_steptab, CGF_NIDX)) return rc;
 		if (int rc = dalloc(h, &h->d_ppmtab, CGF_NIDX)) return rc;

@@ -905,7 +905,8 @@ __global__ void __launch_bounds__(DK3_WARPS * 32) k_decode3(const K3Params p) {
 // group of five samples the reference's order is  f0 f1 f2 f3 | a0 a1 a2 a3 a4 | f4  (FM decoder j at sample 5g + j, the
 // coherent ones when sample 5g + 4 has passed the FIR).  Same word-parallel machine as k_decode3 with ten lanes per row and
 // that rank deciding who has "already stepped" when a frame completes.  The FM decoders see the signal level ScatterPLL
-// left in the tag: the previous group's for f0..f3, the current one's for f4 (DSP.h:100-106, the TAG travels by reference).
+// left in the tag: the previous group's for f0..f3, the current one's for f4 (DSP.h:100-106, the TAG travels by reference --
+// across the two channels as well: a row's first group of a block sees the level the other channel's chain left behind).
 template <int RPW>
 __global__ void __launch_bounds__(DK3_WARPS * 32) k_decode10(const K3Params p) {
 	constexpr int MODEL = 2;
@@ -970,7 +971,11 @@ __global__ void __launch_bounds__(DK3_WARPS * 32) k_decode10(const K3Params p) {
 			if (r2 >= p.rows) continue;
 			for (int e = lane; e < K3_TS + 1; e += 32) { // entry e = level of slot s0 + e - 1
 				const int sl = s0 + e - 1;
-				if (sl < 0) cp_async_f(&tile[g2][buf][e], p.lvl_prev + r2);
+				if (sl < 0) { // the level the tag carries into this row's first group: the OTHER channel's last group (same TAG object,
+					// Rotate feeds channel A's chain, then B's, DSP.cpp:312-313) -- for B the one A has just left in this block
+					if (r2 & 1) cp_async_f(&tile[g2][buf][e], p.lvl + (long long)(r2 - 1) * p.lvl_stride + p.nsym - 1);
+					else cp_async_f(&tile[g2][buf][e], p.lvl_prev + r2);
+				}
 				else if (sl < p.nsym) cp_async_f(&tile[g2][buf][e], p.lvl + (long long)r2 * p.lvl_stride + sl);
 			}
 		}
@@ -1088,7 +1093,7 @@ __global__ void __launch_bounds__(DK3_WARPS * 32) k_decode10(const K3Params p) {
 		d.lastBit = lastBit;
 		p.dec[sidx] = d;
 		// ScatterPLL's level stays in the tag for the FM decoders of the next group: keep the last one for the next submit
-		if (ph10 == 0 && p.nsym > 0) p.lvl_prev[row] = p.lvl[(long long)row * p.lvl_stride + p.nsym - 1];
+		if (ph10 == 0 && (row & 1) && p.nsym > 0) p.lvl_prev_out[row - 1] = p.lvl[(long long)row * p.lvl_stride + p.nsym - 1]; // B's last level is what A starts the next block with
 	}
 }
 

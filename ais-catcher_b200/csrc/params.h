@@ -113,7 +113,8 @@ struct K3Params {
 	uint32_t *dbits;      // ModelDefault: demodulated bits, [rows*5][dwords], bit (s & 31) of word (s >> 5) = symbol s
 	uint32_t *dbits2;     // ModelChallenger: the FM branch's decision bits, same layout
 	int nslots_fm;        // ModelChallenger: slots the FM branch covers this submit
-	float *lvl_prev;      // ModelChallenger: [rows] ScatterPLL level of the last group of the previous submit
+	const float *lvl_prev; // ModelChallenger: [rows] the level the tag carries into this block (read)
+	float *lvl_prev_out;   //                  ... and into the next one (written; double buffered by launch)
 	int dwords;
 	float *lvl;           // ModelDefault: ScatterPLL level of symbol s (TAG::sample_lvl, DSP.h:100-106), [rows][lvl_stride]
 	int lvl_stride;
