@@ -93,6 +93,7 @@ struct aisgpu_handle {
 	FeParams fe_pre;
 	int pre_tile = 0;
 	long long msg_chunk = 0; // ordinal of the caller's submit (what frames are tagged with)
+	long long pre_tap0 = 0, pre_tap1 = 0, pre2_tap0 = 0, pre2_tap1 = 0; // resampler outputs of the last submit (ring positions), for AISGPU_TAP_PRE / _PRE2
 	int obps = 8;            // bytes per sample of the caller's format (bps: of what the front end proper reads)
 	int inner_max = 0;       // longest block the front end proper can be handed
 	int use_fdc = 0;
@@ -816,6 +817,8 @@ int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) 
 	h->msg_chunk = (long long)h->counters[3];
 	const int B = h->cfg.n_streams;
 	int rc = 0;
+	h->pre_tap0 = h->s_produced;
+	h->pre2_tap0 = h->s2_produced;
 	if (h->pre == 0) rc = submit_common(h, dev_in, stride, N);
 	else {
 		const int cur = h->ptail_cur, nxt = cur ^ 1;
@@ -946,6 +949,8 @@ int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) 
 		}
 	}
 	if (rc) return rc;
+	h->pre_tap1 = h->s_produced;
+	h->pre2_tap1 = h->s2_produced;
 	if (int rc2 = mark_ticket(h, (long long)h->counters[3])) return rc2;
 	h->counters[2] += (uint64_t)N;
 	h->counters[3] += 1;
@@ -1609,6 +1614,24 @@ int aisgpu_tap(aisgpu_handle *h, int tap, int stream, int channel, void *dst, si
 			}
 		}
 		break;
+	}
+	case AISGPU_TAP_PRE:
+	case AISGPU_TAP_PRE2: { // what the resampler in front of the decimation chain produced in the last submit (stream, channel ignored)
+		const bool second = tap == AISGPU_TAP_PRE2;
+		const float2 *ring = second ? h->d_S2 : h->d_S;
+		const long long a = second ? h->pre2_tap0 : h->pre_tap0, b = second ? h->pre2_tap1 : h->pre_tap1;
+		const int cap = second ? h->s2_cap : h->s_cap;
+		const long long st = second ? h->s2_stride : h->s_stride;
+		if (!ring || cap <= 0) { h->err = "this rate has no resampler stage"; return AISGPU_EINVAL; }
+		size_t cnt = (size_t)std::min<long long>(b - a, cap);
+		if (dst_bytes < cnt * 8) cnt = dst_bytes / 8;
+		for (size_t i = 0; i < cnt;) { // the ring may wrap
+			const size_t off = (size_t)((a + (long long)i) % cap), run = std::min(cnt - i, (size_t)cap - off);
+			if (dst) CU(cudaMemcpy((float2 *)dst + i, ring + (long long)stream * st + off, run * 8, cudaMemcpyDeviceToHost));
+			i += run;
+		}
+		*n_out = cnt;
+		return 0;
 	}
 	case 6: // debug counters of the decoder kernel, 4 x int64 per row (stream/channel ignored, all rows)
 		if (!h->d_dbg) { h->err = "AISGPU_DEBUG not set"; return AISGPU_EINVAL; }

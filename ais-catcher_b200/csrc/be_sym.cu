@@ -198,6 +198,8 @@ __global__ void __launch_bounds__(32) k_phase_search_ema4(const K3Params p) {
 		cj[k] = c_ps_cos[j];
 		sj[k] = h < 8 ? c_ps_sin[j] : -c_ps_sin[j]; // a - b == a + (-b) and im * (-s) == -(im * s), exactly
 	}
+	const c64 cj01 = pack2(cj[0], cj[1]), cj23 = pack2(cj[2], cj[3]), sj01 = pack2(sj[0], sj[1]), sj23 = pack2(sj[2], sj[3]);
+	const c64 w2 = pack2(weight, weight), o2 = pack2(omw, omw);
 	float ma[4] = { 0.f, 0.f, 0.f, 0.f };
 	uint32_t hist = 0u; // nibble d (bits 4d .. 4d+3) = the sign decisions of the lane's four hypotheses d symbols ago
 	int max_idx = 0, rot = 0;
@@ -233,19 +235,27 @@ __global__ void __launch_bounds__(32) k_phase_search_ema4(const K3Params p) {
 		uint32_t word = 0;
 		// two symbols per trip: the second one's arithmetic (independent of the first's decision chain) fills the issue slots
 		// the first one leaves while its shuffles are in flight
-#pragma unroll 2
+#pragma unroll 4
 		for (int sl = 0; sl < s_end; sl++) {
 			const float2 x = my[sl * 5];
 			// (1j)^rot pre-rotation (Demod.cpp:44-65), branch free: swap on odd rot, negate on rot >= 2 (sign flips are exact)
 			float re = (rot & 1) ? -x.y : x.x, im = (rot & 1) ? x.x : x.y;
 			if (rot & 2) { re = -re; im = -im; }
 			rot = (rot + 1) & 3;
-			uint32_t dnow = 0;
-#pragma unroll
-			for (int k = 0; k < 4; k++) {
-				const float tt = __fadd_rn(__fmul_rn(re, cj[k]), __fmul_rn(im, sj[k]));
-				dnow |= (tt > 0.0f ? 1u : 0u) << k;
-				ma[k] = __fadd_rn(__fmul_rn(weight, ma[k]), __fmul_rn(omw, fabsf(tt))); // Demod.cpp:67-78
+			// products by packed FMUL2 (two hypotheses per instruction), sums by scalar FADD: a packed mul feeding a packed add would
+			// be contracted into FFMA2 by ptxas, a packed mul feeding scalar adds keeps both roundings (checked in SASS)
+			const c64 re2 = pack2(re, re), im2 = pack2(im, im);
+			const float2 a01 = unpack2(pmul(re2, cj01)), a23 = unpack2(pmul(re2, cj23));
+			const float2 b01 = unpack2(pmul(im2, sj01)), b23 = unpack2(pmul(im2, sj23));
+			const float tt0 = __fadd_rn(a01.x, b01.x), tt1 = __fadd_rn(a01.y, b01.y), tt2 = __fadd_rn(a23.x, b23.x), tt3 = __fadd_rn(a23.y, b23.y);
+			const uint32_t dnow = (tt0 > 0.0f ? 1u : 0u) | (tt1 > 0.0f ? 2u : 0u) | (tt2 > 0.0f ? 4u : 0u) | (tt3 > 0.0f ? 8u : 0u);
+			{ // ma = weight * ma + (1 - weight) * |t| (Demod.cpp:67-78)
+				const float2 w01 = unpack2(pmul(w2, pack2(ma[0], ma[1]))), w23 = unpack2(pmul(w2, pack2(ma[2], ma[3])));
+				const float2 o01 = unpack2(pmul(o2, pack2(fabsf(tt0), fabsf(tt1)))), o23 = unpack2(pmul(o2, pack2(fabsf(tt2), fabsf(tt3))));
+				ma[0] = __fadd_rn(w01.x, o01.x);
+				ma[1] = __fadd_rn(w01.y, o01.y);
+				ma[2] = __fadd_rn(w23.x, o23.x);
+				ma[3] = __fadd_rn(w23.y, o23.y);
 			}
 			hist = (hist << 4) | dnow;
 			// bit k: demodulated bit hypothesis 4q + k would deliver = its decisions 3 and 4 symbols ago, XORed (nDelay = 3, Model.h:219)

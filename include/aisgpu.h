@@ -61,6 +61,8 @@ extern "C" {
 #define AISGPU_TAP_CGF 1   /* after SquareFreqOffsetCorrection (DSP.cpp:475-489), float2, whole 512-blocks of this submit */
 #define AISGPU_TAP_FIR 2   /* after FilterComplex (ModelDefault, float2) or Filter (FM models, float) */
 #define AISGPU_TAP_ROT 3   /* the Rotate phasor table of the last submit (DSP.cpp:296-316), float2 */
+#define AISGPU_TAP_PRE 7   /* resampled rates: output of DSP::Upsample (or of DownsampleKFilter when there is no Upsample) in the last submit */
+#define AISGPU_TAP_PRE2 8  /* Upsample -> DownsampleKFilter rates: the /3 filter's output in the last submit */
 
 typedef struct aisgpu_config {
 	uint32_t struct_size;       /* = sizeof(aisgpu_config) */

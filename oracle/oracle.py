@@ -19,7 +19,7 @@ FLAG_PS_EMA, FLAG_AFC_WIDE, FLAG_DROOP, FLAG_TAPS, FLAG_FP_DS, FLAG_DSK = 1, 2, 
 DEFAULT_FLAGS = FLAG_PS_EMA | FLAG_AFC_WIDE | FLAG_DROOP
 
 # complex taps
-TAP_ROT_IN, TAP_UP, TAP_DOWN, TAP_CA, TAP_CB, TAP_CGF_A, TAP_CGF_B, TAP_FC_A, TAP_FC_B = range(9)
+TAP_ROT_IN, TAP_UP, TAP_DOWN, TAP_CA, TAP_CB, TAP_CGF_A, TAP_CGF_B, TAP_FC_A, TAP_FC_B, TAP_US, TAP_DSK = range(11)  # US / DSK: reference harness only
 # float taps
 TAP_DEC_A0, TAP_DEC_B0, TAP_FM_A, TAP_FM_B, TAP_FR_A, TAP_FR_B = 0, 5, 10, 11, 12, 13
 

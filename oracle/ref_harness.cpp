@@ -106,7 +106,7 @@ struct MsgSink : public StreamIn<AIS::Message> {
 
 enum { MODEL_STANDARD = 0, MODEL_BASE = 1, MODEL_DEFAULT = 2, MODEL_CHALLENGER = 4, MODEL_V2 = 11 };
 enum { FLAG_PS_EMA = 1, FLAG_AFC_WIDE = 2, FLAG_DROOP = 4, FLAG_TAPS = 8, FLAG_FP_DS = 16, FLAG_DSK = 32 };
-static const int NTAPS_C = 9;  // 0: ROT in, 1/2: ROT up/down, 3/4: C_a/C_b, 5/6: CGF or (unused), 7/8: FC
+static const int NTAPS_C = 11; // 0: ROT in, 1/2: ROT up/down, 3/4: C_a/C_b, 5/6: CGF or (unused), 7/8: FC, 9: US out, 10: DSK out
 static const int NTAPS_F = 14; // 0..4 / 5..9: per-phase decoder inputs ch A / B; 10/11: FM out; 12/13: FR out
 
 struct Handle {
@@ -199,6 +199,8 @@ void *aisref_create(int model, int sample_rate, int format, unsigned flags, int 
 					c->Connect(&h->tc[0]);
 					break;
 				}
+			fe->US.out.Connect(&h->tc[9]);   // DSP::Upsample / DownsampleKFilter outputs (only fed at resampled rates)
+			fe->DSK.out.Connect(&h->tc[10]);
 			fe->ROT.up.Connect(&h->tc[1]);
 			fe->ROT.down.Connect(&h->tc[2]);
 			fe->C_a->Connect(&h->tc[3]);

@@ -175,6 +175,43 @@ def test_resampled_rates(built, fs, N, model):
     # The reference re-blocks behind the resampler, so per-submit taps do not line up; frames are compared bit for bit.
     n = run_case(built, model, fs, N, 6, 2, check_taps=False, seed0=29)
     assert n >= 2
+    if O.have_ref():
+        resampler_taps(fs, N, 6, model)
+
+
+def resampler_taps(fs, N, nchunks, model, dsk=False):
+    """The resampler outputs themselves (DSP::Upsample, DownsampleKFilter) against taps on the reference's US.out / DSK.out:
+    the sample streams must be bit-identical (the reference emits whole blocks, so the common prefix is compared)."""
+    x = S.random_stream(fs, N * nchunks, 91)[0]
+    eng = aisgpu.Engine(model=model, sample_rate=fs, n_streams=1, max_chunk=N, taps=True, dsk=dsk)
+    ref = O.RefModel(model=model, sample_rate=fs, flags=O.DEFAULT_FLAGS | (O.FLAG_DSK if dsk else 0), taps=True)
+    got = {aisgpu.TAP_PRE: [], aisgpu.TAP_PRE2: []}
+    want = {O.TAP_US: [], O.TAP_DSK: []}
+    for c in range(nchunks):
+        eng.submit(x[None, c * N:(c + 1) * N], N)
+        ref.push(x[c * N:(c + 1) * N])
+        for t in got:
+            try:
+                got[t].append(eng.tap(t))
+            except aisgpu.AisGpuError:
+                pass
+        for t in want:
+            want[t].append(ref.tap_c(t))
+    eng.close()
+    us, dsk_ = np.concatenate(want[O.TAP_US]), np.concatenate(want[O.TAP_DSK])
+    pre = np.concatenate(got[aisgpu.TAP_PRE]) if got[aisgpu.TAP_PRE] else np.zeros(0, np.complex64)
+    pre2 = np.concatenate(got[aisgpu.TAP_PRE2]) if got[aisgpu.TAP_PRE2] else np.zeros(0, np.complex64)
+    pairs = []
+    if len(us) and len(dsk_):
+        pairs = [("US", pre, us), ("DSK", pre2, dsk_)]
+    elif len(us):
+        pairs = [("US", pre, us)]
+    elif len(dsk_):
+        pairs = [("DSK", pre, dsk_)]
+    assert pairs, "no resampler at this rate"
+    for name, g, w in pairs:
+        n = min(len(g), len(w))
+        assert n > 1000 and bits_equal(g[:n], w[:n]), "%s output differs: %r" % (name, first_diff(g[:n], w[:n]))
 
 
 def test_resampled_cu8(built):
@@ -212,6 +249,8 @@ def test_dsk_buckets(built, fs, N, model):
     # DownsampleKFilter /3, exact and interpolated (CIC -> Upsample -> /3); rates outside those buckets keep their chain
     n = run_case(built, model, fs, N, 6, 2, check_taps=False, seed0=51, dsk=True)
     assert n >= 2
+    if fs != 1536000:
+        resampler_taps(fs, N, 6, model, dsk=True)
 
 
 def test_dsk_cu8(built):
@@ -357,4 +396,30 @@ def test_challenger_dense(built):
         r = O.RefModel(model=O.MODEL_CHALLENGER, sample_rate=96000)
         r.run(xs[s], 8192)
         assert got[s] == [(m.key(), m.start_idx, m.end_idx) for m in r.messages()], "stream %d" % s
+    eng.close()
+
+
+@pytest.mark.parametrize("amp,exact", [(0.0, True), (1e-30, True), (3e-39, False)])
+def test_tiny_and_zero_inputs(built, amp, exact):
+    """All-zero and tiny inputs through the front end.  Zero and small NORMAL values are bit-exact.  With SUBNORMAL values the
+    streaming kernel is allowed a deviation: ptxas contracts the exact x 1/32 scaling of a CIC stage with the next stage's
+    first add into one FFMA2, which rounds once where the reference rounds twice -- identical for normal numbers (a power-of-two
+    scaling is exact), not when the scaled value is subnormal.  Bounded here to a few denormal ulps (1.4e-45); no SDR delivers
+    such samples (CU8/CS16 inputs have 8/16-bit granularity)."""
+    fs, N, B = 1536000, 65536, 2
+    rng = np.random.default_rng(5)
+    xs = [((rng.standard_normal(N * 2) + 1j * rng.standard_normal(N * 2)) * amp).astype(np.complex64) for _ in range(B)]
+    eng = aisgpu.Engine(model=aisgpu.MODEL_DEFAULT, sample_rate=fs, n_streams=B, max_chunk=N, taps=True)
+    refs = [oracle_model(model=aisgpu.MODEL_DEFAULT, sample_rate=fs, taps=True) for _ in range(B)]
+    for c in range(2):
+        eng.submit(np.stack([x[c * N:(c + 1) * N] for x in xs]), N)
+        for s in range(B):
+            refs[s].push(xs[s][c * N:(c + 1) * N])
+            for ch in range(2):
+                w = refs[s].tap_c(O.TAP_CA + ch)
+                g = eng.tap(aisgpu.TAP_C, s, ch)
+                if exact:
+                    assert bits_equal(g, w), (amp, c, s, ch, first_diff(g, w))
+                else:
+                    assert len(g) == len(w) and np.max(np.abs(g - w)) <= 8 * 1.4e-45, (amp, float(np.max(np.abs(g - w))))
     eng.close()

@@ -1,7 +1,7 @@
 #!/bin/bash
 # GPU call 8: Challenger + V2 CU8 parity; sanitizer runs for profiles/
 mkdir -p gpurun_out
-echo "== challenger / v2 tests"; timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "challenger or v2" > gpurun_out/pytest8.log 2>&1; tail -25 gpurun_out/pytest8.log | cut -c1-900
+echo "== challenger tests"; timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "challenger" > gpurun_out/pytest9.log 2>&1; tail -12 gpurun_out/pytest9.log | cut -c1-900
 echo "== compute-sanitizer memcheck (smoke + one parity case per model)"
 cat > /tmp/san.py <<'PY'
 import sys
