@@ -957,16 +957,25 @@ int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) 
 	return 0;
 }
 
-// Message::getLetter (Message.cpp:643-662)
-char msg_letter(const uint8_t *data, int length, int pos) {
-	int start = pos * 6, end = start + 6;
-	if (end > 1064 || start < 0) return 0;
-	int x = start >> 3, y = start & 7;
-	unsigned w = ((unsigned)data[x] << 8) | data[x + 1];
-	int l = (w >> (16 - 6 - y)) & 0x3F;
-	int overrun = end - length;
-	if (overrun > 0) l &= 0x3F << overrun;
-	return (char)(l < 40 ? l + 48 : l + 56);
+// The payload of a frame as NMEA six-bit letters, one pass over the bit stream (what Message::getLetter does letter by
+// letter, Message.cpp:643-662): letter i = bits [6i, 6i + 6), MSB first; bits past the message end read as 0; a letter that
+// would cross bit 1064 is the NUL byte the reference returns there; value v prints as v + 48 (v < 40) or v + 56.
+int armour_payload(const uint8_t *data, int nbits, char *out) {
+	const int n = (nbits + 5) / 6;
+	uint32_t window = 0; // the next `have` unread bits, right-aligned
+	int have = 0, next_byte = 0;
+	for (int i = 0; i < n; i++) {
+		if (have < 6) {
+			window = (window << 8) | data[next_byte++];
+			have += 8;
+		}
+		have -= 6;
+		unsigned v = (window >> have) & 0x3Fu;
+		const int past = 6 * (i + 1) - nbits; // bits of this letter beyond the end of the message
+		if (past > 0) v &= 0x3Fu << past;
+		out[i] = 6 * (i + 1) > 1064 ? (char)0 : (char)(v + (v < 40 ? 48 : 56));
+	}
+	return n;
 }
 
 bool msg_validate(const uint8_t *d, int length) { // Message.cpp:398-413
@@ -978,44 +987,44 @@ bool msg_validate(const uint8_t *d, int length) { // Message.cpp:398-413
 	return length >= ml[t - 1];
 }
 
-void build_nmea(aisgpu_msg &m, int own_mmsi, int *seq_counter) { // Message.cpp:569-631
-	static const char hex[] = "0123456789ABCDEF";
-	const uint8_t *data = m.data;
-	const int length = m.nbits;
-	const unsigned mmsi = ((unsigned)data[1] << 22) | (data[2] << 14) | (data[3] << 6) | (data[4] >> 2);
-	int nletters = (length + 5) / 6;
-	int nsent = nletters == 0 ? 1 : (nletters + 55) / 56;
-	char own = (own_mmsi == (int)mmsi) ? 'O' : 'M';
+// Message::buildNMEA (Message.cpp:569-631): "!AIVDM,<sentences>,<index>,<seq>,<channel>,<up to 56 letters>,<fill>*<checksum>";
+// own-ship frames read !AIVDO; the sequence id (Message::nextSeqId, Message.cpp:28-39; one counter per stream here instead of
+// one per process) only exists for multi-sentence messages; fill bits are reported on the last sentence.
+void build_nmea(aisgpu_msg &m, int own_mmsi, int *seq_counter) {
+	char letters[180];
+	const int nletters = armour_payload(m.data, m.nbits, letters);
+	const int nsent = nletters ? (nletters + 55) / 56 : 1;
+	const uint32_t mmsi = ((uint32_t)m.data[1] << 22) | ((uint32_t)m.data[2] << 14) | ((uint32_t)m.data[3] << 6) | (m.data[4] >> 2);
 	char seq = 0;
-	if (nsent > 1) { // Message::nextSeqId (Message.cpp:28-39), one counter per stream instead of per process
-		int &s = *seq_counter;
-		seq = (char)(s + '0');
-		s = (s + 1) % 10;
+	if (nsent > 1) {
+		seq = (char)('0' + *seq_counter);
+		*seq_counter = (*seq_counter + 1) % 10;
 	}
 	m.n_sentences = nsent;
-	for (int s = 0, l = 0; s < nsent && s < 4; s++) {
-		char *p = m.nmea[s];
-		memcpy(p, "!AIVDM,X,X,", 11);
-		p[5] = own;
-		p[7] = (char)(nsent + '0');
-		p[9] = (char)(s + 1 + '0');
-		int i = 11;
-		if (seq) p[i++] = seq;
-		p[i++] = ',';
-		if (m.channel != '?') p[i++] = m.channel;
-		p[i++] = ',';
-		int letters = std::min(nletters - l, 56);
-		for (int k = 0; k < letters; k++) p[i++] = msg_letter(data, length, l + k);
-		l += letters;
-		p[i++] = ',';
-		p[i++] = (char)(((s == nsent - 1) ? nletters * 6 - length : 0) + '0');
-		int c = 0;
-		for (int k = 1; k < i; k++) c ^= (unsigned char)p[k];
-		p[i++] = '*';
-		p[i++] = hex[(c >> 4) & 0xF];
-		p[i++] = hex[c & 0xF];
-		p[i] = 0;
-		m.nmea_len[s] = i; // a 1064-bit message ends in a NUL letter (Message.cpp:646-647), so strlen() is not enough
+	for (int s = 0; s < nsent && s < 4; s++) {
+		char *line = m.nmea[s];
+		int at = 0;
+		uint8_t sum = 0; // XOR of everything between '!' and '*'
+		auto put = [&](char ch) { line[at++] = ch; sum ^= (uint8_t)ch; };
+		line[at++] = '!';
+		for (const char *t = (own_mmsi == (int)mmsi) ? "AIVDO," : "AIVDM,"; *t; t++) put(*t);
+		put((char)('0' + nsent));
+		put(',');
+		put((char)('1' + s));
+		put(',');
+		if (seq) put(seq);
+		put(',');
+		if (m.channel != '?') put(m.channel);
+		put(',');
+		const int first = 56 * s, count = std::min(56, nletters - first);
+		for (int k = 0; k < count; k++) put(letters[first + k]);
+		put(',');
+		put((char)('0' + (s == nsent - 1 ? 6 * nletters - m.nbits : 0)));
+		line[at++] = '*';
+		line[at++] = "0123456789ABCDEF"[sum >> 4];
+		line[at++] = "0123456789ABCDEF"[sum & 15];
+		line[at] = 0;
+		m.nmea_len[s] = at; // a 1064-bit message ends in a NUL letter, so strlen() is not enough
 	}
 }
 

@@ -148,3 +148,23 @@ def test_validate_min_lengths(built):
         for n in (0, 39, 40, 148, 149, 168, 417, 418, 1064, 1065):
             want = 1 if n == 0 else (0 if n > 1064 or t < 1 or t > 28 else int(n >= ml[t - 1]))
             assert lib.aisgpu_validate(d, n) == want, (t, n)
+
+
+def test_nmea_armouring_against_reference_sentences(built):
+    """aisgpu_build_nmea (host-only) against the sentences the oracle printed for the same frames: every length 40..1064,
+    multi-sentence messages with their sequence ids, fill bits -- over the decoder-fuzz stimulus (hundreds of frames)."""
+    import oracle as O
+    Model = O.RefModel if O.have_ref() else O.PortModel
+    n, multi = 0, 0
+    for seed in range(6):
+        x, _ = S.fuzz_stream(96000, 262144, seed)
+        m = Model(model=O.MODEL_STANDARD, sample_rate=96000)
+        m.run(x, 8192)
+        seq = 0
+        for q in m.messages():
+            pay = q.payload + bytes(140 - len(q.payload))
+            got, seq = aisgpu.build_nmea(pay, q.nbits, channel=q.channel, seq=seq)
+            assert got == q.nmea, (seed, q.nbits, got, q.nmea)
+            n += 1
+            multi += len(q.nmea) > 1
+    assert n > 100 and multi > 20
