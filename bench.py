@@ -539,6 +539,18 @@ def main():
         also.append({"workload": "same data and batch, V2::Engine (model 11)", "value": B * N * 4 / (mv * 1e-3) / 1e6, "unit": "MSamples/s (this rank)",
                      "ms_per_step": mv / 4, "frames": nmv, "parity": parv})
         engv.close()
+        # ModelChallenger (model 4) on the same data
+        engc = aisgpu.Engine(model=aisgpu.MODEL_CHALLENGER, sample_rate=FS, n_streams=B, max_chunk=N, device=local_rank, max_frames=1 << 20, host_staging=False)
+        gotc = {s: [] for s in sample_streams[:8]}
+        bc, nc = timed_blocks(engc, x, N, 2, 4, 3)
+        nmc = poll_streams(engc, set(sample_streams[:8]), gotc)
+        parc = None
+        if not args.no_parity:
+            parc = oracle_check(sample_streams[:8], lambda c: {s: x[c % R][s].cpu().numpy() for s in sample_streams[:8]}, nc, gotc, 4, FS)
+        mc = median(bc)
+        also.append({"workload": "same data and batch, ModelChallenger (model 4)", "value": B * N * 4 / (mc * 1e-3) / 1e6, "unit": "MSamples/s (this rank)",
+                     "ms_per_step": mc / 4, "frames": nmc, "parity": parc})
+        engc.close()
         del x
         torch.cuda.empty_cache()
         # BASELINE.json configs[2]: batch 4096 CF32 @6 MSPS (AirSpy shape: 4 CIC stages -> Upsample 125/128 -> 2 CIC stages), coherent chain
