@@ -18,7 +18,8 @@ EXPORTS = ["aisgpu_abi_version", "aisgpu_default_config", "aisgpu_create", "aisg
            "aisgpu_sync", "aisgpu_poll", "aisgpu_tap", "aisgpu_counters", "aisgpu_cuda_stream",
            "aisgpu_last_frontend_ms", "aisgpu_frontend_times", "aisgpu_last_launches", "aisgpu_last_error", "aisgpu_destroy",
            "aisgpu_validate", "aisgpu_build_nmea", "aisgpu_chunk_granule", "aisgpu_join", "aisgpu_submit_v", "aisgpu_submit_async",
-           "aisgpu_poll_upto", "aisgpu_nccl_unique_id", "aisgpu_comm_init", "aisgpu_allreduce_counts"]
+           "aisgpu_poll_upto", "aisgpu_nccl_unique_id", "aisgpu_comm_init", "aisgpu_allreduce_counts",
+           "aisgpu_msg_json", "aisgpu_msg_binary", "aisgpu_feed_files"]
 
 OK, EINVAL, ENODEV, ECUDA, ENOMEM, EOVERFLOW = 0, -1, -2, -3, -4, -5
 
@@ -36,6 +37,15 @@ class MsgStruct(C.Structure):
                 ("end_idx", C.c_int64), ("level", C.c_float), ("ppm", C.c_float), ("chunk", C.c_int64),
                 ("data", C.c_uint8 * 140), ("n_sentences", C.c_int32), ("nmea", (C.c_char * 100) * 4),
                 ("nmea_len", C.c_int32 * 4)]
+
+
+class TagStruct(C.Structure):
+    _fields_ = [("version", C.c_int32), ("driver", C.c_int32), ("hardware", C.c_char_p), ("mode", C.c_int32), ("status", C.c_int32),
+                ("ipv4", C.c_uint32), ("rxtime_us", C.c_int64), ("toa_us", C.c_int64), ("station", C.c_int32),
+                ("include_ssl", C.c_int32), ("uuid", C.c_char_p), ("suffix", C.c_char_p)]
+
+
+MSG_FN = C.CFUNCTYPE(None, C.POINTER(MsgStruct), C.c_int, C.c_void_p)
 
 
 class Msg:
@@ -99,6 +109,9 @@ def load():
     lib.aisgpu_chunk_granule.argtypes = [C.POINTER(Config)]
     lib.aisgpu_validate.argtypes = [C.c_char_p, C.c_int]
     lib.aisgpu_build_nmea.argtypes = [C.POINTER(MsgStruct), C.c_int, C.POINTER(C.c_int)]
+    lib.aisgpu_msg_json.argtypes = [C.POINTER(MsgStruct), C.POINTER(TagStruct), C.c_char_p, C.c_int]
+    lib.aisgpu_msg_binary.argtypes = [C.POINTER(MsgStruct), C.POINTER(TagStruct), C.c_int, C.c_char_p, C.c_int]
+    lib.aisgpu_feed_files.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, MSG_FN, C.c_void_p, C.POINTER(C.c_uint64)]
     lib.aisgpu_destroy.argtypes = [C.c_void_p]
     lib.aisgpu_destroy.restype = None
     _lib = lib
@@ -115,6 +128,46 @@ def chunk_granule(sample_rate, model=MODEL_DEFAULT, dsk=False, fp_ds=False, fmt=
     if g <= 0:
         raise AisGpuError("rc=%d: %s" % (g, lib.aisgpu_last_error(None).decode()))
     return g
+
+
+def make_msg(payload_bytes, nbits, channel="A", start_idx=0, end_idx=0, level=0.0, ppm=0.0, sentences=()):
+    """An aisgpu_msg from raw fields (host-only helpers take it)."""
+    m = MsgStruct()
+    m.nbits = nbits
+    m.channel = channel.encode()
+    m.start_idx, m.end_idx, m.level, m.ppm = start_idx, end_idx, level, ppm
+    for i, b in enumerate(payload_bytes[:140]):
+        m.data[i] = b
+    m.n_sentences = len(sentences)
+    for i, t in enumerate(sentences):
+        raw = t if isinstance(t, bytes) else t.encode("latin-1")
+        C.memmove(m.nmea[i], raw, len(raw))
+        m.nmea_len[i] = len(raw)
+    return m
+
+
+def make_tag(version=0, driver=0, hardware=None, mode=3, status=0, ipv4=0, rxtime_us=0, toa_us=0, station=0, include_ssl=False,
+             uuid=None, suffix=None):
+    enc = lambda t: None if t is None else (t if isinstance(t, bytes) else t.encode("latin-1"))
+    return TagStruct(version, driver, enc(hardware), mode, status, ipv4, rxtime_us, toa_us, station, 1 if include_ssl else 0, enc(uuid), enc(suffix))
+
+
+def msg_json(m, tag, cap=4096):
+    """Host-only: aisgpu_msg_json (reference Message::getNMEAJSON, Message.cpp:93-191) -> bytes."""
+    buf = C.create_string_buffer(cap)
+    n = load().aisgpu_msg_json(C.byref(m), C.byref(tag), buf, cap)
+    if n < 0:
+        raise AisGpuError("aisgpu_msg_json rc=%d" % n)
+    return buf.raw[:n]
+
+
+def msg_binary(m, tag, crc, cap=1024):
+    """Host-only: aisgpu_msg_binary (reference Message::getBinaryNMEA, Message.cpp:277-396) -> bytes."""
+    buf = C.create_string_buffer(cap)
+    n = load().aisgpu_msg_binary(C.byref(m), C.byref(tag), 1 if crc else 0, buf, cap)
+    if n < 0:
+        raise AisGpuError("aisgpu_msg_binary rc=%d" % n)
+    return buf.raw[:n]
 
 
 def build_nmea(payload_bytes, nbits, channel="A", own_mmsi=-1, seq=0):
@@ -195,6 +248,20 @@ class Engine:
         t = C.c_int64(-1)
         self._chk(self.lib.aisgpu_submit_async(self.h, C.c_void_p(host_ptr), n_samples, C.byref(t)))
         return t.value
+
+    def feed_files(self, paths, n):
+        """aisgpu_feed_files: one recording per stream, blocks of n samples; returns (messages, blocks submitted)."""
+        assert len(paths) == self.n_streams
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+        out = []
+        cb = MSG_FN(lambda msgs, k, user: out.extend(Msg(msgs[i]) for i in range(k)))
+        nb = C.c_uint64(0)
+        rc = self.lib.aisgpu_feed_files(self.h, arr, n, cb, None, C.byref(nb))
+        if rc == EOVERFLOW:
+            self.overflows += 1
+        else:
+            self._chk(rc)
+        return out, nb.value
 
     def poll_upto(self, ticket, batch=256):
         out = []

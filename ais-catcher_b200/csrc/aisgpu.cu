@@ -1153,6 +1153,10 @@ void aisgpu_default_config(aisgpu_config *cfg) {
 
 const char *aisgpu_last_error(aisgpu_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+// hooks for the host-only units of the library (host_internal.h)
+const aisgpu_config *aisgpu_internal_config(aisgpu_handle *h) { return &h->cfg; }
+void aisgpu_internal_set_error(aisgpu_handle *h, const char *msg) { h->err = msg; }
+
 static int create_impl(aisgpu_handle *h) {
 	const aisgpu_config &c = h->cfg;
 	if (c.model != AISGPU_MODEL_DEFAULT && c.model != AISGPU_MODEL_STANDARD && c.model != AISGPU_MODEL_BASE && c.model != AISGPU_MODEL_V2 &&

@@ -525,7 +525,8 @@ def main():
             also.append({"workload": "same data and batch, ModelDefault (coherent PhaseSearchEMA chain, the reference's default model)",
                          "value": B * N * args.steps / (m2 * 1e-3) / 1e6, "unit": "MSamples/s (this rank)", "ms_per_step": m2 / args.steps,
                          "whole_chain_frac": ALGO_BYTES_PER_SAMPLE * B * N / (m2 / args.steps * 1e-3) / 1e9 / peaks()[0],
-                         "frontend_ms": sum(fe2) / len(fe2), "frames": nm2, "parity": par2})
+                         "frontend_ms": sum(fe2) / len(fe2), "frames": nm2, "parity": par2,
+                         "blocks_ms_per_step": [round(b / args.steps, 4) for b in b2]})
             eng2.close()
         # the V2 engine (model 11) on the same data
         engv = aisgpu.Engine(model=aisgpu.MODEL_V2, sample_rate=FS, n_streams=B, max_chunk=N, device=local_rank, max_frames=1 << 20, host_staging=False)
@@ -537,7 +538,7 @@ def main():
             parv = oracle_check(sample_streams[:8], lambda c: {s: x[c % R][s].cpu().numpy() for s in sample_streams[:8]}, nv, gotv, 11, FS)
         mv = median(bv)
         also.append({"workload": "same data and batch, V2::Engine (model 11)", "value": B * N * 4 / (mv * 1e-3) / 1e6, "unit": "MSamples/s (this rank)",
-                     "ms_per_step": mv / 4, "frames": nmv, "parity": parv})
+                     "ms_per_step": mv / 4, "frames": nmv, "parity": parv, "blocks_ms_per_step": [round(b / 4, 4) for b in bv]})
         engv.close()
         # ModelChallenger (model 4) on the same data
         engc = aisgpu.Engine(model=aisgpu.MODEL_CHALLENGER, sample_rate=FS, n_streams=B, max_chunk=N, device=local_rank, max_frames=1 << 20, host_staging=False)
@@ -549,7 +550,7 @@ def main():
             parc = oracle_check(sample_streams[:8], lambda c: {s: x[c % R][s].cpu().numpy() for s in sample_streams[:8]}, nc, gotc, 4, FS)
         mc = median(bc)
         also.append({"workload": "same data and batch, ModelChallenger (model 4)", "value": B * N * 4 / (mc * 1e-3) / 1e6, "unit": "MSamples/s (this rank)",
-                     "ms_per_step": mc / 4, "frames": nmc, "parity": parc})
+                     "ms_per_step": mc / 4, "frames": nmc, "parity": parc, "blocks_ms_per_step": [round(b / 4, 4) for b in bc]})
         engc.close()
         del x
         torch.cuda.empty_cache()
@@ -578,7 +579,8 @@ def main():
             also.append({"workload": "BASELINE configs[2]: batch=4096 CF32 @6 MSPS, ModelDefault, %s, chunk %d" % (
                 "PhaseSearchEMA" if ps_ema else "PS_EMA off (Demod::PhaseSearch)", N3),
                 "value": B3 * N3 * 6 / (m3 * 1e-3) / 1e6, "unit": "MSamples/s (this rank)", "ms_per_step": m3 / 6,
-                "whole_chain_frac": 8.0 * B3 * N3 / (m3 / 6 * 1e-3) / 1e9 / peaks()[0], "frames": nm3, "parity": par3})
+                "whole_chain_frac": 8.0 * B3 * N3 / (m3 / 6 * 1e-3) / 1e9 / peaks()[0], "frames": nm3, "parity": par3,
+                "blocks_ms_per_step": [round(b / 6, 4) for b in b3]})
             eng3.close()
         del x3
 

@@ -196,6 +196,43 @@ int aisgpu_last_launches(aisgpu_handle *h);
 int aisgpu_validate(const uint8_t *data, int nbits);
 int aisgpu_build_nmea(aisgpu_msg *m, int own_mmsi, int *seq);
 
+/* ---- Formats either side of the path ---- */
+
+/* The TAG / receiver fields the reference's outputs print next to a message (Source/Library/Common.h:218-250 TAG;
+ * Message::rxtime/toa/station, Message.h:60-75).  level and ppm are taken from the aisgpu_msg. */
+typedef struct aisgpu_tag {
+	int32_t version;      /* TAG::version */
+	int32_t driver;       /* TAG::driver (Type enum as int) */
+	const char *hardware; /* TAG::hardware, may be NULL (printed as "") */
+	int32_t mode;         /* TAG::mode: bit 0 -> signalpower/ppm are printed, bit 1 -> rxuxtime is printed */
+	int32_t status;       /* TAG::status, printed as msg_status when non-zero */
+	uint32_t ipv4;        /* TAG::ipv4, printed when non-zero */
+	int64_t rxtime_us;    /* Message::rxtime (microseconds since the epoch, Message::Stamp) */
+	int64_t toa_us;       /* Message::toa, printed when non-zero */
+	int32_t station;      /* Message::getStation(), printed as station_id when non-zero */
+	int32_t include_ssl;  /* getNMEAJSON's include_ssl: print ssc (start_idx) and sl (end_idx - start_idx) */
+	const char *uuid;     /* getNMEAJSON's uuid argument, may be NULL or "" */
+	const char *suffix;   /* getNMEAJSON's suffix argument (e.g. "\r\n"), may be NULL */
+} aisgpu_tag;
+
+/* == AIS::Message::getNMEAJSON(out, tag, include_ssl, uuid, suffix) (Message.cpp:93-191): the JSON line of the UDP/TCP/HTTP
+ * "NMEA JSON" outputs, number formatting as JSON::Writer (Writer.h:174-218).  Returns the bytes written (no NUL is appended),
+ * AISGPU_EOVERFLOW if cap is too small. Host-only. */
+int aisgpu_msg_json(const aisgpu_msg *m, const aisgpu_tag *tag, char *out, int cap);
+
+/* == AIS::Message::getBinaryNMEA(out, tag, crc) (Message.cpp:277-396): 0xAC 0x00 framed, byte-stuffed binary record with an
+ * optional CRC-16 (Helper.cpp:42-57).  Returns the bytes written, 0 when the reference would emit nothing. Host-only. */
+int aisgpu_msg_binary(const aisgpu_msg *m, const aisgpu_tag *tag, int crc, uint8_t *out, int cap);
+
+/* == n_streams Device::RAWFile receivers (Source/Device/FileRAW.cpp:36-165) feeding one engine: paths[s] is the recording of
+ * stream s in the engine's sample format; the files are read in blocks of n_samples (a multiple of aisgpu_chunk_granule),
+ * the tail of each file is zero-padded to a whole block (FileRAW.cpp:91-94) and the run ends with the longest file.  Reading
+ * block c+1 (threads), the copy and kernels of block c and the delivery of the frames of block c-1 to fn overlap (two pinned
+ * buffers, aisgpu_submit_async / aisgpu_poll_upto).  fn may be NULL (count only: aisgpu_counters).  *n_blocks receives the
+ * number of blocks submitted.  Returns 0, AISGPU_EOVERFLOW (frames were dropped, the rest delivered) or the first error. */
+typedef void (*aisgpu_msg_fn)(const aisgpu_msg *msgs, int n, void *user);
+int aisgpu_feed_files(aisgpu_handle *h, const char *const *paths, int n_samples, aisgpu_msg_fn fn, void *user, uint64_t *n_blocks);
+
 const char *aisgpu_last_error(aisgpu_handle *h); /* h may be NULL: error of the last failed aisgpu_create */
 
 /* == ~Model */

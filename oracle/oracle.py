@@ -86,6 +86,27 @@ def _bind(lib, prefix):
 _libs = {}
 
 
+def ref_format(kind, payload, nbits, channel="A", station=0, own_mmsi=-1, start_idx=0, end_idx=0, rxtime_us=0, toa_us=0, level=0.0,
+               ppm=0.0, version=0, driver=0, hardware="", mode=3, status=0, ipv4=0, uuid="", include_ssl=False, suffix=None):
+    """The reference's own formatters on a message built from these fields (ref_harness.cpp aisref_format):
+    kind 0 Message::getNMEAJSON, 1 getBinaryNMEA without CRC, 2 with CRC.  Returns (output bytes, [sentence bytes])."""
+    lib = _load(ref_lib_path(False), "aisref")
+    f = lib.aisref_format
+    f.restype = C.c_long
+    f.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong,
+                  C.c_float, C.c_float, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_uint, C.c_char_p, C.c_int, C.c_char_p,
+                  C.c_char_p, C.c_long, C.c_char_p, C.c_long]
+    out = C.create_string_buffer(8192)
+    nm = C.create_string_buffer(1024)
+    data = bytes(payload) + bytes(140 - len(payload))
+    n = f(kind, data, nbits, ord(channel), station, own_mmsi, start_idx, end_idx, rxtime_us, toa_us, level, ppm, version, driver,
+          hardware.encode("latin-1"), mode, status, ipv4, uuid.encode("latin-1"), 1 if include_ssl else 0,
+          None if suffix is None else suffix.encode("latin-1"), out, 8192, nm, 1024)
+    if n < 0:
+        raise RuntimeError("aisref_format: buffer too small")
+    return out.raw[:n], nm.raw.split(b"\n")[:-1]
+
+
 def _load(path, prefix):
     if path not in _libs:
         lib = C.CDLL(path)

@@ -327,6 +327,51 @@ long aisref_messages(void *hv, char *dst, long max) {
 	return n;
 }
 
+// The reference's own output formatters on a message built from raw fields (no model involved): checker for the product's
+// aisgpu_msg_json / aisgpu_msg_binary.  kind 0: Message::getNMEAJSON, 1: getBinaryNMEA(crc = false), 2: getBinaryNMEA(crc = true).
+// The message's sentences (built by Message::buildNMEA, hence with the process-global sequence id) are returned newline-terminated
+// in nmea_out so that the caller can hand the very same sentences to the product.
+long aisref_format(int kind, const unsigned char *data, int nbits, int channel, int station, int own_mmsi, long long start_idx,
+				   long long end_idx, long long rxtime_us, long long toa_us, float level, float ppm, int version, int driver,
+				   const char *hardware, int mode, int status, unsigned ipv4, const char *uuid, int include_ssl, const char *suffix,
+				   char *out, long max, char *nmea_out, long nmea_max) {
+	AIS::Message m;
+	m.clear();
+	m.setBytes(data, (nbits + 7) / 8);
+	m.setOrigin((char)channel, station, own_mmsi);
+	m.setLength(nbits);
+	m.setStartIdx(start_idx);
+	m.setEndIdx(end_idx);
+	m.setRxTimeMicros(rxtime_us);
+	m.setTOA(toa_us);
+	TAG tag;
+	tag.mode = (unsigned)mode;
+	tag.level = level;
+	tag.ppm = ppm;
+	tag.version = version;
+	tag.driver = (Type)driver;
+	tag.hardware = hardware ? hardware : "";
+	tag.status = status;
+	tag.ipv4 = ipv4;
+	m.buildNMEA(tag);
+	std::string o;
+	if (kind == 0) m.getNMEAJSON(o, tag, include_ssl != 0, uuid ? std::string(uuid) : std::string(), suffix);
+	else m.getBinaryNMEA(o, tag, kind == 2);
+	if (nmea_out) {
+		std::string all;
+		for (const auto &sv : m.sentences()) {
+			all.append(sv.data(), sv.size());
+			all.push_back('\n');
+		}
+		if ((long)all.size() > nmea_max) return -1;
+		memcpy(nmea_out, all.data(), all.size());
+	}
+	long n = (long)o.size();
+	if (n > max) return -1;
+	memcpy(out, o.data(), (size_t)n);
+	return n;
+}
+
 void aisref_destroy(void *hv) { delete (Handle *)hv; }
 
 } // extern "C"
