@@ -1210,6 +1210,10 @@ static int create_impl(aisgpu_handle *h) {
 	// (large-grid) front end of the next submit frees a slot, instead of queueing behind all of its CTAs.
 	int prio_lo = 0, prio_hi = 0;
 	CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+	if (const char *e = getenv("AISGPU_PRIO")) { // 0: one priority for all streams, 2: front end above the back end (experiments)
+		if (atoi(e) == 0) prio_hi = prio_lo;
+		else if (atoi(e) == 2) std::swap(prio_lo, prio_hi);
+	}
 	CU(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
 	h->be_streams[0] = h->be_streams[1] = h->stream;
 	{

@@ -1,7 +1,13 @@
 #!/bin/bash
-# GPU call 11: whole GPU suite, smoke, default bench line, reference arm
+# GPU call 12: feeder tests, Default-chain step time vs stream priorities / stage pipelining, full bench
 mkdir -p gpurun_out
-echo "== tests"; timeout 2400 python -m pytest tests -m gpu -q > gpurun_out/pytest11.log 2>&1; tail -6 gpurun_out/pytest11.log | cut -c1-600
-echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-echo "== bench"; timeout 1200 python bench.py > gpurun_out/bench11.json 2> gpurun_out/bench11.err; tail -c 6000 gpurun_out/bench11.json; tail -3 gpurun_out/bench11.err
-echo "== ref arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench11_ref.json 2>&1; tail -c 1200 gpurun_out/bench11_ref.json
+echo "== tests"; timeout 900 python -m pytest tests/test_gpu_feeder.py -m gpu -q 2>&1 | tail -5 | cut -c1-600
+echo "== probe"; timeout 900 python tools/default_probe.py 2 - - AISGPU_PRIO=0 AISGPU_PRIO=2 AISGPU_BE_PIPE=1 AISGPU_BE_PIPE=1,AISGPU_PRIO=0 AISGPU_DEC_RPW=3 2>&1 | tee gpurun_out/probe12.jsonl
+timeout 300 python tools/default_probe.py 4 - AISGPU_PRIO=0 2>&1 | tee -a gpurun_out/probe12.jsonl
+timeout 300 python tools/default_probe.py 0 - AISGPU_PRIO=0 2>&1 | tee -a gpurun_out/probe12.jsonl
+echo "== bench"; timeout 1200 python bench.py > gpurun_out/bench12.json 2> gpurun_out/bench12.err; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench12.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e_cu8']['value'])
+for a in d['also']: print(a['workload'][:70], a['ms_per_step'], a.get('blocks_ms_per_step'))
+PY
