@@ -40,7 +40,7 @@ def test_feed_files_matches_oracle(built, tmp_path, fmt):
         have = [(m.key(), m.start_idx, m.end_idx) for m in got if m.stream == s]
         assert have == want, "stream %d" % s
         total += len(want)
-    assert total > 10
+    assert total >= 5  # 0.19 s per stream: a handful of bursts
     c = eng.counters()
     assert c[3] == nblocks and c[2] == nblocks * N
     eng.close()

@@ -16,7 +16,7 @@ if len(sys.argv) > 2 and sys.argv[1] != "--child":
 sys.path.insert(0, os.path.join(ROOT, "ais-catcher_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch, aisgpu, aissynth
 model = int(sys.argv[2])
-B, N, FS, R = 1024, 131072, 1536000, 4
+B, N, FS, R = [int(v) for v in os.environ.get("PROBE_SHAPE", "1024,131072,1536000,4").split(",")]
 u = np.stack([aissynth.random_stream(FS, N * R, 1000 + i)[0] for i in range(8)])
 ud = torch.from_numpy(u.view(np.float32)).cuda().view(8, R, N, 2)
 x = torch.empty((R, B, N, 2), dtype=torch.float32, device="cuda")
