@@ -1210,19 +1210,19 @@ static int create_impl(aisgpu_handle *h) {
 	// (large-grid) front end of the next submit frees a slot, instead of queueing behind all of its CTAs.
 	int prio_lo = 0, prio_hi = 0;
 	CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-	// The coherent chain is the exception: its back end is longer than the front end, and with a privileged back end the run can
-	// lock into a serial pattern (front end c+1 starved while back end c runs, back end c+1 then waiting for it: 0.80 ms per step
-	// instead of 0.55 ms at 1024 x 131072 @1536K, both patterns self-sustaining).  One priority for all streams is stable there.
-	int prio_mode = c.model == AISGPU_MODEL_DEFAULT ? 0 : 1;
-	if (const char *e = getenv("AISGPU_PRIO")) prio_mode = atoi(e); // 0: one priority, 1: back end above front end, 2: the reverse
+	int prio_mode = 1;
+	if (const char *e = getenv("AISGPU_PRIO")) prio_mode = atoi(e); // 0: one priority, 1: back end above front end, 2: the reverse (experiments)
 	if (prio_mode == 0) prio_hi = prio_lo;
 	else if (prio_mode == 2) std::swap(prio_lo, prio_hi);
 	CU(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
 	h->be_streams[0] = h->be_streams[1] = h->stream;
 	{
 		const char *e = getenv("AISGPU_BE_PIPE");
-		// measured: overlapping the stages of consecutive submits pays for the FM chain (+6 %), not for the coherent one
-		const bool pipe = (e ? atoi(e) != 0 : c.model == AISGPU_MODEL_STANDARD) && !c.enable_taps && c.model != AISGPU_MODEL_BASE && c.model != AISGPU_MODEL_V2 &&
+		// Overlapping the stages of consecutive submits over two back-end streams pays +6 % for the FM chain.  For the coherent chain
+		// it is what keeps the step time stable: with one back-end stream the run can lock into a serial pattern (front end c+1 starved
+		// while back end c runs, back end c+1 then waiting for it) -- 0.80 ms per step (or 0.90 ms with one stream priority) instead of
+		// 0.55 ms at 1024 x 131072 @1536K, both patterns self-sustaining from the first submits on (profiles/r2_sweeps.jsonl, probe12/13).
+		const bool pipe = (e ? atoi(e) != 0 : (c.model == AISGPU_MODEL_STANDARD || c.model == AISGPU_MODEL_DEFAULT)) && !c.enable_taps && c.model != AISGPU_MODEL_BASE && c.model != AISGPU_MODEL_V2 &&
 						  c.model != AISGPU_MODEL_CHALLENGER;
 		if (pipe) CU(cudaStreamCreateWithPriority(&h->be_streams[1], cudaStreamNonBlocking, prio_hi));
 	}
