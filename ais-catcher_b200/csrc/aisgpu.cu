@@ -105,7 +105,6 @@ struct aisgpu_handle {
 	int fe_st = 1, st_S = 0, st_g = 32, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
 	int cf_rows = 4; // AISGPU_CF_ROWS: rows per CTA of the fused CGF kernel (4 or 8)
 	int be_v1 = 0; // AISGPU_BE_V1=1: round-1 back-end kernels (k_cgf_rot + k_cgf_derot_fir, one hypothesis per lane) for A/B runs
-	int ps_lanes = 4;
 	int dec_rpw = 6, decoder = 3; // rows per warp / which decoder kernel // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
 	// for timing).  The front end of submit c+1 overlaps the back end of submit c; Cbuf is double buffered for that.
@@ -537,7 +536,7 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.lvl = h->d_lvl2[h->pb];
 		p.lvl_stride = h->dwords * K3_TS;
 		if (int rc = stage_begin(h, 3)) return rc;
-		CU(launch_phase_search(p, h->be_v1 ? 1 : (h->ps_lanes == 2 ? 2 : 0), h->bs));
+		CU(launch_phase_search(p, h->be_v1, h->bs));
 		// the incomplete group of 5 at the end moves to the front for the next submit (Ec is single buffered: the next
 		// submit's derotation waits for this stage)
 		const int nl = total - nsym * 5;
@@ -1190,7 +1189,6 @@ static int create_impl(aisgpu_handle *h) {
 		if (h->decoder != 1 && h->decoder != 2) h->decoder = 3;
 	}
 	if (const char *e = getenv("AISGPU_BE_V1")) h->be_v1 = atoi(e) ? 1 : 0;
-	if (const char *e = getenv("AISGPU_PS_LANES")) h->ps_lanes = atoi(e) == 2 ? 2 : 4; // lanes per PhaseSearchEMA instance
 	if (const char *e = getenv("AISGPU_CF_ROWS")) h->cf_rows = atoi(e) == 8 ? 8 : 4;
 	if (c.model == AISGPU_MODEL_CHALLENGER) { // ModelChallenger always demodulates with PhaseSearchEMA (Model.cpp:646-652) and needs the fused kernel's derotated output
 		h->be_v1 = 0;

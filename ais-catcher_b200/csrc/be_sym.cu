@@ -163,6 +163,9 @@ __global__ void __launch_bounds__(PS_THREADS) k_phase_search(const K3Params p) {
 //   * the only sequential part left is  i0 = (max_idx - 1) & 15; max_idx = (i0 + table[i0]) & 15  -- one shuffle (from the
 //     lane holding entry i0) and integer work that no longer waits for floating-point results of the same symbol;
 //   * the lane that holds hypothesis max_idx contributes the demodulated bit (its decisions 3 and 4 symbols ago, XORed).
+// Measured alternatives at 1024 x 131072 @1536K: one hypothesis per lane (16 lanes per instance, 5120 warps) 340 us; this kernel
+// (4 lanes, 1280 warps) 212 us; eight hypotheses per lane (2 lanes, 640 warps, 28 % fewer warp instructions) 232 us -- below
+// four lanes the per-warp dependency chains are no longer hidden by other warps (2.2 warps per scheduler here).
 // 2.7x fewer warp instructions per (instance, symbol) than one hypothesis per lane, three shuffles (one of them on the
 // sequential chain) instead of four dependent ones.  Demod::PhaseSearch (PS_EMA off) keeps the one-hypothesis-per-lane kernel above.
 // ---------------------------------------------------------------------------------------------
@@ -310,169 +313,6 @@ __global__ void __launch_bounds__(32) k_phase_search_ema4(const K3Params p) {
 		PsState &st = p.ps[inst];
 #pragma unroll
 		for (int k = 0; k < 4; k++) st.ma[4 * q + k] = ma[k];
-		if (q == 0) {
-#pragma unroll
-			for (int dd = 0; dd < 5; dd++) st.plane[dd] = planes[dd];
-			st.max_idx = max_idx;
-			st.rot = rot;
-		}
-	}
-}
-
-// ---------------------------------------------------------------------------------------------
-// K3a'': the same PhaseSearchEMA with EIGHT hypotheses per lane: a one-warp CTA owns 16 consecutive (row, phase) instances,
-// two lanes each (lane q of the pair holds hypotheses 8q .. 8q+7).  The per-symbol work is the same as in k_phase_search_ema4
-// -- products by packed FMUL2, sums by scalar FADD, the "best of three" decisions for all 16 starting points as a table, one
-// shuffle on the sequential chain -- but the fixed per-lane cost (sample load, pre-rotation, chain, bit bookkeeping) is paid
-// by two lanes per instance instead of four, and the table is two 8-bit masks (first comparison / second comparison) set by
-// predicated ORs instead of selects and shifts.
-// ---------------------------------------------------------------------------------------------
-constexpr int PS3_INST = 16;
-constexpr int PS3_TROWS = 4; // rows sixteen consecutive instances can touch (1 + 5 + 5 + 5)
-__global__ void __launch_bounds__(32) k_phase_search_ema8(const K3Params p) {
-	__shared__ float2 tile[2][PS3_TROWS][PS2_ROWP];
-	const int lane = threadIdx.x;
-	const long long ninst = (long long)p.rows * 5;
-	const long long inst0 = (long long)blockIdx.x * PS3_INST;
-	const long long gi = inst0 + (lane >> 1);
-	const int q = lane & 1;
-	const bool active = gi < ninst;
-	const long long inst = active ? gi : ninst - 1;
-	const int row = (int)(inst / 5), phase = (int)(inst - (long long)row * 5);
-	const int r_lo = (int)(inst0 / 5);
-	const int rin = row - r_lo;
-	const int gbase = lane & ~1;
-	const float weight = 0.85f, omw = __fsub_rn(1.0f, 0.85f);
-	c64 cjp[4], sjp[4];
-#pragma unroll
-	for (int m = 0; m < 4; m++) {
-		float cc[2], ss[2];
-#pragma unroll
-		for (int e = 0; e < 2; e++) {
-			const int h = 8 * q + 2 * m + e, j = h < 8 ? h : 15 - h;
-			cc[e] = c_ps_cos[j];
-			ss[e] = h < 8 ? c_ps_sin[j] : -c_ps_sin[j]; // a - b == a + (-b), im * (-s) == -(im * s), exactly
-		}
-		cjp[m] = pack2(cc[0], cc[1]);
-		sjp[m] = pack2(ss[0], ss[1]);
-	}
-	const c64 w2 = pack2(weight, weight), o2 = pack2(omw, omw);
-	float ma[8];
-	uint32_t hist = 0u, hist4 = 0u; // hist: byte d = the lane's eight sign decisions d symbols ago (d = 0..3); hist4: d = 4
-	int max_idx = 0, rot = 0;
-#pragma unroll
-	for (int k = 0; k < 8; k++) ma[k] = 0.0f;
-	if (active) {
-		const PsState &st = p.ps[inst];
-#pragma unroll
-		for (int k = 0; k < 8; k++) ma[k] = st.ma[8 * q + k];
-#pragma unroll
-		for (int dd = 0; dd < 4; dd++) hist |= ((st.plane[dd] >> (8 * q)) & 0xffu) << (8 * dd);
-		hist4 = (st.plane[4] >> (8 * q)) & 0xffu;
-		max_idx = st.max_idx;
-		rot = st.rot;
-	}
-	const int nsamp = p.nsym * 5;
-	auto prefetch = [&](int buf, int s0) {
-		const int base = s0 * 5;
-		for (int e = lane; e < PS3_TROWS * K3_ROWLEN; e += 32) {
-			const int r = e / K3_ROWLEN, c = e - r * K3_ROWLEN;
-			if (r_lo + r < p.rows && base + c < nsamp) cp_async_f(&tile[buf][r][c], p.Ec + (long long)(r_lo + r) * p.e_stride + p.e_begin + base + c);
-		}
-		cp_async_commit();
-	};
-	const int ntiles = (p.nsym + K3_TS - 1) / K3_TS;
-	if (ntiles > 0) prefetch(0, 0);
-	for (int t = 0; t < ntiles; t++) {
-		if (t + 1 < ntiles) {
-			prefetch((t + 1) & 1, (t + 1) * K3_TS);
-			cp_async_wait<1>();
-		}
-		else cp_async_wait<0>();
-		__syncwarp();
-		const float2 *my = &tile[t & 1][rin][phase];
-		const int s_end = min(K3_TS, p.nsym - t * K3_TS);
-		uint32_t word = 0;
-#pragma unroll 2
-		for (int sl = 0; sl < s_end; sl++) {
-			const float2 x = my[sl * 5];
-			// (1j)^rot pre-rotation (Demod.cpp:44-65): swap on odd rot, negate on rot >= 2 (sign flips are exact)
-			float re = (rot & 1) ? -x.y : x.x, im = (rot & 1) ? x.x : x.y;
-			if (rot & 2) { re = -re; im = -im; }
-			rot = (rot + 1) & 3;
-			const c64 re2 = pack2(re, re), im2 = pack2(im, im);
-			float tt[8];
-			uint32_t dnow = 0u;
-#pragma unroll
-			for (int m = 0; m < 4; m++) { // packed products, scalar sums (a packed sum would be contracted into FFMA2)
-				const float2 a = unpack2(pmul(re2, cjp[m])), b = unpack2(pmul(im2, sjp[m]));
-				tt[2 * m] = __fadd_rn(a.x, b.x);
-				tt[2 * m + 1] = __fadd_rn(a.y, b.y);
-				if (tt[2 * m] > 0.0f) dnow |= 1u << (2 * m);
-				if (tt[2 * m + 1] > 0.0f) dnow |= 2u << (2 * m);
-			}
-#pragma unroll
-			for (int m = 0; m < 4; m++) { // ma = weight * ma + (1 - weight) * |t| (Demod.cpp:67-78); (1 - w) * |t| == |(1 - w) * t| exactly
-				const float2 w = unpack2(pmul(w2, pack2(ma[2 * m], ma[2 * m + 1])));
-				const float2 o = unpack2(pmul(o2, pack2(tt[2 * m], tt[2 * m + 1])));
-				ma[2 * m] = __fadd_rn(w.x, fabsf(o.x));
-				ma[2 * m + 1] = __fadd_rn(w.y, fabsf(o.y));
-			}
-			// demodulated bit per hypothesis = its decisions 3 and 4 symbols ago, XORed (nDelay = 3, Model.h:219)
-			hist4 = hist >> 24;
-			hist = (hist << 8) | dnow;
-			const uint32_t xm = (hist >> 24) ^ hist4;
-			// table: search started at i0 = 8q + k looks at v[k], v[k+1], v[k+2] (strict >, the first maximum wins, Demod.cpp:80-91)
-			const float v8 = __shfl_xor_sync(0xffffffffu, ma[0], 1), v9 = __shfl_xor_sync(0xffffffffu, ma[1], 1);
-			const float v[10] = { ma[0], ma[1], ma[2], ma[3], ma[4], ma[5], ma[6], ma[7], v8, v9 };
-			uint32_t tab = 0u; // bit k: v[k+1] > v[k]; bit 8 + k: v[k+2] > max of the first two
-#pragma unroll
-			for (int k = 0; k < 8; k++) {
-				const bool a = v[k + 1] > v[k];
-				const float mv = a ? v[k + 1] : v[k];
-				if (a) tab |= 1u << k;
-				if (v[k + 2] > mv) tab |= 0x100u << k;
-			}
-			const int i0 = (max_idx - 1) & 15;
-			const uint32_t tsel = __shfl_sync(0xffffffffu, tab, gbase | (i0 >> 3)) >> (i0 & 7);
-			max_idx = (i0 + ((tsel & 0x100u) ? 2 : (int)(tsel & 1u))) & 15;
-			const uint32_t bit = ((max_idx >> 3) == q) ? ((xm >> (max_idx & 7)) & 1u) : 0u;
-			word |= bit << sl;
-			if (p.tap_dec) {
-				const uint32_t b = bit | __shfl_xor_sync(0xffffffffu, bit, 1);
-				if (active && q == 0) p.tap_dec[inst * p.nsym + t * K3_TS + sl] = b ? 1.0f : -1.0f;
-			}
-		}
-		word |= __shfl_xor_sync(0xffffffffu, word, 1);
-		if (active && q == 0) p.dbits[inst * p.dwords + t] = word;
-		if (p.mode_level) { // ScatterPLL level (DSP.h:100-106), by the warp that holds the row's phase 0
-#pragma unroll
-			for (int r = 0; r < PS3_TROWS; r++) {
-				const long long first = (long long)(r_lo + r) * 5;
-				if (first >= inst0 && first < inst0 + PS3_INST && r_lo + r < p.rows && lane < s_end) {
-					const float2 *rowt = &tile[t & 1][r][lane * 5];
-					float acc = 0.0f;
-#pragma unroll
-					for (int jx = 0; jx < 5; jx++) {
-						const float2 xx = rowt[jx];
-						acc = __fadd_rn(acc, __fadd_rn(__fmul_rn(xx.x, xx.x), __fmul_rn(xx.y, xx.y)));
-					}
-					p.lvl[(long long)(r_lo + r) * p.lvl_stride + t * K3_TS + lane] = __fdiv_rn(acc, 5.0f);
-				}
-			}
-		}
-		__syncwarp();
-	}
-	uint32_t planes[5];
-#pragma unroll
-	for (int dd = 0; dd < 5; dd++) {
-		const uint32_t mine = (dd < 4 ? (hist >> (8 * dd)) & 0xffu : hist4 & 0xffu) << (8 * q);
-		planes[dd] = mine | __shfl_xor_sync(0xffffffffu, mine, 1);
-	}
-	if (active) {
-		PsState &st = p.ps[inst];
-#pragma unroll
-		for (int k = 0; k < 8; k++) st.ma[8 * q + k] = ma[k];
 		if (q == 0) {
 #pragma unroll
 			for (int dd = 0; dd < 5; dd++) st.plane[dd] = planes[dd];
@@ -1321,10 +1161,6 @@ cudaError_t sym_init(const float *ps_cos8, const float *ps_sin8, const uint32_t 
 	return e;
 }
 cudaError_t launch_phase_search(const K3Params &p, int v1, cudaStream_t s) {
-	if (p.ps_ema && v1 == 2) { // eight hypotheses per lane
-		k_phase_search_ema8<<<(unsigned)(((long long)p.rows * 5 + PS3_INST - 1) / PS3_INST), 32, 0, s>>>(p);
-		return cudaGetLastError();
-	}
 	if (p.ps_ema && !v1) { // four hypotheses per lane (PhaseSearchEMA only)
 		k_phase_search_ema4<<<(unsigned)(((long long)p.rows * 5 + PS2_INST - 1) / PS2_INST), 32, 0, s>>>(p);
 		return cudaGetLastError();
