@@ -102,9 +102,8 @@ struct aisgpu_handle {
 	int rows = 0;
 	int max_n48 = 0;
 	int fe_warps = 4, fe_tile = 0, fe_ctas = 4096;
-	int fe_st = 1, st_S = 0, st_g = 32, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
+	int fe_st = 1, st_S = 0, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
 	int cf_rows = 4; // AISGPU_CF_ROWS: rows per CTA of the fused CGF kernel (4 or 8)
-	int be_v1 = 0; // AISGPU_BE_V1=1: round-1 back-end kernels (k_cgf_rot + k_cgf_derot_fir, one hypothesis per lane) for A/B runs
 	int dec_rpw = 6, decoder = 3; // rows per warp / which decoder kernel // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
 	// for timing).  The front end of submit c+1 overlaps the back end of submit c; Cbuf is double buffered for that.
@@ -151,7 +150,7 @@ struct aisgpu_handle {
 	// CGF
 	long long cgf_abs = 0;
 	int *d_stepidx2[2] = { nullptr, nullptr };
-	float2 *d_steptab = nullptr, *d_omega = nullptr, *d_cgf_rot = nullptr, *d_rots2[2] = { nullptr, nullptr };
+	float2 *d_steptab = nullptr, *d_omega = nullptr, *d_cgf_rot = nullptr;
 	float *d_ppmtab = nullptr;
 	long long r_stride = 0;
 	float2 *d_fir_hist[2] = { nullptr, nullptr };
@@ -413,7 +412,7 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 			p.st_B = B;
 			p.st_first = h->chunk == 0 ? 1 : 0;
 			if (h->fp_ds) CU(launch_frontend_stream_fpds(p, (long long)B * p.st_wps, h->fe_stream));
-			else CU(launch_frontend_stream(p, h->in_fmt, h->k, h->st_g, false, (long long)B * p.st_wps, h->fe_stream));
+			else CU(launch_frontend_stream(p, h->in_fmt, h->k, false, (long long)B * p.st_wps, h->fe_stream));
 			return 0;
 		}
 	}
@@ -536,7 +535,7 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.lvl = h->d_lvl2[h->pb];
 		p.lvl_stride = h->dwords * K3_TS;
 		if (int rc = stage_begin(h, 3)) return rc;
-		CU(launch_phase_search(p, h->be_v1, h->bs));
+		CU(launch_phase_search(p, h->bs));
 		// the incomplete group of 5 at the end moves to the front for the next submit (Ec is single buffered: the next
 		// submit's derotation waits for this stage)
 		const int nl = total - nsym * 5;
@@ -691,22 +690,10 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 		if (nblk > 0) {
 			const int total_blocks = h->rows * nblk;
 			int *stepidx = h->d_stepidx2[h->pb];
-			float2 *rots = h->d_rots2[h->pb]; // round-1 kernels only
-			// stepidx / rots / dbits / lvl are double buffered by submit parity == stream, so stream order protects them
+			// stepidx / dbits / lvl are double buffered by submit parity == stream, so stream order protects them
 			CU(launch_cgf_estimate(Ccur, h->c_stride, c_begin, nblk, total_blocks, h->d_omega, h->cfg.afc_wide, stepidx, h->bs));
 			const int nE = nblk * CGF_N;
-			if (h->be_v1) {
-				if (int rc = stage_begin(h, 1)) return rc;
-				CU(launch_cgf_rot(stepidx, h->d_steptab, h->d_cgf_rot, rots, h->r_stride, nblk, h->rows, h->bs));
-				if (int rc = stage_end(h, 1)) return rc;
-				if (int rc = stage_begin(h, 2)) return rc;
-				if (int rc = stage_begin(h, 3)) return rc; // Ec is free once the previous submit's phase search has read it
-				CU(launch_cgf_derot_fir(Ccur, h->c_stride, c_begin, rots, h->r_stride, nE, h->d_fir_hist[h->fir_cur], h->d_fir_hist[h->fir_cur ^ 1], h->d_Ec2[0],
-										h->e_stride, HE, h->cfg.enable_taps ? h->d_tap_cgf : nullptr, h->r_stride, h->rows, h->bs));
-				if (int rc = stage_end(h, 2)) return rc;
-				h->last_launches++;
-			}
-			else { // phasor chain + derotation + FIR17 in one kernel: waits for what carries its state (stages 1, 2) and for Ec (stage 3)
+			{ // phasor chain + derotation + FIR17 in one kernel: waits for what carries its state (stages 1, 2) and for Ec (stage 3)
 				if (int rc = stage_begin(h, 1)) return rc;
 				if (int rc = stage_begin(h, 2)) return rc;
 				if (int rc = stage_begin(h, 3)) return rc;
@@ -865,7 +852,7 @@ int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) 
 					pp.st_S = S;
 					pp.st_wps = N / (32 * S);
 					pp.st_B = B;
-					CU(launch_frontend_stream(pp, h->cfg.format, h->kA, 16, true, (long long)B * pp.st_wps, h->fe_stream));
+					CU(launch_frontend_stream(pp, h->cfg.format, h->kA, true, (long long)B * pp.st_wps, h->fe_stream));
 					st_done = true;
 				}
 			}
@@ -1188,16 +1175,13 @@ static int create_impl(aisgpu_handle *h) {
 		h->decoder = atoi(e);
 		if (h->decoder != 1 && h->decoder != 2) h->decoder = 3;
 	}
-	if (const char *e = getenv("AISGPU_BE_V1")) h->be_v1 = atoi(e) ? 1 : 0;
 	if (const char *e = getenv("AISGPU_CF_ROWS")) h->cf_rows = atoi(e) == 8 ? 8 : 4;
 	if (c.model == AISGPU_MODEL_CHALLENGER) { // ModelChallenger always demodulates with PhaseSearchEMA (Model.cpp:646-652) and needs the fused kernel's derotated output
-		h->be_v1 = 0;
 		h->cfg.ps_ema = 1;
 	}
 	if (const char *e = getenv("AISGPU_FE_TILE")) h->fe_tile = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_ST")) h->fe_st = atoi(e) ? 1 : 0;
 	if (const char *e = getenv("AISGPU_ST_S")) h->st_S = atoi(e);
-	if (const char *e = getenv("AISGPU_ST_G")) h->st_g = atoi(e) == 64 ? 64 : (atoi(e) == 32 ? 32 : 16);
 	if (const char *e = getenv("AISGPU_ST_KMAX")) h->st_kmax = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_CTAS")) h->fe_ctas = std::max(1, atoi(e));
 	int ndev = 0;
@@ -1351,8 +1335,6 @@ static int create_impl(aisgpu_handle *h) {
 		h->c_hist = 0;
 		for (int i = 0; i < 2; i++) {
 			if (int rc = dalloc(h, &h->d_stepidx2[i], (size_t)h->rows * (nEmax / CGF_N + 1))) return rc;
-			if (h->be_v1)
-				if (int rc = dalloc(h, &h->d_rots2[i], (size_t)h->rows * h->r_stride)) return rc;
 		}
 		if (int rc = dalloc(h, &h->d_cgf_rot, (size_t)h->rows)) return rc;
 		if (int rc = dalloc(h, &h->d_Ec2[0], (size_t)h->rows * h->e_stride)) return rc;
@@ -1858,7 +1840,7 @@ void aisgpu_destroy(aisgpu_handle *h) {
 		if (h->ev_us[i]) cudaEventDestroy(h->ev_us[i]);
 	}
 	void *ptrs[] = { h->d_ptail[0], h->d_ptail[1], h->d_ptail2[0], h->d_ptail2[1], h->d_S2, h->d_D0, h->d_S, h->d_us_src, h->d_us_alpha, h->d_in[0], h->d_in[1], h->d_tail[0], h->d_tail[1], h->d_rot[0], h->d_rot[1], h->d_rot[2], h->d_rot_state, h->d_C2[0], h->d_C2[1], h->d_C2[2],
-					 h->d_steptab, h->d_omega, h->d_cgf_rot, h->d_rots2[0], h->d_rots2[1], h->d_stepidx2[0], h->d_stepidx2[1], h->d_ppmtab, h->d_fir_hist[0], h->d_fir_hist[1], h->d_tap_cgf, h->d_Ec2[0],
+					 h->d_steptab, h->d_omega, h->d_cgf_rot, h->d_stepidx2[0], h->d_stepidx2[1], h->d_ppmtab, h->d_fir_hist[0], h->d_fir_hist[1], h->d_tap_cgf, h->d_Ec2[0],
 					 h->d_Ef2[0], h->d_ps, h->d_ps_mem, h->d_dbits2[0], h->d_dbits2[1], h->d_lvl2[0], h->d_lvl2[1], h->d_dbg, h->d_dec, h->d_dec_data, h->d_pll, h->d_tap_dec, h->d_tap_fm, h->d_tap_cnt, h->d_v2, h->d_tap_coh, h->d_Ed, h->d_dbitsF[0], h->d_dbitsF[1], h->d_lvl_prev, h->d_ring,
 					 h->d_ring_head, h->d_counts };
 	for (void *p : ptrs)

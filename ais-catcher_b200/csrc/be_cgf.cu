@@ -96,81 +96,7 @@ __global__ void __launch_bounds__(CGF_THREADS) k_cgf_estimate(const float2 *__re
 	}
 }
 
-// ---------------------------------------------------------------------------------------------
-// K2b: the CGF derotation phasor chain (DSP.cpp:457-465): rot *= rot_step per sample, rot /= |rot| per block.
-// Strictly sequential per (stream, channel); one thread per row, all rows in flight at once.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_cgf_rot(const int *__restrict__ stepidx, const float2 *__restrict__ steptab, float2 *__restrict__ rot_state,
-												  float2 *__restrict__ rots, long long r_stride, int nblk, int rows) {
-	// lane = row.  The phasors of 32 consecutive steps are staged in shared memory and written out row by row, so that
-	// every store instruction covers 256 contiguous bytes (a store per step and lane would touch 32 separate sectors
-	// and make the store unit, not the multiply chain, the pace).
-	__shared__ float2 tile[32][33];
-	const int lane = threadIdx.x;
-	const int row0 = blockIdx.x * 32;
-	const int row = row0 + lane;
-	const bool act = row < rows;
-	float2 rot = act ? rot_state[row] : make_float2(1.0f, 0.0f);
-	for (int b = 0; b < nblk; b++) {
-		const float2 st = act ? steptab[stepidx[row * nblk + b]] : make_float2(1.0f, 0.0f);
-		for (int i0 = 0; i0 < CGF_N; i0 += 32) {
-#pragma unroll
-			for (int i = 0; i < 32; i++) {
-				rot = cmul(rot, st);
-				tile[lane][i] = rot;
-			}
-			__syncwarp();
-#pragma unroll 8
-			for (int r = 0; r < 32; r++)
-				if (row0 + r < rows) rots[(long long)(row0 + r) * r_stride + b * CGF_N + i0 + lane] = tile[r][lane];
-			__syncwarp();
-		}
-		rot = cnormalize(rot);
-	}
-	if (act) rot_state[row] = rot;
-}
-
-// ---------------------------------------------------------------------------------------------
-// K2c: output[i] *= rot (DSP.cpp:462) fused with FilterComplex 17 taps (DSP.cpp:215-246, Filters.h:35-41).
-// ---------------------------------------------------------------------------------------------
-__constant__ float c_taps_coherent[FIRC_T];
-
-__global__ void __launch_bounds__(FIRC_TILE) k_cgf_derot_fir(const float2 *__restrict__ Cbuf, long long c_stride, int c_begin,
-																const float2 *__restrict__ rots, long long r_stride, int nE,
-																const float2 *__restrict__ hist_old, float2 *__restrict__ hist_new,
-																float2 *__restrict__ Ebuf, long long e_stride, int e_off,
-																float2 *__restrict__ tap_cgf, long long tap_stride) {
-	__shared__ float2 der[FIRC_TILE + FIRC_T - 1];
-	const int row = blockIdx.y, t0 = blockIdx.x * FIRC_TILE, tid = threadIdx.x;
-	for (int i = tid; i < FIRC_TILE + FIRC_T - 1; i += FIRC_TILE) {
-		const int n = t0 + i - (FIRC_T - 1);
-		float2 v = make_float2(0.f, 0.f);
-		if (n < 0) v = hist_old[row * (FIRC_T - 1) + (FIRC_T - 1) + n];
-		else if (n < nE) {
-			v = cmul(Cbuf[(long long)row * c_stride + c_begin + n], rots[(long long)row * r_stride + n]);
-			if (tap_cgf && i >= FIRC_T - 1) tap_cgf[(long long)row * tap_stride + n] = v;
-		}
-		der[i] = v;
-	}
-	__syncthreads();
-	const int n = t0 + tid;
-	if (n < nE) {
-		float2 x = make_float2(0.f, 0.f);
-#pragma unroll
-		for (int k = 0; k < FIRC_T; k++) {
-			const float2 dd = der[tid + k];
-			x.x = __fadd_rn(x.x, __fmul_rn(c_taps_coherent[k], dd.x));
-			x.y = __fadd_rn(x.y, __fmul_rn(c_taps_coherent[k], dd.y));
-		}
-		Ebuf[(long long)row * e_stride + e_off + n] = x;
-	}
-	if (t0 + FIRC_TILE >= nE) { // the CTA holding the end of the row saves the next history
-		for (int i = tid; i < FIRC_T - 1; i += FIRC_TILE) {
-			const int nn = nE - (FIRC_T - 1) + i; // nE >= 512
-			hist_new[row * (FIRC_T - 1) + i] = der[nn - t0 + (FIRC_T - 1)];
-		}
-	}
-}
+__constant__ float c_taps_coherent[FIRC_T]; // FilterComplex 17 taps (Filters.h:35-41)
 
 // ---------------------------------------------------------------------------------------------
 // K2bc: the derotation phasor chain, output[i] *= rot and FilterComplex 17 taps in ONE kernel (DSP.cpp:457-465, 215-246).
@@ -178,8 +104,7 @@ __global__ void __launch_bounds__(FIRC_TILE) k_cgf_derot_fir(const float2 *__res
 // shape: ~17 us is the floor for the whole stage), everything else is parallel.  A CTA owns CF_ROWS rows: warp 0 runs
 // the chains, one lane per row, CF_T steps ahead into a double-buffered shared tile; meanwhile the two consumer warps
 // derotate the previous tile (coalesced loads of the 48 kHz samples, requested one tile ahead), and run the FIR out of a
-// shared ring that keeps the 16-sample history.  The phasors never travel through HBM (the old k_cgf_rot wrote 67 MB per submit and
-// k_cgf_derot_fir read them back).  FIR: products by scalar FMUL, the (re, im) accumulation by one packed FADD2 --
+// shared ring that keeps the 16-sample history.  The phasors never travel through HBM (round 1 wrote them out, 67 MB per submit, and read them back).  FIR: products by scalar FMUL, the (re, im) accumulation by one packed FADD2 --
 // ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, a scalar product feeding a packed add stays two roundings.
 // ---------------------------------------------------------------------------------------------
 constexpr int CF_T = 64;               // samples per tile and row (a 512-block = 8 tiles)
@@ -331,17 +256,6 @@ cudaError_t launch_cgf_estimate(const float2 *Cbuf, long long c_stride, int c_be
 	k_cgf_estimate<<<ctas, CGF_THREADS, CGF_EST_SMEM, s>>>(Cbuf, c_stride, c_begin, nblk, total_blocks, omega, wide, stepidx);
 	return cudaGetLastError();
 }
-cudaError_t launch_cgf_rot(const int *stepidx, const float2 *steptab, float2 *rot_state, float2 *rots, long long r_stride, int nblk, int rows, cudaStream_t s) {
-	k_cgf_rot<<<(rows + 31) / 32, 32, 0, s>>>(stepidx, steptab, rot_state, rots, r_stride, nblk, rows);
-	return cudaGetLastError();
-}
-cudaError_t launch_cgf_derot_fir(const float2 *Cbuf, long long c_stride, int c_begin, const float2 *rots, long long r_stride, int nE, const float2 *hist_old,
-								 float2 *hist_new, float2 *Ebuf, long long e_stride, int e_off, float2 *tap_cgf, long long tap_stride, int rows, cudaStream_t s) {
-	dim3 grid((nE + FIRC_TILE - 1) / FIRC_TILE, rows);
-	k_cgf_derot_fir<<<grid, FIRC_TILE, 0, s>>>(Cbuf, c_stride, c_begin, rots, r_stride, nE, hist_old, hist_new, Ebuf, e_stride, e_off, tap_cgf, tap_stride);
-	return cudaGetLastError();
-}
-
 cudaError_t launch_cgf_fused(const float2 *Cbuf, long long c_stride, int c_begin, const int *stepidx, const float2 *steptab, float2 *rot_state, int nblk, int rows,
 							 const float2 *hist_old, float2 *hist_new, float2 *Ebuf, long long e_stride, int e_off, float2 *tap_cgf, long long tap_stride, int rows_per_cta, cudaStream_t s) {
 	CfParams p;

@@ -1160,8 +1160,8 @@ cudaError_t sym_init(const float *ps_cos8, const float *ps_sin8, const uint32_t 
 	if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_abort_bits, abort_bits35, 35 * sizeof(uint32_t));
 	return e;
 }
-cudaError_t launch_phase_search(const K3Params &p, int v1, cudaStream_t s) {
-	if (p.ps_ema && !v1) { // four hypotheses per lane (PhaseSearchEMA only)
+cudaError_t launch_phase_search(const K3Params &p, cudaStream_t s) {
+	if (p.ps_ema) { // four hypotheses per lane (PhaseSearchEMA only)
 		k_phase_search_ema4<<<(unsigned)(((long long)p.rows * 5 + PS2_INST - 1) / PS2_INST), 32, 0, s>>>(p);
 		return cudaGetLastError();
 	}

@@ -178,16 +178,13 @@ cudaError_t set_taps_bh28_3(const float *taps26);
 // fe_tiled.cu
 cudaError_t launch_frontend_tiled(const FeParams &p, int fmt, int k, bool pre, dim3 grid, size_t smem, cudaStream_t s);
 // fe_stream_f*.cu: n_warps warps (one per 32 lane sub-segments); g = samples per lane per staged chunk (CF32: 16, 32 or 64)
-cudaError_t launch_frontend_stream(const FeParams &p, int fmt, int k, int g, bool pre, long long n_warps, cudaStream_t s);
+cudaError_t launch_frontend_stream(const FeParams &p, int fmt, int k, bool pre, long long n_warps, cudaStream_t s);
 cudaError_t launch_frontend_stream_fpds(const FeParams &p, long long n_warps, cudaStream_t s); // fe_stream_fp.cu: CU8, integer CIC stages, 1536K
 template <int FMT, int G, int NB, int WPC>
 cudaError_t launch_frontend_stream_shape(const FeParams &p, int k, bool pre, long long n_warps, cudaStream_t s);
 // be_cgf.cu
 cudaError_t cgf_init(const float *taps17, const float2 *omega256);
 cudaError_t launch_cgf_estimate(const float2 *Cbuf, long long c_stride, int c_begin, int nblk, int total_blocks, const float2 *omega, int wide, int *stepidx, cudaStream_t s);
-cudaError_t launch_cgf_rot(const int *stepidx, const float2 *steptab, float2 *rot_state, float2 *rots, long long r_stride, int nblk, int rows, cudaStream_t s);
-cudaError_t launch_cgf_derot_fir(const float2 *Cbuf, long long c_stride, int c_begin, const float2 *rots, long long r_stride, int nE, const float2 *hist_old,
-                                 float2 *hist_new, float2 *Ebuf, long long e_stride, int e_off, float2 *tap_cgf, long long tap_stride, int rows, cudaStream_t s);
 cudaError_t launch_cgf_fused(const float2 *Cbuf, long long c_stride, int c_begin, const int *stepidx, const float2 *steptab, float2 *rot_state, int nblk, int rows,
                              const float2 *hist_old, float2 *hist_new, float2 *Ebuf, long long e_stride, int e_off, float2 *tap_cgf, long long tap_stride, int rows_per_cta,
                              cudaStream_t s);
@@ -201,7 +198,7 @@ cudaError_t fm_init(const float *taps37);
 cudaError_t launch_fm_fir5(const Fm5Params &p, int rows, cudaStream_t s);
 // be_sym.cu
 cudaError_t sym_init(const float *ps_cos8, const float *ps_sin8, const uint32_t *abort_bits35);
-cudaError_t launch_phase_search(const K3Params &p, int v1, cudaStream_t s);
+cudaError_t launch_phase_search(const K3Params &p, cudaStream_t s);
 cudaError_t launch_decode(int model, int decoder, int rpw, const K3Params &p, cudaStream_t s);
 cudaError_t launch_decode10(int rpw, const K3Params &p, cudaStream_t s);
 cudaError_t launch_base(const float *Ef, long long e_stride, int e_begin, int n, int rows, PllState *pll, DecState *dec, uint32_t *dec_data, FrameRec *ring,
