@@ -102,7 +102,7 @@ struct aisgpu_handle {
 	int rows = 0;
 	int max_n48 = 0;
 	int fe_warps = 4, fe_tile = 0, fe_ctas = 4096;
-	int fe_st = 1, st_S = 0, st_kmax = 7, st_shape = 0; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
+	int fe_st = 1, st_S = 0, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
 	int cf_rows = 4; // AISGPU_CF_ROWS: rows per CTA of the fused CGF kernel (4 or 8)
 	int dec_rpw = 6, decoder = 3; // rows per warp / which decoder kernel // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
@@ -412,7 +412,7 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 			p.st_B = B;
 			p.st_first = h->chunk == 0 ? 1 : 0;
 			if (h->fp_ds) CU(launch_frontend_stream_fpds(p, (long long)B * p.st_wps, h->fe_stream));
-			else CU(launch_frontend_stream(p, h->in_fmt, h->k, false, (long long)B * p.st_wps, h->fe_stream, h->st_shape));
+			else CU(launch_frontend_stream(p, h->in_fmt, h->k, false, (long long)B * p.st_wps, h->fe_stream));
 			return 0;
 		}
 	}
@@ -1183,7 +1183,6 @@ static int create_impl(aisgpu_handle *h) {
 	if (const char *e = getenv("AISGPU_FE_ST")) h->fe_st = atoi(e) ? 1 : 0;
 	if (const char *e = getenv("AISGPU_ST_S")) h->st_S = atoi(e);
 	if (const char *e = getenv("AISGPU_ST_KMAX")) h->st_kmax = atoi(e);
-	if (const char *e = getenv("AISGPU_ST_SHAPE")) h->st_shape = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_CTAS")) h->fe_ctas = std::max(1, atoi(e));
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {

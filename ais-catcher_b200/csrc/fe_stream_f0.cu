@@ -5,16 +5,13 @@ namespace aisgpu {
 
 template cudaError_t launch_frontend_stream_shape<0, 16, 6, 1>(const FeParams &, int, bool, long long, cudaStream_t);
 
-cudaError_t launch_frontend_stream(const FeParams &p, int fmt, int k, bool pre, long long n_warps, cudaStream_t s, int shape) {
+cudaError_t launch_frontend_stream(const FeParams &p, int fmt, int k, bool pre, long long n_warps, cudaStream_t s) {
 	switch (fmt) {
 	case 0:
 		if (pre) return launch_frontend_stream_shape<0, 16, 6, 1>(p, k, true, n_warps, s);
-		// 32-sample visits, ring of 5, four-warp CTAs: the best of the shapes measured (16 / 32 / 64 samples per visit, one- and
-		// four-warp CTAs; profiles/r2_sweeps.jsonl)
-		if (shape == 24) return launch_frontend_stream_shape<0, 32, 2, 4>(p, k, false, n_warps, s); // experiments (AISGPU_ST_SHAPE = ring depth, warps per CTA)
-		if (shape == 34) return launch_frontend_stream_shape<0, 32, 3, 4>(p, k, false, n_warps, s);
-		if (shape == 32) return launch_frontend_stream_shape<0, 32, 3, 2>(p, k, false, n_warps, s);
-		if (shape == 42) return launch_frontend_stream_shape<0, 32, 4, 2>(p, k, false, n_warps, s);
+		// 32-sample visits, ring of 5, four-warp CTAs (one CTA per SM): the best of the shapes measured -- 16 / 32 / 64 samples per
+		// visit, one-, two- and four-warp CTAs, rings of 2 .. 8 chunks with one to eight CTAs sharing an SM (profiles/r2_sweeps.jsonl):
+		// more resident warps never helped, the kernel is bound by what DRAM delivers for 32768 concurrent sequential streams
 		return launch_frontend_stream_shape<0, 32, 5, 4>(p, k, false, n_warps, s);
 	case 1: return launch_frontend_stream_shape<1, 16, 8, 1>(p, k, pre, n_warps, s);
 	case 2: return launch_frontend_stream_shape<2, 16, 8, 1>(p, k, pre, n_warps, s);

@@ -178,7 +178,7 @@ cudaError_t set_taps_bh28_3(const float *taps26);
 // fe_tiled.cu
 cudaError_t launch_frontend_tiled(const FeParams &p, int fmt, int k, bool pre, dim3 grid, size_t smem, cudaStream_t s);
 // fe_stream_f*.cu: n_warps warps (one per 32 lane sub-segments); g = samples per lane per staged chunk (CF32: 16, 32 or 64)
-cudaError_t launch_frontend_stream(const FeParams &p, int fmt, int k, bool pre, long long n_warps, cudaStream_t s, int shape = 0);
+cudaError_t launch_frontend_stream(const FeParams &p, int fmt, int k, bool pre, long long n_warps, cudaStream_t s);
 cudaError_t launch_frontend_stream_fpds(const FeParams &p, long long n_warps, cudaStream_t s); // fe_stream_fp.cu: CU8, integer CIC stages, 1536K
 template <int FMT, int G, int NB, int WPC>
 cudaError_t launch_frontend_stream_shape(const FeParams &p, int k, bool pre, long long n_warps, cudaStream_t s);
