@@ -112,7 +112,7 @@ struct aisgpu_handle {
 	// stage s of submit c waits for stage s of submit c-1 (its carried state) through ev_stage[s][(c-1) & 1]; the buffers
 	// between stages are double buffered (index c & 1).  With taps enabled everything stays on one stream.
 	cudaStream_t be_streams[2] = { nullptr, nullptr }, bs = nullptr;
-	static const int NSTAGE = 6; // 0 estimate / fm+fir, 1 cgf_rot, 2 derot+fir (+Ec carry), 3 phase search, 4 decode, 5 carry of Cbuf
+	static const int NSTAGE = 7; // 0 estimate / fm+fir, 1 + 2 phasor chain + derot + fir (+Ec carry), 3 phase search, 4 decode, 5 carry of Cbuf, 6 Challenger FM branch (reads Ed)
 	cudaEvent_t ev_stage[6][2] = {};
 	bool stage_rec[6][2] = {};
 	cudaEvent_t ev_join = nullptr;
@@ -557,8 +557,10 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 			f.f_off = HE;
 			f.dbits = h->d_dbitsF[h->pb];
 			f.dwords = h->dwords;
+			if (int rc = stage_begin(h, 6)) return rc;
 			CU(launch_fm_fir5(f, h->rows, h->bs));
 			if (int rc = carry(h, h->d_Ed, h->ed_stride, HD + n_new - HD, 0, HD)) return rc; // the last HD derotated samples stay in front
+			if (int rc = stage_end(h, 6)) return rc;
 			p.dbits2 = h->d_dbitsF[h->pb];
 			p.nslots_fm = f.nslots;
 			p.lvl_prev = h->d_lvl_prev + (size_t)h->lvlp_cur * h->rows;
@@ -566,7 +568,9 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 			h->lvlp_cur ^= 1;
 			p.abs_lo = a0;
 			p.abs_hi = a1;
+			if (int rc = stage_begin(h, 4)) return rc;
 			CU(launch_decode10(h->dec_rpw == 1 ? 1 : 3, p, h->bs));
+			if (int rc = stage_end(h, 4)) return rc;
 			h->last_launches += 3;
 		}
 		else {
@@ -697,6 +701,8 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 				if (int rc = stage_begin(h, 1)) return rc;
 				if (int rc = stage_begin(h, 2)) return rc;
 				if (int rc = stage_begin(h, 3)) return rc;
+				if (h->d_Ed) // ModelChallenger: Ed (single buffered) is free once the previous submit's FM branch has read it
+					if (int rc = stage_begin(h, 6)) return rc;
 				CU(launch_cgf_fused(Ccur, h->c_stride, c_begin, stepidx, h->d_steptab, h->d_cgf_rot, nblk, h->rows, h->d_fir_hist[h->fir_cur],
 									h->d_fir_hist[h->fir_cur ^ 1], h->d_Ec2[0], h->e_stride, HE,
 									h->d_Ed ? h->d_Ed + HD : (h->cfg.enable_taps ? h->d_tap_cgf : nullptr), h->d_Ed ? h->ed_stride : h->r_stride, h->cf_rows, h->bs));
@@ -1210,8 +1216,8 @@ static int create_impl(aisgpu_handle *h) {
 		// it is what keeps the step time stable: with one back-end stream the run can lock into a serial pattern (front end c+1 starved
 		// while back end c runs, back end c+1 then waiting for it) -- 0.80 ms per step (or 0.90 ms with one stream priority) instead of
 		// 0.55 ms at 1024 x 131072 @1536K, both patterns self-sustaining from the first submits on (profiles/r2_sweeps.jsonl, probe12/13).
-		const bool pipe = (e ? atoi(e) != 0 : (c.model == AISGPU_MODEL_STANDARD || c.model == AISGPU_MODEL_DEFAULT)) && !c.enable_taps && c.model != AISGPU_MODEL_BASE && c.model != AISGPU_MODEL_V2 &&
-						  c.model != AISGPU_MODEL_CHALLENGER;
+		const bool pipe = (e ? atoi(e) != 0 : (c.model == AISGPU_MODEL_STANDARD || c.model == AISGPU_MODEL_DEFAULT || c.model == AISGPU_MODEL_CHALLENGER)) && !c.enable_taps &&
+						  c.model != AISGPU_MODEL_BASE && c.model != AISGPU_MODEL_V2;
 		if (pipe) CU(cudaStreamCreateWithPriority(&h->be_streams[1], cudaStreamNonBlocking, prio_hi));
 	}
 	h->bs = h->stream;
