@@ -113,8 +113,8 @@ struct aisgpu_handle {
 	// between stages are double buffered (index c & 1).  With taps enabled everything stays on one stream.
 	cudaStream_t be_streams[2] = { nullptr, nullptr }, bs = nullptr;
 	static const int NSTAGE = 7; // 0 estimate / fm+fir, 1 + 2 phasor chain + derot + fir (+Ec carry), 3 phase search, 4 decode, 5 carry of Cbuf, 6 Challenger FM branch (reads Ed)
-	cudaEvent_t ev_stage[6][2] = {};
-	bool stage_rec[6][2] = {};
+	cudaEvent_t ev_stage[NSTAGE][2] = {};
+	bool stage_rec[NSTAGE][2] = {};
 	cudaEvent_t ev_join = nullptr;
 	int pb = 0; // buffer parity of the submit being enqueued
 	static const int NC = 3; // ring of 48 kHz buffers: the front end may run two submits ahead of the back end

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(FM5_THREADS) k_fm_fir5(const Fm5Params p) {
 			const float2 a = c[m], pv = c[m - 1];
 			const float re = __fsub_rn(__fmul_rn(a.x, pv.x), __fmul_rn(a.y, -pv.y));
 			const float im = __fadd_rn(__fmul_rn(a.x, -pv.y), __fmul_rn(a.y, pv.x));
-			v = __fdiv_rn(fd_atan2f(im, re), 3.14159265358979323846f);
+			v = __fdiv_rn(fd_atan2f_common(im, re), 3.14159265358979323846f);
 			if (p.tap_fm && m >= 0 && i >= FIRF_T - 1) p.tap_fm[(long long)row * p.tap_stride + m] = v;
 		}
 		fm[i] = v;
