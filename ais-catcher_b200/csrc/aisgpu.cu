@@ -552,7 +552,7 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 			f.n = n_new;
 			f.r0 = h->e_left;
 			f.nslots = (int)((a1 - h->e_abs + 4) / 5);
-			f.Fbuf = h->d_Ef2[0];
+			f.Fbuf = h->cfg.enable_taps ? h->d_Ef2[0] : nullptr; // k_decode10 takes the decision bits
 			f.f_stride = h->e_stride;
 			f.f_off = HE;
 			f.dbits = h->d_dbitsF[h->pb];
@@ -737,7 +737,8 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 			f.n = n48;
 			f.r0 = h->cfg.model == AISGPU_MODEL_STANDARD ? (int)(a0 - g0) : 0;
 			f.nslots = nslots;
-			f.Fbuf = h->d_Ef2[0];
+			// the filtered samples themselves are only read by k_base, the bit-serial cross-check decoder and the taps
+			f.Fbuf = (h->cfg.model == AISGPU_MODEL_BASE || h->decoder == 1 || h->cfg.enable_taps) ? h->d_Ef2[0] : nullptr;
 			f.f_stride = h->e_stride;
 			f.f_off = HE;
 			f.dbits = h->d_dbits2[h->pb];
@@ -1598,7 +1599,11 @@ int aisgpu_tap(aisgpu_handle *h, int tap, int stream, int channel, void *dst, si
 			src = h->d_tap_coh + (long long)row * h->r_stride;
 		}
 		else if (h->cfg.model == AISGPU_MODEL_DEFAULT) src = h->d_Ec2[0] + (long long)row * h->e_stride + HE;
-		else { src = h->d_Ef2[0] + (long long)row * h->e_stride + HE; esz = 4; }
+		else {
+			if (!h->cfg.enable_taps && h->cfg.model != AISGPU_MODEL_BASE) { h->err = "taps not enabled"; return AISGPU_EINVAL; } // the FIR37 output is not stored then
+			src = h->d_Ef2[0] + (long long)row * h->e_stride + HE;
+			esz = 4;
+		}
 		n = h->last_nE;
 		break;
 	case AISGPU_TAP_ROT:

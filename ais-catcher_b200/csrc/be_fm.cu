@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(FM5_THREADS) k_fm_fir5(const Fm5Params p) {
 	for (int j = 0; j < 5; j++) {
 		const int m = m0 + j;
 		if (m >= 0 && m < p.n) {
-			p.Fbuf[(long long)row * p.f_stride + p.f_off + m] = y[j];
+			if (p.Fbuf) p.Fbuf[(long long)row * p.f_stride + p.f_off + m] = y[j];
 			if (p.tap_dec) p.tap_dec[(long long)(row * 5 + j) * p.nslots + slot - (j >= p.r0 ? 0 : 1)] = y[j];
 		}
 		const unsigned w = __ballot_sync(0xffffffffu, y[j] > 0.0f);

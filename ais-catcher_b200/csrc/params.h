@@ -62,7 +62,7 @@ struct Fm5Params {
 	int c_new, n;        // new samples start at Cbuf[row][c_new], n of them
 	int r0;              // abs index of new sample 0 modulo 5: slot 0 starts r0 samples before it
 	int nslots;
-	float *Fbuf;         // FIR37 output, [rows][f_stride], new sample m at f_off + m
+	float *Fbuf;         // FIR37 output, [rows][f_stride], new sample m at f_off + m; NULL: nobody reads it (the decoders take dbits)
 	long long f_stride;
 	int f_off;
 	uint32_t *dbits;     // [rows*5][dwords]
