@@ -1,5 +1,4 @@
 #!/bin/bash
-# GPU call 20: FM chain with the front end privileged over its back end
+# GPU call 22: randomised configuration matrix
 mkdir -p gpurun_out
-timeout 900 python tools/default_probe.py 0 - AISGPU_PRIO=2 - AISGPU_PRIO=2 AISGPU_PRIO=2,AISGPU_DEC_RPW=3 AISGPU_PRIO=2,AISGPU_DEC_RPW=1 AISGPU_DEC_RPW=3 2>&1 | tee gpurun_out/probe20.jsonl
-PROBE_SHAPE=8192,65536,1536000,3 timeout 600 python tools/default_probe.py 0 - AISGPU_PRIO=2 2>&1 | tee -a gpurun_out/probe20.jsonl
+timeout 2400 python -m pytest tests/test_gpu_matrix.py -m gpu -q > gpurun_out/pytest22.log 2>&1; tail -30 gpurun_out/pytest22.log | cut -c1-900
