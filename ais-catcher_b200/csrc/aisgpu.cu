@@ -102,7 +102,7 @@ struct aisgpu_handle {
 	int rows = 0;
 	int max_n48 = 0;
 	int fe_warps = 4, fe_tile = 0, fe_ctas = 4096;
-	int fe_st = 1, st_S = 0, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_S: samples per lane; AISGPU_ST_NB: ring depth
+	int fe_st = 1, st_L = 0, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_L: lanes per stream (0: the launcher plans)
 	int cf_rows = 4; // AISGPU_CF_ROWS: rows per CTA of the fused CGF kernel (4 or 8)
 	int dec_rpw = 6, decoder = 3; // rows per warp / which decoder kernel // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
@@ -393,28 +393,15 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 	p.C = h->d_C2[h->chunk % aisgpu_handle::NC];
 	p.c_stride = h->c_stride;
 	p.c_off = HC;
-	// 768 kS/s .. 3072 kS/s: per-thread streaming pipeline (state in registers) when the rows are 16-byte aligned
+	// 768 kS/s and above: per-thread streaming pipeline (state in registers) when the rows are 16-byte aligned; the launcher splits
+	// every stream over as many lanes as make one balanced wave (st_plan, fe_stream.cuh) and declines blocks shorter than four warm-ups
 	if (h->fe_st && h->k >= 3 && h->k <= h->st_kmax && ((stride * h->bps) % 16) == 0 && (((size_t)dev_in) % 16) == 0) {
-		// every lane of a warp gets S samples, S a multiple of a super-step; N must split into whole warps of lanes
-		const int SS = 1 << (h->k + 2);
-		int S = h->st_S > 0 ? h->st_S / SS * SS : 0;
-		if (S <= 0) {
-			S = 2048; // about 10 x the warm-up history P (192 samples at K = 3, doubling per stage)
-			for (int i = 3; i < h->k; i++) S *= 2;
-			// longer sub-segments = smaller warm-up share; a lane's warm-up must not reach beyond its left neighbour's segment start
-			// (only the stream's first lane reads the previous submit's tail), so S >= P always
-			while (S >= 2 * SS && S / 2 >= (h->fp_ds ? 1 : 4) * h->P && N % (32 * S) != 0) S /= 2;
-		}
-		if (S >= SS && N % (32 * S) == 0) {
-			p.in = dev_in;
-			p.st_S = S;
-			p.st_wps = N / (32 * S);
-			p.st_B = B;
-			p.st_first = h->chunk == 0 ? 1 : 0;
-			if (h->fp_ds) CU(launch_frontend_stream_fpds(p, (long long)B * p.st_wps, h->fe_stream));
-			else CU(launch_frontend_stream(p, h->in_fmt, h->k, false, (long long)B * p.st_wps, h->fe_stream));
-			return 0;
-		}
+		p.in = dev_in;
+		p.st_B = B;
+		p.st_first = h->chunk == 0 ? 1 : 0;
+		const cudaError_t e = h->fp_ds ? launch_frontend_stream_fpds(p, h->st_L, h->fe_stream) : launch_frontend_stream(p, h->in_fmt, h->k, false, h->st_L, h->fe_stream);
+		if (e == cudaSuccess) return 0;
+		if (e != cudaErrorNotSupported) CU(e);
 	}
 	if (h->fp_ds) { // the integer CIC stages only exist in the streaming kernel
 		h->err = "FP_DS on: n_samples must be a multiple of 16384 and the batch 16-byte aligned";
@@ -502,6 +489,7 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		K3Params p;
 		memset(&p, 0, sizeof(p));
 		p.ps_ema = h->cfg.ps_ema;
+		p.ps_rot0 = (int)((h->e_abs / 5) & 3); // e_abs counts from 0 at creation: symbols delivered so far
 		p.rows = h->rows;
 		p.nsym = nsym;
 		p.e_stride = h->e_stride;
@@ -851,17 +839,10 @@ int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) 
 			dim3 grid(n_seg, B);
 			bool st_done = false;
 			if (h->fe_st && h->kA >= 3 && h->kA <= 5 && ((stride * h->obps) % 16) == 0 && (((size_t)dev_in) % 16) == 0) {
-				const int SS = 1 << (h->kA + 2);
-				int S = 2048;
-				for (int i = 3; i < h->kA; i++) S *= 2;
-				while (S >= 2 * SS && S / 2 >= 4 * h->PA && N % (32 * S) != 0) S /= 2;
-				if (N % (32 * S) == 0) {
-					pp.st_S = S;
-					pp.st_wps = N / (32 * S);
-					pp.st_B = B;
-					CU(launch_frontend_stream(pp, h->cfg.format, h->kA, true, (long long)B * pp.st_wps, h->fe_stream));
-					st_done = true;
-				}
+				pp.st_B = B;
+				const cudaError_t e = launch_frontend_stream(pp, h->cfg.format, h->kA, true, h->st_L, h->fe_stream);
+				if (e == cudaSuccess) st_done = true;
+				else if (e != cudaErrorNotSupported) CU(e);
 			}
 			if (!st_done) CU(launch_frontend_tiled(pp, h->cfg.format, h->kA, true, grid, smem, h->fe_stream));
 			if (rc) return rc;
@@ -1188,7 +1169,7 @@ static int create_impl(aisgpu_handle *h) {
 	}
 	if (const char *e = getenv("AISGPU_FE_TILE")) h->fe_tile = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_ST")) h->fe_st = atoi(e) ? 1 : 0;
-	if (const char *e = getenv("AISGPU_ST_S")) h->st_S = atoi(e);
+	if (const char *e = getenv("AISGPU_ST_L")) h->st_L = atoi(e);
 	if (const char *e = getenv("AISGPU_ST_KMAX")) h->st_kmax = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_CTAS")) h->fe_ctas = std::max(1, atoi(e));
 	int ndev = 0;

@@ -2,6 +2,7 @@
 #include "exact.cuh"
 #include "params.h"
 #include "dec_core.cuh"
+#include <cstdlib>
 
 namespace aisgpu {
 
@@ -318,6 +319,198 @@ __global__ void __launch_bounds__(32) k_phase_search_ema4(const K3Params p) {
 			for (int dd = 0; dd < 5; dd++) st.plane[dd] = planes[dd];
 			st.max_idx = max_idx;
 			st.rot = rot;
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3a'': the same PhaseSearchEMA mapping (one-warp CTA, eight instances x four lanes x four hypotheses) at half the
+// instructions per symbol.  Against k_phase_search_ema4:
+//   * the (1j)^rot pre-rotation costs nothing: symbols are walked in groups of four, the kernel is instantiated per value of
+//     rot at the start of the submit (the host knows it: symbols delivered so far & 3), so which of (x.re, x.im) feeds "re" is
+//     static and the signs go into the constants (-(x) * c == x * (-c) exactly);
+//   * (1 - w) * |t| is taken as |(1 - w) * t| -- the absolute value rides as an operand modifier on the following add;
+//   * the neighbourhood argmax is evaluated lazily: the lanes put their EMAs into shared memory (one 16-byte store per lane
+//     and symbol) and only the three values around the previous maximum are read back and compared (Demod.cpp:80-91) -- the
+//     16-entry decision table of ema4 (8 compares, 12 selects, 2 shuffles per lane and symbol) is gone, and so is the shuffle
+//     on the sequential chain;
+//   * the stores of group g and the lookups of group g - 1 sit between the same two __syncwarp()s, so the sequential chain
+//     (address from max_idx -> three loads -> two compares -> max_idx) of one group runs under the arithmetic of the next.
+// ---------------------------------------------------------------------------------------------
+constexpr int PS3_G = 4;        // symbols per group
+constexpr int PS3_STRIDE = 20;  // floats per (instance, symbol): 16 EMAs, the first two again (the window wraps), 2 unused
+template <int R0>
+__global__ void __launch_bounds__(32) k_phase_search_ema4b(const K3Params p) {
+	__shared__ float2 tile[2][PS2_TROWS][PS2_ROWP];
+	__shared__ __align__(16) float mav[2][PS3_G][PS2_INST][PS3_STRIDE];
+	const int lane = threadIdx.x;
+	const long long ninst = (long long)p.rows * 5;
+	const long long inst0 = (long long)blockIdx.x * PS2_INST; // first instance of this warp
+	const int il = lane >> 2;                              // instance within the warp
+	const long long gi = inst0 + il;
+	const int q = lane & 3, q4 = 4 * q;                    // hypothesis group
+	const bool active = gi < ninst;
+	const long long inst = active ? gi : ninst - 1;
+	const int row = (int)(inst / 5), phase = (int)(inst - (long long)row * 5);
+	const int r_lo = (int)(inst0 / 5);                    // first row the warp touches
+	const int rin = row - r_lo;
+	auto or4 = [](uint32_t v) {
+		v |= __shfl_xor_sync(0xffffffffu, v, 1);
+		v |= __shfl_xor_sync(0xffffffffu, v, 2);
+		return v;
+	};
+	const float weight = 0.85f, omw = __fsub_rn(1.0f, 0.85f);
+	float cj[4], sj[4];
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const int h = 4 * q + k, j = h < 8 ? h : 15 - h;
+		cj[k] = c_ps_cos[j];
+		sj[k] = h < 8 ? c_ps_sin[j] : -c_ps_sin[j]; // a - b == a + (-b) and im * (-s) == -(im * s), exactly
+	}
+	const c64 cP01 = pack2(cj[0], cj[1]), cP23 = pack2(cj[2], cj[3]), sP01 = pack2(sj[0], sj[1]), sP23 = pack2(sj[2], sj[3]);
+	const c64 cN01 = pack2(-cj[0], -cj[1]), cN23 = pack2(-cj[2], -cj[3]), sN01 = pack2(-sj[0], -sj[1]), sN23 = pack2(-sj[2], -sj[3]);
+	const c64 w2 = pack2(weight, weight), o2 = pack2(omw, omw);
+	float ma[4] = { 0.f, 0.f, 0.f, 0.f };
+	uint32_t hist = 0u; // nibble d (bits 4d .. 4d+3) = the sign decisions of the lane's four hypotheses d symbols ago
+	int max_idx = 0;
+	if (active) {
+		const PsState &st = p.ps[inst];
+#pragma unroll
+		for (int k = 0; k < 4; k++) ma[k] = st.ma[4 * q + k];
+#pragma unroll
+		for (int dd = 0; dd < 5; dd++) hist |= ((st.plane[dd] >> (4 * q)) & 0xfu) << (4 * dd);
+		max_idx = st.max_idx;
+	}
+	const int nsamp = p.nsym * 5;
+	auto prefetch = [&](int buf, int s0) {
+		const int base = s0 * 5;
+		for (int e = lane; e < PS2_TROWS * K3_ROWLEN; e += 32) {
+			const int r = e / K3_ROWLEN, c = e - r * K3_ROWLEN;
+			if (r_lo + r < p.rows && base + c < nsamp) cp_async_f(&tile[buf][r][c], p.Ec + (long long)(r_lo + r) * p.e_stride + p.e_begin + base + c);
+		}
+		cp_async_commit();
+	};
+	// one symbol, first half: hypotheses, EMAs, decisions; the EMAs go to shared memory for the lookup half
+	uint32_t xm[2][PS3_G]; // bit k: the demodulated bit hypothesis 4q + k would deliver for this symbol (nDelay = 3, Model.h:219)
+	auto first_half = [&](const float2 x, const int k, const int buf) {
+		const int r = (R0 + k) & 3;
+		// (1j)^rot (Demod.cpp:44-65): rot 0: (re, im) = (x.re, x.im); 1: (-x.im, x.re); 2: (-x.re, -x.im); 3: (x.im, -x.re)
+		const float X = (r & 1) ? x.y : x.x, Y = (r & 1) ? x.x : x.y;
+		const bool nA = r == 1 || r == 2, nB = r >= 2;
+		const c64 X2 = pack2(X, X), Y2 = pack2(Y, Y);
+		// products by packed FMUL2, sums by scalar FADD (a packed mul feeding a packed add would be contracted into FFMA2 by ptxas)
+		const float2 a01 = unpack2(pmul(X2, nA ? cN01 : cP01)), a23 = unpack2(pmul(X2, nA ? cN23 : cP23));
+		const float2 b01 = unpack2(pmul(Y2, nB ? sN01 : sP01)), b23 = unpack2(pmul(Y2, nB ? sN23 : sP23));
+		const float t0 = __fadd_rn(a01.x, b01.x), t1 = __fadd_rn(a01.y, b01.y), t2 = __fadd_rn(a23.x, b23.x), t3 = __fadd_rn(a23.y, b23.y);
+		hist <<= 4;
+		if (t0 > 0.0f) hist |= 1u;
+		if (t1 > 0.0f) hist |= 2u;
+		if (t2 > 0.0f) hist |= 4u;
+		if (t3 > 0.0f) hist |= 8u;
+		{ // ma = weight * ma + (1 - weight) * |t| (Demod.cpp:67-78); (1 - weight) > 0, so (1 - weight) * |t| == |(1 - weight) * t| bit for bit
+			const float2 w01 = unpack2(pmul(w2, pack2(ma[0], ma[1]))), w23 = unpack2(pmul(w2, pack2(ma[2], ma[3])));
+			const float2 u01 = unpack2(pmul(o2, pack2(t0, t1))), u23 = unpack2(pmul(o2, pack2(t2, t3)));
+			ma[0] = __fadd_rn(w01.x, fabsf(u01.x));
+			ma[1] = __fadd_rn(w01.y, fabsf(u01.y));
+			ma[2] = __fadd_rn(w23.x, fabsf(u23.x));
+			ma[3] = __fadd_rn(w23.y, fabsf(u23.y));
+		}
+		const uint32_t hs = hist >> 12;
+		xm[buf][k] = (hs ^ (hs >> 4)) & 0xfu;
+		float *mv = &mav[buf][k][il][0];
+		*reinterpret_cast<float4 *>(mv + q4) = make_float4(ma[0], ma[1], ma[2], ma[3]);
+		if (q == 0) *reinterpret_cast<float2 *>(mv + 16) = make_float2(ma[0], ma[1]);
+	};
+	// second half: best of (i0, i0+1, i0+2), strict >, the first maximum wins (Demod.cpp:80-91); every lane of the instance
+	// evaluates it (same addresses: a broadcast), the lane that holds hypothesis max_idx contributes the demodulated bit
+	uint32_t word = 0;
+	auto second_half = [&](const int k, const int buf) {
+		const int i0 = (max_idx - 1) & 15;
+		const float *v = &mav[buf][k][il][i0];
+		const float v0 = v[0], v1 = v[1], v2 = v[2];
+		const bool p1 = v1 > v0;
+		const float mvv = p1 ? v1 : v0;
+		const int best = v2 > mvv ? 2 : (p1 ? 1 : 0);
+		max_idx = (i0 + best) & 15;
+		// xm >> (max_idx - 4q) is 0 unless 0 <= max_idx - 4q < 4 (the funnel shift clamps the distance at 32); its bit 0 enters the
+		// word from the top: after 32 symbols the first one sits in bit 0
+		const uint32_t sh = __funnelshift_rc(xm[buf][k], 0u, (uint32_t)(max_idx - q4));
+		word = __funnelshift_r(word, sh, 1);
+	};
+	const int ntiles = (p.nsym + K3_TS - 1) / K3_TS;
+	if (ntiles > 0) prefetch(0, 0);
+	for (int t = 0; t < ntiles; t++) {
+		if (t + 1 < ntiles) {
+			prefetch((t + 1) & 1, (t + 1) * K3_TS);
+			cp_async_wait<1>();
+		}
+		else cp_async_wait<0>();
+		__syncwarp();
+		const float2 *my = &tile[t & 1][rin][phase];
+		const int s_end = min(K3_TS, p.nsym - t * K3_TS);
+		const int ngrp = (s_end + PS3_G - 1) / PS3_G;
+		word = 0;
+		auto trip = [&](const int g, const int buf) { // buf is a literal at both call sites: xm[][] stays in registers
+			const int cnt1 = g < ngrp ? s_end - g * PS3_G : 0;      // symbols of group g (>= 4 except in the last group of the last tile)
+			const int cnt2 = g > 0 ? s_end - (g - 1) * PS3_G : 0;   // symbols of group g - 1
+			const float2 *x = my + g * (PS3_G * 5);
+			if (cnt1 >= PS3_G && cnt2 >= PS3_G) { // the common trip, one basic block: the lookups of group g - 1 run under the arithmetic of group g
+#pragma unroll
+				for (int k = 0; k < PS3_G; k++) first_half(x[k * 5], k, buf);
+#pragma unroll
+				for (int k = 0; k < PS3_G; k++) second_half(k, buf ^ 1);
+			}
+			else {
+#pragma unroll
+				for (int k = 0; k < PS3_G; k++)
+					if (k < cnt1) first_half(x[k * 5], k, buf);
+#pragma unroll
+				for (int k = 0; k < PS3_G; k++)
+					if (k < cnt2) second_half(k, buf ^ 1);
+			}
+			__syncwarp(); // group g's EMAs are visible to the lookups of the next trip; buffer g & 1 is rewritten two trips later
+		};
+		for (int g = 0; g <= ngrp; g += 2) {
+			trip(g, 0);
+			if (g + 1 <= ngrp) trip(g + 1, 1);
+		}
+		word >>= (32 - s_end) & 31; // a short last tile: the first symbol goes to bit 0
+		word = or4(word);
+		if (active && q == 0) p.dbits[inst * p.dwords + t] = word;
+		if (p.tap_dec && active) { // decoder input tap: one float per symbol, eight symbols per lane of the instance
+			for (int sx = 8 * q; sx < min(8 * q + 8, s_end); sx++) p.tap_dec[inst * p.nsym + t * K3_TS + sx] = ((word >> sx) & 1u) ? 1.0f : -1.0f;
+		}
+		if (p.mode_level) { // ScatterPLL level: ((((0+n0)+n1)+n2)+n3)+n4, then / 5 (DSP.h:100-106), by the warp that holds the row's phase 0
+#pragma unroll
+			for (int r = 0; r < PS2_TROWS; r++) {
+				const long long first = (long long)(r_lo + r) * 5; // the row's phase-0 instance
+				if (first >= inst0 && first < inst0 + PS2_INST && r_lo + r < p.rows && lane < s_end) {
+					const float2 *rowt = &tile[t & 1][r][lane * 5];
+					float acc = 0.0f;
+#pragma unroll
+					for (int jx = 0; jx < 5; jx++) {
+						const float2 xx = rowt[jx];
+						acc = __fadd_rn(acc, __fadd_rn(__fmul_rn(xx.x, xx.x), __fmul_rn(xx.y, xx.y)));
+					}
+					p.lvl[(long long)(r_lo + r) * p.lvl_stride + t * K3_TS + lane] = __fdiv_rn(acc, 5.0f);
+				}
+			}
+		}
+		__syncwarp();
+	}
+	// state back: the bit planes are OR-combined over the four lanes of the instance
+	uint32_t planes[5];
+#pragma unroll
+	for (int dd = 0; dd < 5; dd++) planes[dd] = or4(((hist >> (4 * dd)) & 0xfu) << (4 * q));
+	if (active) {
+		PsState &st = p.ps[inst];
+#pragma unroll
+		for (int k = 0; k < 4; k++) st.ma[4 * q + k] = ma[k];
+		if (q == 0) {
+#pragma unroll
+			for (int dd = 0; dd < 5; dd++) st.plane[dd] = planes[dd];
+			st.max_idx = max_idx;
+			st.rot = (R0 + p.nsym) & 3;
 		}
 	}
 }
@@ -1162,7 +1355,15 @@ cudaError_t sym_init(const float *ps_cos8, const float *ps_sin8, const uint32_t 
 }
 cudaError_t launch_phase_search(const K3Params &p, cudaStream_t s) {
 	if (p.ps_ema) { // four hypotheses per lane (PhaseSearchEMA only)
-		k_phase_search_ema4<<<(unsigned)(((long long)p.rows * 5 + PS2_INST - 1) / PS2_INST), 32, 0, s>>>(p);
+		const unsigned grid = (unsigned)(((long long)p.rows * 5 + PS2_INST - 1) / PS2_INST);
+		static const bool old_kernel = getenv("AISGPU_PS_OLD") != nullptr; // A/B switch of this round's measurements
+		if (old_kernel) k_phase_search_ema4<<<grid, 32, 0, s>>>(p);
+		else switch (p.ps_rot0 & 3) { // (1j)^rot at the first symbol of the submit
+			case 0: k_phase_search_ema4b<0><<<grid, 32, 0, s>>>(p); break;
+			case 1: k_phase_search_ema4b<1><<<grid, 32, 0, s>>>(p); break;
+			case 2: k_phase_search_ema4b<2><<<grid, 32, 0, s>>>(p); break;
+			default: k_phase_search_ema4b<3><<<grid, 32, 0, s>>>(p); break;
+		}
 		return cudaGetLastError();
 	}
 	const long long ps_warps = ((long long)p.rows * 5 + 1) / 2;

@@ -1,6 +1,7 @@
 #pragma once
 #include "exact.cuh"
 #include "params.h"
+#include <atomic>
 
 namespace aisgpu {
 
@@ -128,32 +129,56 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p)
 	constexpr int N96 = SS >> K;         // 96 kHz samples per super-step (4)
 	extern __shared__ __align__(16) unsigned char st_ring[]; // [ST_WARPS][ST_NB][32 * SLOT]
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	const long long wg = (long long)blockIdx.x * ST_WARPS + wib;
-	const int stream = (int)(wg / p.st_wps);
-	if (stream >= p.st_B) return; // whole warp
-	const int sub0 = (int)(wg - (long long)stream * p.st_wps) * 32;
-	const int S = p.st_S;
+	// Lane mapping: global lane g owns sub-segment (g % L) of stream (g / L).  A stream's nss = q * L + r super-steps are split
+	// unevenly -- the first L - r lanes take q, the last r take q + 1 -- so that L need not divide the block: the host picks L such
+	// that all CTAs are resident at once (one wave over the 148 SMs) with the longest sub-segments that allow (launch_st_one).
+	const long long g0 = ((long long)blockIdx.x * ST_WARPS + wib) * 32;
+	const int L = p.st_L;
+	if (g0 >= (long long)p.st_B * L) return; // whole warp
+	int stream = (int)((g0 + lane) / L), sub = (int)((g0 + lane) - (long long)stream * L);
+	const bool ghost = stream >= p.st_B; // the last warp's spare lanes replay the batch's last lane without storing
+	if (ghost) { stream = p.st_B - 1; sub = L - 1; }
+	const int n_short = L - p.st_r;
+	const int n_main = ghost ? 0 : p.st_q + (sub >= n_short ? 1 : 0); // super-steps this lane delivers
 	unsigned char(*ring)[32 * F::SLOT] = reinterpret_cast<unsigned char(*)[32 * F::SLOT]>(st_ring + (size_t)wib * ST_NB * 32 * F::SLOT);
-	// every lane owns S samples [a, a + S) (the host only picks this kernel when N is a multiple of 32 * S * st_wps)
-	const long long a = (long long)(sub0 + lane) * S;
-	const int warp_chunks = (S + p.P) / ST_G; // warm-up included
-	const unsigned char *in_b = reinterpret_cast<const unsigned char *>(p.in) + (long long)stream * p.in_stride * F::BPS;
-	const unsigned char *tl_b = reinterpret_cast<const unsigned char *>(p.tail) + ((long long)stream * p.P + p.P) * F::BPS;
-	// staging: in instruction `it` lane j fetches 16-byte piece (j % PIECES) of the chunk of owner it*(32/PIECES) + j / PIECES
+	// the lane owns samples [a, a + n_main * SS); every lane of every warp walks warm_super + q + (r ? 1 : 0) super-steps (a short
+	// lane's last one re-reads the head of its right neighbour's sub-segment -- same stream -- and is not stored)
+	const long long a = ((long long)sub * p.st_q + max(0, sub - n_short)) * SS;
+	const int n_super = p.P / SS + p.st_q + (p.st_r ? 1 : 0);
+	const int warp_chunks = n_super * NCH; // warm-up included
+	// staging: in instruction `it` lane j fetches 16-byte piece (j % PIECES) of the chunk of owner it*(32/PIECES) + j / PIECES;
+	// only the first sub-segment of a stream starts in the previous submit: its warm-up chunks come from the tail buffer
 	constexpr int OWN_PER_IT = 32 / F::PIECES;
 	const int o0 = lane / F::PIECES, q0 = lane % F::PIECES;
-	const long long lane_off = ((long long)(sub0 + o0) * S - p.P) * F::BPS + q0 * 16; // byte offset of chunk 0, piece q0, owner o0
-	const long long it_step = (long long)OWN_PER_IT * S * F::BPS;                        // next instruction: next group of owners
+	// Where the owners' sub-segments start: every lane computes its own start and the fetching lane collects, once, the starts of
+	// the PIECES owners it fetches for (a table in shared memory would put an LDS in front of every LDGSTS, and ptxas pads that
+	// pair with three dummy issue slots).  Main phase: 32-bit offsets in 16-byte units from in0 = p.in - P samples (the launcher
+	// declines batches of 64 GB and more) -- two instructions per 16-byte copy; warm-up phase (the first P / ST_G chunks,
+	// warp-uniform): full addresses by shuffle, because a stream's first lane reads the tail buffer.
+	const unsigned char *in0 = reinterpret_cast<const unsigned char *>(p.in) - (long long)p.P * F::BPS;
+	const unsigned my_off = (unsigned)((((long long)stream * p.in_stride + a) * F::BPS) >> 4);
+	const unsigned long long my_warm = sub == 0 ? (unsigned long long)(reinterpret_cast<const unsigned char *>(p.tail) + (long long)stream * p.P * F::BPS)
+												: (unsigned long long)(in0 + ((unsigned long long)my_off << 4));
 	const int dst_off = o0 * F::SLOT + q0 * 16;
-	const bool from_tail = sub0 == 0 && o0 == 0; // only the first sub-segment of a stream starts in the previous submit
+	unsigned own_off[F::PIECES]; // the owners this lane fetches for, one per instruction of a chunk (registers are not the scarce resource: one CTA per SM)
+#pragma unroll
+	for (int it = 0; it < F::PIECES; it++) own_off[it] = __shfl_sync(0xffffffffu, my_off, it * OWN_PER_IT + o0);
 	auto prefetch = [&](int c) {
 		if (c < warp_chunks) {
-			const long long coff = lane_off + (long long)c * (ST_G * F::BPS);
+			const long long coff = (long long)c * (ST_G * F::BPS) + q0 * 16;
 			unsigned char *dst = &ring[c % ST_NB][dst_off];
+			if (c * ST_G < p.P) {
 #pragma unroll
-			for (int it = 0; it < F::PIECES; it++) {
-				const unsigned char *src = ((it == 0 && from_tail && c * ST_G < p.P) ? tl_b : in_b) + coff + it * it_step;
-				cp_async16(dst + it * OWN_PER_IT * F::SLOT, src);
+				for (int it = 0; it < F::PIECES; it++) {
+					const unsigned long long w = __shfl_sync(0xffffffffu, my_warm, it * OWN_PER_IT + o0);
+					cp_async16(dst + it * OWN_PER_IT * F::SLOT, reinterpret_cast<const unsigned char *>(w) + coff);
+				}
+			}
+			else {
+				unsigned long long base = (unsigned long long)(in0 + coff);
+				asm volatile("" : "+l"(base)); // one register pair: otherwise ptxas keeps p.in uniform and adds it to every address again
+#pragma unroll
+				for (int it = 0; it < F::PIECES; it++) cp_async16(dst + it * OWN_PER_IT * F::SLOT, reinterpret_cast<const unsigned char *>(base + ((unsigned long long)own_off[it] << 4)));
 			}
 		}
 		cp_async_commit();
@@ -173,7 +198,6 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p)
 	const float2 *rot_g = PRE ? nullptr : p.rot + (p.P >> K) + ((a - p.P) >> K);
 	float2 *Cg = PRE ? p.D0 + (long long)stream * p.d0_stride + p.d0_off + ((a - p.P) >> K)
 					 : p.C + (long long)(stream * 2) * p.c_stride + p.c_off + ((a - p.P) >> (K + 1));
-	const int n_super = warp_chunks / NCH;
 	const int warm_super = p.P / SS;
 #pragma unroll
 	for (int c = 0; c < ST_NB - 1; c++) prefetch(c);
@@ -229,7 +253,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p)
 								y = u16pair_to_c64(ds2u_pair<0>(lu[3], pendu[3], yu));
 								// before the first sample of a stream the reference's float stages hold 0.0f, while the all-zero bytes
 								// of the (virtual) history convert to -1.0f: silence the warm-up outputs of the stream's first lane
-								if (p.st_first && sub0 + lane == 0 && ss < warm_super) y = 0ull;
+								if (p.st_first && sub == 0 && ss < warm_super) y = 0ull;
 								idx >>= 1;
 							}
 						}
@@ -279,13 +303,13 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p)
 			__syncwarp(); // the ring slot may be refilled by a later prefetch
 		}
 		if (PRE) {
-			if (ss >= warm_super) {
+			if (ss >= warm_super && ss - warm_super < n_main) {
 				float2 *o = Cg + ss * N96;
 #pragma unroll
 				for (int i = 0; i < N96; i += 2) *reinterpret_cast<ulonglong2 *>(o + i) = make_ulonglong2(lvK[i], lvK[i + 1]);
 			}
 		}
-		else if (ss >= warm_super) { // two 48 kHz samples per channel
+		else if (ss >= warm_super && ss - warm_super < n_main) { // two 48 kHz samples per channel
 			float2 *o = Cg + ss * 2;
 			*reinterpret_cast<ulonglong2 *>(o) = make_ulonglong2(outA0, outA1);
 			*reinterpret_cast<ulonglong2 *>(o + p.c_stride) = make_ulonglong2(outB0, outB1);
@@ -295,12 +319,55 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p)
 }
 
 // ---- launch entry point of one sample format (instantiated by fe_stream_f<FMT>.cu) ----
+// Lanes per stream: the cost of a launch is modelled as waves x (super-steps per lane, warm-up included), a wave being what
+// the SMs hold at once (148 x resident CTAs of this shape).  Sub-segments shorter than `min_ratio` warm-ups are not considered;
+// among (nearly) equal costs the fewest lanes win -- every lane re-reads P samples of warm-up.
+// 1024 streams x 2048 super-steps, four-warp CTAs, one per SM: L = 18 (144 CTAs, 114 + 6 super-steps) against 140 for the
+// power-of-two split L = 32 (256 CTAs = 1.73 waves of 64 + 6).
+static inline bool st_plan(long long B, int nss, int warm, int wpc, int slots, int min_ratio, int forced_L, int &L, int &q, int &r) {
+	const int q_min = warm * min_ratio > 0 ? warm * min_ratio : 1;
+	if (nss < q_min) return false;
+	const int L_max = nss / q_min;
+	auto cost = [&](int l) {
+		const long long ctas = ((B * l + 31) / 32 + wpc - 1) / wpc;
+		const long long waves = (ctas + slots - 1) / slots;
+		return (double)waves * ((nss + l - 1) / l + warm);
+	};
+	int best = 1;
+	double cb = cost(1);
+	for (int l = 2; l <= L_max; l++) {
+		const double c = cost(l);
+		if (c < cb * 0.97) { cb = c; best = l; }
+	}
+	if (forced_L > 0) best = forced_L < L_max ? forced_L : L_max;
+	L = best;
+	q = nss / L;
+	r = nss - q * L;
+	return true;
+}
 template <int FMT, int K, int G, int NB, int WPC, bool PRE>
-static cudaError_t launch_st_one(const FeParams &p, long long n_warps, cudaStream_t s) {
+static cudaError_t launch_st_one(const FeParams &p_in, int forced_L, cudaStream_t s) {
 	constexpr int GG = G <= (1 << (K + 2)) ? G : (1 << (K + 2)); // K = 3: a super-step is 32 samples
+	constexpr int SS = 1 << (K + 2);
 	const size_t smem = (size_t)WPC * NB * 32 * StFmt<FMT, GG>::SLOT;
-	cudaError_t e = cudaFuncSetAttribute(k_frontend_st<FMT, K, GG, NB, WPC, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = cudaFuncSetAttribute(k_frontend_st<FMT, K, GG, NB, WPC, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); // per device
 	if (e != cudaSuccess) return e;
+	static std::atomic<int> slots_cache{0}; // SMs x resident CTAs of this instantiation (all devices of a box are alike)
+	int slots = slots_cache.load(std::memory_order_relaxed);
+	if (!slots) {
+		int dev = 0, sms = 0, occ = 0;
+		if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+		if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+		if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_frontend_st<FMT, K, GG, NB, WPC, PRE>, WPC * 32, smem)) != cudaSuccess) return e;
+		slots = sms * (occ > 0 ? occ : 1);
+		slots_cache.store(slots, std::memory_order_relaxed);
+	}
+	FeParams p = p_in;
+	if (p.N % SS || p.P % SS) return cudaErrorInvalidValue;
+	if ((unsigned long long)p.st_B * (unsigned long long)p.in_stride * StFmt<FMT, GG>::BPS >= (1ull << 36)) return cudaErrorNotSupported; // 32-bit lane offsets (16-byte units)
+	// the integer front end only needs a sub-segment to cover its own warm-up; the float one wants >= 4 warm-ups per lane
+	if (!st_plan(p.st_B, p.N / SS, p.P / SS, WPC, slots, FMT == 4 ? 1 : 4, forced_L, p.st_L, p.st_q, p.st_r)) return cudaErrorNotSupported;
+	const long long n_warps = ((long long)p.st_B * p.st_L + 31) / 32;
 	const unsigned ctas = (unsigned)((n_warps + WPC - 1) / WPC);
 	k_frontend_st<FMT, K, GG, NB, WPC, PRE><<<ctas, WPC * 32, smem, s>>>(p);
 	return cudaGetLastError();
@@ -308,21 +375,21 @@ static cudaError_t launch_st_one(const FeParams &p, long long n_warps, cudaStrea
 // ring depth x warps per CTA: CF32 (128-byte lane chunks) has the shapes {4 or 6 chunks, 1 warp} and {8 chunks, 4 warps}, one
 // translation unit each; the integer formats (32/64-byte lane chunks) always run one-warp CTAs with 8 chunks
 template <int FMT, int G, int NB, int WPC>
-cudaError_t launch_frontend_stream_shape(const FeParams &p, int k, bool pre, long long n_warps, cudaStream_t s) {
+cudaError_t launch_frontend_stream_shape(const FeParams &p, int k, bool pre, int forced_L, cudaStream_t s) {
 	if (pre) {
 		switch (k) { // CIC stages in front of DSP::Upsample
-		case 3: return launch_st_one<FMT, 3, G, NB, WPC, true>(p, n_warps, s);
-		case 4: return launch_st_one<FMT, 4, G, NB, WPC, true>(p, n_warps, s);
-		case 5: return launch_st_one<FMT, 5, G, NB, WPC, true>(p, n_warps, s);
+		case 3: return launch_st_one<FMT, 3, G, NB, WPC, true>(p, forced_L, s);
+		case 4: return launch_st_one<FMT, 4, G, NB, WPC, true>(p, forced_L, s);
+		case 5: return launch_st_one<FMT, 5, G, NB, WPC, true>(p, forced_L, s);
 		default: return cudaErrorInvalidValue;
 		}
 	}
 	switch (k) {
-	case 3: return launch_st_one<FMT, 3, G, NB, WPC, false>(p, n_warps, s);
-	case 4: return launch_st_one<FMT, 4, G, NB, WPC, false>(p, n_warps, s);
-	case 5: return launch_st_one<FMT, 5, G, NB, WPC, false>(p, n_warps, s);
-	case 6: return launch_st_one<FMT, 6, G, NB, WPC, false>(p, n_warps, s);
-	case 7: return launch_st_one<FMT, 7, G, NB, WPC, false>(p, n_warps, s);
+	case 3: return launch_st_one<FMT, 3, G, NB, WPC, false>(p, forced_L, s);
+	case 4: return launch_st_one<FMT, 4, G, NB, WPC, false>(p, forced_L, s);
+	case 5: return launch_st_one<FMT, 5, G, NB, WPC, false>(p, forced_L, s);
+	case 6: return launch_st_one<FMT, 6, G, NB, WPC, false>(p, forced_L, s);
+	case 7: return launch_st_one<FMT, 7, G, NB, WPC, false>(p, forced_L, s);
 	default: return cudaErrorInvalidValue;
 	}
 }

@@ -1,21 +1,27 @@
 // fe_stream_f0.cu -- streaming front end: CF32 in front of DSP::Upsample (one-warp CTAs, 16-sample chunks, ring of 6); one translation unit per shape keeps the build parallel.
 #include "fe_stream.cuh"
+#include <cstdlib>
 
 namespace aisgpu {
 
-template cudaError_t launch_frontend_stream_shape<0, 16, 6, 1>(const FeParams &, int, bool, long long, cudaStream_t);
+template cudaError_t launch_frontend_stream_shape<0, 16, 6, 1>(const FeParams &, int, bool, int, cudaStream_t);
 
-cudaError_t launch_frontend_stream(const FeParams &p, int fmt, int k, bool pre, long long n_warps, cudaStream_t s) {
+cudaError_t launch_frontend_stream(const FeParams &p, int fmt, int k, bool pre, int forced_L, cudaStream_t s) {
 	switch (fmt) {
 	case 0:
-		if (pre) return launch_frontend_stream_shape<0, 16, 6, 1>(p, k, true, n_warps, s);
+		if (pre) return launch_frontend_stream_shape<0, 16, 6, 1>(p, k, true, forced_L, s);
 		// 32-sample visits, ring of 5, four-warp CTAs (one CTA per SM): the best of the shapes measured -- 16 / 32 / 64 samples per
 		// visit, one-, two- and four-warp CTAs, rings of 2 .. 8 chunks with one to eight CTAs sharing an SM (profiles/r2_sweeps.jsonl):
 		// more resident warps never helped, the kernel is bound by what DRAM delivers for 32768 concurrent sequential streams
-		return launch_frontend_stream_shape<0, 32, 5, 4>(p, k, false, n_warps, s);
-	case 1: return launch_frontend_stream_shape<1, 16, 8, 1>(p, k, pre, n_warps, s);
-	case 2: return launch_frontend_stream_shape<2, 16, 8, 1>(p, k, pre, n_warps, s);
-	default: return launch_frontend_stream_shape<3, 16, 8, 1>(p, k, pre, n_warps, s);
+		{
+			static const int nb = getenv("AISGPU_ST_NB") ? atoi(getenv("AISGPU_ST_NB")) : 5; // ring depth: experiment knob of this round
+			if (nb == 3) return launch_frontend_stream_shape<0, 32, 3, 4>(p, k, false, forced_L, s);
+			if (nb == 4) return launch_frontend_stream_shape<0, 32, 4, 4>(p, k, false, forced_L, s);
+		}
+		return launch_frontend_stream_shape<0, 32, 5, 4>(p, k, false, forced_L, s);
+	case 1: return launch_frontend_stream_shape<1, 16, 8, 1>(p, k, pre, forced_L, s);
+	case 2: return launch_frontend_stream_shape<2, 16, 8, 1>(p, k, pre, forced_L, s);
+	default: return launch_frontend_stream_shape<3, 16, 8, 1>(p, k, pre, forced_L, s);
 	}
 }
 

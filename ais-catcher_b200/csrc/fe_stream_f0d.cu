@@ -3,6 +3,6 @@
 
 namespace aisgpu {
 
-template cudaError_t launch_frontend_stream_shape<0, 32, 5, 4>(const FeParams &, int, bool, long long, cudaStream_t);
+template cudaError_t launch_frontend_stream_shape<0, 32, 5, 4>(const FeParams &, int, bool, int, cudaStream_t);
 
 } // namespace aisgpu

@@ -3,6 +3,6 @@
 
 namespace aisgpu {
 
-template cudaError_t launch_frontend_stream_shape<3, 16, 8, 1>(const FeParams &, int, bool, long long, cudaStream_t);
+template cudaError_t launch_frontend_stream_shape<3, 16, 8, 1>(const FeParams &, int, bool, int, cudaStream_t);
 
 } // namespace aisgpu

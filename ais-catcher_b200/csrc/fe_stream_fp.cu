@@ -4,6 +4,6 @@
 
 namespace aisgpu {
 
-cudaError_t launch_frontend_stream_fpds(const FeParams &p, long long n_warps, cudaStream_t s) { return launch_st_one<4, 4, 16, 8, 1, false>(p, n_warps, s); }
+cudaError_t launch_frontend_stream_fpds(const FeParams &p, int forced_L, cudaStream_t s) { return launch_st_one<4, 4, 16, 8, 1, false>(p, forced_L, s); }
 
 } // namespace aisgpu

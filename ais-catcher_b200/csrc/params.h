@@ -33,7 +33,7 @@ struct FeParams {
 	int off_rot[2];          // phasors of the tile
 	int off_lv[FE_MAXK + 1]; // level arrays 1..k (off_lv[0] unused)
 	int off_up, off_dn, off_wa, off_wb;
-	int st_S, st_wps, st_B; // streaming kernel: samples per lane sub-segment, warps per stream, streams
+	int st_L, st_q, st_r, st_B; // streaming kernel: lanes per stream, super-steps per lane (the last st_r lanes of a stream take st_q + 1), streams
 	int st_first;           // 1 in the first block of a stream (the integer front end's virtual history, see fe_stream.cuh)
 	int smem_f2;          // total float2
 	float2 *D0;           // PRE mode (decimation in front of DSP::Upsample): level-K samples, [B][d0_stride], sample i at d0_off + i
@@ -100,6 +100,7 @@ struct FrameRec {
 
 struct K3Params {
 	int ps_ema;
+	int ps_rot0;          // PhaseSearchEMA: (symbols delivered before this submit) & 3 = the (1j)^rot phase of its first symbol
 	int rows;
 	int nsym;             // symbol slots (groups of 5 samples) to walk this submit
 	long long e_stride;
@@ -177,11 +178,11 @@ cudaError_t launch_carry2_f2(const float2 *src, float2 *dst, long long stride, i
 cudaError_t set_taps_bh28_3(const float *taps26);
 // fe_tiled.cu
 cudaError_t launch_frontend_tiled(const FeParams &p, int fmt, int k, bool pre, dim3 grid, size_t smem, cudaStream_t s);
-// fe_stream_f*.cu: n_warps warps (one per 32 lane sub-segments); g = samples per lane per staged chunk (CF32: 16, 32 or 64)
-cudaError_t launch_frontend_stream(const FeParams &p, int fmt, int k, bool pre, long long n_warps, cudaStream_t s);
-cudaError_t launch_frontend_stream_fpds(const FeParams &p, long long n_warps, cudaStream_t s); // fe_stream_fp.cu: CU8, integer CIC stages, 1536K
+// fe_stream_f*.cu: the launcher picks the lanes per stream (st_plan in fe_stream.cuh) unless forced_L > 0
+cudaError_t launch_frontend_stream(const FeParams &p, int fmt, int k, bool pre, int forced_L, cudaStream_t s); // cudaErrorNotSupported: block too short for this kernel
+cudaError_t launch_frontend_stream_fpds(const FeParams &p, int forced_L, cudaStream_t s); // fe_stream_fp.cu: CU8, integer CIC stages, 1536K
 template <int FMT, int G, int NB, int WPC>
-cudaError_t launch_frontend_stream_shape(const FeParams &p, int k, bool pre, long long n_warps, cudaStream_t s);
+cudaError_t launch_frontend_stream_shape(const FeParams &p, int k, bool pre, int forced_L, cudaStream_t s);
 // be_cgf.cu
 cudaError_t cgf_init(const float *taps17, const float2 *omega256);
 cudaError_t launch_cgf_estimate(const float2 *Cbuf, long long c_stride, int c_begin, int nblk, int total_blocks, const float2 *omega, int wide, int *stepidx, cudaStream_t s);

@@ -423,3 +423,20 @@ def test_tiny_and_zero_inputs(built, amp, exact):
                 else:
                     assert len(g) == len(w) and np.max(np.abs(g - w)) <= 8 * 1.4e-45, (amp, float(np.max(np.abs(g - w))))
     eng.close()
+
+
+@pytest.mark.parametrize("lanes", ["0", "1", "3", "7", "18", "33", "100"])
+def test_streaming_frontend_lane_split(built, monkeypatch, lanes):
+    """The streaming front end splits a stream's super-steps over L lanes, L not dividing the block (uneven q / q + 1 split,
+    warps spanning streams, spare lanes in the last warp): AISGPU_ST_L forces L, "0" lets the launcher plan it.
+    N = 64 * 1017 has no power-of-two lane split at all."""
+    monkeypatch.setenv("AISGPU_ST_L", lanes)
+    n = run_case(built, aisgpu.MODEL_STANDARD, 1536000, 64 * 1017, 4, 5, seed0=41)
+    assert n >= 6
+
+
+@pytest.mark.parametrize("fmt,fs,N", [(aisgpu.FMT_CU8, 1536000, 64 * 1017), (aisgpu.FMT_CS16, 768000, 32 * 999), (aisgpu.FMT_CF32, 3072000, 128 * 613)])
+def test_streaming_frontend_lane_split_formats(built, monkeypatch, fmt, fs, N):
+    for lanes in ("5", "19"):
+        monkeypatch.setenv("AISGPU_ST_L", lanes)
+        run_case(built, aisgpu.MODEL_DEFAULT, fs, N, 3, 3, fmt=fmt, seed0=43)
