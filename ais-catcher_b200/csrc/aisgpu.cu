@@ -102,7 +102,7 @@ struct aisgpu_handle {
 	int rows = 0;
 	int max_n48 = 0;
 	int fe_warps = 4, fe_tile = 0, fe_ctas = 4096;
-	int fe_st = 1, st_L = 0, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_L: lanes per stream (0: the launcher plans)
+	int fe_st = 1, st_L = 0, st_ring = 0, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_L: lanes per stream (0: the launcher plans); AISGPU_ST_NB: ring depth 3 | 5 (0: per chain)
 	int cf_rows = 4; // AISGPU_CF_ROWS: rows per CTA of the fused CGF kernel (4 or 8)
 	int dec_rpw = 6, decoder = 3; // rows per warp / which decoder kernel // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
@@ -115,6 +115,12 @@ struct aisgpu_handle {
 	static const int NSTAGE = 7; // 0 estimate / fm+fir, 1 + 2 phasor chain + derot + fir (+Ec carry), 3 phase search, 4 decode, 5 carry of Cbuf, 6 Challenger FM branch (reads Ed)
 	cudaEvent_t ev_stage[NSTAGE][2] = {};
 	bool stage_rec[NSTAGE][2] = {};
+	// Ec (FIR17 output, coherent chains) is double buffered: the fused derotation kernel of submit c + 1 writes one buffer while the
+	// phase search of submit c still reads the other (with a single buffer the chain fused -> phase search of ALL submits was one
+	// serial sequence).  ec_cur: the buffer the next block of symbols goes to; ev_ec_read[i]: the last reader of buffer i.
+	int ec_cur = 0, ec_last = 0;
+	cudaEvent_t ev_ec_read[2] = { nullptr, nullptr };
+	bool ec_read_rec[2] = { false, false };
 	cudaEvent_t ev_join = nullptr;
 	int pb = 0; // buffer parity of the submit being enqueued
 	static const int NC = 3; // ring of 48 kHz buffers: the front end may run two submits ahead of the back end
@@ -399,7 +405,22 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 		p.in = dev_in;
 		p.st_B = B;
 		p.st_first = h->chunk == 0 ? 1 : 0;
-		const cudaError_t e = h->fp_ds ? launch_frontend_stream_fpds(p, h->st_L, h->fe_stream) : launch_frontend_stream(p, h->in_fmt, h->k, false, h->st_L, h->fe_stream);
+		int L = h->st_L;
+		const bool fm_chain = h->cfg.model == AISGPU_MODEL_STANDARD || h->cfg.model == AISGPU_MODEL_BASE;
+		p.st_ring = h->st_ring ? h->st_ring : (fm_chain ? 5 : 3);
+		p.st_cap = fm_chain ? 0 : 1; // coherent chains: ONE front-end CTA per SM (the ring of 3 would let two in), the rest of the SM is the back end's
+		if (L <= 0 && fm_chain) {
+			// FM chain: its back end (k_fm_fir5) saturates the issue slots of the SMs it lands on, and a front end made of ONE
+			// balanced wave of long CTAs is as slow as the SM that was disturbed most.  Shorter sub-segments in ~1.7 waves let the
+			// block scheduler even that out: live 0.293 vs 0.302-0.310 ms per step at 1024 x 131072 (alone it is the other way round,
+			// 0.230 vs 0.216 ms).  The coherent chains (latency-bound back ends) run 4 % faster on the balanced single wave.
+			const int SS = 1 << (h->k + 2);
+			int S = 2048;
+			for (int i = 3; i < h->k; i++) S *= 2;
+			while (S >= 2 * SS && S / 2 >= 4 * h->P && N % (32 * S) != 0) S /= 2;
+			if (N % (32 * S) == 0) L = N / S;
+		}
+		const cudaError_t e = h->fp_ds ? launch_frontend_stream_fpds(p, L, h->fe_stream) : launch_frontend_stream(p, h->in_fmt, h->k, false, L, h->fe_stream);
 		if (e == cudaSuccess) return 0;
 		if (e != cudaErrorNotSupported) CU(e);
 	}
@@ -497,7 +518,7 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.abs_begin = h->e_abs;
 		p.abs_lo = h->e_abs;
 		p.abs_hi = h->e_abs + (long long)nsym * 5;
-		p.Ec = h->d_Ec2[0];
+		p.Ec = h->d_Ec2[h->ec_cur];
 		p.Ef = h->d_Ef2[0];
 		p.ps = h->d_ps;
 		p.ps_mem = h->d_ps_mem;
@@ -524,11 +545,12 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 		p.lvl_stride = h->dwords * K3_TS;
 		if (int rc = stage_begin(h, 3)) return rc;
 		CU(launch_phase_search(p, h->bs));
-		// the incomplete group of 5 at the end moves to the front for the next submit (Ec is single buffered: the next
-		// submit's derotation waits for this stage)
+		// the incomplete group of 5 at the end moves to the front of the OTHER Ec buffer, where the next block of symbols lands
 		const int nl = total - nsym * 5;
-		if (carry(h, h->d_Ec2[0], h->e_stride, e_begin + nsym * 5, HE - nl, nl)) return AISGPU_ECUDA;
+		if (carry2(h, h->d_Ec2[h->ec_cur], h->d_Ec2[h->ec_cur ^ 1], h->e_stride, e_begin + nsym * 5, HE - nl, nl)) return AISGPU_ECUDA;
 		if (int rc = stage_end(h, 3)) return rc;
+		CU(cudaEventRecord(h->ev_ec_read[h->ec_cur], h->bs));
+		h->ec_read_rec[h->ec_cur] = true;
 		if (h->cfg.model == AISGPU_MODEL_CHALLENGER) {
 			// FM branch on the derotated samples: Demod::FM -> Filter 37 -> Deinterleave (Model.cpp:637-639), all new samples at once
 			const long long a0 = h->e_abs + h->e_left, a1 = a0 + n_new; // absolute indices of the new samples
@@ -571,9 +593,13 @@ int run_symbols(aisgpu_handle *h, int n_new) {
 	const int new_left = total - nsym * 5;
 	if (nsym == 0) {
 		if (int rc = stage_begin(h, 3)) return rc;
-		if (carry(h, h->d_Ec2[0], h->e_stride, e_begin + nsym * 5, HE - new_left, new_left)) return AISGPU_ECUDA;
+		if (carry2(h, h->d_Ec2[h->ec_cur], h->d_Ec2[h->ec_cur ^ 1], h->e_stride, e_begin, HE - new_left, new_left)) return AISGPU_ECUDA;
 		if (int rc = stage_end(h, 3)) return rc;
+		CU(cudaEventRecord(h->ev_ec_read[h->ec_cur], h->bs));
+		h->ec_read_rec[h->ec_cur] = true;
 	}
+	h->ec_last = h->ec_cur;
+	h->ec_cur ^= 1;
 	h->e_left = new_left;
 	h->e_abs += (long long)nsym * 5;
 	return 0;
@@ -685,14 +711,15 @@ int submit_common(aisgpu_handle *h, const void *dev_in, long long stride, int N)
 			// stepidx / dbits / lvl are double buffered by submit parity == stream, so stream order protects them
 			CU(launch_cgf_estimate(Ccur, h->c_stride, c_begin, nblk, total_blocks, h->d_omega, h->cfg.afc_wide, stepidx, h->bs));
 			const int nE = nblk * CGF_N;
-			{ // phasor chain + derotation + FIR17 in one kernel: waits for what carries its state (stages 1, 2) and for Ec (stage 3)
+			{ // phasor chain + derotation + FIR17 in one kernel: waits for what carries its state (stages 1, 2) and for the last reader of
+				// the Ec buffer it writes (the phase search two blocks of symbols ago)
 				if (int rc = stage_begin(h, 1)) return rc;
 				if (int rc = stage_begin(h, 2)) return rc;
-				if (int rc = stage_begin(h, 3)) return rc;
+				if (h->ec_read_rec[h->ec_cur]) CU(cudaStreamWaitEvent(h->bs, h->ev_ec_read[h->ec_cur], 0));
 				if (h->d_Ed) // ModelChallenger: Ed (single buffered) is free once the previous submit's FM branch has read it
 					if (int rc = stage_begin(h, 6)) return rc;
 				CU(launch_cgf_fused(Ccur, h->c_stride, c_begin, stepidx, h->d_steptab, h->d_cgf_rot, nblk, h->rows, h->d_fir_hist[h->fir_cur],
-									h->d_fir_hist[h->fir_cur ^ 1], h->d_Ec2[0], h->e_stride, HE,
+									h->d_fir_hist[h->fir_cur ^ 1], h->d_Ec2[h->ec_cur], h->e_stride, HE,
 									h->d_Ed ? h->d_Ed + HD : (h->cfg.enable_taps ? h->d_tap_cgf : nullptr), h->d_Ed ? h->ed_stride : h->r_stride, h->cf_rows, h->bs));
 				if (int rc = stage_end(h, 1)) return rc;
 				if (int rc = stage_end(h, 2)) return rc;
@@ -1170,6 +1197,7 @@ static int create_impl(aisgpu_handle *h) {
 	if (const char *e = getenv("AISGPU_FE_TILE")) h->fe_tile = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_ST")) h->fe_st = atoi(e) ? 1 : 0;
 	if (const char *e = getenv("AISGPU_ST_L")) h->st_L = atoi(e);
+	if (const char *e = getenv("AISGPU_ST_NB")) h->st_ring = atoi(e) == 3 ? 3 : 5;
 	if (const char *e = getenv("AISGPU_ST_KMAX")) h->st_kmax = atoi(e);
 	if (const char *e = getenv("AISGPU_FE_CTAS")) h->fe_ctas = std::max(1, atoi(e));
 	int ndev = 0;
@@ -1205,6 +1233,7 @@ static int create_impl(aisgpu_handle *h) {
 	h->bs = h->stream;
 	for (int st = 0; st < aisgpu_handle::NSTAGE; st++)
 		for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&h->ev_stage[st][i], cudaEventDisableTiming));
+	for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&h->ev_ec_read[i], cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
 	CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
@@ -1325,7 +1354,8 @@ static int create_impl(aisgpu_handle *h) {
 			if (int rc = dalloc(h, &h->d_stepidx2[i], (size_t)h->rows * (nEmax / CGF_N + 1))) return rc;
 		}
 		if (int rc = dalloc(h, &h->d_cgf_rot, (size_t)h->rows)) return rc;
-		if (int rc = dalloc(h, &h->d_Ec2[0], (size_t)h->rows * h->e_stride)) return rc;
+		for (int i = 0; i < 2; i++)
+			if (int rc = dalloc(h, &h->d_Ec2[i], (size_t)h->rows * h->e_stride)) return rc;
 		if (int rc = dalloc(h, &h->d_ps, (size_t)h->rows * 5)) return rc;
 		h->dwords = (nEmax / 5 + 1 + K3_TS - 1) / K3_TS + 1;
 		for (int i = 0; i < 2; i++) {
@@ -1579,7 +1609,7 @@ int aisgpu_tap(aisgpu_handle *h, int tap, int stream, int channel, void *dst, si
 			if (!h->d_tap_coh) { h->err = "taps not enabled"; return AISGPU_EINVAL; }
 			src = h->d_tap_coh + (long long)row * h->r_stride;
 		}
-		else if (h->cfg.model == AISGPU_MODEL_DEFAULT) src = h->d_Ec2[0] + (long long)row * h->e_stride + HE;
+		else if (h->cfg.model == AISGPU_MODEL_DEFAULT) src = h->d_Ec2[h->ec_last] + (long long)row * h->e_stride + HE;
 		else {
 			if (!h->cfg.enable_taps && h->cfg.model != AISGPU_MODEL_BASE) { h->err = "taps not enabled"; return AISGPU_EINVAL; } // the FIR37 output is not stored then
 			src = h->d_Ef2[0] + (long long)row * h->e_stride + HE;
@@ -1816,6 +1846,8 @@ void aisgpu_destroy(aisgpu_handle *h) {
 	for (int st = 0; st < aisgpu_handle::NSTAGE; st++)
 		for (int i = 0; i < 2; i++)
 			if (h->ev_stage[st][i]) cudaEventDestroy(h->ev_stage[st][i]);
+	for (int i = 0; i < 2; i++)
+		if (h->ev_ec_read[i]) cudaEventDestroy(h->ev_ec_read[i]);
 	if (h->ev_join) cudaEventDestroy(h->ev_join);
 	if (h->nccl_comm) {
 		std::string e;
@@ -1832,7 +1864,7 @@ void aisgpu_destroy(aisgpu_handle *h) {
 		if (h->ev_us[i]) cudaEventDestroy(h->ev_us[i]);
 	}
 	void *ptrs[] = { h->d_ptail[0], h->d_ptail[1], h->d_ptail2[0], h->d_ptail2[1], h->d_S2, h->d_D0, h->d_S, h->d_us_src, h->d_us_alpha, h->d_in[0], h->d_in[1], h->d_tail[0], h->d_tail[1], h->d_rot[0], h->d_rot[1], h->d_rot[2], h->d_rot_state, h->d_C2[0], h->d_C2[1], h->d_C2[2],
-					 h->d_steptab, h->d_omega, h->d_cgf_rot, h->d_stepidx2[0], h->d_stepidx2[1], h->d_ppmtab, h->d_fir_hist[0], h->d_fir_hist[1], h->d_tap_cgf, h->d_Ec2[0],
+					 h->d_steptab, h->d_omega, h->d_cgf_rot, h->d_stepidx2[0], h->d_stepidx2[1], h->d_ppmtab, h->d_fir_hist[0], h->d_fir_hist[1], h->d_tap_cgf, h->d_Ec2[0], h->d_Ec2[1],
 					 h->d_Ef2[0], h->d_ps, h->d_ps_mem, h->d_dbits2[0], h->d_dbits2[1], h->d_lvl2[0], h->d_lvl2[1], h->d_dbg, h->d_dec, h->d_dec_data, h->d_pll, h->d_tap_dec, h->d_tap_fm, h->d_tap_cnt, h->d_v2, h->d_tap_coh, h->d_Ed, h->d_dbitsF[0], h->d_dbitsF[1], h->d_lvl_prev, h->d_ring,
 					 h->d_ring_head, h->d_counts };
 	for (void *p : ptrs)

@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(32) k_phase_search_ema4(const K3Params p) {
 constexpr int PS3_G = 4;        // symbols per group
 constexpr int PS3_STRIDE = 20;  // floats per (instance, symbol): 16 EMAs, the first two again (the window wraps), 2 unused
 template <int R0>
-__global__ void __launch_bounds__(32) k_phase_search_ema4b(const K3Params p) {
+__global__ void __launch_bounds__(32, 28) k_phase_search_ema4b(const K3Params p) { // 61 registers, no spills: left alone ptxas takes 110 and the 1280 one-warp CTAs of the bench shape no longer fit next to the other kernels' CTAs
 	__shared__ float2 tile[2][PS2_TROWS][PS2_ROWP];
 	__shared__ __align__(16) float mav[2][PS3_G][PS2_INST][PS3_STRIDE];
 	const int lane = threadIdx.x;

@@ -2,6 +2,7 @@
 #include "exact.cuh"
 #include "params.h"
 #include <atomic>
+#include <algorithm>
 
 namespace aisgpu {
 
@@ -352,7 +353,7 @@ static cudaError_t launch_st_one(const FeParams &p_in, int forced_L, cudaStream_
 	const size_t smem = (size_t)WPC * NB * 32 * StFmt<FMT, GG>::SLOT;
 	cudaError_t e = cudaFuncSetAttribute(k_frontend_st<FMT, K, GG, NB, WPC, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); // per device
 	if (e != cudaSuccess) return e;
-	static std::atomic<int> slots_cache{0}; // SMs x resident CTAs of this instantiation (all devices of a box are alike)
+	static std::atomic<int> slots_cache{0}, sms_cache{0}; // SMs x resident CTAs of this instantiation (all devices of a box are alike)
 	int slots = slots_cache.load(std::memory_order_relaxed);
 	if (!slots) {
 		int dev = 0, sms = 0, occ = 0;
@@ -361,7 +362,9 @@ static cudaError_t launch_st_one(const FeParams &p_in, int forced_L, cudaStream_
 		if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_frontend_st<FMT, K, GG, NB, WPC, PRE>, WPC * 32, smem)) != cudaSuccess) return e;
 		slots = sms * (occ > 0 ? occ : 1);
 		slots_cache.store(slots, std::memory_order_relaxed);
+		sms_cache.store(sms, std::memory_order_relaxed);
 	}
+	if (p_in.st_cap > 0) slots = std::min(slots, sms_cache.load(std::memory_order_relaxed) * p_in.st_cap);
 	FeParams p = p_in;
 	if (p.N % SS || p.P % SS) return cudaErrorInvalidValue;
 	if ((unsigned long long)p.st_B * (unsigned long long)p.in_stride * StFmt<FMT, GG>::BPS >= (1ull << 36)) return cudaErrorNotSupported; // 32-bit lane offsets (16-byte units)

@@ -35,6 +35,7 @@ struct FeParams {
 	int off_up, off_dn, off_wa, off_wb;
 	int st_L, st_q, st_r, st_B; // streaming kernel: lanes per stream, super-steps per lane (the last st_r lanes of a stream take st_q + 1), streams
 	int st_first;           // 1 in the first block of a stream (the integer front end's virtual history, see fe_stream.cuh)
+	int st_ring, st_cap;    // CF32 launch shape: chunks in the staging ring (3 or 5; 0 = 5) and resident CTAs per SM the lane planner counts on (0 = what fits)
 	int smem_f2;          // total float2
 	float2 *D0;           // PRE mode (decimation in front of DSP::Upsample): level-K samples, [B][d0_stride], sample i at d0_off + i
 	long long d0_stride;
