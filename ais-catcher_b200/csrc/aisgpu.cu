@@ -405,21 +405,16 @@ int launch_frontend(aisgpu_handle *h, const void *dev_in, long long stride, int 
 		p.in = dev_in;
 		p.st_B = B;
 		p.st_first = h->chunk == 0 ? 1 : 0;
-		int L = h->st_L;
-		const bool fm_chain = h->cfg.model == AISGPU_MODEL_STANDARD || h->cfg.model == AISGPU_MODEL_BASE;
-		p.st_ring = h->st_ring ? h->st_ring : (fm_chain ? 5 : 3);
-		p.st_cap = fm_chain ? 0 : 1; // coherent chains: ONE front-end CTA per SM (the ring of 3 would let two in), the rest of the SM is the back end's
-		if (L <= 0 && fm_chain) {
-			// FM chain: its back end (k_fm_fir5) saturates the issue slots of the SMs it lands on, and a front end made of ONE
-			// balanced wave of long CTAs is as slow as the SM that was disturbed most.  Shorter sub-segments in ~1.7 waves let the
-			// block scheduler even that out: live 0.293 vs 0.302-0.310 ms per step at 1024 x 131072 (alone it is the other way round,
-			// 0.230 vs 0.216 ms).  The coherent chains (latency-bound back ends) run 4 % faster on the balanced single wave.
-			const int SS = 1 << (h->k + 2);
-			int S = 2048;
-			for (int i = 3; i < h->k; i++) S *= 2;
-			while (S >= 2 * SS && S / 2 >= 4 * h->P && N % (32 * S) != 0) S /= 2;
-			if (N % (32 * S) == 0) L = N / S;
-		}
+		// CF32 launch shape, measured live at 1024 x 131072 (gpurun probes r2b-1 .. r2b-9, per-block step times):
+		//   ring of 3 chunks (104 KB per CTA) + ONE balanced wave (the planner, one CTA per SM: L = 18, 144 CTAs):
+		//       ModelStandard 0.266 ms, ModelDefault 0.43 ms, Challenger 0.54 ms  <- shipped for every chain
+		//   ring of 5 (174 KB) + power-of-two split L = 32 (256 CTAs, 1.73 waves; the round-2a shape):   0.294 / 0.475 / 0.56 ms
+		//   ring of 5 + L = 18: 0.302-0.310 / 0.455 ms;   ring of 3 + L = 32: 0.311 ms;   ring of 3, two CTAs per SM (L = 37): 0.292-0.313 / 0.446 ms
+		// The smaller ring leaves 123 KB of the SM to the back-end CTAs that run beside the front end of the next submit.
+		// (Throttling the FM kernel's occupancy with unused shared memory so that it cannot crowd the front end: 0.33-0.38 ms, worse.)
+		const int L = h->st_L;
+		p.st_ring = h->st_ring ? h->st_ring : 3;
+		p.st_cap = (h->in_fmt == 0 && !h->fp_ds) ? 1 : 0; // the integer formats run one-warp CTAs, as many per SM as fit
 		const cudaError_t e = h->fp_ds ? launch_frontend_stream_fpds(p, L, h->fe_stream) : launch_frontend_stream(p, h->in_fmt, h->k, false, L, h->fe_stream);
 		if (e == cudaSuccess) return 0;
 		if (e != cudaErrorNotSupported) CU(e);
@@ -867,6 +862,11 @@ int submit_outer(aisgpu_handle *h, const void *dev_in, long long stride, int N) 
 			bool st_done = false;
 			if (h->fe_st && h->kA >= 3 && h->kA <= 5 && ((stride * h->obps) % 16) == 0 && (((size_t)dev_in) % 16) == 0) {
 				pp.st_B = B;
+				// the decimation in front of the resampler runs the same launch shape as the front end proper (four-warp CTAs, ring of 3, one
+				// balanced wave): configs[2] (4096 x 65536 @6 MSPS) 0.70 -> 0.66 ms per step, 1024 x 393216 @6 MSPS 0.91 -> 0.83 ms against
+				// one-warp CTAs with 16-sample chunks
+				pp.st_ring = h->st_ring ? h->st_ring : 3;
+				pp.st_cap = h->cfg.format == 0 ? 1 : 0;
 				const cudaError_t e = launch_frontend_stream(pp, h->cfg.format, h->kA, true, h->st_L, h->fe_stream);
 				if (e == cudaSuccess) st_done = true;
 				else if (e != cudaErrorNotSupported) CU(e);

@@ -8,7 +8,10 @@ template cudaError_t launch_frontend_stream_shape<0, 16, 6, 1>(const FeParams &,
 cudaError_t launch_frontend_stream(const FeParams &p, int fmt, int k, bool pre, int forced_L, cudaStream_t s) {
 	switch (fmt) {
 	case 0:
-		if (pre) return launch_frontend_stream_shape<0, 16, 6, 1>(p, k, true, forced_L, s);
+		if (pre) {
+			if (p.st_ring == 3) return launch_frontend_stream_shape<0, 32, 3, 4>(p, k, true, forced_L, s);
+			return launch_frontend_stream_shape<0, 16, 6, 1>(p, k, true, forced_L, s);
+		}
 		// 32-sample visits, ring of 5, four-warp CTAs (one CTA per SM): the best of the shapes measured -- 16 / 32 / 64 samples per
 		// visit, one-, two- and four-warp CTAs, rings of 2 .. 8 chunks with one to eight CTAs sharing an SM (profiles/r2_sweeps.jsonl):
 		// more resident warps never helped, the kernel is bound by what DRAM delivers for 32768 concurrent sequential streams.

@@ -1,8 +1,12 @@
 #!/bin/bash
-# GPU call r2b-7: per-chain front-end shape (coherent: ring 3, one balanced wave), V2 engine with one converged decoder pass per group
+# GPU call r2b-12: A/B of the front-end shape under bench.py's own timed region (same box, alternating)
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_all.log 2>&1; tail -5 gpurun_out/pytest_all.log | cut -c1-800
-timeout 600 python tools/default_probe.py 11 - > gpurun_out/probe7_m11.jsonl 2>&1; cat gpurun_out/probe7_m11.jsonl | cut -c1-300
-timeout 600 python tools/default_probe.py 2 - AISGPU_ST_NB=5 > gpurun_out/probe7_m2.jsonl 2>&1; cat gpurun_out/probe7_m2.jsonl | cut -c1-300
-timeout 600 python tools/default_probe.py 4 - > gpurun_out/probe7_m4.jsonl 2>&1; cat gpurun_out/probe7_m4.jsonl | cut -c1-300
-timeout 600 python tools/default_probe.py 0 - > gpurun_out/probe7_m0.jsonl 2>&1; cat gpurun_out/probe7_m0.jsonl | cut -c1-300
+for rep in 1 2 3; do
+  for cfg in "" "AISGPU_ST_NB=5 AISGPU_ST_L=32" "AISGPU_ST_L=16" ; do
+    env $cfg timeout 600 python bench.py --no-also --no-cpu --no-parity --e2e-steps 2 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('$cfg'.ljust(32), round(d['ms_per_step'],4), d['spread']['min_ms_per_step'], d['spread']['max_ms_per_step'], 'fe_live', round(d['roofline']['frontend_ms_per_launch'],4), 'iso', round(d['roofline']['isolated_ms_per_launch'],4))
+"
+  done
+done
