@@ -103,7 +103,7 @@ struct aisgpu_handle {
 	int max_n48 = 0;
 	int fe_warps = 4, fe_tile = 0, fe_ctas = 4096;
 	int fe_st = 1, st_L = 0, st_ring = 0, st_kmax = 7; // AISGPU_FE_ST=0 disables the per-thread streaming kernel; AISGPU_ST_L: lanes per stream (0: the launcher plans); AISGPU_ST_NB: ring depth 3 | 5 (0: per chain)
-	int cf_rows = 4; // AISGPU_CF_ROWS: rows per CTA of the fused CGF kernel (4 or 8)
+	int cf_rows = 8; // AISGPU_CF_ROWS: rows per CTA of the fused CGF kernel (4 or 8); 8 halves the chain warp's instructions: 0.427 vs 0.433 ms per step (ModelDefault, bench.py A/B, twice)
 	int dec_rpw = 6, decoder = 3; // rows per warp / which decoder kernel // front-end launch shape (tunable through AISGPU_FE_WARPS / _TILE / _CTAS)
 	// fe_stream: front end + input history; stream: everything behind the 48 kHz buffers (the stream handed to callers
 	// for timing).  The front end of submit c+1 overlaps the back end of submit c; Cbuf is double buffered for that.

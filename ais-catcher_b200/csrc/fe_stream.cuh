@@ -366,7 +366,7 @@ static cudaError_t launch_st_one(const FeParams &p_in, int forced_L, cudaStream_
 	}
 	if (p_in.st_cap > 0) slots = std::min(slots, sms_cache.load(std::memory_order_relaxed) * p_in.st_cap);
 	FeParams p = p_in;
-	if (p.N % SS || p.P % SS) return cudaErrorInvalidValue;
+	if (p.N % SS || p.P % SS) return cudaErrorNotSupported; // the caller falls back to the tiled kernel
 	if ((unsigned long long)p.st_B * (unsigned long long)p.in_stride * StFmt<FMT, GG>::BPS >= (1ull << 36)) return cudaErrorNotSupported; // 32-bit lane offsets (16-byte units)
 	// the integer front end only needs a sub-segment to cover its own warm-up; the float one wants >= 4 warm-ups per lane
 	if (!st_plan(p.st_B, p.N / SS, p.P / SS, WPC, slots, FMT == 4 ? 1 : 4, forced_L, p.st_L, p.st_q, p.st_r)) return cudaErrorNotSupported;
