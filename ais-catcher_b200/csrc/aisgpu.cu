@@ -1181,7 +1181,9 @@ static int create_impl(aisgpu_handle *h) {
 #else
 	h->fe_warps = 4;
 #endif
-	h->dec_rpw = c.model == AISGPU_MODEL_DEFAULT ? 1 : 6; // measured best per chain
+	// rows per warp of the decoder kernel, measured per chain: the coherent chain 1; the FM chain 3 with the round-2b front-end shape
+	// (bench.py A/B, three pairs: 0.266 / 0.276 / 0.263 ms per step against 0.273 / 0.278 / 0.278 with 6 rows per warp)
+	h->dec_rpw = c.model == AISGPU_MODEL_DEFAULT ? 1 : (c.model == AISGPU_MODEL_STANDARD ? 3 : 6);
 	if (const char *e = getenv("AISGPU_DEC_RPW")) {
 		h->dec_rpw = atoi(e);
 		if (h->dec_rpw != 1 && h->dec_rpw != 3) h->dec_rpw = 6;
