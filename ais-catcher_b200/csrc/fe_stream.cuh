@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p)
 		if (c < warp_chunks) {
 			const long long coff = (long long)c * (ST_G * F::BPS) + q0 * 16;
 			unsigned char *dst = &ring[c % ST_NB][dst_off];
-			if (c * ST_G < p.P) {
-#pragma unroll
+			if (c * ST_G < p.P) { // a rolled loop: this branch runs for 5 % of the chunks and would otherwise be inlined at every prefetch site (K + 2 .. 20 of them)
+#pragma unroll 1
 				for (int it = 0; it < F::PIECES; it++) {
 					const unsigned long long w = __shfl_sync(0xffffffffu, my_warm, it * OWN_PER_IT + o0);
 					cp_async16(dst + it * OWN_PER_IT * F::SLOT, reinterpret_cast<const unsigned char *>(w) + coff);
