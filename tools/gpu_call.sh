@@ -1,16 +1,22 @@
 #!/bin/bash
-# GPU call r2b-17: warm-up prefetch as a rolled loop (code size at K = 6, 7): parity, high-rate sweep, configs[2] launch list
+# GPU call r2b-19: front-end register footprint live: prev (164 regs, droop filter branched) / a (160, selected) / b (152 via __maxnreg__, 3 spilled pairs)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_matrix.py -m gpu -x -q > gpurun_out/pytest_fe.log 2>&1; tail -3 gpurun_out/pytest_fe.log | cut -c1-600
-timeout 900 python tools/rate_sweep.py 12288000:512:1048576:0:1 6144000:1024:524288:0:1 3072000:1024:262144:0:1 1536000:1024:131072:0:1 768000:1024:65536:0:1 > gpurun_out/r2j_rate_sweep_hi.jsonl 2>/dev/null; cut -c1-260 gpurun_out/r2j_rate_sweep_hi.jsonl
-AISGPU_ST_NB=5 AISGPU_ST_L=32 timeout 900 python tools/rate_sweep.py 12288000:512:1048576:0:1 6144000:1024:524288:0:1 > gpurun_out/r2j_rate_sweep_hi_old.jsonl 2>/dev/null; cut -c1-260 gpurun_out/r2j_rate_sweep_hi_old.jsonl
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 120 --csv --log-file gpurun_out/r2j_launches_c2.csv python tools/ncu_run.py 2 4096 65536 6000000 > /dev/null 2>&1
-python - <<PY
-import csv,collections
-rows=[r for r in csv.reader(open('gpurun_out/r2j_launches_c2.csv')) if len(r)>10]
-hdr=rows[0]; ki=hdr.index('Kernel Name'); vi=hdr.index('Metric Value')
-d=collections.OrderedDict()
-for r in rows[1:]:
-    d.setdefault(r[ki][:70],[]).append(float(r[vi].replace(',','')))
-for k,v in d.items(): print('  %-72s n=%2d last=%9.1f us' % (k,len(v),v[-1]/1000))
-PY
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "1536k or lane_split or cu8" > gpurun_out/pytest_fe.log 2>&1; tail -2 gpurun_out/pytest_fe.log | cut -c1-300
+for rep in 1 2 3; do
+  for lib in "b:" "a:AISGPU_LIB=/root/repo/ais-catcher_b200/libaisgpu_a.so" "prev:AISGPU_LIB=/root/repo/ais-catcher_b200/libaisgpu_prev.so"; do
+    name=${lib%%:*}; envs=${lib#*:}
+    env $envs timeout 600 python bench.py --model 0 --no-also --no-cpu --no-parity --e2e-steps 2 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('m0', '$name'.ljust(6), round(d['ms_per_step'],4), round(d['spread']['min_ms_per_step'],4), round(d['spread']['max_ms_per_step'],4), 'fe_live', round(d['roofline']['frontend_ms_per_launch'],4), 'iso', round(d['roofline']['isolated_ms_per_launch'],4))
+"
+  done
+done
+for lib in "b:" "a:AISGPU_LIB=/root/repo/ais-catcher_b200/libaisgpu_a.so" "prev:AISGPU_LIB=/root/repo/ais-catcher_b200/libaisgpu_prev.so"; do
+    name=${lib%%:*}; envs=${lib#*:}
+    env $envs timeout 600 python bench.py --model 2 --no-also --no-cpu --no-parity --e2e-steps 2 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('m2', '$name'.ljust(6), round(d['ms_per_step'],4), round(d['spread']['min_ms_per_step'],4), round(d['spread']['max_ms_per_step'],4), 'fe_live', round(d['roofline']['frontend_ms_per_launch'],4))
+"
+done
