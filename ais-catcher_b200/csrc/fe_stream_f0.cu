@@ -28,3 +28,10 @@ cudaError_t launch_frontend_stream(const FeParams &p, int fmt, int k, bool pre, 
 }
 
 } // namespace aisgpu
+
+// Test hook (not part of include/aisgpu.h): the lane planner of the streaming front end as the launcher calls it, so that the CPU
+// suite can check its invariants without a device.  Returns 0 when the block is too short for the streaming kernel.
+extern "C" int aisgpu_dbg_plan_lanes(long long n_streams, int super_steps, int warm_super_steps, int warps_per_cta, int cta_slots, int min_ratio, int forced_lanes,
+									 int *lanes, int *q, int *r) {
+	return aisgpu::st_plan(n_streams, super_steps, warm_super_steps, warps_per_cta, cta_slots, min_ratio, forced_lanes, *lanes, *q, *r) ? 1 : 0;
+}
