@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32) k_frontend_st(const FeParams p)
 	// Measured on this loop and dropped (bench.py A/B against the previous build of the library on one box, AISGPU_LIB):
 	//   two super-steps per trip (the ~60 register moves at the back edge paid once per two: 7 % fewer instructions, but 178 instead of
 	//   164 registers and twice the code): live step 0.288 vs 0.269 ms; the droop filter selected instead of branched (30 fewer
-	//   instructions per super-step): 0.277 vs 0.278 ms; __maxnreg__(152) (three spilled pairs): 0.338 ms.
+	//   instructions per super-step): 0.277 vs 0.278 ms; __maxnreg__(152) (three spilled pairs): 0.338 ms; the chunk loop below rolled
+	//   (kernel 1136 instead of 1552 instructions, but the state moves are paid per chunk: +21 % executed): 0.285 vs 0.269 ms.
 	for (int ss = 0; ss < n_super; ss++) {
 		float2 rt[N96];
 #pragma unroll
