@@ -19,6 +19,14 @@ for model in (aisgpu.MODEL_STANDARD, aisgpu.MODEL_BASE, aisgpu.MODEL_DEFAULT, ai
         n += len(eng.poll())
         eng.close()
         print("model", model, "taps", taps, "messages", n)
+for fmt, nodd in ((aisgpu.FMT_CF32, 64 * 257), (aisgpu.FMT_CU8, 64 * 131)):  # block lengths with no power-of-two lane split: uneven sub-segments, spare lanes
+    xo = np.stack([aissynth.random_stream(fs, nodd * 3, 350 + s)[0] for s in range(5)])
+    eng = aisgpu.Engine(model=aisgpu.MODEL_DEFAULT, sample_rate=fs, fmt=fmt, n_streams=5, max_chunk=nodd)
+    for c in range(3):
+        blk = np.ascontiguousarray(xo[:, c * nodd:(c + 1) * nodd])
+        eng.submit(np.stack([aissynth.to_cu8(r) for r in blk]) if fmt == aisgpu.FMT_CU8 else blk, nodd)
+    print("odd block", nodd, "fmt", fmt, "messages", len(eng.poll()))
+    eng.close()
 eng = aisgpu.Engine(model=aisgpu.MODEL_DEFAULT, sample_rate=6000000, n_streams=2, max_chunk=32768)  # resampler pre-stage
 x6 = np.stack([aissynth.random_stream(6000000, 32768 * 3, 400 + s)[0] for s in range(2)])
 for c in range(3):
