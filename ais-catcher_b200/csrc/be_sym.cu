@@ -382,11 +382,26 @@ __global__ void __launch_bounds__(32, 28) k_phase_search_ema4b(const K3Params p)
 		max_idx = st.max_idx;
 	}
 	const int nsamp = p.nsym * 5;
+	// a tile row is K3_ROWLEN = 5 x 32 samples: five 8-byte copies per lane and row, no index arithmetic beyond the row's base
+	static_assert(K3_ROWLEN == 5 * 32, "tile row = five warp-wide copies");
+	const float2 *rowsrc[PS2_TROWS];
+#pragma unroll
+	for (int r = 0; r < PS2_TROWS; r++) rowsrc[r] = p.Ec + (long long)min(r_lo + r, p.rows - 1) * p.e_stride + p.e_begin + lane;
 	auto prefetch = [&](int buf, int s0) {
 		const int base = s0 * 5;
-		for (int e = lane; e < PS2_TROWS * K3_ROWLEN; e += 32) {
-			const int r = e / K3_ROWLEN, c = e - r * K3_ROWLEN;
-			if (r_lo + r < p.rows && base + c < nsamp) cp_async_f(&tile[buf][r][c], p.Ec + (long long)(r_lo + r) * p.e_stride + p.e_begin + base + c);
+		if (base + K3_ROWLEN <= nsamp) { // a whole tile (all but the submit's last one)
+#pragma unroll
+			for (int r = 0; r < PS2_TROWS; r++)
+				if (r_lo + r < p.rows) {
+#pragma unroll
+					for (int j = 0; j < 5; j++) cp_async_f(&tile[buf][r][lane + 32 * j], rowsrc[r] + base + 32 * j);
+				}
+		}
+		else {
+			for (int e = lane; e < PS2_TROWS * K3_ROWLEN; e += 32) {
+				const int r = e / K3_ROWLEN, c = e - r * K3_ROWLEN;
+				if (r_lo + r < p.rows && base + c < nsamp) cp_async_f(&tile[buf][r][c], p.Ec + (long long)(r_lo + r) * p.e_stride + p.e_begin + base + c);
+			}
 		}
 		cp_async_commit();
 	};
@@ -470,9 +485,33 @@ __global__ void __launch_bounds__(32, 28) k_phase_search_ema4b(const K3Params p)
 			}
 			__syncwarp(); // group g's EMAs are visible to the lookups of the next trip; buffer g & 1 is rewritten two trips later
 		};
-		for (int g = 0; g <= ngrp; g += 2) {
-			trip(g, 0);
-			if (g + 1 <= ngrp) trip(g + 1, 1);
+		if (s_end == K3_TS) { // a whole tile: eight groups, the trip structure is static (no per-trip counts, no per-symbol tests)
+			static_assert(K3_TS == 8 * PS3_G, "eight groups per tile");
+			auto full_trip = [&](const int g, const int buf) { // first halves of group g, lookups of group g - 1
+				const float2 *x = my + g * (PS3_G * 5);
+#pragma unroll
+				for (int k = 0; k < PS3_G; k++) first_half(x[k * 5], k, buf);
+#pragma unroll
+				for (int k = 0; k < PS3_G; k++) second_half(k, buf ^ 1);
+				__syncwarp();
+			};
+#pragma unroll
+			for (int k = 0; k < PS3_G; k++) first_half(my[k * 5], k, 0);
+			__syncwarp();
+			for (int g = 1; g < 7; g += 2) {
+				full_trip(g, 1);
+				full_trip(g + 1, 0);
+			}
+			full_trip(7, 1);
+#pragma unroll
+			for (int k = 0; k < PS3_G; k++) second_half(k, 1);
+			__syncwarp();
+		}
+		else {
+			for (int g = 0; g <= ngrp; g += 2) {
+				trip(g, 0);
+				if (g + 1 <= ngrp) trip(g + 1, 1);
+			}
 		}
 		word >>= (32 - s_end) & 31; // a short last tile: the first symbol goes to bit 0
 		word = or4(word);
